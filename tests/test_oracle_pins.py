@@ -1,0 +1,117 @@
+"""Pins the CPU oracle against every numeric known-answer the reference's own tests
+hold for this path (SURVEY.md section 4 "Numeric pins"), and cross-checks the C oracle
+against the independent NumPy mirror."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import oracle_np
+from lancedb_b200.index import train_ivf_pq
+
+
+def test_l2_doctest_pin():
+    # python/python/lancedb/table.py:3595-3603: q=[0.4,1.4,2.4] -> 5.220000, 23.089996
+    q = [0.4, 1.4, 2.4]
+    assert f"{oracle.l2(q, [0.5, 3.4, 1.3]):.6f}" == "5.220000"
+    assert f"{oracle.l2(q, [0.3, 6.2, 2.6]):.6f}" == "23.089996"
+    assert oracle.l2(q, [0.1, 2.3, 4.5]) > 5.22
+
+
+def test_cosine_doctest_pin():
+    # python/python/lancedb/query.py:1563-1571
+    assert f"{oracle.cosine([0.4, 0.4], [0.4, 0.4]):.6f}" == "0.000000"
+    assert f"{oracle.cosine([0.4, 0.4], [1.1, 1.2]):.6f}" == "0.000944"
+
+
+def test_cosine_matches_numpy_formula():
+    # python/python/tests/test_query.py:993-1014,1045-1046 (abs=1e-6, in [0,1])
+    rng = np.random.default_rng(0)
+    for x, y in [([4, 8], [1, 2]), ([4, 8], [3, 4])] + [
+        (rng.random(16), rng.random(16)) for _ in range(20)]:
+        x = np.asarray(x, np.float64); y = np.asarray(y, np.float64)
+        want = 1 - np.dot(x, y) / (np.linalg.norm(x) * np.linalg.norm(y))
+        got = oracle.cosine(x, y)
+        assert got == pytest.approx(want, abs=1e-6)
+        assert -1e-6 <= got <= 1 + 1e-6
+
+
+def test_exact_match_is_zero():
+    # python/python/tests/test_db.py:198-199, test_table.py:2975-2978
+    v = np.random.default_rng(1).standard_normal(128).astype(np.float32)
+    assert oracle.l2(v, v) == 0.0
+
+
+def test_flat_order_and_tiebreak():
+    # test_query.py:562-570 ([0,0] -> id 1 then id 2); tie-break (_distance, _rowid)
+    # pinned by the plan doctest python/python/lancedb/query.py:1364-1370
+    vec = np.array([[1, 2], [3, 4]], np.float32)
+    ids, dist, cnt = oracle.flat_search(vec, [[0, 0]], k=10, row_ids=[1, 2])
+    assert cnt[0] == 2 and list(ids[0, :2]) == [1, 2] and list(dist[0, :2]) == [5.0, 25.0]
+    dup = np.array([[1, 1], [2, 2], [1, 1], [1, 1]], np.float32)
+    ids, dist, cnt = oracle.flat_search(dup, [[1, 1]], k=2, row_ids=[9, 3, 7, 5])
+    assert list(ids[0]) == [5, 7] and list(dist[0]) == [0.0, 0.0]
+
+
+def test_distance_range_semantics():
+    # [lower, upper): python/python/tests/test_query.py:655-676
+    vec = np.array([[1, 2], [3, 4]], np.float32)
+    lo, hi = 5.0, 25.0
+    assert oracle.flat_search(vec, [[0, 0]], upper=lo)[2][0] == 0
+    ids, dist, cnt = oracle.flat_search(vec, [[0, 0]], lower=hi)
+    assert cnt[0] == 1 and dist[0, 0] == hi
+    ids, dist, cnt = oracle.flat_search(vec, [[0, 0]], upper=hi)
+    assert cnt[0] == 1 and dist[0, 0] == lo
+    assert oracle.flat_search(vec, [[0, 0]], lower=lo)[2][0] == 2
+
+
+@pytest.mark.parametrize("d", [3, 8, 16, 17, 40, 128])
+def test_c_vs_numpy_mirror_distances(d):
+    rng = np.random.default_rng(d)
+    for _ in range(5):
+        x = rng.standard_normal(d).astype(np.float32)
+        y = rng.standard_normal(d).astype(np.float32)
+        assert oracle.l2(x, y) == oracle_np.l2(x, y)
+        assert oracle.dot(x, y) == oracle_np.dot(x, y)
+        assert oracle.cosine(x, y) == oracle_np.cosine(x, y)
+        assert np.array_equal(oracle.normalize(x), oracle_np.normalize(x))
+
+
+@pytest.mark.parametrize("dsub", [4, 8, 16])
+def test_subvec_tree_order(dsub):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(dsub).astype(np.float32)
+    cb = rng.standard_normal((256, dsub)).astype(np.float32)
+    want = oracle_np.l2_subvec_batch(x, cb)
+    got = np.array([oracle.l2_subvec(x, c) for c in cb], np.float32)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_ivfpq_c_vs_numpy_mirror(metric):
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal((600, 32)).astype(np.float32)
+    ix = train_ivf_pq(x, num_partitions=6, num_sub_vectors=4, distance_type=metric, max_iterations=4)
+    oix = oracle.OracleIndex.from_data(ix)
+    q = np.random.default_rng(43).standard_normal((5, 32)).astype(np.float32)
+    ids, dist, cnt = oix.search(q, k=7, nprobes=3)
+    for i in range(5):
+        wi, wd = oracle_np.ivfpq_search_one(ix, q[i], 7, 3)
+        assert cnt[i] == len(wi)
+        assert np.array_equal(ids[i, :cnt[i]], wi)
+        assert np.array_equal(dist[i, :cnt[i]], wd)
+    # multi-threaded run is identical
+    ids2, dist2, cnt2 = oix.search(q, k=7, nprobes=3, nthreads=3)
+    assert np.array_equal(ids, ids2) and np.array_equal(dist, dist2) and np.array_equal(cnt, cnt2)
+
+
+def test_ivfpq_multivector_relational():
+    # test_query.py:791-850: same query twice gives same per-query distances
+    # (the "2x" multivector sum is applied above the ANN path and is out of scope)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((256, 8)).astype(np.float32)
+    ix = train_ivf_pq(x, num_partitions=1, num_sub_vectors=2, distance_type="cosine", max_iterations=4)
+    oix = oracle.OracleIndex.from_data(ix)
+    q = rng.standard_normal(8).astype(np.float32)
+    ids, dist, cnt = oix.search(np.stack([q, q]), k=10, nprobes=1)
+    assert np.array_equal(ids[0], ids[1]) and np.array_equal(dist[0], dist[1])
+    assert (dist[0] >= 0).all() and (dist[0] <= 2).all()
