@@ -1,0 +1,248 @@
+"""ctypes binding of the C ABI in include/lancedb_b200.h.
+
+This is the same binding a non-Python host would write (see INTEGRATION.md for the Rust
+`extern "C"` version).  There is no CPU fallback: if the shared library is missing or no
+CUDA device is present, every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "liblancedb_b200.so")
+_lib = None
+
+LGPU_OK, LGPU_INVALID_INPUT, LGPU_RUNTIME, LGPU_TIMEOUT, LGPU_OOM = 0, 1, 2, 3, 4
+METRICS = {"l2": 0, "euclidean": 0, "cosine": 1, "dot": 2}
+ABI_VERSION = 1
+
+EXPORTS = [
+    "lgpu_last_error", "lgpu_abi_version", "lgpu_device_count",
+    "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
+    "lgpu_search", "lgpu_search_device", "lgpu_merge_topk_device",
+    "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_device",
+    "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_last_stage_ms", "lgpu_set_profiling",
+]
+
+
+class IndexDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("dim", C.c_uint32), ("nlist", C.c_uint32), ("m", C.c_uint32),
+        ("nbits", C.c_uint32), ("metric", C.c_int32), ("codes_layout", C.c_int32), ("device", C.c_int32),
+        ("nrows", C.c_uint64),
+        ("centroids", C.c_void_p), ("codebook", C.c_void_p), ("part_offsets", C.c_void_p),
+        ("codes", C.c_void_p), ("row_ids", C.c_void_p), ("vectors", C.c_void_p),
+    ]
+
+
+class SearchParams(C.Structure):
+    _fields_ = [
+        ("k", C.c_uint32), ("nprobes", C.c_uint32), ("refine_factor", C.c_uint32),
+        ("has_lower", C.c_int32), ("has_upper", C.c_int32), ("lower", C.c_float), ("upper", C.c_float),
+        ("flags", C.c_uint32),
+    ]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    r = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building liblancedb_b200.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+def load():
+    """Load the shared library; raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(lancedb_b200 has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
+    lib.lgpu_last_error.restype = C.c_char_p
+    lib.lgpu_abi_version.restype = u32
+    lib.lgpu_device_count.argtypes = [C.POINTER(C.c_int)]
+    lib.lgpu_index_open.argtypes = [C.POINTER(IndexDesc), C.POINTER(vp)]
+    lib.lgpu_index_close.argtypes = [vp]
+    lib.lgpu_index_close.restype = None
+    lib.lgpu_index_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.lgpu_last_scanned_code_bytes.argtypes = [C.POINTER(C.c_uint64)]
+    lib.lgpu_search.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
+    lib.lgpu_search_device.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
+    lib.lgpu_merge_topk_device.argtypes = [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]
+    lib.lgpu_flat_open.argtypes = [vp, C.c_uint64, u32, vp, i32, C.POINTER(vp)]
+    lib.lgpu_flat_close.argtypes = [vp]
+    lib.lgpu_flat_close.restype = None
+    lib.lgpu_flat_search.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
+    lib.lgpu_flat_search_device.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
+    lib.lgpu_debug_coarse.argtypes = [vp, vp, u32, u32, vp, vp]
+    lib.lgpu_debug_partition_distances.argtypes = [vp, vp, u32, vp]
+    lib.lgpu_last_stage_ms.argtypes = [vp]
+    lib.lgpu_set_profiling.argtypes = [i32]
+    for name in EXPORTS:
+        getattr(lib, name)          # every declared symbol must be exported
+    if lib.lgpu_abi_version() != ABI_VERSION:
+        raise ImportError("liblancedb_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    """Map an lgpu_status onto the exception the reference's Python surface raises
+    (InvalidInput -> ValueError, Runtime -> RuntimeError: python/python/tests/test_query.py:917-929)."""
+    if rc == LGPU_OK:
+        return
+    msg = (load().lgpu_last_error() or b"").decode("utf-8", "replace")
+    if rc == LGPU_INVALID_INPUT:
+        raise ValueError(msg)
+    if rc == LGPU_TIMEOUT:
+        raise TimeoutError(msg)
+    if rc == LGPU_OOM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(load().lgpu_device_count(C.byref(n)))
+    return n.value
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_params(k=10, nprobes=20, refine_factor=0, lower=None, upper=None) -> SearchParams:
+    return SearchParams(int(k), int(nprobes), int(refine_factor or 0), lower is not None, upper is not None,
+                        0.0 if lower is None else float(lower), 0.0 if upper is None else float(upper), 0)
+
+
+class GpuIvfPq:
+    """An IVF_PQ index pinned in HBM (lgpu_index)."""
+
+    def __init__(self, data, device: int = 0, with_vectors: bool = True):
+        lib = load()
+        data.validate()
+        self.dim, self.nlist, self.m, self.metric = data.dim, data.nlist, data.m, data.metric
+        self.device = device
+        vec = data.vectors if with_vectors else None
+        keep = [np.ascontiguousarray(data.centroids, np.float32), np.ascontiguousarray(data.codebook, np.float32),
+                np.ascontiguousarray(data.part_offsets, np.uint64), np.ascontiguousarray(data.codes_t, np.uint8),
+                np.ascontiguousarray(data.row_ids, np.uint64),
+                None if vec is None else np.ascontiguousarray(vec, np.float32)]
+        desc = IndexDesc(ABI_VERSION, data.dim, data.nlist, data.m, 8, METRICS[data.metric], 1, device,
+                         data.nrows, _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(keep[4]),
+                         _ptr(keep[5]))
+        h = C.c_void_p()
+        check(lib.lgpu_index_open(C.byref(desc), C.byref(h)))
+        self._h = h
+        self.has_vectors = vec is not None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().lgpu_index_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def device_bytes(self) -> int:
+        b = C.c_uint64(0)
+        check(load().lgpu_index_device_bytes(self._h, C.byref(b)))
+        return b.value
+
+    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None):
+        """Host-buffer search: returns (ids [B,k] u64, dist [B,k] f32, count [B] u32)."""
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
+        B = q.shape[0]
+        ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
+        p = make_params(k, nprobes, refine_factor, lower, upper)
+        check(load().lgpu_search(self._h, _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist), _ptr(cnt)))
+        return ids, dist, cnt
+
+    def search_into(self, q: np.ndarray, p: SearchParams, ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray):
+        """Host-buffer search into caller-owned (e.g. pinned) arrays; no allocation."""
+        check(load().lgpu_search(self._h, q.ctypes.data, q.shape[0], C.byref(p), ids.ctypes.data,
+                                 dist.ctypes.data, cnt.ctypes.data))
+
+    def search_device(self, d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int, d_cnt: int, stream: int = 0):
+        """Device-pointer search (raw addresses), enqueued on `stream`, not synchronised."""
+        check(load().lgpu_search_device(self._h, d_q, B, C.byref(p), d_ids, d_dist, d_cnt, stream))
+
+    def debug_coarse(self, queries, nprobes):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
+        B = q.shape[0]
+        nprobes = min(nprobes, self.nlist)
+        parts = np.empty((B, nprobes), np.uint32); dists = np.empty((B, nprobes), np.float32)
+        check(load().lgpu_debug_coarse(self._h, _ptr(q), B, nprobes, _ptr(parts), _ptr(dists)))
+        return parts, dists
+
+    def debug_partition_distances(self, query, part, n_p):
+        q = np.ascontiguousarray(query, np.float32).reshape(self.dim)
+        out = np.empty(n_p, np.float32)
+        check(load().lgpu_debug_partition_distances(self._h, _ptr(q), int(part), _ptr(out)))
+        return out
+
+
+class GpuFlat:
+    """A raw vector column pinned in HBM (lgpu_flat)."""
+
+    def __init__(self, vectors, row_ids=None, device: int = 0):
+        v = np.ascontiguousarray(vectors, np.float32)
+        self.nrows, self.dim = v.shape
+        rid = None if row_ids is None else np.ascontiguousarray(row_ids, np.uint64)
+        h = C.c_void_p()
+        check(load().lgpu_flat_open(_ptr(v), self.nrows, self.dim, _ptr(rid), device, C.byref(h)))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load().lgpu_flat_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def search(self, queries, k=10, metric="l2", lower=None, upper=None):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
+        B = q.shape[0]
+        ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
+        p = make_params(k, 0, 0, lower, upper)
+        check(load().lgpu_flat_search(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist),
+                                      _ptr(cnt)))
+        return ids, dist, cnt
+
+    def search_device(self, metric: str, d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int, d_cnt: int,
+                      stream: int = 0):
+        check(load().lgpu_flat_search_device(self._h, METRICS[metric], d_q, B, C.byref(p), d_ids, d_dist, d_cnt,
+                                             stream))
+
+
+def merge_topk_device(device: int, nlists: int, B: int, k: int, d_ids: int, d_dist: int, d_out_ids: int,
+                      d_out_dist: int, d_out_cnt: int, stream: int = 0):
+    check(load().lgpu_merge_topk_device(device, nlists, B, k, d_ids, d_dist, d_out_ids, d_out_dist, d_out_cnt,
+                                        stream))
+
+
+def set_profiling(enabled: bool) -> None:
+    check(load().lgpu_set_profiling(1 if enabled else 0))
+
+
+def last_stage_ms():
+    t = (C.c_float * 7)()
+    check(load().lgpu_last_stage_ms(t))
+    return dict(zip(["coarse", "select_probes", "group", "scan", "topk", "refine", "total"], list(t)))
+
+
+def last_scanned_code_bytes() -> int:
+    b = C.c_uint64(0)
+    check(load().lgpu_last_scanned_code_bytes(C.byref(b)))
+    return b.value

@@ -1,0 +1,680 @@
+// api.cu -- the extern "C" boundary (include/lancedb_b200.h): handle management,
+// workspaces, and the host-side orchestration of one batched vector query:
+//   [cosine: normalise] -> K1 exact centroid distances -> select nprobes ->
+//   regroup probe slots by partition -> K2+K3 fused LUT build + code scan ->
+//   K4 top-k by (_distance,_rowid) -> [refine: exact re-rank] .
+// Everything runs on one stream per call with no host round trip in between.
+// The reference-side equivalent is NativeTable::create_plan + execute_plan
+// (rust/lancedb/src/table/query.rs:131-328, :121).
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace lgpu {
+
+static thread_local std::string g_err;
+static thread_local float g_stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
+static thread_local uint64_t g_scanned_bytes = 0;
+void set_error(const std::string &msg) { g_err = msg; }
+
+static int g_profiling = -1;
+static bool profiling_enabled()
+{
+    if (g_profiling < 0) { const char *e = getenv("LGPU_PROFILE"); g_profiling = (e && e[0] == '1') ? 1 : 0; }
+    return g_profiling == 1;
+}
+static size_t workspace_budget()
+{
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("LGPU_WS_BYTES");
+        v = e ? (size_t)strtoull(e, nullptr, 10) : ((size_t)8 << 30);
+        if (v < ((size_t)1 << 20)) v = (size_t)1 << 20;
+    }
+    return v;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t n)
+    {
+        if (n <= bytes) return;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        size_t want = n + n / 8;
+        LGPU_CUDA(cudaMalloc(&p, want));
+        bytes = want;
+    }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;     // private stream (host-buffer entry points)
+    cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
+    cudaEvent_t ev[8] = {};
+    DevBuf q, qn, xnorm, D, probes, probe_dist, probe_cnt;
+    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars;
+    DevBuf dist_out, out_ids, out_dist, out_count;
+    DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
+    Workspace()
+    {
+        LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        LGPU_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        for (auto &e : ev) LGPU_CUDA(cudaEventCreate(&e));
+    }
+    ~Workspace()
+    {
+        if (stream) cudaStreamDestroy(stream);
+        if (done) cudaEventDestroy(done);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
+struct WorkspacePool {
+    std::mutex mu;
+    std::vector<Workspace *> free_list;
+    Workspace *take()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!free_list.empty()) { Workspace *w = free_list.back(); free_list.pop_back(); return w; }
+        }
+        return new Workspace();
+    }
+    void give(Workspace *w) { std::lock_guard<std::mutex> g(mu); free_list.push_back(w); }
+    ~WorkspacePool() { for (auto *w : free_list) delete w; }
+};
+
+}  // namespace lgpu
+
+using namespace lgpu;
+
+struct lgpu_index {
+    int device = 0, num_sms = 0;
+    uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0;
+    int metric = 0;
+    uint64_t nrows = 0, device_bytes = 0;
+    DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
+    bool has_vectors = false;
+    std::vector<uint64_t> pad_prefix;   // prefix sums of pad4(n_p) sorted descending
+    std::vector<uint32_t> h_part_n;
+    WorkspacePool pool;
+};
+
+struct lgpu_flat {
+    int device = 0;
+    uint64_t nrows = 0;
+    uint32_t dim = 0;
+    DevBuf vectors, row_ids, ysqrt;
+    bool has_ids = false, has_norms = false;
+    std::mutex mu;
+    WorkspacePool pool;
+};
+
+namespace {
+
+struct WsLease {
+    WorkspacePool &pool;
+    Workspace *ws;
+    cudaStream_t st;
+    WsLease(WorkspacePool &p, cudaStream_t user, bool use_user) : pool(p), ws(p.take())
+    {
+        st = use_user ? user : ws->stream;
+        // the workspace may still be in use by an earlier call on another stream
+        cudaStreamWaitEvent(st, ws->done, 0);
+    }
+    ~WsLease()
+    {
+        cudaEventRecord(ws->done, st);
+        pool.give(ws);
+    }
+};
+
+void check_params(const lgpu_search_params *p)
+{
+    LGPU_REQUIRE(p != nullptr, "search params are null");
+    LGPU_REQUIRE(p->k >= 1, "limit must be greater than 0");
+    LGPU_REQUIRE(p->k <= SELECT_KMAX, "limit+offset above 2048 is not supported on the GPU path");
+    if (p->refine_factor)
+        LGPU_REQUIRE((uint64_t)p->k * p->refine_factor <= SELECT_KMAX, "limit*refine_factor above 2048 is not supported");
+}
+
+// one sub-batch of an IVF_PQ search, everything device-side on `st`
+void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *d_q, uint32_t B,
+                   const lgpu_search_params &sp, uint32_t nprobes, uint64_t *d_ids, float *d_dist,
+                   uint32_t *d_cnt, bool prof, const uint64_t *forced_probes = nullptr)
+{
+    const uint32_t dim = ix->dim, nlist = ix->nlist;
+    const uint32_t slots = B * nprobes;
+    int evi = 0;
+    auto mark = [&]() { if (prof) cudaEventRecord(ws->ev[evi++], st); };
+    mark();
+    // ---- queries (normalised copy for cosine) ----
+    const float *qsearch = d_q;
+    if (ix->metric == LGPU_COSINE) {
+        ws->qn.ensure((size_t)B * dim * 4);
+        launch_normalize(d_q, B, dim, ws->qn.as<float>(), st);
+        qsearch = ws->qn.as<float>();
+    }
+    // ---- K1: exact centroid distances + nprobes nearest ----
+    ws->probes.ensure((size_t)slots * 8);
+    ws->probe_dist.ensure((size_t)slots * 4);
+    ws->probe_cnt.ensure((size_t)B * 4);
+    if (forced_probes) {
+        LGPU_CUDA(cudaMemcpyAsync(ws->probes.p, forced_probes, (size_t)slots * 8, cudaMemcpyHostToDevice, st));
+        mark();
+    } else {
+        ws->D.ensure((size_t)B * nlist * 4);
+        launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, ix->metric == LGPU_DOT ? 1 : 0,
+                           nullptr, nullptr, ws->D.as<float>(), nlist, st);
+        mark();
+        SelectArgs sa{};
+        sa.mode = 1; sa.dense = ws->D.as<float>(); sa.ncols = nlist; sa.row_stride = nlist;
+        sa.B = B; sa.k = nprobes;
+        sa.out_ids = ws->probes.as<uint64_t>(); sa.out_dist = ws->probe_dist.as<float>();
+        sa.out_count = ws->probe_cnt.as<uint32_t>();
+        launch_select(sa, st);
+    }
+    mark();
+    // ---- regroup probe slots by partition ----
+    ws->part_cnt.ensure((size_t)nlist * 4);
+    ws->slot_pos.ensure((size_t)slots * 4);
+    ws->seg_local.ensure((size_t)slots * 8);
+    ws->qtot.ensure((size_t)B * 8);
+    ws->seg_off.ensure((size_t)slots * 8);
+    ws->qlist_off.ensure((size_t)nlist * 4);
+    ws->tile_off.ensure((size_t)(nlist + 1) * 4);
+    ws->qlist.ensure((size_t)slots * 4);
+    ws->scalars.ensure(64);
+    GroupArgs ga{};
+    ga.probes = ws->probes.as<uint64_t>(); ga.B = B; ga.nprobes = nprobes; ga.nlist = nlist;
+    ga.part_n = ix->part_n.as<uint32_t>(); ga.part_cnt = ws->part_cnt.as<uint32_t>();
+    ga.slot_pos = ws->slot_pos.as<uint32_t>(); ga.seg_local = ws->seg_local.as<uint64_t>();
+    ga.qtot = ws->qtot.as<uint64_t>(); ga.seg_off = ws->seg_off.as<uint64_t>();
+    ga.qlist_off = ws->qlist_off.as<uint32_t>(); ga.tile_off = ws->tile_off.as<uint32_t>();
+    ga.qlist = ws->qlist.as<uint32_t>();
+    ga.total_tiles = ws->scalars.as<uint32_t>(); ga.tile_counter = ws->scalars.as<uint32_t>() + 1;
+    ga.scanned_rows = reinterpret_cast<unsigned long long *>(ws->scalars.as<char>() + 16);
+    launch_group(ga, st);
+    mark();
+    // ---- K2+K3: fused distance-table build + code scan ----
+    uint32_t np_eff = std::min<uint32_t>(nprobes, nlist);
+    size_t cap_floats = (size_t)B * ix->pad_prefix[np_eff];
+    ws->dist_out.ensure(std::max<size_t>(cap_floats, 4) * 4);
+    ScanArgs sc{};
+    sc.centroids = ix->centroids.as<float>(); sc.cb_tiled = ix->cb_tiled.as<float>();
+    sc.codes = ix->codes.as<unsigned char>(); sc.code_base = ix->code_base.as<uint64_t>();
+    sc.part_n = ix->part_n.as<uint32_t>(); sc.part_npad = ix->part_npad.as<uint32_t>();
+    sc.dim = dim; sc.m = ix->m; sc.nch = ix->nch; sc.metric = (uint32_t)ix->metric; sc.nlist = nlist;
+    sc.queries = qsearch; sc.nprobes = nprobes;
+    sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
+    sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
+    sc.dist_out = ws->dist_out.as<float>();
+    launch_scan(sc, ix->dsub, ix->num_sms, st);
+    mark();
+    if (!d_ids) { mark(); mark(); return; }     // debug: distances only
+    // ---- K4: top-k ----
+    SelectArgs sa{};
+    sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ga.seg_off; sa.probes = ga.probes;
+    sa.nprobes = nprobes; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
+    sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B;
+    sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
+    if (sp.refine_factor == 0) {
+        sa.k = sp.k; sa.out_ids = d_ids; sa.out_dist = d_dist; sa.out_count = d_cnt;
+        launch_select(sa, st);
+        mark(); mark();
+        return;
+    }
+    // ---- refine (query.rs:1302-1332): exact distance of the k*rf candidates, re-sort ----
+    const uint32_t kk = sp.k * sp.refine_factor;
+    ws->t_ids.ensure((size_t)B * kk * 8); ws->t_dist.ensure((size_t)B * kk * 4);
+    ws->t_pos.ensure((size_t)B * kk * 8); ws->t_cnt.ensure((size_t)B * 4);
+    ws->t_exact.ensure((size_t)B * kk * 4);
+    sa.k = kk; sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
+    sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
+    launch_select(sa, st);
+    mark();
+    launch_pair_distance(d_q, ix->vectors.as<float>(), ws->t_pos.as<uint64_t>(), B, kk, dim, ix->metric,
+                         ws->t_exact.as<float>(), st);
+    SelectArgs sb{};
+    sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
+    sb.ncols = kk; sb.inner = kk; sb.row_stride = kk; sb.outer_stride = 0;
+    sb.B = B; sb.k = sp.k; sb.out_ids = d_ids; sb.out_dist = d_dist; sb.out_count = d_cnt;
+    launch_select(sb, st);
+    mark();
+}
+
+uint32_t ivf_sub_batch_size(lgpu_index *ix, uint32_t B, uint32_t nprobes)
+{
+    uint32_t np_eff = std::min<uint32_t>(nprobes, ix->nlist);
+    size_t per_q = std::max<size_t>(ix->pad_prefix[np_eff] * 4 + (size_t)ix->nlist * 4, 4);
+    size_t bs = workspace_budget() / per_q;
+    bs = std::max<size_t>(1, std::min<size_t>(bs, 65535));
+    return (uint32_t)std::min<size_t>(bs, B);
+}
+
+void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *d_q, uint32_t B,
+                       const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt)
+{
+    const uint32_t nprobes = std::min<uint32_t>(std::max<uint32_t>(sp.nprobes, 1), ix->nlist);
+    const uint32_t bs = ivf_sub_batch_size(ix, B, nprobes);
+    const bool prof = profiling_enabled();
+    for (uint32_t q0 = 0; q0 < B; q0 += bs) {
+        uint32_t b = std::min(bs, B - q0);
+        ivf_sub_batch(ix, ws, st, d_q + (size_t)q0 * ix->dim, b, sp, nprobes, d_ids + (size_t)q0 * sp.k,
+                      d_dist + (size_t)q0 * sp.k, d_cnt + q0, prof && q0 == 0);
+    }
+    if (prof) {
+        LGPU_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&g_stage_ms[i], ws->ev[i], ws->ev[i + 1]);
+        cudaEventElapsedTime(&g_stage_ms[6], ws->ev[0], ws->ev[6]);
+        unsigned long long rows = 0;
+        LGPU_CUDA(cudaMemcpy(&rows, ws->scalars.as<char>() + 16, 8, cudaMemcpyDeviceToHost));
+        g_scanned_bytes = (uint64_t)rows * ix->m;
+    }
+}
+
+void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metric, const float *d_q, uint32_t B,
+                        const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt)
+{
+    const uint64_t N = fl->nrows;
+    const uint64_t ld = (N + 3) & ~3ull;
+    if (metric == LGPU_COSINE) {
+        std::lock_guard<std::mutex> g(fl->mu);
+        if (!fl->has_norms) {
+            fl->ysqrt.ensure(std::max<size_t>(N, 1) * 4);
+            launch_row_norms(fl->vectors.as<float>(), N, fl->dim, fl->ysqrt.as<float>(), st);
+            LGPU_CUDA(cudaStreamSynchronize(st));
+            fl->has_norms = true;
+        }
+    }
+    size_t per_q = std::max<size_t>(ld * 4, 4);
+    uint32_t bs = (uint32_t)std::max<size_t>(1, std::min<size_t>(workspace_budget() / per_q, B));
+    for (uint32_t q0 = 0; q0 < B; q0 += bs) {
+        uint32_t b = std::min(bs, B - q0);
+        const float *q = d_q + (size_t)q0 * fl->dim;
+        ws->D.ensure(std::max<size_t>((size_t)b * ld, 4) * 4);
+        const float *xn = nullptr;
+        if (metric == LGPU_COSINE) {
+            ws->xnorm.ensure((size_t)b * 4);
+            launch_row_norms(q, b, fl->dim, ws->xnorm.as<float>(), st);
+            xn = ws->xnorm.as<float>();
+        }
+        launch_dist_matrix(q, fl->vectors.as<float>(), b, N, fl->dim, metric == LGPU_L2 ? 0 : (metric == LGPU_DOT ? 1 : 2),
+                           xn, fl->ysqrt.as<float>(), ws->D.as<float>(), ld, st);
+        SelectArgs sa{};
+        sa.mode = 1; sa.dense = ws->D.as<float>(); sa.ncols = N; sa.row_stride = ld;
+        sa.col_ids = fl->has_ids ? fl->row_ids.as<uint64_t>() : nullptr;
+        sa.B = b; sa.k = sp.k;
+        sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
+        sa.out_ids = d_ids + (size_t)q0 * sp.k; sa.out_dist = d_dist + (size_t)q0 * sp.k; sa.out_count = d_cnt + q0;
+        launch_select(sa, st);
+    }
+}
+
+template <class F> int guarded(F &&f)
+{
+    try { f(); return LGPU_OK; }
+    catch (const Failure &e) { return e.status; }
+    catch (const std::bad_alloc &) { set_error("host allocation failed"); return LGPU_OOM; }
+    catch (const std::exception &e) { set_error(e.what()); return LGPU_RUNTIME; }
+}
+
+void require_device(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available: lancedb_b200 has no CPU fallback");
+        throw Failure{LGPU_RUNTIME};
+    }
+    LGPU_REQUIRE(device >= 0 && device < n, "invalid CUDA device ordinal");
+    LGPU_CUDA(cudaSetDevice(device));
+}
+
+// host-buffer wrapper: stage in, run, stage out, synchronise
+template <class Run>
+void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t dim, uint32_t k, uint64_t *out_ids,
+               float *out_dist, uint32_t *out_count, Run &&run)
+{
+    WsLease lease(pool, nullptr, false);
+    Workspace *ws = lease.ws;
+    cudaStream_t st = lease.st;
+    ws->q.ensure(std::max<size_t>((size_t)B * dim, 1) * 4);
+    ws->out_ids.ensure(std::max<size_t>((size_t)B * k, 1) * 8);
+    ws->out_dist.ensure(std::max<size_t>((size_t)B * k, 1) * 4);
+    ws->out_count.ensure(std::max<size_t>(B, 1) * 4);
+    LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
+    run(ws, st, ws->q.as<float>(), ws->out_ids.as<uint64_t>(), ws->out_dist.as<float>(), ws->out_count.as<uint32_t>());
+    LGPU_CUDA(cudaMemcpyAsync(out_ids, ws->out_ids.p, (size_t)B * k * 8, cudaMemcpyDeviceToHost, st));
+    LGPU_CUDA(cudaMemcpyAsync(out_dist, ws->out_dist.p, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
+    LGPU_CUDA(cudaMemcpyAsync(out_count, ws->out_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    LGPU_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *lgpu_last_error(void) { return g_err.c_str(); }
+uint32_t lgpu_abi_version(void) { return LGPU_ABI_VERSION; }
+
+int lgpu_device_count(int *count)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(count != nullptr, "count is null");
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        *count = n;
+    });
+}
+
+int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
+{
+    lgpu_index *ix = nullptr;
+    int rc = guarded([&] {
+        LGPU_REQUIRE(d != nullptr && out != nullptr, "null argument");
+        LGPU_REQUIRE(d->abi_version == LGPU_ABI_VERSION, "ABI version mismatch");
+        LGPU_REQUIRE(d->dim > 0 && d->nlist > 0 && d->m > 0, "dim, nlist and m must be positive");
+        LGPU_REQUIRE(d->dim % d->m == 0, "num_sub_vectors must divide the vector dimension");
+        LGPU_REQUIRE(d->nbits == 8, "only 8-bit PQ codes are supported");
+        LGPU_REQUIRE(d->metric == LGPU_L2 || d->metric == LGPU_COSINE || d->metric == LGPU_DOT, "unknown distance type");
+        LGPU_REQUIRE(d->codes_layout == LGPU_CODES_ROW_MAJOR || d->codes_layout == LGPU_CODES_PARTITION_TRANSPOSED,
+                     "unknown codes layout");
+        LGPU_REQUIRE(scan_dsub_supported(d->dim / d->m),
+                     "unsupported PQ sub-vector length (dim/num_sub_vectors must be 1,2,4,8,16 or 32)");
+        LGPU_REQUIRE(d->centroids && d->codebook && d->part_offsets, "null index array");
+        LGPU_REQUIRE(d->nrows == 0 || (d->codes && d->row_ids), "null codes / row_ids");
+        LGPU_REQUIRE(d->part_offsets[0] == 0 && d->part_offsets[d->nlist] == d->nrows,
+                     "part_offsets must start at 0 and end at nrows");
+        for (uint32_t p = 0; p < d->nlist; p++) {
+            LGPU_REQUIRE(d->part_offsets[p + 1] >= d->part_offsets[p], "part_offsets must be non-decreasing");
+            LGPU_REQUIRE(d->part_offsets[p + 1] - d->part_offsets[p] < (1ull << 31), "partition too large");
+        }
+        require_device(d->device);
+        ix = new lgpu_index();
+        ix->device = d->device;
+        cudaDeviceProp prop;
+        LGPU_CUDA(cudaGetDeviceProperties(&prop, d->device));
+        ix->num_sms = prop.multiProcessorCount;
+        ix->dim = d->dim; ix->nlist = d->nlist; ix->m = d->m; ix->dsub = d->dim / d->m;
+        ix->nch = (d->m + 7) / 8; ix->metric = d->metric; ix->nrows = d->nrows;
+
+        const uint32_t nlist = d->nlist;
+        std::vector<uint32_t> part_n(nlist), part_npad(nlist);
+        std::vector<uint64_t> code_base(nlist), pads(nlist);
+        uint64_t cb = 0;
+        for (uint32_t p = 0; p < nlist; p++) {
+            uint32_t n = (uint32_t)(d->part_offsets[p + 1] - d->part_offsets[p]);
+            part_n[p] = n; part_npad[p] = (n + 31u) & ~31u;
+            code_base[p] = cb;
+            cb += (uint64_t)(ix->nch + 1) * part_npad[p] * 8;
+            pads[p] = (n + 3ull) & ~3ull;
+        }
+        ix->h_part_n = part_n;
+        std::sort(pads.begin(), pads.end(), std::greater<uint64_t>());
+        ix->pad_prefix.assign(nlist + 1, 0);
+        for (uint32_t p = 0; p < nlist; p++) ix->pad_prefix[p + 1] = ix->pad_prefix[p] + pads[p];
+
+        cudaStream_t st = nullptr;
+        auto up = [&](DevBuf &b, const void *src, size_t bytes) {
+            b.ensure(std::max<size_t>(bytes, 16));
+            if (bytes) LGPU_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+            ix->device_bytes += b.bytes;
+        };
+        up(ix->centroids, d->centroids, (size_t)nlist * d->dim * 4);
+        up(ix->part_n, part_n.data(), (size_t)nlist * 4);
+        up(ix->part_npad, part_npad.data(), (size_t)nlist * 4);
+        up(ix->code_base, code_base.data(), (size_t)nlist * 8);
+        up(ix->part_off, d->part_offsets, (size_t)(nlist + 1) * 8);
+        up(ix->row_ids, d->row_ids, (size_t)d->nrows * 8);
+        if (d->vectors) { up(ix->vectors, d->vectors, (size_t)d->nrows * d->dim * 4); ix->has_vectors = true; }
+        // codebook -> [nch][256][8][dsub]
+        {
+            DevBuf tmp;
+            size_t bytes = (size_t)d->m * 256 * ix->dsub * 4;
+            tmp.ensure(bytes);
+            LGPU_CUDA(cudaMemcpyAsync(tmp.p, d->codebook, bytes, cudaMemcpyHostToDevice, st));
+            ix->cb_tiled.ensure((size_t)ix->nch * 256 * 8 * ix->dsub * 4);
+            ix->device_bytes += ix->cb_tiled.bytes;
+            launch_retile_codebook(tmp.as<float>(), d->m, ix->dsub, ix->nch, ix->cb_tiled.as<float>(), st);
+            LGPU_CUDA(cudaStreamSynchronize(st));
+        }
+        // codes -> skewed streams
+        {
+            ix->codes.ensure(std::max<uint64_t>(cb, 16));
+            ix->device_bytes += ix->codes.bytes;
+            LGPU_CUDA(cudaMemsetAsync(ix->codes.p, 0, ix->codes.bytes, st));
+            DevBuf tmp;
+            size_t bytes = (size_t)d->nrows * d->m;
+            if (bytes) {
+                tmp.ensure(bytes);
+                LGPU_CUDA(cudaMemcpyAsync(tmp.p, d->codes, bytes, cudaMemcpyHostToDevice, st));
+                launch_retile_codes(tmp.as<unsigned char>(), d->codes_layout, ix->part_off.as<uint64_t>(), nlist,
+                                    d->nrows, d->m, ix->nch, ix->code_base.as<uint64_t>(),
+                                    ix->part_npad.as<uint32_t>(), ix->codes.as<unsigned char>(), st);
+            }
+            LGPU_CUDA(cudaStreamSynchronize(st));
+        }
+        *out = ix;
+    });
+    if (rc != LGPU_OK && ix) delete ix;
+    return rc;
+}
+
+void lgpu_index_close(lgpu_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaDeviceSynchronize();
+    delete ix;
+}
+
+int lgpu_index_device_bytes(const lgpu_index *ix, uint64_t *bytes)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(ix && bytes, "null argument");
+        *bytes = ix->device_bytes;
+    });
+}
+
+int lgpu_last_scanned_code_bytes(uint64_t *bytes)
+{
+    return guarded([&] { LGPU_REQUIRE(bytes, "null argument"); *bytes = g_scanned_bytes; });
+}
+
+int lgpu_set_profiling(int enabled)
+{
+    g_profiling = enabled ? 1 : 0;
+    return LGPU_OK;
+}
+
+int lgpu_last_stage_ms(float *times)
+{
+    return guarded([&] { LGPU_REQUIRE(times, "null argument"); memcpy(times, g_stage_ms, sizeof(g_stage_ms)); });
+}
+
+static void check_ivf_call(lgpu_index *ix, const void *q, uint32_t B, const lgpu_search_params *p,
+                           const void *a, const void *b, const void *c)
+{
+    LGPU_REQUIRE(ix != nullptr, "index handle is null");
+    check_params(p);
+    LGPU_REQUIRE(p->nprobes >= 1, "minimum_nprobes must be greater than 0");
+    LGPU_REQUIRE(p->nprobes <= SELECT_KMAX || p->nprobes >= ix->nlist, "nprobes above 2048 is not supported");
+    LGPU_REQUIRE(B == 0 || (q && a && b && c), "null buffer");
+    LGPU_REQUIRE(p->refine_factor == 0 || ix->has_vectors,
+                 "refine_factor needs the raw vectors: open the index with desc.vectors");
+}
+
+int lgpu_search(lgpu_index *ix, const float *queries, uint32_t B, const lgpu_search_params *params,
+                uint64_t *out_ids, float *out_dist, uint32_t *out_count)
+{
+    return guarded([&] {
+        check_ivf_call(ix, queries, B, params, out_ids, out_dist, out_count);
+        if (B == 0) return;
+        require_device(ix->device);
+        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
+                      ivf_search_device(ix, ws, st, dq, B, *params, di, dd, dc);
+                  });
+    });
+}
+
+int lgpu_search_device(lgpu_index *ix, const float *d_queries, uint32_t B, const lgpu_search_params *params,
+                       uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count, void *cuda_stream)
+{
+    return guarded([&] {
+        check_ivf_call(ix, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
+        if (B == 0) return;
+        require_device(ix->device);
+        WsLease lease(ix->pool, (cudaStream_t)cuda_stream, true);
+        ivf_search_device(ix, lease.ws, lease.st, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
+    });
+}
+
+int lgpu_merge_topk_device(int device, uint32_t nlists, uint32_t B, uint32_t k, const uint64_t *d_ids,
+                           const float *d_dist, uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
+                           void *cuda_stream)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(nlists >= 1 && k >= 1 && k <= SELECT_KMAX, "bad merge shape");
+        LGPU_REQUIRE(B == 0 || (d_ids && d_dist && d_out_ids && d_out_dist && d_out_count), "null buffer");
+        if (B == 0) return;
+        require_device(device);
+        SelectArgs sb{};
+        sb.mode = 2; sb.dense = d_dist; sb.cand_ids = d_ids;
+        sb.ncols = (uint64_t)nlists * k; sb.inner = k; sb.row_stride = k; sb.outer_stride = (uint64_t)B * k;
+        sb.B = B; sb.k = k; sb.out_ids = d_out_ids; sb.out_dist = d_out_dist; sb.out_count = d_out_count;
+        launch_select(sb, (cudaStream_t)cuda_stream);
+    });
+}
+
+int lgpu_flat_open(const float *vectors, uint64_t nrows, uint32_t dim, const uint64_t *row_ids, int device,
+                   lgpu_flat **out)
+{
+    lgpu_flat *fl = nullptr;
+    int rc = guarded([&] {
+        LGPU_REQUIRE(out != nullptr && dim > 0, "null argument / zero dimension");
+        LGPU_REQUIRE(nrows == 0 || vectors != nullptr, "null vectors");
+        require_device(device);
+        fl = new lgpu_flat();
+        fl->device = device; fl->nrows = nrows; fl->dim = dim;
+        fl->vectors.ensure(std::max<size_t>((size_t)nrows * dim * 4, 16));
+        if (nrows) LGPU_CUDA(cudaMemcpy(fl->vectors.p, vectors, (size_t)nrows * dim * 4, cudaMemcpyHostToDevice));
+        if (row_ids && nrows) {
+            fl->row_ids.ensure((size_t)nrows * 8);
+            LGPU_CUDA(cudaMemcpy(fl->row_ids.p, row_ids, (size_t)nrows * 8, cudaMemcpyHostToDevice));
+            fl->has_ids = true;
+        }
+        *out = fl;
+    });
+    if (rc != LGPU_OK && fl) delete fl;
+    return rc;
+}
+
+void lgpu_flat_close(lgpu_flat *fl)
+{
+    if (!fl) return;
+    cudaSetDevice(fl->device);
+    cudaDeviceSynchronize();
+    delete fl;
+}
+
+static void check_flat_call(lgpu_flat *fl, int metric, const void *q, uint32_t B, const lgpu_search_params *p,
+                            const void *a, const void *b, const void *c)
+{
+    LGPU_REQUIRE(fl != nullptr, "flat handle is null");
+    LGPU_REQUIRE(metric == LGPU_L2 || metric == LGPU_COSINE || metric == LGPU_DOT, "unknown distance type");
+    check_params(p);
+    LGPU_REQUIRE(B == 0 || (q && a && b && c), "null buffer");
+}
+
+int lgpu_flat_search(lgpu_flat *fl, int metric, const float *queries, uint32_t B, const lgpu_search_params *params,
+                     uint64_t *out_ids, float *out_dist, uint32_t *out_count)
+{
+    return guarded([&] {
+        check_flat_call(fl, metric, queries, B, params, out_ids, out_dist, out_count);
+        if (B == 0) return;
+        require_device(fl->device);
+        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
+                      flat_search_device(fl, ws, st, metric, dq, B, *params, di, dd, dc);
+                  });
+    });
+}
+
+int lgpu_flat_search_device(lgpu_flat *fl, int metric, const float *d_queries, uint32_t B,
+                            const lgpu_search_params *params, uint64_t *d_out_ids, float *d_out_dist,
+                            uint32_t *d_out_count, void *cuda_stream)
+{
+    return guarded([&] {
+        check_flat_call(fl, metric, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
+        if (B == 0) return;
+        require_device(fl->device);
+        WsLease lease(fl->pool, (cudaStream_t)cuda_stream, true);
+        flat_search_device(fl, lease.ws, lease.st, metric, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
+    });
+}
+
+int lgpu_debug_coarse(lgpu_index *ix, const float *queries, uint32_t B, uint32_t nprobes, uint32_t *out_parts,
+                      float *out_dists)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(ix && queries && out_parts && out_dists && B > 0 && nprobes > 0, "bad argument");
+        require_device(ix->device);
+        nprobes = std::min(nprobes, ix->nlist);
+        WsLease lease(ix->pool, nullptr, false);
+        Workspace *ws = lease.ws; cudaStream_t st = lease.st;
+        ws->q.ensure((size_t)B * ix->dim * 4);
+        LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * ix->dim * 4, cudaMemcpyHostToDevice, st));
+        const float *qs = ws->q.as<float>();
+        if (ix->metric == LGPU_COSINE) {
+            ws->qn.ensure((size_t)B * ix->dim * 4);
+            launch_normalize(qs, B, ix->dim, ws->qn.as<float>(), st);
+            qs = ws->qn.as<float>();
+        }
+        ws->D.ensure((size_t)B * ix->nlist * 4);
+        ws->probes.ensure((size_t)B * nprobes * 8); ws->probe_dist.ensure((size_t)B * nprobes * 4);
+        ws->probe_cnt.ensure((size_t)B * 4);
+        launch_dist_matrix(qs, ix->centroids.as<float>(), B, ix->nlist, ix->dim, ix->metric == LGPU_DOT ? 1 : 0,
+                           nullptr, nullptr, ws->D.as<float>(), ix->nlist, st);
+        SelectArgs sa{};
+        sa.mode = 1; sa.dense = ws->D.as<float>(); sa.ncols = ix->nlist; sa.row_stride = ix->nlist;
+        sa.B = B; sa.k = nprobes; sa.out_ids = ws->probes.as<uint64_t>(); sa.out_dist = ws->probe_dist.as<float>();
+        sa.out_count = ws->probe_cnt.as<uint32_t>();
+        launch_select(sa, st);
+        std::vector<uint64_t> tmp((size_t)B * nprobes);
+        LGPU_CUDA(cudaMemcpyAsync(tmp.data(), ws->probes.p, tmp.size() * 8, cudaMemcpyDeviceToHost, st));
+        LGPU_CUDA(cudaMemcpyAsync(out_dists, ws->probe_dist.p, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
+        LGPU_CUDA(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < tmp.size(); i++) out_parts[i] = (uint32_t)tmp[i];
+    });
+}
+
+int lgpu_debug_partition_distances(lgpu_index *ix, const float *query, uint32_t part, float *out)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(ix && query && out, "null argument");
+        LGPU_REQUIRE(part < ix->nlist, "partition out of range");
+        require_device(ix->device);
+        WsLease lease(ix->pool, nullptr, false);
+        Workspace *ws = lease.ws; cudaStream_t st = lease.st;
+        ws->q.ensure((size_t)ix->dim * 4);
+        LGPU_CUDA(cudaMemcpyAsync(ws->q.p, query, (size_t)ix->dim * 4, cudaMemcpyHostToDevice, st));
+        uint64_t forced = part;
+        lgpu_search_params sp{};
+        sp.k = 1; sp.nprobes = 1;
+        ivf_sub_batch(ix, ws, st, ws->q.as<float>(), 1, sp, 1, nullptr, nullptr, nullptr, false, &forced);
+        uint32_t n = ix->h_part_n[part];
+        if (n) LGPU_CUDA(cudaMemcpyAsync(out, ws->dist_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        LGPU_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+}  // extern "C"

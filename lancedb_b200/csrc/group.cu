@@ -1,0 +1,123 @@
+// group.cu -- batch preparation between the coarse step and the scan: regroup the
+// B x nprobes probe slots by partition so the scan kernel can process, per partition,
+// groups of up to 8 queries against one read of that partition's codes.  This is the
+// structural change versus the reference, which plans and runs each query vector
+// independently (rust/lancedb/src/table/query.rs:201-215, 334-381: "B independent
+// plans + UnionExec"); all of it is index arithmetic and exact.
+#include "kernels.cuh"
+
+namespace lgpu {
+
+namespace {
+
+__device__ __forceinline__ uint64_t pad4(uint64_t n) { return (n + 3) & ~3ull; }
+
+// one thread per query: count probes per partition, lay the query's distance segments
+// out back to back (each padded to 4 floats)
+__global__ void group_count_kernel(GroupArgs a)
+{
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.B) return;
+    uint64_t off = 0, rows = 0;
+    for (uint32_t j = 0; j < a.nprobes; j++) {
+        uint32_t slot = q * a.nprobes + j;
+        uint32_t p = (uint32_t)a.probes[slot];
+        uint32_t n = a.part_n[p];
+        a.slot_pos[slot] = atomicAdd(&a.part_cnt[p], 1u);
+        a.seg_local[slot] = off;
+        off += pad4(n);
+        rows += n;
+    }
+    a.qtot[q] = off;
+    atomicAdd(a.scanned_rows, (unsigned long long)rows);
+}
+
+// single CTA: exclusive scans over queries (segment bases) and partitions (query-list
+// and tile offsets)
+__global__ void group_scan_kernel(GroupArgs a)
+{
+    __shared__ uint64_t s_part[1024];
+    __shared__ uint64_t s_carry;
+    const int tid = threadIdx.x;
+    // --- queries: qtot -> exclusive prefix (in place) ---
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < a.B; base += 1024) {
+        uint32_t i = base + tid;
+        uint64_t v = i < a.B ? a.qtot[i] : 0;
+        s_part[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            uint64_t t = tid >= o ? s_part[tid - o] : 0;
+            __syncthreads();
+            s_part[tid] += t;
+            __syncthreads();
+        }
+        uint64_t incl = s_part[tid], carry = s_carry;
+        if (i < a.B) a.qtot[i] = carry + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + incl;
+        __syncthreads();
+    }
+    // --- partitions: query-list offsets and tile offsets ---
+    for (int pass = 0; pass < 2; pass++) {
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        for (uint32_t base = 0; base < a.nlist; base += 1024) {
+            uint32_t p = base + tid;
+            uint64_t v = 0;
+            if (p < a.nlist) {
+                uint32_t cnt = a.part_cnt[p];
+                v = pass == 0 ? cnt : (uint64_t)((cnt + SCAN_G - 1) / SCAN_G) * scan_nrb(a.part_n[p]);
+            }
+            s_part[tid] = v;
+            __syncthreads();
+            for (int o = 1; o < 1024; o <<= 1) {
+                uint64_t t = tid >= o ? s_part[tid - o] : 0;
+                __syncthreads();
+                s_part[tid] += t;
+                __syncthreads();
+            }
+            uint64_t incl = s_part[tid], carry = s_carry;
+            if (p < a.nlist) {
+                if (pass == 0) a.qlist_off[p] = (uint32_t)(carry + incl - v);
+                else a.tile_off[p] = (uint32_t)(carry + incl - v);
+            }
+            __syncthreads();
+            if (tid == 1023) s_carry = carry + incl;
+            __syncthreads();
+        }
+        if (pass == 1 && tid == 0) {
+            a.tile_off[a.nlist] = (uint32_t)s_carry;
+            *a.total_tiles = (uint32_t)s_carry;
+            *a.tile_counter = 0;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void group_fill_kernel(GroupArgs a)
+{
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= a.B * a.nprobes) return;
+    uint32_t q = slot / a.nprobes;
+    uint32_t p = (uint32_t)a.probes[slot];
+    a.seg_off[slot] = a.qtot[q] + a.seg_local[slot];
+    a.qlist[a.qlist_off[p] + a.slot_pos[slot]] = slot;
+}
+
+}  // namespace
+
+void launch_group(const GroupArgs &a, cudaStream_t st)
+{
+    if (a.B == 0) return;
+    LGPU_CUDA(cudaMemsetAsync(a.part_cnt, 0, sizeof(uint32_t) * a.nlist, st));
+    LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
+    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a);
+    group_scan_kernel<<<1, 1024, 0, st>>>(a);
+    uint32_t slots = a.B * a.nprobes;
+    group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a);
+    LGPU_CUDA(cudaGetLastError());
+}
+
+}  // namespace lgpu

@@ -1,0 +1,121 @@
+// kernels.cuh -- kernel argument blocks and host launchers shared by the C-ABI layer.
+#pragma once
+
+#include "common.cuh"
+
+namespace lgpu {
+
+// ---------------- scan (K2+K3) geometry ------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_G = 8;                         // queries per tile
+constexpr int SCAN_RMAX = 4;                      // rows per thread
+constexpr int SCAN_ROWS_TILE = SCAN_THREADS * SCAN_RMAX;
+constexpr int SCAN_LUT_HALF = 32768;              // [256 c][8 s][4 g] f32
+constexpr int SCAN_LUT_BYTES = 2 * SCAN_LUT_HALF; // [2 h] halves
+
+__host__ __device__ __forceinline__ uint32_t scan_nrb(uint32_t n)
+{
+    return (n + SCAN_ROWS_TILE - 1) / SCAN_ROWS_TILE;
+}
+__host__ __device__ __forceinline__ uint32_t scan_rb_rows(uint32_t n, uint32_t nrb)
+{
+    return nrb ? (((n + nrb - 1) / nrb + 31u) & ~31u) : 0u;
+}
+
+struct ScanArgs {
+    // index (device)
+    const float *centroids;       // [nlist][dim]
+    const float *cb_tiled;        // [nch][256][8][dsub]
+    const unsigned char *codes;   // skewed code streams, see index.cu
+    const uint64_t *code_base;    // [nlist] byte offset of partition p's stream block
+    const uint32_t *part_n;       // [nlist]
+    const uint32_t *part_npad;    // [nlist] rows rounded up to 32
+    uint32_t dim, m, nch, metric, nlist;
+    // batch (device)
+    const float *queries;         // [B][dim] (normalised for cosine)
+    uint32_t nprobes;
+    const uint32_t *part_cnt;     // [nlist] queries probing p
+    const uint32_t *qlist_off;    // [nlist] start of p's slice of qlist
+    const uint32_t *tile_off;     // [nlist+1]
+    const uint32_t *qlist;        // [B*nprobes] probe-slot ids (q*nprobes+j) grouped by partition
+    const uint64_t *seg_off;      // [B*nprobes] offset of the slot's distance segment
+    const uint32_t *total_tiles;  // [1]
+    uint32_t *tile_counter;       // [1], zeroed before launch
+    float *dist_out;
+};
+bool scan_dsub_supported(uint32_t dsub);
+void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
+
+// ---------------- batch preparation (grouping probes by partition) ----------------
+struct GroupArgs {
+    const uint64_t *probes;       // [B*nprobes] partition ids (u64 from the selector)
+    uint32_t B, nprobes, nlist;
+    const uint32_t *part_n;
+    uint32_t *part_cnt;           // [nlist] zeroed before
+    uint32_t *slot_pos;           // [B*nprobes]
+    uint64_t *seg_local;          // [B*nprobes] offset inside the query's block
+    uint64_t *qtot;               // [B]
+    uint64_t *seg_off;            // [B*nprobes]
+    uint32_t *qlist_off;          // [nlist]
+    uint32_t *tile_off;           // [nlist+1]
+    uint32_t *qlist;              // [B*nprobes]
+    uint32_t *total_tiles;        // [1]
+    uint32_t *tile_counter;       // [1]
+    unsigned long long *scanned_rows;  // [1] sum over probe slots of n_p (roofline bytes / m)
+};
+void launch_group(const GroupArgs &a, cudaStream_t st);
+
+// ---------------- exact distance matrix (K1 coarse, flat v1) ----------------------
+// D[q][c] for q < B, c < N.  mode 0: L2 (squared), 1: dot distance 1 - x.y,
+// 2: cosine 1 - x.y/|x|/|y| (xnorm[B] = |x|, ysqrt[N] = |y| required).
+void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
+                        const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st);
+// row norms |x| = sqrt(dot(x,x)) in lance order; out[n]
+void launch_row_norms(const float *X, uint64_t n, uint32_t d, float *out, cudaStream_t st);
+// out[q] = x[q] / |x[q]|
+void launch_normalize(const float *X, uint32_t B, uint32_t d, float *out, cudaStream_t st);
+// exact distances of (query, stored row) pairs: out[q][c] = dist(Q[q], V[pos[q][c]]),
+// pos == UINT64_MAX => +inf
+void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, uint32_t B, uint32_t nc,
+                          uint32_t d, int metric, float *out, cudaStream_t st);
+
+// ---------------- top-k select (K4) ------------------------------------------------
+constexpr uint32_t SELECT_KMAX = 2048;
+struct SelectArgs {
+    int mode;                     // 0: IVF distance segments, 1: dense row (ids = column / col_ids),
+                                  // 2: strided candidate lists with per-entry ids
+    // mode 0
+    const float *dist;            // dist_out
+    const uint64_t *seg_off;      // [B*nprobes]
+    const uint64_t *probes;       // [B*nprobes]
+    uint32_t nprobes;
+    const uint32_t *part_n;
+    const uint64_t *part_off;     // [nlist+1] storage row offsets
+    const uint64_t *row_ids;      // [nrows]
+    // mode 1 / 2
+    const float *dense;           // values
+    uint64_t ncols;               // candidates per query
+    uint64_t row_stride;          // mode 1: ld; mode 2: stride between queries
+    uint64_t inner, outer_stride; // mode 2: col -> (col/inner)*outer_stride + q*row_stride + col%inner
+    const uint64_t *col_ids;      // mode 1: optional id per column (NULL => column index)
+    const uint64_t *cand_ids;     // mode 2: id per entry (same addressing as dense)
+    const uint64_t *cand_pos;     // mode 2: optional pos per entry
+    // common
+    uint32_t B, k;
+    int has_lower, has_upper;
+    float lower, upper;
+    uint64_t *out_ids;            // [B][k]
+    float *out_dist;              // [B][k]
+    uint32_t *out_count;          // [B]
+    uint64_t *out_pos;            // optional [B][k] storage position (mode 0) / column (mode 1)
+};
+void launch_select(const SelectArgs &a, cudaStream_t st);
+
+// ---------------- index re-layout (open time) --------------------------------------
+void launch_retile_codes(const unsigned char *codes, int layout, const uint64_t *part_off, uint32_t nlist,
+                         uint64_t nrows, uint32_t m, uint32_t nch, const uint64_t *code_base,
+                         const uint32_t *part_npad, unsigned char *out, cudaStream_t st);
+void launch_retile_codebook(const float *codebook, uint32_t m, uint32_t dsub, uint32_t nch, float *out,
+                            cudaStream_t st);
+
+}  // namespace lgpu

@@ -1,0 +1,244 @@
+// select.cu -- K4: per-query top-k by (_distance ASC, _rowid ASC).
+//
+// Replaces the per-partition bounded heap + SortExec TopK(fetch=k) merge
+// [lance, recalled; tie-break pinned by
+// /root/reference/python/python/lancedb/query.py:1366-1368].  Also used to pick the
+// nprobes nearest centroids (IvfModel::find_partitions' sort_to_indices) and for the
+// flat / refine / multi-GPU merge paths.
+//
+// One CTA per query streams that query's candidate distances (coalesced float4),
+// keeps only those not worse than the current k-th best, and stages survivors
+// (ordered-uint distance key, row id) in shared memory; when `trigger` survivors have
+// piled up it bitonic-sorts them, keeps k, and tightens the threshold.  The first sort
+// happens after the first 1024 candidates, after which the pass rate collapses to
+// ~k/seen, so a query costs one ~1024-element sort plus a small final sort.
+// Integer work (ids, ordering) is exact; distances are passed through untouched.
+#include "kernels.cuh"
+
+#include <math_constants.h>
+
+namespace lgpu {
+
+namespace {
+
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_ITER = SEL_THREADS * 4;
+
+struct Stage {
+    uint32_t *keys;
+    uint64_t *ids;
+    uint64_t *pos;   // may be null
+};
+
+__device__ __forceinline__ bool key_less(uint32_t ka, uint64_t ia, uint32_t kb, uint64_t ib)
+{
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+// bitonic sort of the first n2 (power of two) staged entries, ascending
+template <bool POS>
+__device__ void bitonic_sort(Stage s, uint32_t n2)
+{
+    for (uint32_t size = 2; size <= n2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = threadIdx.x; i < (n2 >> 1); i += SEL_THREADS) {
+                uint32_t lo = 2 * i - (i & (stride - 1));
+                uint32_t hi = lo + stride;
+                bool asc = (lo & size) == 0;
+                uint32_t ka = s.keys[lo], kb = s.keys[hi];
+                uint64_t ia = s.ids[lo], ib = s.ids[hi];
+                bool gt = key_less(kb, ib, ka, ia);
+                if (gt == asc) {
+                    s.keys[lo] = kb; s.keys[hi] = ka;
+                    s.ids[lo] = ib; s.ids[hi] = ia;
+                    if (POS) { uint64_t pa = s.pos[lo]; s.pos[lo] = s.pos[hi]; s.pos[hi] = pa; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <bool POS>
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint32_t cap, uint32_t trigger)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    Stage st;
+    st.ids = reinterpret_cast<uint64_t *>(smem);
+    st.pos = POS ? st.ids + cap : nullptr;
+    st.keys = reinterpret_cast<uint32_t *>(smem + (size_t)cap * 8 * (POS ? 2 : 1));
+    __shared__ uint32_t s_cnt, s_tau;
+
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) { s_cnt = 0; s_tau = 0xffffffffu; }
+    __syncthreads();
+
+    auto in_range = [&](float v) -> bool {
+        if (v != v) return false;                           // FilterExec: _distance IS NOT NULL
+        if (a.has_lower && !(v >= a.lower)) return false;
+        if (a.has_upper && !(v < a.upper)) return false;
+        return true;
+    };
+    // sort what is staged, keep the k best, tighten the threshold
+    auto compact = [&]() {
+        uint32_t cnt = s_cnt;
+        uint32_t n2 = 2;
+        while (n2 < cnt) n2 <<= 1;
+        for (uint32_t i = cnt + tid; i < n2; i += SEL_THREADS) { st.keys[i] = 0xffffffffu; st.ids[i] = UINT64_MAX; }
+        __syncthreads();
+        bitonic_sort<POS>(st, n2);
+        if (tid == 0) {
+            uint32_t keep = cnt < a.k ? cnt : a.k;
+            s_cnt = keep;
+            if (keep == a.k && a.k > 0) s_tau = st.keys[a.k - 1];
+        }
+        __syncthreads();
+    };
+    // offer up to 4 candidates per thread; warp-aggregated staging
+    auto offer4 = [&](const float v[4], const bool ok[4], const uint64_t idbase, const uint64_t *idsrc,
+                      const uint64_t posbase) {
+        const uint32_t tau = s_tau;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float f = v[u];
+            if (f == 0.f) f = 0.f;                           // -0 and +0 tie
+            uint32_t key = f32_key(f);
+            bool pass = ok[u] && in_range(f) && key <= tau;
+            unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+                uint32_t base = 0;
+                if (lane == (__ffs(mask) - 1)) base = atomicAdd(&s_cnt, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+                if (pass) {
+                    uint32_t slot = base + __popc(mask & ((1u << lane) - 1));
+                    st.keys[slot] = key;
+                    st.ids[slot] = idsrc ? idsrc[idbase + u] : idbase + u;
+                    if (POS) st.pos[slot] = posbase + u;
+                }
+            }
+        }
+    };
+
+    if (a.mode == 0) {
+        for (uint32_t j = 0; j < a.nprobes; j++) {
+            const uint32_t slot = q * a.nprobes + j;
+            const uint32_t p = (uint32_t)a.probes[slot];
+            const uint32_t n = a.part_n[p];
+            const float *src = a.dist + a.seg_off[slot];
+            const uint64_t rowbase = a.part_off[p];
+            for (uint32_t r0 = 0; r0 < n; r0 += SEL_ITER) {
+                uint32_t r = r0 + tid * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                bool ok[4];
+                if (r < n) {
+                    float4 t = *reinterpret_cast<const float4 *>(src + r);   // segment padded to 4
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) ok[u] = r + u < n;
+                offer4(v, ok, rowbase + r, a.row_ids, rowbase + r);
+                __syncthreads();
+                if (s_cnt >= trigger) compact();
+            }
+        }
+    } else if (a.mode == 1) {
+        const float *src = a.dense + (size_t)q * a.row_stride;
+        const bool aligned = ((a.row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dense) & 15) == 0);
+        for (uint64_t c0 = 0; c0 < a.ncols; c0 += SEL_ITER) {
+            uint64_t c = c0 + (uint64_t)tid * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            bool ok[4];
+            if (aligned && c + 3 < a.ncols) {
+                float4 t = *reinterpret_cast<const float4 *>(src + c);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (c + u < a.ncols) v[u] = src[c + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) ok[u] = c + u < a.ncols;
+            offer4(v, ok, c, a.col_ids, c);
+            __syncthreads();
+            if (s_cnt >= trigger) compact();
+        }
+    } else {
+        for (uint64_t c0 = 0; c0 < a.ncols; c0 += SEL_ITER) {
+            uint64_t c = c0 + (uint64_t)tid * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            bool ok[4];
+            uint64_t idv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                ok[u] = false; idv[u] = UINT64_MAX;
+                if (c + u < a.ncols) {
+                    uint64_t cc = c + u;
+                    uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
+                    idv[u] = a.cand_ids[addr];
+                    v[u] = a.dense[addr];
+                    ok[u] = idv[u] != UINT64_MAX;           // unused slot of a shorter list
+                }
+            }
+            // ids differ per entry: stage them through the id "source" one at a time
+            const uint32_t tau = s_tau;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float f = v[u];
+                if (f == 0.f) f = 0.f;
+                uint32_t key = f32_key(f);
+                bool pass = ok[u] && in_range(f) && key <= tau;
+                unsigned mask = __ballot_sync(0xffffffffu, pass);
+                if (mask) {
+                    uint32_t base = 0;
+                    if (lane == (__ffs(mask) - 1)) base = atomicAdd(&s_cnt, __popc(mask));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(mask) - 1);
+                    if (pass) {
+                        uint32_t slot = base + __popc(mask & ((1u << lane) - 1));
+                        st.keys[slot] = key;
+                        st.ids[slot] = idv[u];
+                        if (POS) {
+                            uint64_t cc = c + u;
+                            uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
+                            st.pos[slot] = a.cand_pos ? a.cand_pos[addr] : cc;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_cnt >= trigger) compact();
+        }
+    }
+    __syncthreads();
+    compact();
+    const uint32_t cnt = s_cnt;
+    for (uint32_t i = tid; i < a.k; i += SEL_THREADS) {
+        bool have = i < cnt;
+        a.out_ids[(size_t)q * a.k + i] = have ? st.ids[i] : UINT64_MAX;
+        a.out_dist[(size_t)q * a.k + i] = have ? key_f32(st.keys[i]) : CUDART_INF_F;
+        if (POS) a.out_pos[(size_t)q * a.k + i] = have ? st.pos[i] : UINT64_MAX;
+    }
+    if (tid == 0) a.out_count[q] = cnt;
+}
+
+}  // namespace
+
+void launch_select(const SelectArgs &a, cudaStream_t st)
+{
+    if (a.B == 0) return;
+    LGPU_REQUIRE(a.k >= 1 && a.k <= SELECT_KMAX, "limit+offset (k) must be in [1, 2048] on the GPU path");
+    uint32_t trigger = a.k * 2 < 512 ? 512 : a.k * 2;
+    uint32_t cap = 2;
+    while (cap < trigger + SEL_ITER) cap <<= 1;
+    const bool pos = a.out_pos != nullptr;
+    size_t smem = (size_t)cap * (pos ? 20 : 12);
+    if (pos) {
+        LGPU_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        select_kernel<true><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger);
+    } else {
+        LGPU_CUDA(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        select_kernel<false><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger);
+    }
+    LGPU_CUDA(cudaGetLastError());
+}
+
+}  // namespace lgpu

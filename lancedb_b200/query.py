@@ -1,0 +1,155 @@
+"""Query builder mirroring the reference's vector-search surface.
+
+Same names, argument meaning, defaults and error behaviour as
+`lancedb.query.LanceVectorQueryBuilder` (/root/reference/python/python/lancedb/query.py:1552-1862)
+and the request it lowers to, `VectorQueryRequest`
+(/root/reference/rust/lancedb/src/query.rs:1066-1114): limit 10, nprobes 20 (min == max),
+no refine, L2.  Everything below `to_arrow()` runs on the GPU through the C ABI; only the
+`Take` of the non-vector columns for the k result rows happens in
+pyarrow on the host.  Filters (`where`), FTS and rerankers are outside the hot path and
+raise NotImplementedError.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Union
+
+import numpy as np
+import pyarrow as pa
+
+DEFAULT_TOP_K = 10          # rust/lancedb/src/query.rs:36
+DEFAULT_NPROBES = 20        # rust/lancedb/src/query.rs:1097-1113
+
+
+class LanceVectorQueryBuilder:
+    def __init__(self, table, query, vector_column: str):
+        self._table = table
+        q = np.asarray(query, dtype=np.float32)      # every query vector is cast to Float32 (query.rs:1013)
+        if q.ndim == 1:
+            q = q[None, :]
+            self._multi = False
+        elif q.ndim == 2:
+            self._multi = q.shape[0] > 1
+        else:
+            raise ValueError("query must be a vector or a list of vectors")
+        self._query = np.ascontiguousarray(q)
+        self._vector_column = vector_column
+        self._distance_type: Optional[str] = None
+        self._minimum_nprobes: Optional[int] = None
+        self._maximum_nprobes: Optional[int] = None
+        self._lower_bound: Optional[float] = None
+        self._upper_bound: Optional[float] = None
+        self._refine_factor: Optional[int] = None
+        self._limit: Optional[int] = None
+        self._offset: int = 0
+        self._columns: Optional[List[str]] = None
+        self._with_row_id = False
+        self._use_index = True
+
+    # ---- setters (same names as the reference) ----
+    def metric(self, metric: str) -> "LanceVectorQueryBuilder":
+        return self.distance_type(metric)
+
+    def distance_type(self, distance_type: str) -> "LanceVectorQueryBuilder":
+        self._distance_type = distance_type.lower()
+        return self
+
+    def nprobes(self, nprobes: int) -> "LanceVectorQueryBuilder":
+        self._minimum_nprobes = nprobes
+        self._maximum_nprobes = nprobes
+        return self
+
+    def minimum_nprobes(self, n: int) -> "LanceVectorQueryBuilder":
+        self._minimum_nprobes = n
+        return self
+
+    def maximum_nprobes(self, n: int) -> "LanceVectorQueryBuilder":
+        self._maximum_nprobes = n
+        return self
+
+    def distance_range(self, lower_bound: Optional[float] = None,
+                       upper_bound: Optional[float] = None) -> "LanceVectorQueryBuilder":
+        self._lower_bound = lower_bound
+        self._upper_bound = upper_bound
+        return self
+
+    def refine_factor(self, refine_factor: int) -> "LanceVectorQueryBuilder":
+        self._refine_factor = refine_factor
+        return self
+
+    def limit(self, limit: Optional[int]) -> "LanceVectorQueryBuilder":
+        if limit is None or limit <= 0:
+            raise ValueError("Limit is required for ANN/KNN queries and must be greater than 0")
+        self._limit = int(limit)
+        return self
+
+    def offset(self, offset: int) -> "LanceVectorQueryBuilder":
+        self._offset = max(0, int(offset or 0))
+        return self
+
+    def select(self, columns: List[str]) -> "LanceVectorQueryBuilder":
+        self._columns = list(columns)
+        return self
+
+    def with_row_id(self, with_row_id: bool = True) -> "LanceVectorQueryBuilder":
+        self._with_row_id = with_row_id
+        return self
+
+    def bypass_vector_index(self) -> "LanceVectorQueryBuilder":
+        """Exhaustive flat search even when an index exists (use_index = false)."""
+        self._use_index = False
+        return self
+
+    def where(self, *a, **k):
+        raise NotImplementedError("filters (prefilter/postfilter) are outside the GPU hot path (SURVEY.md 8f-3)")
+
+    def rerank(self, *a, **k):
+        raise NotImplementedError("rerankers are out of scope")
+
+    # ---- execution ----
+    def _resolve(self):
+        lim = self._limit if self._limit is not None else DEFAULT_TOP_K
+        k = lim + self._offset                          # table/query.rs:231
+        min_np = self._minimum_nprobes if self._minimum_nprobes is not None else DEFAULT_NPROBES
+        max_np = self._maximum_nprobes if self._maximum_nprobes is not None else (
+            min_np if self._minimum_nprobes is not None else DEFAULT_NPROBES)
+        if min_np <= 0:
+            raise ValueError("minimum_nprobes must be greater than 0")     # query.rs:1233-1236
+        if max_np != 0 and max_np < min_np:
+            raise ValueError("maximum_nprobes must be greater than or equal to minimum_nprobes")
+        # with no filter every probed partition yields rows, so min == effective probes;
+        # maximum_nprobes only matters for filtered queries (query.py:1676-1692)
+        return k, lim, min_np
+
+    def to_arrow(self, *, timeout=None) -> pa.Table:
+        k, lim, nprobes = self._resolve()
+        t = self._table
+        if self._query.shape[1] != t._dim(self._vector_column):
+            raise ValueError(
+                f"No vector column found to match with the query vector dimension: {self._query.shape[1]}")
+        ids, dist, cnt = t._vector_search(
+            self._query, column=self._vector_column, k=k, nprobes=nprobes,
+            refine_factor=self._refine_factor, distance_type=self._distance_type,
+            lower=self._lower_bound, upper=self._upper_bound, use_index=self._use_index)
+        out = []
+        for qi in range(self._query.shape[0]):
+            n = int(cnt[qi])
+            sel_ids = ids[qi, self._offset:n][:lim]
+            sel_dist = dist[qi, self._offset:n][:lim]
+            tbl = t._take(sel_ids, self._columns)
+            tbl = tbl.append_column("_distance", pa.array(sel_dist, pa.float32()))
+            if self._with_row_id:
+                tbl = tbl.append_column("_rowid", pa.array(sel_ids, pa.uint64()))
+            if self._multi:                                # table/query.rs:360-366
+                tbl = tbl.append_column("query_index", pa.array(np.full(len(sel_ids), qi, np.int32)))
+            out.append(tbl)
+        return pa.concat_tables(out) if len(out) > 1 else out[0]
+
+    def to_batches(self, max_batch_length: Optional[int] = None, *, timeout=None):
+        return pa.RecordBatchReader.from_batches(
+            self.to_arrow().schema, self.to_arrow().to_batches(max_chunksize=max_batch_length or 1024))
+
+    def to_pandas(self, **kw):
+        return self.to_arrow().to_pandas(**kw)
+
+    def to_list(self) -> list:
+        return self.to_arrow().to_pylist()

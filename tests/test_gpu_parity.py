@@ -1,0 +1,185 @@
+"""GPU parity tests proper: every call goes through the C ABI (ctypes) and is compared
+with the CPU oracle on the same seeded inputs.  Bars: row ids / partition ids / counts
+bit-exact; distances bit-exact too (the kernels reproduce the oracle's rounding order),
+which is stricter than the 1e-4 relative tolerance north_star allows."""
+import numpy as np
+import pytest
+
+import oracle
+from lancedb_b200 import _native
+from tests.util import queries, random_index
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_search(ix, q, k, nprobes, **kw):
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    gi, gd, gc = gpu.search(q, k=k, nprobes=nprobes, **kw)
+    oi, od, oc = orc.search(q, k=k, nprobes=nprobes, nthreads=8, **kw)
+    gpu.close()
+    assert np.array_equal(gc, oc), f"counts differ: {np.nonzero(gc != oc)[0][:10]}"
+    bad = np.nonzero((gi != oi).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} queries with different row ids, first {bad[:5]}: {gi[bad[0]]} vs {oi[bad[0]]}"
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32)), "distances not bit-identical"
+    return gi, gd, gc
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+@pytest.mark.parametrize("dim,nlist", [(32, 7), (768, 64), (100, 33)])
+def test_coarse_partitions(metric, dim, nlist):
+    rng = np.random.default_rng(1)
+    m = 4 if dim % 4 == 0 else 1
+    ix = random_index(rng, dim=dim, nlist=nlist, m=m if (dim // m) in (1, 2, 4, 8, 16, 32) else dim // 4,
+                      metric=metric, n=500)
+    q = queries(rng, 37, dim)
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    nprobes = min(5, nlist)
+    parts, dists = gpu.debug_coarse(q, nprobes)
+    for i in range(q.shape[0]):
+        qn = oracle.normalize(q[i]) if metric == "cosine" else q[i]
+        op, od, _ = orc.find_partitions(qn, nprobes)
+        assert np.array_equal(parts[i], op)
+        assert np.array_equal(dists[i].view(np.uint32), od.view(np.uint32))
+    gpu.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+@pytest.mark.parametrize("dim,m", [(768, 96), (64, 4), (80, 10), (32, 8), (64, 2), (24, 24)])
+def test_partition_distances_bit_exact(metric, dim, m):
+    """LUT build + code scan (K2+K3) against oracle: dsub 8/16/8/4/32/1, chunk padding (m=10)."""
+    rng = np.random.default_rng(2)
+    sizes = [0, 1, 31, 33, 977, 2048, 2049, 5000]
+    ix = random_index(rng, dim=dim, nlist=len(sizes), m=m, metric=metric, sizes=sizes)
+    q = queries(rng, 1, dim)[0]
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    for p, n in enumerate(sizes):
+        if n == 0:
+            continue
+        g = gpu.debug_partition_distances(q, p, n)
+        o = orc.partition_distances(q, p)
+        assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), (
+            f"partition {p} (n={n}): {np.nonzero(g != o)[0][:8]} {g[:4]} {o[:4]}")
+    gpu.close()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_search_small(metric):
+    rng = np.random.default_rng(3)
+    ix = random_index(rng, dim=64, nlist=16, m=8, metric=metric, n=4000)
+    _check_search(ix, queries(rng, 50, 64), k=10, nprobes=4)
+
+
+@pytest.mark.parametrize("B", [1, 7, 8, 9, 129])
+def test_search_batch_shapes(B):
+    rng = np.random.default_rng(4)
+    ix = random_index(rng, dim=128, nlist=20, m=16, n=6000)
+    _check_search(ix, queries(rng, B, 128), k=10, nprobes=5)
+
+
+def test_search_ragged_partitions():
+    """empty, 1-row and multi-tile partitions; nprobes == nlist; k above the candidate count"""
+    rng = np.random.default_rng(5)
+    sizes = [0, 0, 1, 2, 40, 3000, 0, 4500, 17, 900]
+    ix = random_index(rng, dim=64, nlist=len(sizes), m=8, sizes=sizes)
+    q = queries(rng, 33, 64)
+    _check_search(ix, q, k=10, nprobes=len(sizes))
+    _check_search(ix, q, k=100, nprobes=3)
+    _check_search(ix, q, k=1, nprobes=1)
+    tiny = random_index(rng, dim=64, nlist=4, m=8, sizes=[1, 0, 2, 0])
+    gi, gd, gc = _check_search(tiny, q, k=10, nprobes=4)
+    assert (gc == 3).all() and (gi[:, 3:] == np.iinfo(np.uint64).max).all() and np.isinf(gd[:, 3:]).all()
+
+
+def test_search_duplicate_codes_tiebreak():
+    """identical PQ codes => identical distances; order must be by row id"""
+    rng = np.random.default_rng(6)
+    ix = random_index(rng, dim=32, nlist=3, m=4, sizes=[300, 200, 100])
+    ct = ix.codes_t.copy()
+    for p in range(3):            # make every row of a partition share one code word
+        a, b = int(ix.part_offsets[p]), int(ix.part_offsets[p + 1])
+        blk = ct[a * 4:b * 4].reshape(4, b - a)
+        blk[:] = blk[:, :1]
+    ix.codes_t = ct
+    gi, gd, gc = _check_search(ix, queries(rng, 9, 32), k=25, nprobes=3)
+    assert (np.diff(gd, axis=1) >= 0).all()
+
+
+def test_search_distance_range_and_large_k():
+    rng = np.random.default_rng(7)
+    ix = random_index(rng, dim=64, nlist=8, m=8, n=3000)
+    q = queries(rng, 20, 64)
+    gi, gd, gc = _check_search(ix, q, k=50, nprobes=4)
+    lo, hi = float(gd[0, 5]), float(gd[0, 30])
+    _check_search(ix, q, k=50, nprobes=4, lower=lo, upper=hi)
+    _check_search(ix, q, k=50, nprobes=4, upper=lo)
+    _check_search(ix, q, k=50, nprobes=4, lower=hi)
+    _check_search(ix, q, k=1024, nprobes=8)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_search_refine(metric):
+    rng = np.random.default_rng(8)
+    ix = random_index(rng, dim=48, nlist=6, m=6, metric=metric, n=2000, with_vectors=True)
+    _check_search(ix, queries(rng, 17, 48), k=10, nprobes=3, refine_factor=5)
+
+
+def test_search_config2_shape_subset():
+    """BASELINE config 2's geometry (d=768, m=96, nprobes=20, k=10) at 1/8 of its rows."""
+    rng = np.random.default_rng(9)
+    ix = random_index(rng, dim=768, nlist=128, m=96, n=125_000)
+    _check_search(ix, queries(rng, 256, 768), k=10, nprobes=20)
+
+
+def test_search_k100_cosine_config3_shape():
+    rng = np.random.default_rng(10)
+    ix = random_index(rng, dim=768, nlist=64, m=96, metric="cosine", n=150_000)
+    _check_search(ix, queries(rng, 96, 768), k=100, nprobes=50)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+@pytest.mark.parametrize("n,dim", [(1000, 128), (5000, 40), (257, 1536)])
+def test_flat_parity(metric, n, dim):
+    rng = np.random.default_rng(11)
+    v = queries(rng, n, dim)
+    v[n // 2] = v[3]                               # an exact duplicate row -> tie
+    rid = rng.permutation(n).astype(np.uint64)
+    q = queries(rng, 19, dim)
+    q[0] = v[3]
+    fl = _native.GpuFlat(v, row_ids=rid)
+    gi, gd, gc = fl.search(q, k=10, metric=metric)
+    oi, od, oc = oracle.flat_search(v, q, k=10, metric=metric, row_ids=rid, nthreads=8)
+    fl.close()
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+def test_flat_reference_doctest_pins():
+    """python/python/lancedb/table.py:3595-3603 and query.py:1563-1571 through the C ABI"""
+    fl = _native.GpuFlat(np.array([[0.1, 2.3, 4.5], [0.5, 3.4, 1.3], [0.3, 6.2, 2.6]], np.float32))
+    ids, dist, cnt = fl.search([[0.4, 1.4, 2.4]], k=2)
+    assert list(ids[0]) == [1, 2] and [f"{d:.6f}" for d in dist[0]] == ["5.220000", "23.089996"]
+    fl.close()
+    fl = _native.GpuFlat(np.array([[1.1, 1.2], [0.5, 1.3], [0.4, 0.4], [0.4, 0.4]], np.float32))
+    ids, dist, cnt = fl.search([[0.4, 0.4]], k=3, metric="cosine")
+    assert list(ids[0]) == [2, 3, 0] and [f"{d:.6f}" for d in dist[0]] == ["0.000000", "0.000000", "0.000944"]
+    fl.close()
+
+
+def test_error_contract():
+    rng = np.random.default_rng(12)
+    ix = random_index(rng, dim=32, nlist=4, m=4, n=100)
+    gpu = _native.GpuIvfPq(ix)
+    q = queries(rng, 2, 32)
+    with pytest.raises(ValueError, match="minimum_nprobes must be greater than 0"):
+        gpu.search(q, nprobes=0)
+    with pytest.raises(ValueError, match="limit"):
+        gpu.search(q, k=0)
+    with pytest.raises(ValueError, match="refine_factor needs the raw vectors"):
+        gpu.search(q, refine_factor=2)
+    gpu.close()
+    bad = random_index(rng, dim=30, nlist=2, m=2, n=10)      # dsub = 15
+    with pytest.raises(ValueError, match="sub-vector length"):
+        _native.GpuIvfPq(bad)
