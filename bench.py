@@ -263,8 +263,8 @@ def main():
     def step_device(i):
         gpu.search_device(d_q[i % nb].data_ptr(), B, p, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(), stream)
         if par == "sharded":
-            dist.all_gather_into_tensor(g_ids, d_ids)
-            dist.all_gather_into_tensor(g_dist, d_dist)
+            dist.all_gather_into_tensor(g_ids.view(-1, k), d_ids)
+            dist.all_gather_into_tensor(g_dist.view(-1, k), d_dist)
             _native.merge_topk_device(local, world, B, k, g_ids.data_ptr(), g_dist.data_ptr(), m_ids.data_ptr(),
                                       m_dist.data_ptr(), m_cnt.data_ptr(), stream)
 

@@ -58,10 +58,8 @@ class ShardedIvfPq:
         self.local.search_device(d_q.data_ptr(), B, p, ids.data_ptr(), dst.data_ptr(), cnt.data_ptr(), stream)
         g_ids = torch.empty(gather_shape(self.world, B, k), dtype=torch.int64, device=dev)
         g_dst = torch.empty(gather_shape(self.world, B, k), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(g_ids, ids, group=self.group)
-        dist.all_gather_into_tensor(g_dst, dst, group=self.group)
-        p2 = _native.make_params(k=k)
-        del p2
+        dist.all_gather_into_tensor(g_ids.view(-1, k), ids, group=self.group)
+        dist.all_gather_into_tensor(g_dst.view(-1, k), dst, group=self.group)
         _native.merge_topk_device(self.device, self.world, B, k, g_ids.data_ptr(), g_dst.data_ptr(),
                                   ids.data_ptr(), dst.data_ptr(), cnt.data_ptr(), stream)
         return ids, dst, cnt

@@ -1,0 +1,145 @@
+"""Host-side logic that needs no GPU: builder defaults / validation mirroring the reference,
+index parameter defaults, partition sharding, and the world_size-2 all-gather + merge pattern
+over gloo (the oracle stands in for the per-rank GPU search)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import lancedb_b200
+from lancedb_b200.index import assign_partitions, suggested_num_partitions, suggested_num_sub_vectors
+from lancedb_b200.query import LanceVectorQueryBuilder
+from tests.util import queries, random_index
+
+
+class _FakeTable:
+    def __init__(self, dim=4):
+        self.dim = dim
+        self.calls = []
+
+    def _dim(self, column):
+        return self.dim
+
+    def _vector_search(self, q, **kw):
+        self.calls.append(kw)
+        B, k = q.shape[0], kw["k"]
+        ids = np.tile(np.arange(k, dtype=np.uint64), (B, 1))
+        return ids, np.tile(np.arange(k, dtype=np.float32), (B, 1)), np.full(B, k, np.uint32)
+
+    def _take(self, row_ids, columns):
+        import pyarrow as pa
+        return pa.table({"id": pa.array(np.asarray(row_ids, np.int64))})
+
+
+def test_request_defaults_match_reference():
+    # rust/lancedb/src/query.rs:36, 1097-1113: k=10, nprobes min=max=20, no refine
+    t = _FakeTable()
+    out = LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").to_arrow()
+    kw = t.calls[0]
+    assert kw["k"] == 10 and kw["nprobes"] == 20 and kw["refine_factor"] is None
+    assert kw["distance_type"] is None and kw["lower"] is None and kw["upper"] is None and kw["use_index"]
+    assert out.schema.names == ["id", "_distance"] and str(out.schema.field("_distance").type) == "float"
+
+
+def test_limit_offset_and_multivector():
+    t = _FakeTable()
+    out = (LanceVectorQueryBuilder(t, [[1, 2, 3, 4], [4, 3, 2, 1]], "vector").limit(3).offset(2)
+           .with_row_id(True).to_arrow())
+    assert t.calls[0]["k"] == 5                       # top_k = limit + offset (table/query.rs:231)
+    assert out.num_rows == 6 and out["query_index"].to_pylist() == [0, 0, 0, 1, 1, 1]
+    assert out["_rowid"].to_pylist()[:3] == [2, 3, 4]
+
+
+def test_builder_validation_errors():
+    t = _FakeTable()
+    with pytest.raises(ValueError, match="minimum_nprobes must be greater than 0"):
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").nprobes(0).to_arrow()
+    with pytest.raises(ValueError, match="No vector column found to match with the query vector dimension: 3"):
+        LanceVectorQueryBuilder(t, [1, 2, 3], "vector").to_arrow()
+    with pytest.raises(ValueError):
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").limit(0)
+    with pytest.raises(ValueError, match="maximum_nprobes"):
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").minimum_nprobes(10).maximum_nprobes(5).to_arrow()
+    with pytest.raises(NotImplementedError):
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").where("a > 1")
+
+
+def test_index_parameter_defaults():
+    # rust/lancedb/src/index/vector.rs:306-319; create_index.rs:734-795
+    assert suggested_num_sub_vectors(768) == 48 and suggested_num_sub_vectors(24) == 3
+    assert suggested_num_sub_vectors(7) == 1
+    assert suggested_num_partitions(16384) == 2
+
+
+def test_table_surface_and_column_inference():
+    db = lancedb_b200.connect("memory://")
+    t = db.create_table("t", [{"vector": [1.0, 2.0], "id": 1}, {"vector": [3.0, 4.0], "id": 2}])
+    assert db.table_names() == ["t"] and t.count_rows() == 2
+    assert t.search([0.0, 0.0])._vector_column == "vector"
+    with pytest.raises(ValueError, match="dimension: 3"):
+        t.search([0.0, 0.0, 0.0])
+    with pytest.raises(ValueError, match="already exists"):
+        db.create_table("t", [{"vector": [1.0, 2.0]}])
+
+
+def test_shard_partitions_cover_index_exactly():
+    rng = np.random.default_rng(0)
+    ix = random_index(rng, dim=16, nlist=13, m=2, n=900)
+    sizes = np.diff(ix.part_offsets.astype(np.int64))
+    owner = assign_partitions(sizes, 4)
+    loads = [int(sizes[owner == r].sum()) for r in range(4)]
+    assert max(loads) - min(loads) <= sizes.max()
+    seen = []
+    for r in range(4):
+        sh = ix.shard(r, 4)
+        sh.validate()
+        assert np.array_equal(sh.centroids, ix.centroids) and np.array_equal(sh.codebook, ix.codebook)
+        for p in range(ix.nlist):
+            if owner[p] == r:
+                assert np.array_equal(sh.partition_codes(p), ix.partition_codes(p))
+            else:
+                assert sh.part_offsets[p + 1] == sh.part_offsets[p]
+        seen.append(sh.row_ids)
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.sort(ix.row_ids))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _rank_main(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import oracle
+    from lancedb_b200.distributed import gather_shape
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    rng = np.random.default_rng(7)
+    ix = random_index(rng, dim=32, nlist=9, m=4, n=1500)
+    q = queries(rng, 11, 32)
+    k, nprobes = 10, 5
+    ids, dst, cnt = oracle.OracleIndex.from_data(ix.shard(rank, world)).search(q, k=k, nprobes=nprobes)
+    g_ids = torch.empty(gather_shape(world, 11, k), dtype=torch.int64)
+    g_dst = torch.empty(gather_shape(world, 11, k), dtype=torch.float32)
+    dist.all_gather_into_tensor(g_ids.view(-1, k), torch.from_numpy(ids.view(np.int64)))
+    dist.all_gather_into_tensor(g_dst.view(-1, k), torch.from_numpy(dst))
+    gi = g_ids.numpy().view(np.uint64); gd = g_dst.numpy()
+    full_ids, full_dst, full_cnt = oracle.OracleIndex.from_data(ix).search(q, k=k, nprobes=nprobes)
+    for b in range(11):                      # merge exactly as lgpu_merge_topk_device does
+        c = [(gd[r, b, i], gi[r, b, i]) for r in range(world) for i in range(k) if gi[r, b, i] != np.iinfo(np.uint64).max]
+        c.sort()
+        c = c[:k]
+        assert [x[1] for x in c] == list(full_ids[b, :full_cnt[b]])
+        assert [x[0] for x in c] == list(full_dst[b, :full_cnt[b]])
+    dist.barrier()
+    dist.destroy_process_group()
+    open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+
+
+def test_sharded_search_pattern_world2_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
