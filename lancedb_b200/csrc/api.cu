@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -96,7 +97,7 @@ using namespace lgpu;
 
 struct lgpu_index {
     int device = 0, num_sms = 0;
-    uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0;
+    uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0, rows_tile = SCAN_ROWS_TILE_MID;
     int metric = 0;
     uint64_t nrows = 0, device_bytes = 0;
     DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
@@ -193,6 +194,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     ws->scalars.ensure(64);
     GroupArgs ga{};
     ga.probes = ws->probes.as<uint64_t>(); ga.B = B; ga.nprobes = nprobes; ga.nlist = nlist;
+    ga.rows_tile = ix->rows_tile;
     ga.part_n = ix->part_n.as<uint32_t>(); ga.part_cnt = ws->part_cnt.as<uint32_t>();
     ga.slot_pos = ws->slot_pos.as<uint32_t>(); ga.seg_local = ws->seg_local.as<uint64_t>();
     ga.qtot = ws->qtot.as<uint64_t>(); ga.seg_off = ws->seg_off.as<uint64_t>();
@@ -211,6 +213,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sc.codes = ix->codes.as<unsigned char>(); sc.code_base = ix->code_base.as<uint64_t>();
     sc.part_n = ix->part_n.as<uint32_t>(); sc.part_npad = ix->part_npad.as<uint32_t>();
     sc.dim = dim; sc.m = ix->m; sc.nch = ix->nch; sc.metric = (uint32_t)ix->metric; sc.nlist = nlist;
+    sc.rows_tile = ix->rows_tile; sc.fzero2 = 0ull;
     sc.queries = qsearch; sc.nprobes = nprobes;
     sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
     sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
@@ -418,6 +421,21 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             pads[p] = (n + 3ull) & ~3ull;
         }
         ix->h_part_n = part_n;
+        {   // pick the scan kernel's warp-role split from the partition-size distribution:
+            // fewest row blocks for a (mean + 2 sigma) partition, ties to the producer-heavy split
+            double mean = 0, var = 0;
+            for (uint32_t p = 0; p < nlist; p++) mean += part_n[p];
+            mean /= nlist;
+            for (uint32_t p = 0; p < nlist; p++) var += (part_n[p] - mean) * (part_n[p] - mean);
+            double big = mean + 2.0 * std::sqrt(var / nlist);
+            uint32_t x = (uint32_t)std::max(1.0, big);
+            uint32_t nm = scan_nrb(x, SCAN_ROWS_TILE_MID), nl = scan_nrb(x, SCAN_ROWS_TILE_LARGE);
+            ix->rows_tile = nl < nm ? SCAN_ROWS_TILE_LARGE : SCAN_ROWS_TILE_MID;
+            if (const char *e = getenv("LGPU_SCAN_ROWS_TILE")) {
+                uint32_t v = (uint32_t)atoi(e);
+                if (v == SCAN_ROWS_TILE_MID || v == SCAN_ROWS_TILE_LARGE) ix->rows_tile = v;
+            }
+        }
         std::sort(pads.begin(), pads.end(), std::greater<uint64_t>());
         ix->pad_prefix.assign(nlist + 1, 0);
         for (uint32_t p = 0; p < nlist; p++) ix->pad_prefix[p + 1] = ix->pad_prefix[p] + pads[p];

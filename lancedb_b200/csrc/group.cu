@@ -68,7 +68,7 @@ __global__ void group_scan_kernel(GroupArgs a)
             uint64_t v = 0;
             if (p < a.nlist) {
                 uint32_t cnt = a.part_cnt[p];
-                v = pass == 0 ? cnt : (uint64_t)((cnt + SCAN_G - 1) / SCAN_G) * scan_nrb(a.part_n[p]);
+                v = pass == 0 ? cnt : (uint64_t)((cnt + SCAN_G - 1) / SCAN_G) * scan_nrb(a.part_n[p], a.rows_tile);
             }
             s_part[tid] = v;
             __syncthreads();

@@ -6,16 +6,16 @@
 namespace lgpu {
 
 // ---------------- scan (K2+K3) geometry ------------------------------------------
-constexpr int SCAN_THREADS = 512;
 constexpr int SCAN_G = 8;                         // queries per tile
-constexpr int SCAN_RMAX = 4;                      // rows per thread
-constexpr int SCAN_ROWS_TILE = SCAN_THREADS * SCAN_RMAX;
+// two warp-role splits of the 512-thread CTA (producer warps / consumer warps x 8 rows per thread)
+constexpr uint32_t SCAN_ROWS_TILE_MID = 4 * 32 * 12;    // 12 producer + 4 consumer warps x 12 rows: <= 1536 rows per tile
+constexpr uint32_t SCAN_ROWS_TILE_LARGE = 8 * 32 * 8;   //  8 producer + 8 consumer warps x  8 rows: <= 2048 rows per tile
 constexpr int SCAN_LUT_HALF = 32768;              // [256 c][8 s][4 g] f32
 constexpr int SCAN_LUT_BYTES = 2 * SCAN_LUT_HALF; // [2 h] halves
 
-__host__ __device__ __forceinline__ uint32_t scan_nrb(uint32_t n)
+__host__ __device__ __forceinline__ uint32_t scan_nrb(uint32_t n, uint32_t rows_tile)
 {
-    return (n + SCAN_ROWS_TILE - 1) / SCAN_ROWS_TILE;
+    return (n + rows_tile - 1) / rows_tile;
 }
 __host__ __device__ __forceinline__ uint32_t scan_rb_rows(uint32_t n, uint32_t nrb)
 {
@@ -31,6 +31,8 @@ struct ScanArgs {
     const uint32_t *part_n;       // [nlist]
     const uint32_t *part_npad;    // [nlist] rows rounded up to 32
     uint32_t dim, m, nch, metric, nlist;
+    uint32_t rows_tile;           // SCAN_ROWS_TILE_MID or _LARGE (selects the kernel variant)
+    unsigned long long fzero2;    // packed (+0.f, +0.f); opaque to ptxas on purpose (scan.cu)
     // batch (device)
     const float *queries;         // [B][dim] (normalised for cosine)
     uint32_t nprobes;
@@ -49,7 +51,7 @@ void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
 // ---------------- batch preparation (grouping probes by partition) ----------------
 struct GroupArgs {
     const uint64_t *probes;       // [B*nprobes] partition ids (u64 from the selector)
-    uint32_t B, nprobes, nlist;
+    uint32_t B, nprobes, nlist, rows_tile;
     const uint32_t *part_n;
     uint32_t *part_cnt;           // [nlist] zeroed before
     uint32_t *slot_pos;           // [B*nprobes]

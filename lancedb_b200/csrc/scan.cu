@@ -10,7 +10,7 @@
 // sequential over sub-vectors).
 //
 // Work decomposition (B200-first, not the reference's per-query loop):
-//   tile = (partition p, up to 8 of the queries that probe p, up to 2048 of its rows).
+//   tile = (partition p, up to 8 of the queries that probe p, up to rows_tile of its rows).
 //   A persistent grid (one 512-thread CTA per SM) pulls tiles from an atomic counter;
 //   tiles are ordered by partition so a partition's codes are read from HBM once and
 //   then hit in L2 for the other query groups.
@@ -19,10 +19,15 @@
 //   (h = query half, c = code, s = sub-space within the chunk), so one LDS.128 returns
 //   the entries of 4 queries.  The codebook chunk is read (coalesced, L2-resident) once
 //   per tile and amortised over the 8 queries.
+//   Warp specialisation: the table build is FP32-pipe work (23 flops per entry, done
+//   with packed FADD2/FFMA2), the scan is shared-memory-gather work; PW producer warps
+//   build chunk ch+1/ch+2 while CW consumer warps scan chunk ch, handing buffers over
+//   with named barriers (bar.arrive / bar.sync), so the two pipes overlap instead of
+//   alternating behind a CTA-wide barrier.
 //   Bank conflicts: a straightforward "lane = row" scan makes 8 lanes of a quarter-warp
 //   gather at random codes => ~2.6-way conflicts.  Here lane l runs `l % 8` sub-space
 //   slots behind lane 0 (the code stream in HBM is pre-skewed by row % 8 bytes, see
-//   index.cu), so at any instant the 8 lanes of a quarter-warp read 8 *different*
+//   retile.cu), so at any instant the 8 lanes of a quarter-warp read 8 *different*
 //   sub-spaces = 8 different 16-byte bank groups: conflict-free by construction, while
 //   each row still accumulates its sub-vectors strictly in order 0..m-1 in its own
 //   register.
@@ -34,218 +39,385 @@ namespace lgpu {
 
 namespace {
 
+constexpr int BAR_FULL = 1;    // named barriers 1..3: chunk buffer b is built
+constexpr int BAR_EMPTY = 4;   // named barriers 4..6: chunk buffer b may be overwritten
+
+__device__ __forceinline__ void bar_sync(int id, int n)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int n)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 template <int DSUB>
 __device__ __forceinline__ void load_vec(float *dst, const float *src)
 {
     if constexpr (DSUB % 4 == 0) {
 #pragma unroll
         for (int i = 0; i < DSUB / 4; i++) {
-            float4 v = reinterpret_cast<const float4 *>(src)[i];
+            float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
             dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < DSUB; i++) dst[i] = src[i];
+        for (int i = 0; i < DSUB; i++) dst[i] = __ldg(src + i);
     }
 }
 
-template <int DSUB>
-__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(ScanArgs a)
+// ---- packed f32x2 arithmetic (FADD2 / FFMA2 on sm_100a): two IEEE round-to-nearest
+// f32 ops per instruction, bit-identical to the scalar ops.  ptxas contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with -fmad=false), which would change
+// the rounding, so the square is written as fma(d, d, zero) with `zero` an opaque
+// kernel argument: round(d*d + 0) == round(d*d) and nothing is left to contract. ----
+__device__ __forceinline__ uint64_t pk2(float a, float b)
 {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+{
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sq2(uint64_t d, uint64_t zero)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(d), "l"(zero));
+    return r;
+}
+// l2_once::<f32x8>: ((s0+s4)+(s2+s6)) + ((s1+s5)+(s3+s7)), s_k = (r_k-c_k)^2
+__device__ __forceinline__ float l2_tree8_packed(const uint64_t r[4], const uint64_t c[4], uint64_t zero)
+{
+    uint64_t q01 = sq2(sub2(r[0], c[0]), zero), q23 = sq2(sub2(r[1], c[1]), zero);
+    uint64_t q45 = sq2(sub2(r[2], c[2]), zero), q67 = sq2(sub2(r[3], c[3]), zero);
+    uint64_t t01 = add2(q01, q45);     // (s0+s4, s1+s5)
+    uint64_t t23 = add2(q23, q67);     // (s2+s6, s3+s7)
+    uint64_t u = add2(t01, t23);       // ((s0+s4)+(s2+s6), (s1+s5)+(s3+s7))
+    float u0, u1;
+    upk2(u, u0, u1);
+    return __fadd_rn(u0, u1);
+}
+
+// ------------------------------------------------------------------ producer side
+template <int DSUB, int PW, int NT>
+__device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *lut, uint32_t p, int ng,
+                                             const uint32_t *s_q, int tid)
+{
+    const int lane = tid & 31, pw = tid >> 5;
+    const int s = lane & 7, gp = lane >> 3, g0 = 2 * gp;
+    const bool active = g0 < ng;
+    const bool has_g1 = g0 + 1 < ng;
+    const uint32_t nch = a.nch;
+    const float *q0p = active ? a.queries + (size_t)s_q[g0] * a.dim : nullptr;
+    const float *q1p = has_g1 ? a.queries + (size_t)s_q[g0 + 1] * a.dim : nullptr;
+    const float *cenp = a.centroids + (size_t)p * a.dim;
+
+    for (uint32_t ch = 0; ch <= nch; ch++) {
+        const int b = ch % 3;
+        if (ch >= 2) bar_sync(BAR_EMPTY + b, NT);   // consumers are done with iteration ch-2
+        if (ch == 0 && tid < 64)       // "chunk -1": lagging lanes read code 0 of buffer 2 in iteration 0
+            reinterpret_cast<float *>(lut + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+        if (ch == nch) {               // "chunk nch": zero row for the lanes that ran out of sub-vectors
+            if (tid < 64)
+                reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+        } else if (active) {
+            const uint32_t i = ch * 8 + s;
+            const bool sub_ok = i < a.m;
+            float r0[DSUB], r1[DSUB];
+#pragma unroll
+            for (int e = 0; e < DSUB; e++) { r0[e] = 0.f; r1[e] = 0.f; }
+            if (sub_ok) {              // residual of this lane's sub-space for its two queries
+                float cen[DSUB];
+                load_vec<DSUB>(r0, q0p + (size_t)i * DSUB);
+                if (has_g1) load_vec<DSUB>(r1, q1p + (size_t)i * DSUB);
+                if (a.metric != LGPU_DOT) {
+                    load_vec<DSUB>(cen, cenp + (size_t)i * DSUB);
+#pragma unroll
+                    for (int e = 0; e < DSUB; e++) { r0[e] = __fsub_rn(r0[e], cen[e]); r1[e] = __fsub_rn(r1[e], cen[e]); }
+                }
+            }
+            unsigned char *dst = lut + b * SCAN_LUT_BYTES + (gp >> 1) * SCAN_LUT_HALF + s * 16 + (gp & 1) * 8;
+            const float *cbp = a.cb_tiled + ((size_t)ch * 256 * 8 + s) * DSUB;
+            constexpr int UNR = (DSUB <= 8) ? 4 : (DSUB <= 16 ? 2 : 1);
+            if constexpr (DSUB == 8) {
+                uint64_t pr0[4], pr1[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) { pr0[e] = pk2(r0[2 * e], r0[2 * e + 1]); pr1[e] = pk2(r1[2 * e], r1[2 * e + 1]); }
+                const bool packed = sub_ok && a.metric != LGPU_DOT;
+                for (int c0 = pw; c0 < 256; c0 += PW * UNR) {
+                    float cbv[UNR][8];
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        int c = c0 + u * PW;
+                        if (c < 256) load_vec<8>(cbv[u], cbp + (size_t)c * 8 * 8);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        int c = c0 + u * PW;
+                        if (c < 256) {
+                            float e0 = 0.f, e1 = 0.f;
+                            if (packed) {
+                                uint64_t pc[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) pc[e] = pk2(cbv[u][2 * e], cbv[u][2 * e + 1]);
+                                e0 = l2_tree8_packed(pr0, pc, a.fzero2);
+                                e1 = l2_tree8_packed(pr1, pc, a.fzero2);
+                            } else if (sub_ok) {
+                                e0 = subvec_dot_dist<8>(r0, cbv[u]);
+                                e1 = subvec_dot_dist<8>(r1, cbv[u]);
+                            }
+                            *reinterpret_cast<float2 *>(dst + c * 128) = make_float2(e0, e1);
+                        }
+                    }
+                }
+            } else {
+                for (int c0 = pw; c0 < 256; c0 += PW * UNR) {
+                    float cbv[UNR][DSUB];
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        int c = c0 + u * PW;
+                        if (c < 256) load_vec<DSUB>(cbv[u], cbp + (size_t)c * 8 * DSUB);
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNR; u++) {
+                        int c = c0 + u * PW;
+                        if (c < 256) {
+                            float e0 = 0.f, e1 = 0.f;
+                            if (sub_ok) {
+                                if (a.metric == LGPU_DOT) {
+                                    e0 = subvec_dot_dist<DSUB>(r0, cbv[u]);
+                                    e1 = subvec_dot_dist<DSUB>(r1, cbv[u]);
+                                } else {
+                                    e0 = subvec_l2<DSUB>(r0, cbv[u]);
+                                    e1 = subvec_l2<DSUB>(r1, cbv[u]);
+                                }
+                            }
+                            *reinterpret_cast<float2 *>(dst + c * 128) = make_float2(e0, e1);
+                        }
+                    }
+                }
+            }
+        }
+        bar_arrive(BAR_FULL + b, NT);
+    }
+}
+
+// ------------------------------------------------------------------ consumer side
+template <int R, int CT, int NT>
+__device__ __forceinline__ void consume_tile(const ScanArgs &a, const unsigned char *lut, uint32_t p, int ng,
+                                             uint32_t row0, uint32_t nrows, const uint64_t *s_out, int ct)
+{
+    const int sig = ct & 7;                       // this lane's skew (== row % 8)
+    const uint32_t nch = a.nch;
+    const uint32_t n_p = a.part_n[p], npad = a.part_npad[p];
+    const uint2 *cs = reinterpret_cast<const uint2 *>(a.codes + a.code_base[p]);   // [nch+1][npad]
+    const bool two_halves = ng > 4;
+
+    float acc[R][SCAN_G];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int g = 0; g < SCAN_G; g++) acc[r][g] = 0.f;
+
+    bool valid[R];
+    uint2 wn[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        uint32_t row = row0 + ct + r * CT;
+        valid[r] = row < row0 + nrows && row < n_p;
+        wn[r] = valid[r] ? __ldg(cs + row) : make_uint2(0u, 0u);
+    }
+
+    for (uint32_t it = 0; it <= nch; it++) {
+        uint2 w[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) w[r] = wn[r];
+        if (it < nch) {                            // prefetch the next block of code bytes
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                uint32_t row = row0 + ct + r * CT;
+                wn[r] = valid[r] ? __ldg(cs + (size_t)(it + 1) * npad + row) : make_uint2(0u, 0u);
+            }
+        }
+        bar_sync(BAR_FULL + (int)(it % 3), NT);
+        const uint32_t base_cur = (it % 3) * SCAN_LUT_BYTES;
+        const uint32_t base_prev = ((it + 2) % 3) * SCAN_LUT_BYTES;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const uint32_t off = ((e < sig) ? base_prev : base_cur) + (((e - sig) & 7) << 4);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t word = (e < 4) ? w[r].x : w[r].y;
+                const uint32_t c = (word >> (8 * (e & 3))) & 0xffu;
+                const unsigned char *ent = lut + off + (c << 7);
+                const float4 v0 = *reinterpret_cast<const float4 *>(ent);
+                acc[r][0] = __fadd_rn(acc[r][0], v0.x);
+                acc[r][1] = __fadd_rn(acc[r][1], v0.y);
+                acc[r][2] = __fadd_rn(acc[r][2], v0.z);
+                acc[r][3] = __fadd_rn(acc[r][3], v0.w);
+                if (two_halves) {
+                    const float4 v1 = *reinterpret_cast<const float4 *>(ent + SCAN_LUT_HALF);
+                    acc[r][4] = __fadd_rn(acc[r][4], v1.x);
+                    acc[r][5] = __fadd_rn(acc[r][5], v1.y);
+                    acc[r][6] = __fadd_rn(acc[r][6], v1.z);
+                    acc[r][7] = __fadd_rn(acc[r][7], v1.w);
+                }
+            }
+        }
+        // buffer (it+2)%3 == (it-1)%3 (chunk it-1, or the zero row before chunk 0) is no longer
+        // read by anyone; the producers wait for it iff they still have chunk it+2 (or the
+        // final zero row) to put there
+        if (it + 2 <= nch) bar_arrive(BAR_EMPTY + (int)((it + 2) % 3), NT);
+    }
+
+    // ---- epilogue: metric post-processing, one f32 per (row, query) to HBM ----
+    const float mcorr = (float)(a.m - 1);
+#pragma unroll
+    for (int g = 0; g < SCAN_G; g++) {
+        if (g < ng) {
+            float *out = a.dist_out + s_out[g];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (valid[r]) {
+                    float v = acc[r][g];
+                    if (a.metric == LGPU_COSINE) v = __fmul_rn(v, 0.5f);
+                    else if (a.metric == LGPU_DOT) v = __fsub_rn(v, mcorr);
+                    out[row0 + ct + r * CT] = v;
+                }
+            }
+        }
+    }
+}
+
+// Per-tile bookkeeping shared by both roles (every thread of the CTA runs it, so the two
+// __syncthreads line up across the role-specific loops).
+struct TileInfo {
+    uint32_t p, row0, nrows;
+    int ng;
+    bool done;
+};
+
+template <int NT>
+__device__ __forceinline__ TileInfo next_tile(const ScanArgs &a, uint32_t total, uint32_t *s_tile, uint32_t *s_p,
+                                              uint32_t *s_q, uint64_t *s_out, int tid)
+{
+    TileInfo ti;
+    __syncthreads();                            // previous tile fully drained
+    if (tid == 0) {
+        uint32_t t = atomicAdd(a.tile_counter, 1u);
+        *s_tile = t;
+        if (t < total) {                        // smallest p with tile_off[p+1] > t
+            uint32_t lo = 0, hi = a.nlist - 1;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (a.tile_off[mid + 1] > t) hi = mid; else lo = mid + 1;
+            }
+            *s_p = lo;
+        }
+    }
+    __syncthreads();
+    const uint32_t t = *s_tile;
+    ti.done = t >= total;
+    if (ti.done) { ti.p = 0; ti.row0 = 0; ti.nrows = 0; ti.ng = 0; return ti; }
+    const uint32_t p = *s_p;
+    const uint32_t n_p = a.part_n[p];
+    const uint32_t nrb = scan_nrb(n_p, a.rows_tile), rbr = scan_rb_rows(n_p, nrb);
+    const uint32_t local = t - a.tile_off[p];
+    const uint32_t grp = local / nrb, rb = local - grp * nrb;
+    ti.p = p;
+    ti.ng = (int)min((uint32_t)SCAN_G, a.part_cnt[p] - grp * SCAN_G);
+    ti.row0 = rb * rbr;
+    ti.nrows = ti.row0 < n_p ? min(rbr, n_p - ti.row0) : 0;
+    if (tid < SCAN_G) {
+        if (tid < ti.ng) {
+            uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + tid];
+            s_q[tid] = e / a.nprobes;
+            s_out[tid] = a.seg_off[e];
+        } else {
+            s_q[tid] = 0xffffffffu;
+        }
+    }
+    __syncthreads();
+    return ti;
+}
+
+// PW producer warps + CW consumer warps (both multiples of 4: setmaxnreg works on
+// warpgroups).  The CTA is launched with 128 registers per thread; producers give
+// registers back (PREG) and consumers take them (CREG) so that a consumer thread can hold
+// RMAX rows x 8 queries of accumulators plus two blocks of code bytes.
+template <int DSUB, int PW, int CW, int RMAX, int PREG, int CREG>
+__global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
+{
+    constexpr int NT = (PW + CW) * 32, CT = CW * 32;
+    static_assert(PW % 4 == 0 && CW % 4 == 0, "roles must be whole warpgroups");
+    static_assert(PW * 32 * PREG + CW * 32 * CREG <= 65536, "register budget");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *lut = smem;                                              // 3 x 64 KB ring
-    float *rbuf = reinterpret_cast<float *>(smem + 3 * SCAN_LUT_BYTES);      // 2 x [8 g][8 s][DSUB]
     __shared__ uint32_t s_tile, s_p;
     __shared__ uint32_t s_q[SCAN_G];
     __shared__ uint64_t s_out[SCAN_G];
 
     const int tid = threadIdx.x;
-    const int sig = tid & 7;                       // this lane's skew (== row % 8)
     const uint32_t total = *a.total_tiles;
-    const uint32_t nch = a.nch;
-    constexpr int RB_FLOATS = SCAN_G * 8 * DSUB;
 
-    for (;;) {
-        __syncthreads();                            // previous tile fully drained
-        if (tid == 0) {
-            uint32_t t = atomicAdd(a.tile_counter, 1u);
-            s_tile = t;
-            if (t < total) {                        // smallest p with tile_off[p+1] > t
-                uint32_t lo = 0, hi = a.nlist - 1;
-                while (lo < hi) {
-                    uint32_t mid = (lo + hi) >> 1;
-                    if (a.tile_off[mid + 1] > t) hi = mid; else lo = mid + 1;
-                }
-                s_p = lo;
-            }
+    if (tid < PW * 32) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREG));
+        for (;;) {
+            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
+            if (ti.done) break;
+            produce_tile<DSUB, PW, NT>(a, lut, ti.p, ti.ng, s_q, tid);
         }
-        __syncthreads();
-        const uint32_t t = s_tile;
-        if (t >= total) break;
-        const uint32_t p = s_p;
-        const uint32_t n_p = a.part_n[p], npad = a.part_npad[p];
-        const uint32_t nrb = scan_nrb(n_p), rbr = scan_rb_rows(n_p, nrb);
-        const uint32_t local = t - a.tile_off[p];
-        const uint32_t grp = local / nrb, rb = local - grp * nrb;
-        const int ng = (int)min((uint32_t)SCAN_G, a.part_cnt[p] - grp * SCAN_G);
-        const uint32_t row0 = rb * rbr;
-        const uint32_t nrows = row0 < n_p ? min(rbr, n_p - row0) : 0;
-        const int R = (int)((nrows + SCAN_THREADS - 1) / SCAN_THREADS);
-
-        if (tid < SCAN_G) {
-            if (tid < ng) {
-                uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + tid];
-                s_q[tid] = e / a.nprobes;
-                s_out[tid] = a.seg_off[e];
-            } else {
-                s_q[tid] = 0xffffffffu;
-            }
-        }
-        // "chunk -1" is read by lagging lanes during iteration 0 at code 0 only: zero it
-        if (tid < 64)
-            reinterpret_cast<float *>(lut + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
-        __syncthreads();
-
-        // ---- residual chunk: rbuf[g][s][e] = q_g[i*DSUB+e] - centroid_p[i*DSUB+e] ----
-        auto compute_rbuf = [&](uint32_t ch) {
-            float *dst = rbuf + (ch & 1) * RB_FLOATS;
-            for (int idx = tid; idx < RB_FLOATS; idx += SCAN_THREADS) {
-                int g = idx / (8 * DSUB), rem = idx - g * (8 * DSUB);
-                int s = rem / DSUB, e = rem - s * DSUB;
-                uint32_t i = ch * 8 + s;
-                float val = 0.f;
-                if (g < ng && i < a.m) {
-                    uint32_t dimi = i * DSUB + e;
-                    float qv = a.queries[(size_t)s_q[g] * a.dim + dimi];
-                    val = (a.metric == LGPU_DOT) ? qv
-                                                 : __fsub_rn(qv, a.centroids[(size_t)p * a.dim + dimi]);
-                }
-                dst[idx] = val;
-            }
-        };
-        // ---- distance-table chunk: lut[ch%3][h][c][s][g&3] ----
-        auto build = [&](uint32_t ch) {
-            const int s = tid & 7, gp = (tid >> 3) & 3, cg = tid >> 5;
-            const int g0 = 2 * gp;
-            if (g0 >= ng) return;
-            const bool sub_ok = (ch * 8 + s) < a.m;
-            const float *rb0 = rbuf + (ch & 1) * RB_FLOATS + (g0 * 8 + s) * DSUB;
-            float r0[DSUB], r1[DSUB];
-            load_vec<DSUB>(r0, rb0);
-            load_vec<DSUB>(r1, rb0 + 8 * DSUB);
-            unsigned char *dst = lut + (ch % 3) * SCAN_LUT_BYTES + (gp >> 1) * SCAN_LUT_HALF + s * 16 +
-                                 (gp & 1) * 8 + (cg * 16) * 128;
-            const float *cbp = a.cb_tiled + ((size_t)(ch * 256 + cg * 16) * 8 + s) * DSUB;
-            constexpr int UNR = (DSUB <= 8) ? 4 : (DSUB <= 16 ? 2 : 1);
-            for (int jj = 0; jj < 16; jj += UNR) {
-                float cbv[UNR][DSUB];
-#pragma unroll
-                for (int u = 0; u < UNR; u++) load_vec<DSUB>(cbv[u], cbp + (size_t)(jj + u) * 8 * DSUB);
-#pragma unroll
-                for (int u = 0; u < UNR; u++) {
-                    float e0 = 0.f, e1 = 0.f;
-                    if (sub_ok) {
-                        if (a.metric == LGPU_DOT) {
-                            e0 = subvec_dot_dist<DSUB>(r0, cbv[u]);
-                            e1 = subvec_dot_dist<DSUB>(r1, cbv[u]);
-                        } else {
-                            e0 = subvec_l2<DSUB>(r0, cbv[u]);
-                            e1 = subvec_l2<DSUB>(r1, cbv[u]);
-                        }
-                    }
-                    *reinterpret_cast<float2 *>(dst + (jj + u) * 128) = make_float2(e0, e1);
-                }
-            }
-        };
-
-        compute_rbuf(0);
-        if (nch > 1) compute_rbuf(1);
-        __syncthreads();
-        build(0);
-        __syncthreads();
-
-        float acc[SCAN_RMAX][SCAN_G];
-#pragma unroll
-        for (int r = 0; r < SCAN_RMAX; r++)
-#pragma unroll
-            for (int g = 0; g < SCAN_G; g++) acc[r][g] = 0.f;
-
-        const uint2 *cs = reinterpret_cast<const uint2 *>(a.codes + a.code_base[p]);   // [nch+1][npad]
-        const bool two_halves = ng > 4;
-
-        for (uint32_t it = 0; it <= nch; it++) {
-            if (it + 1 < nch) build(it + 1);
-            else if (it + 1 == nch && tid < 64)     // "chunk nch": zero row for the drained lanes
-                reinterpret_cast<float *>(lut + (nch % 3) * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
-            if (it + 2 < nch) compute_rbuf(it + 2);
-
-            const uint32_t base_cur = (it % 3) * SCAN_LUT_BYTES;
-            const uint32_t base_prev = ((it + 2) % 3) * SCAN_LUT_BYTES;
-            uint2 w[SCAN_RMAX];
-#pragma unroll
-            for (int r = 0; r < SCAN_RMAX; r++) {
-                uint32_t row = row0 + tid + r * SCAN_THREADS;
-                w[r] = (r < R && row < n_p) ? __ldg(cs + (size_t)it * npad + row) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const uint32_t off = ((e < sig) ? base_prev : base_cur) + (((e - sig) & 7) << 4);
-#pragma unroll
-                for (int r = 0; r < SCAN_RMAX; r++) {
-                    if (r < R) {
-                        const uint32_t word = (e < 4) ? w[r].x : w[r].y;
-                        const uint32_t c = (word >> (8 * (e & 3))) & 0xffu;
-                        const unsigned char *ent = lut + off + (c << 7);
-                        const float4 v0 = *reinterpret_cast<const float4 *>(ent);
-                        acc[r][0] = __fadd_rn(acc[r][0], v0.x);
-                        acc[r][1] = __fadd_rn(acc[r][1], v0.y);
-                        acc[r][2] = __fadd_rn(acc[r][2], v0.z);
-                        acc[r][3] = __fadd_rn(acc[r][3], v0.w);
-                        if (two_halves) {
-                            const float4 v1 = *reinterpret_cast<const float4 *>(ent + SCAN_LUT_HALF);
-                            acc[r][4] = __fadd_rn(acc[r][4], v1.x);
-                            acc[r][5] = __fadd_rn(acc[r][5], v1.y);
-                            acc[r][6] = __fadd_rn(acc[r][6], v1.z);
-                            acc[r][7] = __fadd_rn(acc[r][7], v1.w);
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- epilogue: metric post-processing, one f32 per (row, query) to HBM ----
-        const float mcorr = (float)(a.m - 1);
-#pragma unroll
-        for (int g = 0; g < SCAN_G; g++) {
-            if (g < ng) {
-                float *out = a.dist_out + s_out[g];
-#pragma unroll
-                for (int r = 0; r < SCAN_RMAX; r++) {
-                    uint32_t row = row0 + tid + r * SCAN_THREADS;
-                    if (r < R && row < row0 + nrows) {
-                        float v = acc[r][g];
-                        if (a.metric == LGPU_COSINE) v = __fmul_rn(v, 0.5f);
-                        else if (a.metric == LGPU_DOT) v = __fsub_rn(v, mcorr);
-                        out[row] = v;
-                    }
-                }
-            }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
+        const int ct = tid - PW * 32;
+        for (;;) {
+            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
+            if (ti.done) break;
+            const int R = (int)((ti.nrows + CT - 1) / CT);     // uniform per tile; rounded up to even
+#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, lut, ti.p, ti.ng, ti.row0, ti.nrows, s_out, ct)
+            if (R <= 2) LGPU_CONSUME(2);
+            else if (R <= 4) LGPU_CONSUME(4);
+            else if (R <= 6) LGPU_CONSUME(6);
+            else if (R <= 8 || RMAX <= 8) LGPU_CONSUME(8);
+            else if constexpr (RMAX > 8) { if (R <= 10) LGPU_CONSUME(10); else LGPU_CONSUME(12); }
+#undef LGPU_CONSUME
         }
     }
 }
 
-template <int DSUB>
+template <int DSUB, int PW, int CW, int RMAX, int PREG, int CREG>
 void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
 {
-    size_t smem = 3 * (size_t)SCAN_LUT_BYTES + 2 * (size_t)SCAN_G * 8 * DSUB * sizeof(float);
-    static bool configured = false;   // per template instance
-    if (!configured) {
-        LGPU_CUDA(cudaFuncSetAttribute(scan_kernel<DSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    size_t smem = 3 * (size_t)SCAN_LUT_BYTES;
+    auto kern = scan_kernel<DSUB, PW, CW, RMAX, PREG, CREG>;
+    LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.rows_tile != (uint32_t)(CW * 32 * RMAX)) {
+        set_error("internal: rows_tile does not match the scan kernel variant");
+        throw Failure{LGPU_RUNTIME};
     }
-    scan_kernel<DSUB><<<grid, SCAN_THREADS, smem, st>>>(a);
+    kern<<<grid, (PW + CW) * 32, smem, st>>>(a);
     LGPU_CUDA(cudaGetLastError());
+}
+
+template <int DSUB>
+void launch_variant(const ScanArgs &a, int grid, cudaStream_t st)
+{
+    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 88, 232>(a, grid, st);
+    else launch_one<DSUB, 8, 8, 8, 88, 168>(a, grid, st);
 }
 
 }  // namespace
@@ -258,12 +430,12 @@ bool scan_dsub_supported(uint32_t dsub)
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st)
 {
     switch (dsub) {
-    case 1: launch_one<1>(a, grid, st); break;
-    case 2: launch_one<2>(a, grid, st); break;
-    case 4: launch_one<4>(a, grid, st); break;
-    case 8: launch_one<8>(a, grid, st); break;
-    case 16: launch_one<16>(a, grid, st); break;
-    case 32: launch_one<32>(a, grid, st); break;
+    case 1: launch_variant<1>(a, grid, st); break;
+    case 2: launch_variant<2>(a, grid, st); break;
+    case 4: launch_variant<4>(a, grid, st); break;
+    case 8: launch_variant<8>(a, grid, st); break;
+    case 16: launch_variant<16>(a, grid, st); break;
+    case 32: launch_variant<32>(a, grid, st); break;
     default:
         set_error("unsupported PQ sub-vector length (dim/num_sub_vectors must be 1,2,4,8,16 or 32)");
         throw Failure{LGPU_INVALID_INPUT};
