@@ -113,21 +113,60 @@ __device__ __forceinline__ float l2_tree8_packed(const uint64_t r[4], const uint
 }
 
 // ------------------------------------------------------------------ producer side
+constexpr int BAR_PROD = 7;    // named barrier 7: producer-only (residual chunk hand-over)
+
+// One (c, s, h) task = one 8-float codebook entry against the residuals of the 4 queries of
+// half h: 4 table entries (one STS.128).  Lane -> s = lane&7, h = (lane>>3)&1, cc = lane>>4;
+// warp pw takes the code pairs {2*(pw + PW*k) + cc}.  Codebook loads are double-buffered
+// two tasks deep in registers so an L2 round trip is covered by the previous batch's math.
 template <int DSUB, int PW, int NT>
-__device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *lut, uint32_t p, int ng,
-                                             const uint32_t *s_q, int tid)
+__device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *lut, float *rbuf, uint32_t p,
+                                             int ng, const uint32_t *s_q, int tid)
 {
+    constexpr int PT = PW * 32;
+    constexpr int RB = SCAN_G * 8 * DSUB;             // floats per residual chunk [g][s][e]
     const int lane = tid & 31, pw = tid >> 5;
-    const int s = lane & 7, gp = lane >> 3, g0 = 2 * gp;
-    const bool active = g0 < ng;
-    const bool has_g1 = g0 + 1 < ng;
+    const int s = lane & 7, h = (lane >> 3) & 1, cc = lane >> 4;
+    const bool active = 4 * h < ng;
     const uint32_t nch = a.nch;
-    const float *q0p = active ? a.queries + (size_t)s_q[g0] * a.dim : nullptr;
-    const float *q1p = has_g1 ? a.queries + (size_t)s_q[g0 + 1] * a.dim : nullptr;
     const float *cenp = a.centroids + (size_t)p * a.dim;
+
+    // residual chunk ch -> registers (global loads issued now, consumed by store_resid later)
+    constexpr int RPT = (RB + PT - 1) / PT;
+    float rq[RPT], rc[RPT];
+    auto load_resid = [&](uint32_t ch) {
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            int idx = tid + u * PT;
+            rq[u] = 0.f; rc[u] = 0.f;
+            if (idx < RB) {
+                int g = idx / (8 * DSUB), rem = idx - g * (8 * DSUB);
+                int ss = rem / DSUB, e = rem - ss * DSUB;
+                uint32_t i = ch * 8 + ss;
+                if (g < ng && i < a.m) {
+                    uint32_t dimi = i * DSUB + e;
+                    rq[u] = __ldg(a.queries + (size_t)s_q[g] * a.dim + dimi);
+                    if (a.metric != LGPU_DOT) rc[u] = __ldg(cenp + dimi);
+                }
+            }
+        }
+    };
+    auto store_resid = [&](uint32_t ch) {
+        float *dst = rbuf + (ch & 1) * RB;
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            int idx = tid + u * PT;
+            if (idx < RB) dst[idx] = __fsub_rn(rq[u], rc[u]);      // q - 0 == q for dot
+        }
+    };
+
+    load_resid(0);
+    store_resid(0);
+    bar_sync(BAR_PROD, PT);
 
     for (uint32_t ch = 0; ch <= nch; ch++) {
         const int b = ch % 3;
+        if (ch + 1 < nch) load_resid(ch + 1);
         if (ch >= 2) bar_sync(BAR_EMPTY + b, NT);   // consumers are done with iteration ch-2
         if (ch == 0 && tid < 64)       // "chunk -1": lagging lanes read code 0 of buffer 2 in iteration 0
             reinterpret_cast<float *>(lut + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
@@ -135,86 +174,93 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *l
             if (tid < 64)
                 reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
         } else if (active) {
-            const uint32_t i = ch * 8 + s;
-            const bool sub_ok = i < a.m;
-            float r0[DSUB], r1[DSUB];
-#pragma unroll
-            for (int e = 0; e < DSUB; e++) { r0[e] = 0.f; r1[e] = 0.f; }
-            if (sub_ok) {              // residual of this lane's sub-space for its two queries
-                float cen[DSUB];
-                load_vec<DSUB>(r0, q0p + (size_t)i * DSUB);
-                if (has_g1) load_vec<DSUB>(r1, q1p + (size_t)i * DSUB);
-                if (a.metric != LGPU_DOT) {
-                    load_vec<DSUB>(cen, cenp + (size_t)i * DSUB);
-#pragma unroll
-                    for (int e = 0; e < DSUB; e++) { r0[e] = __fsub_rn(r0[e], cen[e]); r1[e] = __fsub_rn(r1[e], cen[e]); }
-                }
-            }
-            unsigned char *dst = lut + b * SCAN_LUT_BYTES + (gp >> 1) * SCAN_LUT_HALF + s * 16 + (gp & 1) * 8;
+            const bool sub_ok = (ch * 8 + s) < a.m;
+            const float *rsrc = rbuf + (ch & 1) * RB + ((4 * h) * 8 + s) * DSUB;   // + j*8*DSUB per query
+            unsigned char *dst = lut + b * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16;
             const float *cbp = a.cb_tiled + ((size_t)ch * 256 * 8 + s) * DSUB;
-            constexpr int UNR = (DSUB <= 8) ? 4 : (DSUB <= 16 ? 2 : 1);
+            constexpr int NPAIR = 128;                          // code pairs per chunk
             if constexpr (DSUB == 8) {
-                uint64_t pr0[4], pr1[4];
+                uint64_t pr[4][4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) { pr0[e] = pk2(r0[2 * e], r0[2 * e + 1]); pr1[e] = pk2(r1[2 * e], r1[2 * e + 1]); }
-                const bool packed = sub_ok && a.metric != LGPU_DOT;
-                for (int c0 = pw; c0 < 256; c0 += PW * UNR) {
-                    float cbv[UNR][8];
+                for (int j = 0; j < 4; j++) {
+                    const float4 lo = *reinterpret_cast<const float4 *>(rsrc + j * 8 * 8);
+                    const float4 hi = *reinterpret_cast<const float4 *>(rsrc + j * 8 * 8 + 4);
+                    pr[j][0] = pk2(lo.x, lo.y); pr[j][1] = pk2(lo.z, lo.w);
+                    pr[j][2] = pk2(hi.x, hi.y); pr[j][3] = pk2(hi.z, hi.w);
+                }
+                const bool l2 = a.metric != LGPU_DOT;
+                // software pipeline over this warp's code pairs, 2 tasks per stage
+                float4 cur[2][2], nxt[2][2];
+                auto fetch = [&](float4 (&buf)[2][2], int k) {
 #pragma unroll
-                    for (int u = 0; u < UNR; u++) {
-                        int c = c0 + u * PW;
-                        if (c < 256) load_vec<8>(cbv[u], cbp + (size_t)c * 8 * 8);
-                    }
-#pragma unroll
-                    for (int u = 0; u < UNR; u++) {
-                        int c = c0 + u * PW;
-                        if (c < 256) {
-                            float e0 = 0.f, e1 = 0.f;
-                            if (packed) {
-                                uint64_t pc[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) pc[e] = pk2(cbv[u][2 * e], cbv[u][2 * e + 1]);
-                                e0 = l2_tree8_packed(pr0, pc, a.fzero2);
-                                e1 = l2_tree8_packed(pr1, pc, a.fzero2);
-                            } else if (sub_ok) {
-                                e0 = subvec_dot_dist<8>(r0, cbv[u]);
-                                e1 = subvec_dot_dist<8>(r1, cbv[u]);
-                            }
-                            *reinterpret_cast<float2 *>(dst + c * 128) = make_float2(e0, e1);
+                    for (int u = 0; u < 2; u++) {
+                        int pair = pw + PW * (k + u);
+                        if (pair < NPAIR) {
+                            const float4 *src = reinterpret_cast<const float4 *>(cbp + (size_t)(2 * pair + cc) * 8 * 8);
+                            buf[u][0] = __ldg(src); buf[u][1] = __ldg(src + 1);
                         }
                     }
-                }
-            } else {
-                for (int c0 = pw; c0 < 256; c0 += PW * UNR) {
-                    float cbv[UNR][DSUB];
+                };
+                fetch(cur, 0);
+                for (int k = 0; pw + PW * k < NPAIR; k += 2) {
+                    fetch(nxt, k + 2);
 #pragma unroll
-                    for (int u = 0; u < UNR; u++) {
-                        int c = c0 + u * PW;
-                        if (c < 256) load_vec<DSUB>(cbv[u], cbp + (size_t)c * 8 * DSUB);
-                    }
-#pragma unroll
-                    for (int u = 0; u < UNR; u++) {
-                        int c = c0 + u * PW;
-                        if (c < 256) {
-                            float e0 = 0.f, e1 = 0.f;
+                    for (int u = 0; u < 2; u++) {
+                        int pair = pw + PW * (k + u);
+                        if (pair < NPAIR) {
+                            const int c = 2 * pair + cc;
+                            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (sub_ok) {
-                                if (a.metric == LGPU_DOT) {
-                                    e0 = subvec_dot_dist<DSUB>(r0, cbv[u]);
-                                    e1 = subvec_dot_dist<DSUB>(r1, cbv[u]);
+                                if (l2) {
+                                    uint64_t pc[4] = {pk2(cur[u][0].x, cur[u][0].y), pk2(cur[u][0].z, cur[u][0].w),
+                                                      pk2(cur[u][1].x, cur[u][1].y), pk2(cur[u][1].z, cur[u][1].w)};
+                                    out.x = l2_tree8_packed(pr[0], pc, a.fzero2);
+                                    out.y = l2_tree8_packed(pr[1], pc, a.fzero2);
+                                    out.z = l2_tree8_packed(pr[2], pc, a.fzero2);
+                                    out.w = l2_tree8_packed(pr[3], pc, a.fzero2);
                                 } else {
-                                    e0 = subvec_l2<DSUB>(r0, cbv[u]);
-                                    e1 = subvec_l2<DSUB>(r1, cbv[u]);
+                                    float cv[8] = {cur[u][0].x, cur[u][0].y, cur[u][0].z, cur[u][0].w,
+                                                   cur[u][1].x, cur[u][1].y, cur[u][1].z, cur[u][1].w};
+                                    float rr[8];
+                                    float o[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                                        for (int e = 0; e < 4; e++) upk2(pr[j][e], rr[2 * e], rr[2 * e + 1]);
+                                        o[j] = subvec_dot_dist<8>(rr, cv);
+                                    }
+                                    out = make_float4(o[0], o[1], o[2], o[3]);
                                 }
                             }
-                            *reinterpret_cast<float2 *>(dst + c * 128) = make_float2(e0, e1);
+                            *reinterpret_cast<float4 *>(dst + c * 128) = out;
                         }
                     }
+#pragma unroll
+                    for (int u = 0; u < 2; u++) { cur[u][0] = nxt[u][0]; cur[u][1] = nxt[u][1]; }
+                }
+            } else {
+                for (int k = 0; pw + PW * k < NPAIR; k++) {
+                    const int c = 2 * (pw + PW * k) + cc;
+                    float cbv[DSUB], rr[DSUB], o[4] = {0.f, 0.f, 0.f, 0.f};
+                    load_vec<DSUB>(cbv, cbp + (size_t)c * 8 * DSUB);
+                    if (sub_ok) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+#pragma unroll
+                            for (int e = 0; e < DSUB; e++) rr[e] = rsrc[j * 8 * DSUB + e];
+                            o[j] = (a.metric == LGPU_DOT) ? subvec_dot_dist<DSUB>(rr, cbv) : subvec_l2<DSUB>(rr, cbv);
+                        }
+                    }
+                    *reinterpret_cast<float4 *>(dst + c * 128) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }
         bar_arrive(BAR_FULL + b, NT);
+        if (ch + 1 < nch) store_resid(ch + 1);
+        if (ch < nch) bar_sync(BAR_PROD, PT);      // residual chunk ch+1 visible; chunk ch's reads done
     }
 }
+
 
 // ------------------------------------------------------------------ consumer side
 template <int R, int CT, int NT>
@@ -367,6 +413,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
     static_assert(PW * 32 * PREG + CW * 32 * CREG <= 65536, "register budget");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *lut = smem;                                              // 3 x 64 KB ring
+    float *rbuf = reinterpret_cast<float *>(smem + 3 * SCAN_LUT_BYTES);      // 2 x [8 g][8 s][DSUB] residuals
     __shared__ uint32_t s_tile, s_p;
     __shared__ uint32_t s_q[SCAN_G];
     __shared__ uint64_t s_out[SCAN_G];
@@ -379,7 +426,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
         for (;;) {
             TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
             if (ti.done) break;
-            produce_tile<DSUB, PW, NT>(a, lut, ti.p, ti.ng, s_q, tid);
+            produce_tile<DSUB, PW, NT>(a, lut, rbuf, ti.p, ti.ng, s_q, tid);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
@@ -402,7 +449,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
 template <int DSUB, int PW, int CW, int RMAX, int PREG, int CREG>
 void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
 {
-    size_t smem = 3 * (size_t)SCAN_LUT_BYTES;
+    size_t smem = 3 * (size_t)SCAN_LUT_BYTES + 2 * (size_t)SCAN_G * 8 * DSUB * sizeof(float);
     auto kern = scan_kernel<DSUB, PW, CW, RMAX, PREG, CREG>;
     LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (a.rows_tile != (uint32_t)(CW * 32 * RMAX)) {
@@ -416,8 +463,8 @@ void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
 template <int DSUB>
 void launch_variant(const ScanArgs &a, int grid, cudaStream_t st)
 {
-    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 88, 232>(a, grid, st);
-    else launch_one<DSUB, 8, 8, 8, 88, 168>(a, grid, st);
+    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 96, 224>(a, grid, st);
+    else launch_one<DSUB, 8, 8, 8, 96, 160>(a, grid, st);
 }
 
 }  // namespace
