@@ -120,9 +120,11 @@ constexpr int BAR_PROD = 7;    // named barrier 7: producer-only (residual chunk
 // warp pw takes the code pairs {2*(pw + PW*k) + cc}.  Codebook loads are double-buffered
 // two tasks deep in registers so an L2 round trip is covered by the previous batch's math.
 template <int DSUB, int PW, int NT>
-__device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *lut, float *rbuf, uint32_t p,
-                                             int ng, const uint32_t *s_q, int tid)
+__device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int ng, const uint32_t *s_q, int tid)
 {
+    extern __shared__ __align__(1024) unsigned char smem[];      // declared here so every access is a
+    unsigned char *const lut = smem;                             // plain shared-space LDS/STS
+    float *const rbuf = reinterpret_cast<float *>(smem + 3 * SCAN_LUT_BYTES);
     constexpr int PT = PW * 32;
     constexpr int RB = SCAN_G * 8 * DSUB;             // floats per residual chunk [g][s][e]
     const int lane = tid & 31, pw = tid >> 5;
@@ -190,7 +192,7 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *l
                 }
                 const bool l2 = a.metric != LGPU_DOT;
                 // software pipeline over this warp's code pairs, 2 tasks per stage
-                float4 cur[2][2], nxt[2][2];
+                float4 bufA[2][2], bufB[2][2];
                 auto fetch = [&](float4 (&buf)[2][2], int k) {
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
@@ -201,9 +203,7 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *l
                         }
                     }
                 };
-                fetch(cur, 0);
-                for (int k = 0; pw + PW * k < NPAIR; k += 2) {
-                    fetch(nxt, k + 2);
+                auto compute = [&](const float4 (&cur)[2][2], int k) {
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         int pair = pw + PW * (k + u);
@@ -235,8 +235,16 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *l
                             *reinterpret_cast<float4 *>(dst + c * 128) = out;
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 2; u++) { cur[u][0] = nxt[u][0]; cur[u][1] = nxt[u][1]; }
+                };
+                // ping-pong: the loads of stage k+2 are in flight while stage k is computed
+                fetch(bufA, 0);
+                for (int k = 0;; k += 4) {
+                    fetch(bufB, k + 2);
+                    compute(bufA, k);
+                    if (pw + PW * (k + 2) >= NPAIR) break;
+                    fetch(bufA, k + 4);
+                    compute(bufB, k + 2);
+                    if (pw + PW * (k + 4) >= NPAIR) break;
                 }
             } else {
                 for (int k = 0; pw + PW * k < NPAIR; k++) {
@@ -264,9 +272,11 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, unsigned char *l
 
 // ------------------------------------------------------------------ consumer side
 template <int R, int CT, int NT>
-__device__ __forceinline__ void consume_tile(const ScanArgs &a, const unsigned char *lut, uint32_t p, int ng,
-                                             uint32_t row0, uint32_t nrows, const uint64_t *s_out, int ct)
+__device__ __forceinline__ void consume_tile(const ScanArgs &a, uint32_t p, int ng, uint32_t row0, uint32_t nrows,
+                                             const uint64_t *s_out, int ct)
 {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const unsigned char *const lut = smem;
     const int sig = ct & 7;                       // this lane's skew (== row % 8)
     const uint32_t nch = a.nch;
     const uint32_t n_p = a.part_n[p], npad = a.part_npad[p];
@@ -411,9 +421,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
     constexpr int NT = (PW + CW) * 32, CT = CW * 32;
     static_assert(PW % 4 == 0 && CW % 4 == 0, "roles must be whole warpgroups");
     static_assert(PW * 32 * PREG + CW * 32 * CREG <= 65536, "register budget");
-    extern __shared__ __align__(1024) unsigned char smem[];
-    unsigned char *lut = smem;                                              // 3 x 64 KB ring
-    float *rbuf = reinterpret_cast<float *>(smem + 3 * SCAN_LUT_BYTES);      // 2 x [8 g][8 s][DSUB] residuals
+    // dynamic smem: 3 x 64 KB table ring, then 2 x [8 g][8 s][DSUB] residual chunks
     __shared__ uint32_t s_tile, s_p;
     __shared__ uint32_t s_q[SCAN_G];
     __shared__ uint64_t s_out[SCAN_G];
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
         for (;;) {
             TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
             if (ti.done) break;
-            produce_tile<DSUB, PW, NT>(a, lut, rbuf, ti.p, ti.ng, s_q, tid);
+            produce_tile<DSUB, PW, NT>(a, ti.p, ti.ng, s_q, tid);
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
             TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
             if (ti.done) break;
             const int R = (int)((ti.nrows + CT - 1) / CT);     // uniform per tile; rounded up to even
-#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, lut, ti.p, ti.ng, ti.row0, ti.nrows, s_out, ct)
+#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ti.p, ti.ng, ti.row0, ti.nrows, s_out, ct)
             if (R <= 2) LGPU_CONSUME(2);
             else if (R <= 4) LGPU_CONSUME(4);
             else if (R <= 6) LGPU_CONSUME(6);
