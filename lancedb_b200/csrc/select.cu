@@ -220,12 +220,145 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
     if (tid == 0) a.out_count[q] = cnt;
 }
 
+// ---------------------------------------------------------------------------------
+// k <= 32: one warp per query, the k best live in registers (lane i = i-th best, sorted by
+// (key, id)); candidates stream through 4 per lane per iteration and only the ones not
+// worse than the current k-th best are inserted (ballot loop).  After warm-up almost
+// nothing passes, so a query costs ~1 compare per candidate.
+constexpr int SELW_WARPS = 4;
+
+template <bool POS>
+__global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t q = blockIdx.x * SELW_WARPS + (threadIdx.x >> 5);
+    if (q >= a.B) return;                                   // whole warp exits together
+    const uint32_t k = a.k;
+    uint32_t qk = 0xffffffffu;                              // queue entry of this lane
+    uint64_t qid = UINT64_MAX, qpos = UINT64_MAX;
+    uint32_t tau_k = 0xffffffffu;                           // (key, id) of the k-th best so far
+    uint64_t tau_id = UINT64_MAX;
+
+    auto in_range = [&](float v) -> bool {
+        if (v != v) return false;
+        if (a.has_lower && !(v >= a.lower)) return false;
+        if (a.has_upper && !(v < a.upper)) return false;
+        return true;
+    };
+    // offer one candidate per lane (pass == false for lanes without one)
+    auto offer = [&](bool pass, uint32_t key, uint64_t id, uint64_t pos) {
+        unsigned m = __ballot_sync(0xffffffffu, pass);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t ck = __shfl_sync(0xffffffffu, key, src);
+            const uint64_t cid = __shfl_sync(0xffffffffu, id, src);
+            if (!key_less(ck, cid, tau_k, tau_id)) continue;          // threshold moved meanwhile
+            const uint64_t cpos = POS ? __shfl_sync(0xffffffffu, pos, src) : 0;
+            const unsigned lessm = __ballot_sync(0xffffffffu, key_less(qk, qid, ck, cid));
+            const int at = __popc(lessm);                  // queue is sorted: entries before `at` are smaller
+            const uint32_t uk = __shfl_up_sync(0xffffffffu, qk, 1);
+            const uint64_t uid = __shfl_up_sync(0xffffffffu, qid, 1);
+            const uint64_t upos = POS ? __shfl_up_sync(0xffffffffu, qpos, 1) : 0;
+            if (lane == at) { qk = ck; qid = cid; if (POS) qpos = cpos; }
+            else if (lane > at) { qk = uk; qid = uid; if (POS) qpos = upos; }
+            if (lane >= (int)k) { qk = 0xffffffffu; qid = UINT64_MAX; }
+            tau_k = __shfl_sync(0xffffffffu, qk, k - 1);
+            tau_id = __shfl_sync(0xffffffffu, qid, k - 1);
+        }
+    };
+    auto offer4 = [&](const float v[4], const bool ok[4], uint64_t idbase, const uint64_t *idsrc, uint64_t posbase) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float f = v[u];
+            if (f == 0.f) f = 0.f;                          // -0 and +0 tie
+            const uint32_t key = f32_key(f);
+            const bool pass = ok[u] && in_range(f) && key <= tau_k;
+            uint64_t id = 0;
+            if (pass) id = idsrc ? idsrc[idbase + u] : idbase + u;
+            offer(pass, key, id, posbase + u);
+        }
+    };
+
+    if (a.mode == 0) {
+        for (uint32_t j = 0; j < a.nprobes; j++) {
+            const uint32_t slot = q * a.nprobes + j;
+            const uint32_t p = (uint32_t)a.probes[slot];
+            const uint32_t n = a.part_n[p];
+            const float *src = a.dist + a.seg_off[slot];
+            const uint64_t rowbase = a.part_off[p];
+            for (uint32_t r0 = 0; r0 < n; r0 += 128) {
+                const uint32_t r = r0 + lane * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                bool ok[4];
+                if (r < n) {
+                    const float4 t = *reinterpret_cast<const float4 *>(src + r);
+                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) ok[u] = r + u < n;
+                offer4(v, ok, rowbase + r, a.row_ids, rowbase + r);
+            }
+        }
+    } else if (a.mode == 1) {
+        const float *src = a.dense + (size_t)q * a.row_stride;
+        const bool aligned = ((a.row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dense) & 15) == 0);
+        for (uint64_t c0 = 0; c0 < a.ncols; c0 += 128) {
+            const uint64_t c = c0 + (uint64_t)lane * 4;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            bool ok[4];
+            if (aligned && c + 3 < a.ncols) {
+                const float4 t = *reinterpret_cast<const float4 *>(src + c);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (c + u < a.ncols) v[u] = src[c + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) ok[u] = c + u < a.ncols;
+            offer4(v, ok, c, a.col_ids, c);
+        }
+    } else {
+        for (uint64_t c0 = 0; c0 < a.ncols; c0 += 32) {
+            const uint64_t cc = c0 + lane;
+            bool pass = false;
+            uint32_t key = 0;
+            uint64_t id = UINT64_MAX, pos = cc;
+            if (cc < a.ncols) {
+                const uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
+                id = a.cand_ids[addr];
+                float f = a.dense[addr];
+                if (f == 0.f) f = 0.f;
+                key = f32_key(f);
+                pass = id != UINT64_MAX && in_range(f) && key <= tau_k;
+                if (POS && a.cand_pos) pos = a.cand_pos[addr];
+            }
+            offer(pass, key, id, pos);
+        }
+    }
+    const unsigned havem = __ballot_sync(0xffffffffu, qid != UINT64_MAX || qk != 0xffffffffu);
+    if (lane < (int)k) {
+        const bool have = (havem >> lane) & 1u;
+        a.out_ids[(size_t)q * k + lane] = have ? qid : UINT64_MAX;
+        a.out_dist[(size_t)q * k + lane] = have ? key_f32(qk) : CUDART_INF_F;
+        if (POS) a.out_pos[(size_t)q * k + lane] = have ? qpos : UINT64_MAX;
+    }
+    if (lane == 0) a.out_count[q] = min((uint32_t)__popc(havem), k);
+}
+
 }  // namespace
 
 void launch_select(const SelectArgs &a, cudaStream_t st)
 {
     if (a.B == 0) return;
     LGPU_REQUIRE(a.k >= 1 && a.k <= SELECT_KMAX, "limit+offset (k) must be in [1, 2048] on the GPU path");
+    if (a.k <= 32) {
+        const unsigned grid = (a.B + SELW_WARPS - 1) / SELW_WARPS;
+        if (a.out_pos) select_warp_kernel<true><<<grid, SELW_WARPS * 32, 0, st>>>(a);
+        else select_warp_kernel<false><<<grid, SELW_WARPS * 32, 0, st>>>(a);
+        LGPU_CUDA(cudaGetLastError());
+        return;
+    }
     uint32_t trigger = a.k * 2 < 512 ? 512 : a.k * 2;
     uint32_t cap = 2;
     while (cap < trigger + SEL_ITER) cap <<= 1;
