@@ -166,114 +166,87 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
     store_resid(0);
     bar_sync(BAR_PROD, PT);
 
-    constexpr int NPAIR = 128;                              // code pairs per chunk
-    // chunk hand-over, shared by both code paths below
-    auto chunk_begin = [&](uint32_t ch) {
-        if (ch + 1 < nch) load_resid(ch + 1);               // consumed by store_resid in chunk_end
-        if (ch >= 2) bar_sync(BAR_EMPTY + (int)(ch % 3), NT);   // consumers are done with iteration ch-2
+    for (uint32_t ch = 0; ch <= nch; ch++) {
+        const int b = ch % 3;
+        if (ch + 1 < nch) load_resid(ch + 1);
+        if (ch >= 2) bar_sync(BAR_EMPTY + b, NT);   // consumers are done with iteration ch-2
         if (ch == 0 && tid < 64)       // "chunk -1": lagging lanes read code 0 of buffer 2 in iteration 0
             reinterpret_cast<float *>(lut + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
-    };
-    auto chunk_end = [&](uint32_t ch) {
-        bar_arrive(BAR_FULL + (int)(ch % 3), NT);
-        if (ch + 1 < nch) store_resid(ch + 1);
-        bar_sync(BAR_PROD, PT);        // residual chunk ch+1 visible; chunk ch's residual reads done
-    };
-
-    if constexpr (DSUB == 8) {
-        // The warp's tasks of ALL chunks form one stream of stages (2 tasks each); codebook
-        // loads run one stage ahead across chunk boundaries (they do not depend on the
-        // barriers), so an L2 round trip is exposed once per tile, not once per chunk.
-        const int npw = (NPAIR - pw + PW - 1) / PW;         // code pairs of this warp per chunk
-        const int S = (npw + 1) / 2;                        // stages per chunk
-        const bool l2 = a.metric != LGPU_DOT;
-        uint64_t pr[4][4];
-        bool sub_ok = false;
-        unsigned char *dst = nullptr;
-        auto load_pr = [&](uint32_t ch) {
-            sub_ok = (ch * 8 + s) < a.m;
-            dst = lut + (ch % 3) * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16;
-            if (!active) return;
-            const float *rsrc = rbuf + (ch & 1) * RB + ((4 * h) * 8 + s) * 8;
+        if (ch == nch) {               // "chunk nch": zero row for the lanes that ran out of sub-vectors
+            if (tid < 64)
+                reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+        } else if (active) {
+            const bool sub_ok = (ch * 8 + s) < a.m;
+            const float *rsrc = rbuf + (ch & 1) * RB + ((4 * h) * 8 + s) * DSUB;   // + j*8*DSUB per query
+            unsigned char *dst = lut + b * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16;
+            const float *cbp = a.cb_tiled + ((size_t)ch * 256 * 8 + s) * DSUB;
+            constexpr int NPAIR = 128;                          // code pairs per chunk
+            if constexpr (DSUB == 8) {
+                uint64_t pr[4][4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float4 lo = *reinterpret_cast<const float4 *>(rsrc + j * 64);
-                const float4 hi = *reinterpret_cast<const float4 *>(rsrc + j * 64 + 4);
-                pr[j][0] = pk2(lo.x, lo.y); pr[j][1] = pk2(lo.z, lo.w);
-                pr[j][2] = pk2(hi.x, hi.y); pr[j][3] = pk2(hi.z, hi.w);
-            }
-        };
-        auto fetch = [&](float4 (&buf)[2][2], uint32_t ch, int st) {
-            if (!active || ch >= nch) return;
-            const float *cbp = a.cb_tiled + ((size_t)ch * 256 * 8 + s) * 8;
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int pair = pw + PW * (2 * st + u);
-                if (pair < NPAIR) {
-                    const float4 *src = reinterpret_cast<const float4 *>(cbp + (size_t)(2 * pair + cc) * 64);
-                    buf[u][0] = __ldg(src); buf[u][1] = __ldg(src + 1);
+                for (int j = 0; j < 4; j++) {
+                    const float4 lo = *reinterpret_cast<const float4 *>(rsrc + j * 8 * 8);
+                    const float4 hi = *reinterpret_cast<const float4 *>(rsrc + j * 8 * 8 + 4);
+                    pr[j][0] = pk2(lo.x, lo.y); pr[j][1] = pk2(lo.z, lo.w);
+                    pr[j][2] = pk2(hi.x, hi.y); pr[j][3] = pk2(hi.z, hi.w);
                 }
-            }
-        };
-        auto compute = [&](const float4 (&cur)[2][2], int st) {
-            if (!active) return;
+                const bool l2 = a.metric != LGPU_DOT;
+                // software pipeline over this warp's code pairs, 2 tasks per stage
+                float4 bufA[2][2], bufB[2][2];
+                auto fetch = [&](float4 (&buf)[2][2], int k) {
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int pair = pw + PW * (2 * st + u);
-                if (pair < NPAIR) {
-                    const int c = 2 * pair + cc;
-                    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (sub_ok) {
-                        if (l2) {
-                            uint64_t pc[4] = {pk2(cur[u][0].x, cur[u][0].y), pk2(cur[u][0].z, cur[u][0].w),
-                                              pk2(cur[u][1].x, cur[u][1].y), pk2(cur[u][1].z, cur[u][1].w)};
-                            out.x = l2_tree8_packed(pr[0], pc, a.fzero2);
-                            out.y = l2_tree8_packed(pr[1], pc, a.fzero2);
-                            out.z = l2_tree8_packed(pr[2], pc, a.fzero2);
-                            out.w = l2_tree8_packed(pr[3], pc, a.fzero2);
-                        } else {
-                            float cv[8] = {cur[u][0].x, cur[u][0].y, cur[u][0].z, cur[u][0].w,
-                                           cur[u][1].x, cur[u][1].y, cur[u][1].z, cur[u][1].w};
-                            float rr[8], o[4];
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
-#pragma unroll
-                                for (int e = 0; e < 4; e++) upk2(pr[j][e], rr[2 * e], rr[2 * e + 1]);
-                                o[j] = subvec_dot_dist<8>(rr, cv);
-                            }
-                            out = make_float4(o[0], o[1], o[2], o[3]);
+                    for (int u = 0; u < 2; u++) {
+                        int pair = pw + PW * (k + u);
+                        if (pair < NPAIR) {
+                            const float4 *src = reinterpret_cast<const float4 *>(cbp + (size_t)(2 * pair + cc) * 8 * 8);
+                            buf[u][0] = __ldg(src); buf[u][1] = __ldg(src + 1);
                         }
                     }
-                    *reinterpret_cast<float4 *>(dst + c * 128) = out;
+                };
+                auto compute = [&](const float4 (&cur)[2][2], int k) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                        int pair = pw + PW * (k + u);
+                        if (pair < NPAIR) {
+                            const int c = 2 * pair + cc;
+                            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (sub_ok) {
+                                if (l2) {
+                                    uint64_t pc[4] = {pk2(cur[u][0].x, cur[u][0].y), pk2(cur[u][0].z, cur[u][0].w),
+                                                      pk2(cur[u][1].x, cur[u][1].y), pk2(cur[u][1].z, cur[u][1].w)};
+                                    out.x = l2_tree8_packed(pr[0], pc, a.fzero2);
+                                    out.y = l2_tree8_packed(pr[1], pc, a.fzero2);
+                                    out.z = l2_tree8_packed(pr[2], pc, a.fzero2);
+                                    out.w = l2_tree8_packed(pr[3], pc, a.fzero2);
+                                } else {
+                                    float cv[8] = {cur[u][0].x, cur[u][0].y, cur[u][0].z, cur[u][0].w,
+                                                   cur[u][1].x, cur[u][1].y, cur[u][1].z, cur[u][1].w};
+                                    float rr[8];
+                                    float o[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                                        for (int e = 0; e < 4; e++) upk2(pr[j][e], rr[2 * e], rr[2 * e + 1]);
+                                        o[j] = subvec_dot_dist<8>(rr, cv);
+                                    }
+                                    out = make_float4(o[0], o[1], o[2], o[3]);
+                                }
+                            }
+                            *reinterpret_cast<float4 *>(dst + c * 128) = out;
+                        }
+                    }
+                };
+                // ping-pong: the loads of stage k+2 are in flight while stage k is computed
+                fetch(bufA, 0);
+                for (int k = 0;; k += 4) {
+                    fetch(bufB, k + 2);
+                    compute(bufA, k);
+                    if (pw + PW * (k + 2) >= NPAIR) break;
+                    fetch(bufA, k + 4);
+                    compute(bufB, k + 2);
+                    if (pw + PW * (k + 4) >= NPAIR) break;
                 }
-            }
-        };
-        float4 bufA[2][2], bufB[2][2];
-        uint32_t ch = 0;
-        int st = 0;
-        fetch(bufA, 0, 0);
-        for (;;) {
-            // ---- stage (ch, st) from bufA; bufB <- next stage ----
-            if (st == 0) { chunk_begin(ch); load_pr(ch); }
-            { const bool last = st + 1 == S; fetch(bufB, last ? ch + 1 : ch, last ? 0 : st + 1); }
-            compute(bufA, st);
-            if (st + 1 == S) { chunk_end(ch); ch++; st = 0; } else st++;
-            if (ch >= nch) break;
-            // ---- stage (ch, st) from bufB; bufA <- next stage ----
-            if (st == 0) { chunk_begin(ch); load_pr(ch); }
-            { const bool last = st + 1 == S; fetch(bufA, last ? ch + 1 : ch, last ? 0 : st + 1); }
-            compute(bufB, st);
-            if (st + 1 == S) { chunk_end(ch); ch++; st = 0; } else st++;
-            if (ch >= nch) break;
-        }
-    } else {
-        for (uint32_t ch = 0; ch < nch; ch++) {
-            chunk_begin(ch);
-            if (active) {
-                const bool sub_ok = (ch * 8 + s) < a.m;
-                const float *rsrc = rbuf + (ch & 1) * RB + ((4 * h) * 8 + s) * DSUB;   // + j*8*DSUB per query
-                unsigned char *dst = lut + (ch % 3) * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16;
-                const float *cbp = a.cb_tiled + ((size_t)ch * 256 * 8 + s) * DSUB;
+            } else {
                 for (int k = 0; pw + PW * k < NPAIR; k++) {
                     const int c = 2 * (pw + PW * k) + cc;
                     float cbv[DSUB], rr[DSUB], o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -289,18 +262,13 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
                     *reinterpret_cast<float4 *>(dst + c * 128) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
-            chunk_end(ch);
         }
-    }
-    // "chunk nch": zero row for the lanes that ran out of sub-vectors
-    {
-        const int b = nch % 3;
-        if (nch >= 2) bar_sync(BAR_EMPTY + b, NT);
-        if (tid < 64)
-            reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
         bar_arrive(BAR_FULL + b, NT);
+        if (ch + 1 < nch) store_resid(ch + 1);
+        if (ch < nch) bar_sync(BAR_PROD, PT);      // residual chunk ch+1 visible; chunk ch's reads done
     }
 }
+
 
 // ------------------------------------------------------------------ consumer side
 template <int R, int CT, int NT>
@@ -503,8 +471,8 @@ void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
 template <int DSUB>
 void launch_variant(const ScanArgs &a, int grid, cudaStream_t st)
 {
-    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 104, 200>(a, grid, st);
-    else launch_one<DSUB, 8, 8, 8, 104, 152>(a, grid, st);
+    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 96, 224>(a, grid, st);
+    else launch_one<DSUB, 8, 8, 8, 96, 160>(a, grid, st);
 }
 
 }  // namespace

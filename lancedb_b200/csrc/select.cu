@@ -221,18 +221,21 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
 }
 
 // ---------------------------------------------------------------------------------
-// k <= 32: one warp per query, the k best live in registers (lane i = i-th best, sorted by
-// (key, id)); candidates stream through 4 per lane per iteration and only the ones not
-// worse than the current k-th best are inserted (ballot loop).  After warm-up almost
-// nothing passes, so a query costs ~1 compare per candidate.
+// k <= 32: four warps per query; every warp keeps the k best of its share in registers
+// (lane i = i-th best, sorted by (key, id)).  Candidates stream through 8 per lane per
+// iteration (two float4 loads in flight) and only the ones not worse than the warp's
+// current k-th best are inserted (ballot loop).  After warm-up almost nothing passes, so
+// a query costs ~1 compare per candidate.  The four queues are merged through shared memory.
 constexpr int SELW_WARPS = 4;
 
 template <bool POS>
 __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t q = blockIdx.x * SELW_WARPS + (threadIdx.x >> 5);
-    if (q >= a.B) return;                                   // whole warp exits together
+    __shared__ uint32_t m_key[SELW_WARPS - 1][32];
+    __shared__ uint64_t m_id[SELW_WARPS - 1][32];
+    __shared__ uint64_t m_pos[SELW_WARPS - 1][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t q = blockIdx.x;
     const uint32_t k = a.k;
     uint32_t qk = 0xffffffffu;                              // queue entry of this lane
     uint64_t qid = UINT64_MAX, qpos = UINT64_MAX;
@@ -267,59 +270,58 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
             tau_id = __shfl_sync(0xffffffffu, qid, k - 1);
         }
     };
-    auto offer4 = [&](const float v[4], const bool ok[4], uint64_t idbase, const uint64_t *idsrc, uint64_t posbase) {
+    auto offer4 = [&](const float4 t, uint64_t n_left, uint64_t idbase, const uint64_t *idsrc, uint64_t posbase) {
+        const float v[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             float f = v[u];
             if (f == 0.f) f = 0.f;                          // -0 and +0 tie
             const uint32_t key = f32_key(f);
-            const bool pass = ok[u] && in_range(f) && key <= tau_k;
+            const bool pass = (uint64_t)u < n_left && in_range(f) && key <= tau_k;
             uint64_t id = 0;
             if (pass) id = idsrc ? idsrc[idbase + u] : idbase + u;
             offer(pass, key, id, posbase + u);
         }
     };
+    // one warp-iteration = 256 consecutive values of `src` starting at r0 (n values in total)
+    auto scan256 = [&](const float *src, uint64_t r0, uint64_t n, bool vec, uint64_t idbase, const uint64_t *idsrc) {
+        const uint64_t ra = r0 + (uint64_t)lane * 4, rb = ra + 128;
+        float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
+        if (vec) {
+            if (ra < n) ta = *reinterpret_cast<const float4 *>(src + ra);   // rows padded to 4 floats
+            if (rb < n) tb = *reinterpret_cast<const float4 *>(src + rb);
+        } else {
+            float *pa = reinterpret_cast<float *>(&ta), *pb = reinterpret_cast<float *>(&tb);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (ra + u < n) pa[u] = src[ra + u];
+                if (rb + u < n) pb[u] = src[rb + u];
+            }
+        }
+        offer4(ta, ra < n ? n - ra : 0, idbase + ra, idsrc, idbase + ra);
+        offer4(tb, rb < n ? n - rb : 0, idbase + rb, idsrc, idbase + rb);
+    };
 
     if (a.mode == 0) {
+        uint32_t itc = 0;                                   // iteration counter across segments
         for (uint32_t j = 0; j < a.nprobes; j++) {
             const uint32_t slot = q * a.nprobes + j;
             const uint32_t p = (uint32_t)a.probes[slot];
             const uint32_t n = a.part_n[p];
             const float *src = a.dist + a.seg_off[slot];
             const uint64_t rowbase = a.part_off[p];
-            for (uint32_t r0 = 0; r0 < n; r0 += 128) {
-                const uint32_t r = r0 + lane * 4;
-                float v[4] = {0.f, 0.f, 0.f, 0.f};
-                bool ok[4];
-                if (r < n) {
-                    const float4 t = *reinterpret_cast<const float4 *>(src + r);
-                    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) ok[u] = r + u < n;
-                offer4(v, ok, rowbase + r, a.row_ids, rowbase + r);
-            }
+            for (uint32_t r0 = 0; r0 < n; r0 += 256, itc++)
+                if ((itc & (SELW_WARPS - 1)) == (uint32_t)w) scan256(src, r0, n, true, rowbase, a.row_ids);
         }
     } else if (a.mode == 1) {
         const float *src = a.dense + (size_t)q * a.row_stride;
         const bool aligned = ((a.row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dense) & 15) == 0);
-        for (uint64_t c0 = 0; c0 < a.ncols; c0 += 128) {
-            const uint64_t c = c0 + (uint64_t)lane * 4;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            bool ok[4];
-            if (aligned && c + 3 < a.ncols) {
-                const float4 t = *reinterpret_cast<const float4 *>(src + c);
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-            } else {
-#pragma unroll
-                for (int u = 0; u < 4; u++) if (c + u < a.ncols) v[u] = src[c + u];
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) ok[u] = c + u < a.ncols;
-            offer4(v, ok, c, a.col_ids, c);
+        for (uint64_t c0 = (uint64_t)w * 256; c0 < a.ncols; c0 += 256 * SELW_WARPS) {
+            const bool vec = aligned && c0 + 256 <= a.ncols;
+            scan256(src, c0, a.ncols, vec, 0, a.col_ids);
         }
     } else {
-        for (uint64_t c0 = 0; c0 < a.ncols; c0 += 32) {
+        for (uint64_t c0 = (uint64_t)w * 32; c0 < a.ncols; c0 += 32 * SELW_WARPS) {
             const uint64_t cc = c0 + lane;
             bool pass = false;
             uint32_t key = 0;
@@ -335,6 +337,16 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
             }
             offer(pass, key, id, pos);
         }
+    }
+    // merge the four queues: warps 1..3 publish, warp 0 inserts
+    if (w > 0) { m_key[w - 1][lane] = qk; m_id[w - 1][lane] = qid; if (POS) m_pos[w - 1][lane] = qpos; }
+    __syncthreads();
+    if (w > 0) return;
+#pragma unroll
+    for (int o = 0; o < SELW_WARPS - 1; o++) {
+        const uint32_t ck = m_key[o][lane];
+        const uint64_t cid = m_id[o][lane];
+        offer(cid != UINT64_MAX || ck != 0xffffffffu, ck, cid, POS ? m_pos[o][lane] : 0);
     }
     const unsigned havem = __ballot_sync(0xffffffffu, qid != UINT64_MAX || qk != 0xffffffffu);
     if (lane < (int)k) {
@@ -353,7 +365,7 @@ void launch_select(const SelectArgs &a, cudaStream_t st)
     if (a.B == 0) return;
     LGPU_REQUIRE(a.k >= 1 && a.k <= SELECT_KMAX, "limit+offset (k) must be in [1, 2048] on the GPU path");
     if (a.k <= 32) {
-        const unsigned grid = (a.B + SELW_WARPS - 1) / SELW_WARPS;
+        const unsigned grid = a.B;
         if (a.out_pos) select_warp_kernel<true><<<grid, SELW_WARPS * 32, 0, st>>>(a);
         else select_warp_kernel<false><<<grid, SELW_WARPS * 32, 0, st>>>(a);
         LGPU_CUDA(cudaGetLastError());
