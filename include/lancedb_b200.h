@@ -156,6 +156,10 @@ int lgpu_debug_coarse(lgpu_index *ix, const float *queries, uint32_t B, uint32_t
  * buffers; out has n_p floats) -- exercises the LUT build + code scan kernels */
 int lgpu_debug_partition_distances(lgpu_index *ix, const float *query, uint32_t part,
                                    float *out);
+/* the tensor-core shortlist GEMM alone: out[q][x] = |x|^2 - 2 bf16(Q[q]).bf16(X[x]) (host buffers,
+ * out is [B][N] f32); dim must be a multiple of 8 */
+int lgpu_debug_gemm(const float *queries, const float *vectors, uint32_t B, uint64_t N, uint32_t dim,
+                    int device, float *out);
 /* per-kernel device time (ms) of the most recent lgpu_search* call made with
  * LGPU_PROFILE=1 in the environment: coarse, select-probes, group, scan, top-k,
  * refine, total.  times: [7] */

@@ -26,7 +26,7 @@ EXPORTS = [
     "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
     "lgpu_search", "lgpu_search_device", "lgpu_merge_topk_device",
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_device",
-    "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_last_stage_ms", "lgpu_set_profiling",
+    "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
 ]
 
 
@@ -86,6 +86,7 @@ def load():
     lib.lgpu_flat_search_device.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
     lib.lgpu_debug_coarse.argtypes = [vp, vp, u32, u32, vp, vp]
     lib.lgpu_debug_partition_distances.argtypes = [vp, vp, u32, vp]
+    lib.lgpu_debug_gemm.argtypes = [vp, vp, u32, C.c_uint64, u32, i32, vp]
     lib.lgpu_last_stage_ms.argtypes = [vp]
     lib.lgpu_set_profiling.argtypes = [i32]
     for name in EXPORTS:
@@ -230,6 +231,13 @@ def merge_topk_device(device: int, nlists: int, B: int, k: int, d_ids: int, d_di
                       d_out_dist: int, d_out_cnt: int, stream: int = 0):
     check(load().lgpu_merge_topk_device(device, nlists, B, k, d_ids, d_dist, d_out_ids, d_out_dist, d_out_cnt,
                                         stream))
+
+
+def debug_gemm(queries, vectors, device: int = 0) -> np.ndarray:
+    q = np.ascontiguousarray(queries, np.float32); x = np.ascontiguousarray(vectors, np.float32)
+    out = np.empty((q.shape[0], x.shape[0]), np.float32)
+    check(load().lgpu_debug_gemm(_ptr(q), _ptr(x), q.shape[0], x.shape[0], q.shape[1], device, _ptr(out)))
+    return out
 
 
 def set_profiling(enabled: bool) -> None:

@@ -62,6 +62,7 @@ struct Workspace {
     DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars;
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
+    DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
     Workspace()
     {
         LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -101,6 +102,9 @@ struct lgpu_index {
     int metric = 0;
     uint64_t nrows = 0, device_bytes = 0;
     DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
+    DevBuf cent_b, cent_n2;             // bf16 centroids + |c|^2 for the tensor-core coarse step
+    float cent_max = 0.f;
+    bool has_tc = false;
     bool has_vectors = false;
     std::vector<uint64_t> pad_prefix;   // prefix sums of pad4(n_p) sorted descending
     std::vector<uint32_t> h_part_n;
@@ -112,6 +116,10 @@ struct lgpu_flat {
     uint64_t nrows = 0;
     uint32_t dim = 0;
     DevBuf vectors, row_ids, ysqrt;
+    DevBuf vec_b, vec_n2;               // bf16 rows + |x|^2 for the tensor-core path
+    float vec_max = 0.f;
+    int num_sms = 0;
+    bool has_tc = false;
     bool has_ids = false, has_norms = false;
     std::mutex mu;
     WorkspacePool pool;
@@ -135,6 +143,66 @@ struct WsLease {
         pool.give(ws);
     }
 };
+
+
+static bool tc_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LGPU_NO_TENSOR_CORE"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// bf16 copy + squared norms + max norm of a row-major f32 matrix (open time)
+static void prepare_tc_operand(const float *X, uint64_t n, uint32_t d, DevBuf &Xb, DevBuf &n2, float &xmax, cudaStream_t st)
+{
+    Xb.ensure(std::max<size_t>((size_t)n * d * 2, 16));
+    n2.ensure(std::max<size_t>((size_t)n * 4, 16));
+    launch_to_bf16(X, n, d, Xb.p, n2.as<float>(), st);
+    std::vector<float> h(n);
+    LGPU_CUDA(cudaMemcpyAsync(h.data(), n2.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    LGPU_CUDA(cudaStreamSynchronize(st));
+    float m = 0.f;
+    for (float v : h) m = std::max(m, v);
+    xmax = std::sqrt(m) * 1.0001f;
+}
+
+// Tensor-core shortlist + exact re-score (squared L2 only): the k best of the N rows of X for each
+// of B queries by exact lance-order distance, ids from col_ids (or the row index), ascending by
+// (distance, id).  Dbuf: [B][ld] f32 scratch.  Queries whose shortlist cannot be proven complete
+// (band_check) are redone by the exact kernels in the same stream, without a host round trip.
+static void tc_topk_l2(Workspace *ws, cudaStream_t st, int num_sms, const float *Q, uint32_t B, const float *X,
+                       const void *Xb, const float *xnorm2, float xmax, uint64_t N, uint32_t d,
+                       const uint64_t *col_ids, uint32_t k, uint32_t kp, uint64_t *out_ids, float *out_dist,
+                       uint32_t *out_cnt, float *Dbuf, uint64_t ld)
+{
+    ws->qb.ensure((size_t)B * d * 2); ws->qn2.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
+    ws->t_ids.ensure((size_t)B * kp * 8); ws->t_dist.ensure((size_t)B * kp * 4);
+    ws->t_pos.ensure((size_t)B * kp * 8); ws->t_cnt.ensure((size_t)B * 4); ws->t_exact.ensure((size_t)B * kp * 4);
+    launch_to_bf16(Q, B, d, ws->qb.p, ws->qn2.as<float>(), st);
+    launch_gemm_dist(ws->qb.p, Xb, xnorm2, B, N, d, Dbuf, ld, num_sms, st);
+    SelectArgs sa{};
+    sa.mode = 1; sa.dense = Dbuf; sa.ncols = N; sa.row_stride = ld; sa.col_ids = col_ids;
+    sa.B = B; sa.k = kp;
+    sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
+    sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
+    launch_select(sa, st);
+    if (kp >= N) LGPU_CUDA(cudaMemsetAsync(ws->flags.p, 0, (size_t)B * 4, st));   // every row is a candidate
+    else launch_band_check(ws->t_dist.as<float>(), ws->t_cnt.as<uint32_t>(), ws->qn2.as<float>(), xmax, d, B, k, kp,
+                           ws->flags.as<uint32_t>(), st);
+    launch_pair_distance(Q, X, ws->t_pos.as<uint64_t>(), B, kp, d, LGPU_L2, ws->t_exact.as<float>(), st);
+    SelectArgs sb{};
+    sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
+    sb.ncols = kp; sb.inner = kp; sb.row_stride = kp; sb.outer_stride = 0;
+    sb.B = B; sb.k = k; sb.out_ids = out_ids; sb.out_dist = out_dist; sb.out_count = out_cnt;
+    launch_select(sb, st);
+    // fix-up pass (no-ops unless a query was flagged)
+    launch_dist_matrix(Q, X, B, N, d, 0, nullptr, nullptr, Dbuf, ld, st, ws->flags.as<uint32_t>());
+    SelectArgs sc{};
+    sc.mode = 1; sc.dense = Dbuf; sc.ncols = N; sc.row_stride = ld; sc.col_ids = col_ids;
+    sc.B = B; sc.k = k; sc.out_ids = out_ids; sc.out_dist = out_dist; sc.out_count = out_cnt;
+    sc.only = ws->flags.as<uint32_t>();
+    launch_select(sc, st);
+}
 
 void check_params(const lgpu_search_params *p)
 {
@@ -170,16 +238,27 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         LGPU_CUDA(cudaMemcpyAsync(ws->probes.p, forced_probes, (size_t)slots * 8, cudaMemcpyHostToDevice, st));
         mark();
     } else {
-        ws->D.ensure((size_t)B * nlist * 4);
-        launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, ix->metric == LGPU_DOT ? 1 : 0,
-                           nullptr, nullptr, ws->D.as<float>(), nlist, st);
-        mark();
-        SelectArgs sa{};
-        sa.mode = 1; sa.dense = ws->D.as<float>(); sa.ncols = nlist; sa.row_stride = nlist;
-        sa.B = B; sa.k = nprobes;
-        sa.out_ids = ws->probes.as<uint64_t>(); sa.out_dist = ws->probe_dist.as<float>();
-        sa.out_count = ws->probe_cnt.as<uint32_t>();
-        launch_select(sa, st);
+        const uint64_t ldc = (nlist + 3u) & ~3u;
+        ws->D.ensure((size_t)B * ldc * 4);
+        const uint32_t kp = nprobes <= 20 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * nprobes);
+        if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes) {
+            // tcgen05 GEMM shortlist + exact re-score (bit-identical probe sets, see gemm.cu)
+            mark();
+            tc_topk_l2(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
+                       ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes, std::min(kp, nlist),
+                       ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(), ws->probe_cnt.as<uint32_t>(),
+                       ws->D.as<float>(), ldc);
+        } else {
+            launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, ix->metric == LGPU_DOT ? 1 : 0,
+                               nullptr, nullptr, ws->D.as<float>(), ldc, st);
+            mark();
+            SelectArgs sa{};
+            sa.mode = 1; sa.dense = ws->D.as<float>(); sa.ncols = nlist; sa.row_stride = ldc;
+            sa.B = B; sa.k = nprobes;
+            sa.out_ids = ws->probes.as<uint64_t>(); sa.out_dist = ws->probe_dist.as<float>();
+            sa.out_count = ws->probe_cnt.as<uint32_t>();
+            launch_select(sa, st);
+        }
     }
     mark();
     // ---- regroup probe slots by partition ----
@@ -307,6 +386,13 @@ void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metri
             ws->xnorm.ensure((size_t)b * 4);
             launch_row_norms(q, b, fl->dim, ws->xnorm.as<float>(), st);
             xn = ws->xnorm.as<float>();
+        }
+        const uint32_t kp = (uint32_t)std::min<uint64_t>(N, std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(4 * sp.k, 64)));
+        if (fl->has_tc && tc_enabled() && metric == LGPU_L2 && !sp.has_lower && !sp.has_upper && b >= 8 && N >= 4096) {
+            tc_topk_l2(ws, st, fl->num_sms, q, b, fl->vectors.as<float>(), fl->vec_b.p, fl->vec_n2.as<float>(),
+                       fl->vec_max, N, fl->dim, fl->has_ids ? fl->row_ids.as<uint64_t>() : nullptr, sp.k, kp,
+                       d_ids + (size_t)q0 * sp.k, d_dist + (size_t)q0 * sp.k, d_cnt + q0, ws->D.as<float>(), ld);
+            continue;
         }
         launch_dist_matrix(q, fl->vectors.as<float>(), b, N, fl->dim, metric == LGPU_L2 ? 0 : (metric == LGPU_DOT ? 1 : 2),
                            xn, fl->ysqrt.as<float>(), ws->D.as<float>(), ld, st);
@@ -453,6 +539,12 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
         up(ix->part_off, d->part_offsets, (size_t)(nlist + 1) * 8);
         up(ix->row_ids, d->row_ids, (size_t)d->nrows * 8);
         if (d->vectors) { up(ix->vectors, d->vectors, (size_t)d->nrows * d->dim * 4); ix->has_vectors = true; }
+        if (gemm_shape_supported(d->dim) && d->metric != LGPU_DOT) {
+            LGPU_CUDA(cudaStreamSynchronize(st));
+            prepare_tc_operand(ix->centroids.as<float>(), nlist, d->dim, ix->cent_b, ix->cent_n2, ix->cent_max, st);
+            ix->device_bytes += ix->cent_b.bytes + ix->cent_n2.bytes;
+            ix->has_tc = true;
+        }
         // codebook -> [nch][256][8][dsub]
         {
             DevBuf tmp;
@@ -585,6 +677,13 @@ int lgpu_flat_open(const float *vectors, uint64_t nrows, uint32_t dim, const uin
         fl->device = device; fl->nrows = nrows; fl->dim = dim;
         fl->vectors.ensure(std::max<size_t>((size_t)nrows * dim * 4, 16));
         if (nrows) LGPU_CUDA(cudaMemcpy(fl->vectors.p, vectors, (size_t)nrows * dim * 4, cudaMemcpyHostToDevice));
+        cudaDeviceProp prop;
+        LGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+        fl->num_sms = prop.multiProcessorCount;
+        if (gemm_shape_supported(dim) && nrows >= 4096) {
+            prepare_tc_operand(fl->vectors.as<float>(), nrows, dim, fl->vec_b, fl->vec_n2, fl->vec_max, nullptr);
+            fl->has_tc = true;
+        }
         if (row_ids && nrows) {
             fl->row_ids.ensure((size_t)nrows * 8);
             LGPU_CUDA(cudaMemcpy(fl->row_ids.p, row_ids, (size_t)nrows * 8, cudaMemcpyHostToDevice));
@@ -672,6 +771,28 @@ int lgpu_debug_coarse(lgpu_index *ix, const float *queries, uint32_t B, uint32_t
         LGPU_CUDA(cudaMemcpyAsync(out_dists, ws->probe_dist.p, tmp.size() * 4, cudaMemcpyDeviceToHost, st));
         LGPU_CUDA(cudaStreamSynchronize(st));
         for (size_t i = 0; i < tmp.size(); i++) out_parts[i] = (uint32_t)tmp[i];
+    });
+}
+
+int lgpu_debug_gemm(const float *Q, const float *X, uint32_t B, uint64_t N, uint32_t d, int device, float *out)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(Q && X && out && B > 0 && N > 0, "bad argument");
+        LGPU_REQUIRE(gemm_shape_supported(d), "dimension must be a multiple of 8");
+        require_device(device);
+        cudaDeviceProp prop;
+        LGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+        DevBuf q, x, qb, xb, xn2, o;
+        const uint64_t ld = (N + 3) & ~3ull;
+        q.ensure((size_t)B * d * 4); x.ensure((size_t)N * d * 4); qb.ensure((size_t)B * d * 2); xb.ensure((size_t)N * d * 2);
+        xn2.ensure((size_t)N * 4); o.ensure((size_t)B * ld * 4);
+        LGPU_CUDA(cudaMemcpy(q.p, Q, (size_t)B * d * 4, cudaMemcpyHostToDevice));
+        LGPU_CUDA(cudaMemcpy(x.p, X, (size_t)N * d * 4, cudaMemcpyHostToDevice));
+        launch_to_bf16(q.as<float>(), B, d, qb.p, nullptr, nullptr);
+        launch_to_bf16(x.as<float>(), N, d, xb.p, xn2.as<float>(), nullptr);
+        launch_gemm_dist(qb.p, xb.p, xn2.as<float>(), B, N, d, o.as<float>(), ld, prop.multiProcessorCount, nullptr);
+        LGPU_CUDA(cudaDeviceSynchronize());
+        LGPU_CUDA(cudaMemcpy2D(out, (size_t)N * 4, o.p, (size_t)ld * 4, (size_t)N * 4, B, cudaMemcpyDeviceToHost));
     });
 }
 

@@ -20,8 +20,17 @@ constexpr int DM_Q = 16, DM_C = 32, DM_KT = 32, DM_STR = 36, DM_THREADS = 256;
 
 __global__ void __launch_bounds__(DM_THREADS) dist_matrix_kernel(
     const float *__restrict__ Q, const float *__restrict__ C, uint32_t B, uint64_t N, uint32_t d, int mode,
-    const float *__restrict__ xnorm, const float *__restrict__ ysqrt, float *__restrict__ D, uint64_t ldD)
+    const float *__restrict__ xnorm, const float *__restrict__ ysqrt, float *__restrict__ D, uint64_t ldD,
+    const uint32_t *__restrict__ only)
 {
+    if (only) {                                  // fix-up pass: skip query tiles with no flagged query
+        bool any = false;
+        for (uint32_t i = 0; i < DM_Q; i++) {
+            uint32_t gq = blockIdx.y * DM_Q + i;
+            if (gq < B && only[gq]) any = true;
+        }
+        if (!any) return;
+    }
     __shared__ float qs[DM_Q][DM_STR];
     __shared__ float cs[DM_C][DM_STR];
     __shared__ float red[DM_Q * DM_C][17];
@@ -182,11 +191,12 @@ __global__ void pair_distance_kernel(const float *__restrict__ Q, const float *_
 }  // namespace
 
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
-                        const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st)
+                        const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st,
+                        const uint32_t *only)
 {
     if (B == 0 || N == 0) return;
     dim3 grid((unsigned)((N + DM_C - 1) / DM_C), (B + DM_Q - 1) / DM_Q);
-    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD);
+    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only);
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -70,8 +70,10 @@ void launch_group(const GroupArgs &a, cudaStream_t st);
 // ---------------- exact distance matrix (K1 coarse, flat v1) ----------------------
 // D[q][c] for q < B, c < N.  mode 0: L2 (squared), 1: dot distance 1 - x.y,
 // 2: cosine 1 - x.y/|x|/|y| (xnorm[B] = |x|, ysqrt[N] = |y| required).
+// `only` (optional, [B]): rows whose flag is 0 are skipped (used by the tensor-core paths' fix-up pass)
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
-                        const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st);
+                        const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st,
+                        const uint32_t *only = nullptr);
 // row norms |x| = sqrt(dot(x,x)) in lance order; out[n]
 void launch_row_norms(const float *X, uint64_t n, uint32_t d, float *out, cudaStream_t st);
 // out[q] = x[q] / |x[q]|
@@ -110,8 +112,22 @@ struct SelectArgs {
     float *out_dist;              // [B][k]
     uint32_t *out_count;          // [B]
     uint64_t *out_pos;            // optional [B][k] storage position (mode 0) / column (mode 1)
+    const uint32_t *only;         // optional [B]: queries whose flag is 0 are left untouched
 };
 void launch_select(const SelectArgs &a, cudaStream_t st);
+
+// ---------------- tensor-core shortlist (gemm.cu) ------------------------------------
+bool gemm_shape_supported(uint32_t d);
+// X f32 [n][d] -> bf16 [n][d]; norm2[n] = |x|^2 (f32) if norm2 != nullptr
+void launch_to_bf16(const float *X, uint64_t n, uint32_t d, void *Xb, float *norm2, cudaStream_t st);
+// out[q][x] = xnorm2[x] - 2 * bf16(Q[q]) . bf16(X[x])   (tcgen05 + TMA), q < B, x < N
+void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint32_t B, uint64_t N, uint32_t d,
+                      float *out, uint64_t ld_out, int num_sms, cudaStream_t st);
+// flags[q] = 1 when the approximate shortlist of query q cannot be proven to contain the exact top-k:
+// approx[q][0..kp) ascending, cnt[q] entries valid; proven iff cnt < kp or approx[kp-1] > approx[k-1] + 2E_q,
+// E_q = 2^-7 (1+2^-8) |q| xmax + 4 d 2^-24 (|q| + xmax)^2
+void launch_band_check(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
+                       uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st);
 
 // ---------------- index re-layout (open time) --------------------------------------
 void launch_retile_codes(const unsigned char *codes, int layout, const uint64_t *part_off, uint32_t nlist,

@@ -1,0 +1,77 @@
+"""tcgen05 GEMM shortlist: numerics of the GEMM itself (tolerance: it is bf16), and bit-exact
+parity of the paths that use it as a candidate generator (flat L2, IVF coarse step) -- the
+exact re-score decides, so ids/distances must still equal the oracle's bit for bit."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from lancedb_b200 import _native
+from tests.util import queries, random_index
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(a):
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("B,N,d", [(128, 256, 64), (1, 1, 8), (130, 300, 72), (1000, 5000, 768), (16, 70000, 128)])
+def test_gemm_numerics(B, N, d):
+    rng = np.random.default_rng(B + N + d)
+    q = queries(rng, B, d); x = queries(rng, N, d)
+    got = _native.debug_gemm(q, x)
+    qb, xb = _bf16(q).astype(np.float64), _bf16(x).astype(np.float64)
+    want = (x.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * qb @ xb.T
+    scale = np.abs(want).max() + 1.0
+    err = np.abs(got - want).max()
+    assert err <= 2e-5 * scale * max(1.0, d / 256), f"max abs err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("n,dim,B,k", [(20000, 128, 64, 10), (6000, 1536, 33, 10), (9000, 64, 200, 100)])
+def test_flat_tensorcore_path_bit_exact(n, dim, B, k):
+    rng = np.random.default_rng(n)
+    v = queries(rng, n, dim)
+    v[n // 2] = v[3]; v[n // 3] = v[3]                    # exact duplicates -> ties by row id
+    rid = rng.permutation(n).astype(np.uint64)
+    q = queries(rng, B, dim)
+    q[0] = v[3]
+    fl = _native.GpuFlat(v, row_ids=rid)
+    gi, gd, gc = fl.search(q, k=k, metric="l2")
+    oi, od, oc = oracle.flat_search(v, q, k=k, metric="l2", row_ids=rid, nthreads=8)
+    fl.close()
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+def test_flat_tensorcore_clustered_fallback():
+    """near-duplicate rows make the error band overflow the shortlist -> exact fix-up path"""
+    rng = np.random.default_rng(5)
+    base = queries(rng, 1, 64)
+    v = (base + 1e-3 * rng.standard_normal((8192, 64))).astype(np.float32)
+    q = (base + 1e-3 * rng.standard_normal((16, 64))).astype(np.float32)
+    fl = _native.GpuFlat(v)
+    gi, gd, gc = fl.search(q, k=10)
+    oi, od, oc = oracle.flat_search(v, q, k=10, nthreads=8)
+    fl.close()
+    assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("nprobes", [20, 37])
+def test_coarse_tensorcore_path_bit_exact(metric, nprobes):
+    rng = np.random.default_rng(11)
+    ix = random_index(rng, dim=128, nlist=700, m=16, metric=metric, n=30000)
+    q = queries(rng, 70, 128)
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    parts, dists = gpu.debug_coarse(q, nprobes)              # exact reference path
+    gi, gd, gc = gpu.search(q, k=10, nprobes=nprobes)        # tensor-core shortlist path inside
+    oi, od, oc = orc.search(q, k=10, nprobes=nprobes, nthreads=8)
+    gpu.close()
+    for i in range(q.shape[0]):
+        qn = oracle.normalize(q[i]) if metric == "cosine" else q[i]
+        op, _, _ = orc.find_partitions(qn, nprobes)
+        assert np.array_equal(parts[i], op)
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
