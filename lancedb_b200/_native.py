@@ -149,8 +149,8 @@ class GpuIvfPq:
         self.has_vectors = vec is not None
 
     def close(self):
-        if getattr(self, "_h", None):
-            load().lgpu_index_close(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.lgpu_index_close(self._h)
             self._h = None
 
     __del__ = close
@@ -206,8 +206,8 @@ class GpuFlat:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
-            load().lgpu_flat_close(self._h)
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.lgpu_flat_close(self._h)
             self._h = None
 
     __del__ = close

@@ -240,8 +240,11 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     } else {
         const uint64_t ldc = (nlist + 3u) & ~3u;
         ws->D.ensure((size_t)B * ldc * 4);
-        const uint32_t kp = nprobes <= 20 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * nprobes);
-        if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes) {
+        // the bf16 error band around the nprobes-th centroid has to fit in the shortlist, so take 3x
+        // nprobes (>= 64) candidates; below ~8M (query, centroid) pairs the exact kernel is as fast
+        const uint32_t kp = std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(64, 3 * nprobes));
+        const bool big = (uint64_t)B * nlist >= ((uint64_t)1 << 23) || getenv("LGPU_FORCE_TC_COARSE");
+        if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes && big) {
             // tcgen05 GEMM shortlist + exact re-score (bit-identical probe sets, see gemm.cu)
             mark();
             tc_topk_l2(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
@@ -387,7 +390,7 @@ void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metri
             launch_row_norms(q, b, fl->dim, ws->xnorm.as<float>(), st);
             xn = ws->xnorm.as<float>();
         }
-        const uint32_t kp = (uint32_t)std::min<uint64_t>(N, std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(4 * sp.k, 64)));
+        const uint32_t kp = (uint32_t)std::min<uint64_t>(N, std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(8 * sp.k, 256)));
         if (fl->has_tc && tc_enabled() && metric == LGPU_L2 && !sp.has_lower && !sp.has_upper && b >= 8 && N >= 4096) {
             tc_topk_l2(ws, st, fl->num_sms, q, b, fl->vectors.as<float>(), fl->vec_b.p, fl->vec_n2.as<float>(),
                        fl->vec_max, N, fl->dim, fl->has_ids ? fl->row_ids.as<uint64_t>() : nullptr, sp.k, kp,

@@ -59,7 +59,8 @@ def test_flat_tensorcore_clustered_fallback():
 
 @pytest.mark.parametrize("metric", ["l2", "cosine"])
 @pytest.mark.parametrize("nprobes", [20, 37])
-def test_coarse_tensorcore_path_bit_exact(metric, nprobes):
+def test_coarse_tensorcore_path_bit_exact(metric, nprobes, monkeypatch):
+    monkeypatch.setenv("LGPU_FORCE_TC_COARSE", "1")
     rng = np.random.default_rng(11)
     ix = random_index(rng, dim=128, nlist=700, m=16, metric=metric, n=30000)
     q = queries(rng, 70, 128)
