@@ -12,6 +12,8 @@
 
 #include <math_constants.h>
 
+#include <algorithm>
+
 namespace lgpu {
 
 namespace {
@@ -38,9 +40,12 @@ __global__ void __launch_bounds__(DM_THREADS) dist_matrix_kernel(
     const int tid = threadIdx.x;
     const int klane = tid & 15, pt = tid >> 4;
     const int tq = pt & 3, tc = pt >> 2;
-    const uint64_t c0 = (uint64_t)blockIdx.x * DM_C;
     const uint32_t q0 = blockIdx.y * DM_Q;
     const uint32_t d16 = d & ~15u;
+    const uint64_t ncol_tiles = (N + DM_C - 1) / DM_C;
+  for (uint64_t ctile = blockIdx.x; ctile < ncol_tiles; ctile += gridDim.x) {     // column tiles of this CTA
+    const uint64_t c0 = ctile * DM_C;
+    __syncthreads();
 
     float acc[4][8];
 #pragma unroll
@@ -112,6 +117,7 @@ __global__ void __launch_bounds__(DM_THREADS) dist_matrix_kernel(
         else if (mode == 2) v = __fsub_rn(1.0f, __fdiv_rn(__fdiv_rn(v, xnorm[gq]), ysqrt[gc]));
         D[(size_t)gq * ldD + gc] = v;
     }
+  }
 }
 
 // half-warp per row: lane l (< 16) is lance's accumulator lane l
@@ -195,7 +201,9 @@ void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, 
                         const uint32_t *only)
 {
     if (B == 0 || N == 0) return;
-    dim3 grid((unsigned)((N + DM_C - 1) / DM_C), (B + DM_Q - 1) / DM_Q);
+    // the fix-up pass (`only`) is almost always a no-op: keep its CTA count small
+    const uint64_t ct = (N + DM_C - 1) / DM_C;
+    dim3 grid((unsigned)std::min<uint64_t>(ct, only ? 256 : ((uint64_t)1 << 30)), (B + DM_Q - 1) / DM_Q);
     dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only);
     LGPU_CUDA(cudaGetLastError());
 }
