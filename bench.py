@@ -297,8 +297,8 @@ def main():
     sampler = ClockSampler(local)      # samples clocks / throttle reasons through regions (1) and (2)
     sampler.start()
     t_wait = time.time()
-    while not sampler.rows and time.time() - t_wait < 3.0:
-        step_device(0)
+    while not sampler.rows and time.time() - t_wait < 3.0:      # rank-local work only: no collectives here
+        gpu.search_device(d_q[0].data_ptr(), B, p, d_ids.data_ptr(), d_dist.data_ptr(), d_cnt.data_ptr(), stream)
         torch.cuda.synchronize()
     for i in range(args.warmup):
         step_device(i)
