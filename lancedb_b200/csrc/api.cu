@@ -63,6 +63,7 @@ struct Workspace {
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
+    DevBuf tq, sbound, probe_A, amax;   // two-pass scan: per-query tables, bounds, per-probe scalars
     Workspace()
     {
         LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -102,6 +103,8 @@ struct lgpu_index {
     int metric = 0;
     uint64_t nrows = 0, device_bytes = 0;
     DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
+    DevBuf row_R, rmax_bits;            // two-pass scan: per-row constant 2 b.c and max |R| (tables.cu)
+    bool has_tables = false;
     DevBuf cent_b, cent_n2;             // bf16 centroids + |c|^2 for the tensor-core coarse step
     float cent_max = 0.f;
     bool has_tc = false;
@@ -144,6 +147,13 @@ struct WsLease {
     }
 };
 
+
+static bool two_pass_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LGPU_EXACT_SCAN"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
 
 static bool tc_enabled()
 {
@@ -300,6 +310,57 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
     sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
     sc.dist_out = ws->dist_out.as<float>();
+    // ---- two-pass form (tables.cu): approximate scan with per-QUERY tables as a filter, exact
+    // re-score of the shortlist, exact redo of the queries whose shortlist cannot be proven ----
+    const uint32_t kp2 = sp.k <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * sp.k + 32);
+    const bool two_pass = ix->has_tables && two_pass_enabled() && ix->metric != LGPU_DOT && !sp.has_lower &&
+                          !sp.has_upper && sp.refine_factor == 0 && !forced_probes && d_ids && kp2 > sp.k;
+    if (two_pass) {
+        const size_t tq_floats = (size_t)ix->nch * 256 * 8;
+        ws->tq.ensure((size_t)B * tq_floats * 4); ws->sbound.ensure((size_t)B * 4);
+        ws->probe_A.ensure((size_t)slots * 4); ws->qn2.ensure((size_t)B * 4); ws->amax.ensure((size_t)B * 4);
+        ws->flags.ensure((size_t)B * 4);
+        ws->t_ids.ensure((size_t)B * kp2 * 8); ws->t_dist.ensure((size_t)B * kp2 * 4);
+        ws->t_pos.ensure((size_t)B * kp2 * 8); ws->t_cnt.ensure((size_t)B * 4); ws->t_exact.ensure((size_t)B * kp2 * 4);
+        launch_query_tables(qsearch, ix->cb_tiled.as<float>(), B, dim, ix->m, ix->nch, ix->dsub, ix->metric,
+                            ws->tq.as<float>(), ws->sbound.as<float>(), st);
+        launch_probe_terms(ws->probe_dist.as<float>(), qsearch, B, nprobes, dim, ws->probe_A.as<float>(),
+                           ws->qn2.as<float>(), ws->amax.as<float>(), st);
+        sc.tq = ws->tq.as<float>(); sc.probe_A = ws->probe_A.as<float>(); sc.row_R = ix->row_R.as<float>();
+        sc.part_off = ix->part_off.as<uint64_t>();
+        launch_scan(sc, ix->dsub, ix->num_sms, st);
+        mark();
+        SelectArgs sa{};
+        sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ga.seg_off; sa.probes = ga.probes;
+        sa.nprobes = nprobes; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
+        sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B; sa.k = kp2;
+        sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
+        sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
+        launch_select(sa, st);
+        launch_band_check2(ws->t_dist.as<float>(), ws->t_cnt.as<uint32_t>(), ws->sbound.as<float>(),
+                           ws->amax.as<float>(), ix->rmax_bits.as<int>(), ix->metric == LGPU_COSINE ? 0.5f : 1.0f,
+                           B, sp.k, kp2, ws->flags.as<uint32_t>(), st);
+        launch_pq_rescore(qsearch, ws->t_pos.as<uint64_t>(), B, kp2, ix->codes.as<unsigned char>(),
+                          ix->code_base.as<uint64_t>(), ix->part_npad.as<uint32_t>(), ix->part_off.as<uint64_t>(), nlist,
+                          ix->centroids.as<float>(), ix->cb_tiled.as<float>(), dim, ix->m, ix->dsub, ix->metric,
+                          ws->t_exact.as<float>(), st);
+        SelectArgs sb{};
+        sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
+        sb.ncols = kp2; sb.inner = kp2; sb.row_stride = kp2; sb.outer_stride = 0;
+        sb.B = B; sb.k = sp.k; sb.out_ids = d_ids; sb.out_dist = d_dist; sb.out_count = d_cnt;
+        launch_select(sb, st);
+        // fix-up (no work unless a query was flagged): regroup only the flagged queries, exact scan, exact top-k
+        ga.only = ws->flags.as<uint32_t>();
+        launch_group(ga, st);
+        sc.tq = nullptr;
+        launch_scan(sc, ix->dsub, ix->num_sms, st);
+        SelectArgs sf = sa;
+        sf.k = sp.k; sf.out_ids = d_ids; sf.out_dist = d_dist; sf.out_count = d_cnt; sf.out_pos = nullptr;
+        sf.only = ws->flags.as<uint32_t>();
+        launch_select(sf, st);
+        mark(); mark();
+        return;
+    }
     launch_scan(sc, ix->dsub, ix->num_sms, st);
     mark();
     if (!d_ids) { mark(); mark(); return; }     // debug: distances only
@@ -337,7 +398,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
 uint32_t ivf_sub_batch_size(lgpu_index *ix, uint32_t B, uint32_t nprobes)
 {
     uint32_t np_eff = std::min<uint32_t>(nprobes, ix->nlist);
-    size_t per_q = std::max<size_t>(ix->pad_prefix[np_eff] * 4 + (size_t)ix->nlist * 4, 4);
+    size_t per_q = std::max<size_t>(ix->pad_prefix[np_eff] * 4 + (size_t)ix->nlist * 4 + (size_t)ix->nch * 256 * 8 * 4, 4);
     size_t bs = workspace_budget() / per_q;
     bs = std::max<size_t>(1, std::min<size_t>(bs, 65535));
     return (uint32_t)std::min<size_t>(bs, B);
@@ -574,6 +635,17 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
                                     ix->part_npad.as<uint32_t>(), ix->codes.as<unsigned char>(), st);
             }
             LGPU_CUDA(cudaStreamSynchronize(st));
+        }
+        if (d->metric != LGPU_DOT) {   // per-row constants of the two-pass scan (tables.cu)
+            ix->row_R.ensure(std::max<size_t>((size_t)d->nrows * 4, 16));
+            ix->rmax_bits.ensure(16);
+            ix->device_bytes += ix->row_R.bytes;
+            launch_row_const(ix->codes.as<unsigned char>(), ix->code_base.as<uint64_t>(), ix->part_npad.as<uint32_t>(),
+                             ix->part_off.as<uint64_t>(), nlist, d->nrows, ix->centroids.as<float>(),
+                             ix->cb_tiled.as<float>(), d->dim, d->m, ix->dsub, ix->row_R.as<float>(),
+                             ix->rmax_bits.as<int>(), st);
+            LGPU_CUDA(cudaStreamSynchronize(st));
+            ix->has_tables = true;
         }
         *out = ix;
     });

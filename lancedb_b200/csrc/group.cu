@@ -18,18 +18,19 @@ __global__ void group_count_kernel(GroupArgs a)
 {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.B) return;
+    const bool take = !a.only || a.only[q];             // fix-up pass: only flagged queries get tiles
     uint64_t off = 0, rows = 0;
     for (uint32_t j = 0; j < a.nprobes; j++) {
         uint32_t slot = q * a.nprobes + j;
         uint32_t p = (uint32_t)a.probes[slot];
         uint32_t n = a.part_n[p];
-        a.slot_pos[slot] = atomicAdd(&a.part_cnt[p], 1u);
+        a.slot_pos[slot] = take ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
         a.seg_local[slot] = off;
         off += pad4(n);
         rows += n;
     }
     a.qtot[q] = off;
-    atomicAdd(a.scanned_rows, (unsigned long long)rows);
+    if (!a.only) atomicAdd(a.scanned_rows, (unsigned long long)rows);
 }
 
 // single CTA: exclusive scans over queries (segment bases) and partitions (query-list
@@ -103,7 +104,7 @@ __global__ void group_fill_kernel(GroupArgs a)
     uint32_t q = slot / a.nprobes;
     uint32_t p = (uint32_t)a.probes[slot];
     a.seg_off[slot] = a.qtot[q] + a.seg_local[slot];
-    a.qlist[a.qlist_off[p] + a.slot_pos[slot]] = slot;
+    if (a.slot_pos[slot] != 0xffffffffu) a.qlist[a.qlist_off[p] + a.slot_pos[slot]] = slot;
 }
 
 }  // namespace
@@ -112,7 +113,7 @@ void launch_group(const GroupArgs &a, cudaStream_t st)
 {
     if (a.B == 0) return;
     LGPU_CUDA(cudaMemsetAsync(a.part_cnt, 0, sizeof(uint32_t) * a.nlist, st));
-    LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
+    if (!a.only) LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
     group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a);
     group_scan_kernel<<<1, 1024, 0, st>>>(a);
     uint32_t slots = a.B * a.nprobes;

@@ -44,6 +44,11 @@ struct ScanArgs {
     const uint32_t *total_tiles;  // [1]
     uint32_t *tile_counter;       // [1], zeroed before launch
     float *dist_out;
+    // approximate pass (tables.cu); tq == nullptr selects the exact kernel
+    const float *tq;              // [B][nch][256][8] per-query tables |q_i - codebook_i[c]|^2
+    const float *probe_A;         // [B*nprobes] |q - c_p|^2 - |q|^2
+    const float *row_R;           // [nrows] 2 * codeword(row) . c_p
+    const uint64_t *part_off;     // [nlist+1]
 };
 bool scan_dsub_supported(uint32_t dsub);
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
@@ -64,6 +69,7 @@ struct GroupArgs {
     uint32_t *total_tiles;        // [1]
     uint32_t *tile_counter;       // [1]
     unsigned long long *scanned_rows;  // [1] sum over probe slots of n_p (roofline bytes / m)
+    const uint32_t *only;         // optional [B]: regroup only the flagged queries (fix-up pass)
 };
 void launch_group(const GroupArgs &a, cudaStream_t st);
 
@@ -128,6 +134,28 @@ void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint3
 // E_q = 2^-7 (1+2^-8) |q| xmax + 4 d 2^-24 (|q| + xmax)^2
 void launch_band_check(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st);
+
+// ---------------- two-pass PQ scan: filter + verify (tables.cu) ------------------------
+// T[q][ch][c][s] = |q_i - codebook_i[c]|^2 (i = 8 ch + s), sbound[q] = sum_i max_c T
+void launch_query_tables(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
+                         uint32_t dsub, int metric, float *T, float *sbound, cudaStream_t st);
+// R[row] = 2 * codeword(row) . centroid(partition(row)); *rmax_bits = float bits of max |R|
+void launch_row_const(const unsigned char *codes, const uint64_t *code_base, const uint32_t *part_npad,
+                      const uint64_t *part_off, uint32_t nlist, uint64_t nrows, const float *centroids,
+                      const float *cb_tiled, uint32_t dim, uint32_t m, uint32_t dsub, float *R, int *rmax_bits,
+                      cudaStream_t st);
+// exact PQ distances (oracle order) of (query, storage row) pairs; pos == UINT64_MAX -> +inf
+void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t nc, const unsigned char *codes,
+                       const uint64_t *code_base, const uint32_t *part_npad, const uint64_t *part_off, uint32_t nlist,
+                       const float *centroids, const float *cb_tiled, uint32_t dim, uint32_t m, uint32_t dsub, int metric,
+                       float *out, cudaStream_t st);
+// probe_A[slot] = coarse_dist[slot] - |q|^2, qn2[q] = |q|^2, amax[q] = max_j coarse + |q|^2
+void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uint32_t nprobes, uint32_t dim,
+                        float *probe_A, float *qn2, float *amax, cudaStream_t st);
+// flags[q] = 1 when the approximate shortlist of q cannot be proven complete (scale: 0.5 for cosine)
+void launch_band_check2(const float *approx, const uint32_t *cnt, const float *sbound, const float *amax,
+                        const int *rmax_bits, float scale, uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags,
+                        cudaStream_t st);
 
 // ---------------- index re-layout (open time) --------------------------------------
 void launch_retile_codes(const unsigned char *codes, int layout, const uint64_t *part_off, uint32_t nlist,

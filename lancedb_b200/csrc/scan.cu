@@ -270,10 +270,63 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
 }
 
 
+// ------------------------------------------------------------------ approximate pass
+// Producer of the approximate pass: nothing is computed per (query, partition).  The per-QUERY
+// tables T_q[ch][c][s] = |q_i - codebook_i[c]|^2 (tables.cu) are copied into the same
+// [h][c][s][4 queries] ring, 4 scalar loads + one STS.128 per task.
+template <int PW, int NT>
+__device__ __forceinline__ void produce_tile_copy(const ScanArgs &a, int ng, const uint32_t *s_q, int tid)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *const lut = smem;
+    const int lane = tid & 31, pw = tid >> 5;
+    const int s = lane & 7, h = (lane >> 3) & 1, cc = lane >> 4;
+    const bool active = 4 * h < ng;
+    const uint32_t nch = a.nch;
+    const size_t tq_stride = (size_t)nch * 256 * 8;          // floats per query table
+    const float *tp[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int g = 4 * h + j;
+        tp[j] = a.tq + (size_t)s_q[g < ng ? g : 0] * tq_stride + s;     // idle slots alias query 0 (ignored later)
+    }
+    constexpr int NPAIR = 128, UNR = 4;
+    for (uint32_t ch = 0; ch <= nch; ch++) {
+        const int b = ch % 3;
+        if (ch >= 2) bar_sync(BAR_EMPTY + b, NT);
+        if (ch == 0 && tid < 64)
+            reinterpret_cast<float *>(lut + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+        if (ch == nch) {
+            if (tid < 64)
+                reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+        } else if (active) {
+            unsigned char *dst = lut + b * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16;
+            const size_t choff = (size_t)ch * 256 * 8;
+            for (int k0 = 0; pw + PW * k0 < NPAIR; k0 += UNR) {
+                float4 v[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int pair = pw + PW * (k0 + u);
+                    if (pair < NPAIR) {
+                        const size_t o = choff + (size_t)(2 * pair + cc) * 8;
+                        v[u] = make_float4(__ldg(tp[0] + o), __ldg(tp[1] + o), __ldg(tp[2] + o), __ldg(tp[3] + o));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int pair = pw + PW * (k0 + u);
+                    if (pair < NPAIR) *reinterpret_cast<float4 *>(dst + (2 * pair + cc) * 128) = v[u];
+                }
+            }
+        }
+        bar_arrive(BAR_FULL + b, NT);
+    }
+}
+
 // ------------------------------------------------------------------ consumer side
 template <int R, int CT, int NT>
 __device__ __forceinline__ void consume_tile(const ScanArgs &a, uint32_t p, int ng, uint32_t row0, uint32_t nrows,
-                                             const uint64_t *s_out, int ct)
+                                             const uint64_t *s_out, const float *s_A, int ct)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const unsigned char *const lut = smem;
@@ -350,6 +403,7 @@ __device__ __forceinline__ void consume_tile(const ScanArgs &a, uint32_t p, int 
             for (int r = 0; r < R; r++) {
                 if (valid[r]) {
                     float v = acc[r][g];
+                    if (a.tq) v = (v + s_A[g]) + a.row_R[a.part_off[p] + row0 + ct + r * CT];   // approximate pass
                     if (a.metric == LGPU_COSINE) v = __fmul_rn(v, 0.5f);
                     else if (a.metric == LGPU_DOT) v = __fsub_rn(v, mcorr);
                     out[row0 + ct + r * CT] = v;
@@ -369,7 +423,7 @@ struct TileInfo {
 
 template <int NT>
 __device__ __forceinline__ TileInfo next_tile(const ScanArgs &a, uint32_t total, uint32_t *s_tile, uint32_t *s_p,
-                                              uint32_t *s_q, uint64_t *s_out, int tid)
+                                              uint32_t *s_q, uint64_t *s_out, float *s_A, int tid)
 {
     TileInfo ti;
     __syncthreads();                            // previous tile fully drained
@@ -403,6 +457,7 @@ __device__ __forceinline__ TileInfo next_tile(const ScanArgs &a, uint32_t total,
             uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + tid];
             s_q[tid] = e / a.nprobes;
             s_out[tid] = a.seg_off[e];
+            if (a.tq) s_A[tid] = a.probe_A[e];
         } else {
             s_q[tid] = 0xffffffffu;
         }
@@ -425,25 +480,27 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
     __shared__ uint32_t s_tile, s_p;
     __shared__ uint32_t s_q[SCAN_G];
     __shared__ uint64_t s_out[SCAN_G];
+    __shared__ float s_A[SCAN_G];
 
     const int tid = threadIdx.x;
     const uint32_t total = *a.total_tiles;
 
     if (tid < PW * 32) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREG));
+        if constexpr (PREG != CREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREG));
         for (;;) {
-            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
+            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, s_A, tid);
             if (ti.done) break;
-            produce_tile<DSUB, PW, NT>(a, ti.p, ti.ng, s_q, tid);
+            if constexpr (DSUB == 0) produce_tile_copy<PW, NT>(a, ti.ng, s_q, tid);
+            else produce_tile<DSUB, PW, NT>(a, ti.p, ti.ng, s_q, tid);
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
+        if constexpr (PREG != CREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
         const int ct = tid - PW * 32;
         for (;;) {
-            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, tid);
+            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, s_A, tid);
             if (ti.done) break;
             const int R = (int)((ti.nrows + CT - 1) / CT);     // uniform per tile; rounded up to even
-#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ti.p, ti.ng, ti.row0, ti.nrows, s_out, ct)
+#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ti.p, ti.ng, ti.row0, ti.nrows, s_out, s_A, ct)
             if (R <= 2) LGPU_CONSUME(2);
             else if (R <= 4) LGPU_CONSUME(4);
             else if (R <= 6) LGPU_CONSUME(6);
@@ -468,6 +525,20 @@ void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
     LGPU_CUDA(cudaGetLastError());
 }
 
+template <>
+void launch_one<0, 4, 12, 6, 128, 128>(const ScanArgs &a, int grid, cudaStream_t st)
+{
+    size_t smem = 3 * (size_t)SCAN_LUT_BYTES;
+    auto kern = scan_kernel<0, 4, 12, 6, 128, 128>;
+    LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (a.rows_tile > 12u * 32u * 6u) {
+        set_error("internal: rows_tile too large for the approximate scan variant");
+        throw Failure{LGPU_RUNTIME};
+    }
+    kern<<<grid, 512, smem, st>>>(a);
+    LGPU_CUDA(cudaGetLastError());
+}
+
 template <int DSUB>
 void launch_variant(const ScanArgs &a, int grid, cudaStream_t st)
 {
@@ -484,6 +555,7 @@ bool scan_dsub_supported(uint32_t dsub)
 
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st)
 {
+    if (a.tq) { launch_one<0, 4, 12, 6, 128, 128>(a, grid, st); return; }   // approximate pass (any dsub)
     switch (dsub) {
     case 1: launch_variant<1>(a, grid, st); break;
     case 2: launch_variant<2>(a, grid, st); break;
