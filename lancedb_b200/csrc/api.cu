@@ -581,6 +581,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             uint32_t x = (uint32_t)std::max(1.0, big);
             uint32_t nm = scan_nrb(x, SCAN_ROWS_TILE_MID), nl = scan_nrb(x, SCAN_ROWS_TILE_LARGE);
             ix->rows_tile = nl < nm ? SCAN_ROWS_TILE_LARGE : SCAN_ROWS_TILE_MID;
+            if (ix->rows_tile > SCAN_ROWS_TILE_MID) ix->rows_tile = SCAN_ROWS_TILE_MID;   // the two-pass variant holds 1536 rows
             if (const char *e = getenv("LGPU_SCAN_ROWS_TILE")) {
                 uint32_t v = (uint32_t)atoi(e);
                 if (v == SCAN_ROWS_TILE_MID || v == SCAN_ROWS_TILE_LARGE) ix->rows_tile = v;

@@ -290,7 +290,7 @@ __device__ __forceinline__ void produce_tile_copy(const ScanArgs &a, int ng, con
         const int g = 4 * h + j;
         tp[j] = a.tq + (size_t)s_q[g < ng ? g : 0] * tq_stride + s;     // idle slots alias query 0 (ignored later)
     }
-    constexpr int NPAIR = 128, UNR = 4;
+    constexpr int NPAIR = 128, UNR = 8;
     for (uint32_t ch = 0; ch <= nch; ch++) {
         const int b = ch % 3;
         if (ch >= 2) bar_sync(BAR_EMPTY + b, NT);
@@ -503,9 +503,11 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
 #define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ti.p, ti.ng, ti.row0, ti.nrows, s_out, s_A, ct)
             if (R <= 2) LGPU_CONSUME(2);
             else if (R <= 4) LGPU_CONSUME(4);
-            else if (R <= 6) LGPU_CONSUME(6);
-            else if (R <= 8 || RMAX <= 8) LGPU_CONSUME(8);
-            else if constexpr (RMAX > 8) { if (R <= 10) LGPU_CONSUME(10); else LGPU_CONSUME(12); }
+            else if (R <= 6 || RMAX <= 6) LGPU_CONSUME(6);
+            else if constexpr (RMAX >= 8) {
+                if (R <= 8 || RMAX <= 8) LGPU_CONSUME(8);
+                else if constexpr (RMAX > 8) { if (R <= 10) LGPU_CONSUME(10); else LGPU_CONSUME(12); }
+            }
 #undef LGPU_CONSUME
         }
     }
@@ -526,12 +528,12 @@ void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
 }
 
 template <>
-void launch_one<0, 4, 12, 6, 128, 128>(const ScanArgs &a, int grid, cudaStream_t st)
+void launch_one<0, 8, 8, 6, 128, 128>(const ScanArgs &a, int grid, cudaStream_t st)
 {
     size_t smem = 3 * (size_t)SCAN_LUT_BYTES;
-    auto kern = scan_kernel<0, 4, 12, 6, 128, 128>;
+    auto kern = scan_kernel<0, 8, 8, 6, 128, 128>;
     LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (a.rows_tile > 12u * 32u * 6u) {
+    if (a.rows_tile > 8u * 32u * 6u) {
         set_error("internal: rows_tile too large for the approximate scan variant");
         throw Failure{LGPU_RUNTIME};
     }
@@ -555,7 +557,7 @@ bool scan_dsub_supported(uint32_t dsub)
 
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st)
 {
-    if (a.tq) { launch_one<0, 4, 12, 6, 128, 128>(a, grid, st); return; }   // approximate pass (any dsub)
+    if (a.tq) { launch_one<0, 8, 8, 6, 128, 128>(a, grid, st); return; }   // approximate pass (any dsub)
     switch (dsub) {
     case 1: launch_variant<1>(a, grid, st); break;
     case 2: launch_variant<2>(a, grid, st); break;

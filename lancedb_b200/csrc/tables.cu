@@ -38,10 +38,18 @@ __global__ void query_tables_kernel(const float *__restrict__ Q, const float *__
     float v = 0.f;
     if (i < m) {
         float qv[DSUB], cv[DSUB];
+        const float *qp = Q + (size_t)q * dim + i * DSUB, *cp = cb_tiled + e * DSUB;
+        if constexpr (DSUB % 4 == 0) {
 #pragma unroll
-        for (int t = 0; t < DSUB; t++) {
-            qv[t] = Q[(size_t)q * dim + i * DSUB + t];
-            cv[t] = cb_tiled[e * DSUB + t];
+            for (int t = 0; t < DSUB; t += 4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(qp + t));
+                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(cp + t));
+                qv[t] = a4.x; qv[t + 1] = a4.y; qv[t + 2] = a4.z; qv[t + 3] = a4.w;
+                cv[t] = b4.x; cv[t + 1] = b4.y; cv[t + 2] = b4.z; cv[t + 3] = b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < DSUB; t++) { qv[t] = qp[t]; cv[t] = cp[t]; }
         }
         v = subvec_l2<DSUB>(qv, cv);
     }
@@ -155,19 +163,26 @@ __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const f
                                    uint32_t nprobes, uint32_t dim, float *__restrict__ probe_A, float *__restrict__ qn2,
                                    float *__restrict__ amax)
 {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // one warp per query
+    const int lane = threadIdx.x & 31;
     if (q >= B) return;
     double n2d = 0.0;                                   // f64: |q|^2 within 1 ulp(f32)
-    for (uint32_t t = 0; t < dim; t++) { double v = Q[(size_t)q * dim + t]; n2d = fma(v, v, n2d); }
+    for (uint32_t t = lane; t < dim; t += 32) { double v = Q[(size_t)q * dim + t]; n2d = fma(v, v, n2d); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n2d += __shfl_xor_sync(0xffffffffu, n2d, o);
     const float n2 = (float)n2d;
     float mx = 0.f;
-    for (uint32_t j = 0; j < nprobes; j++) {
+    for (uint32_t j = lane; j < nprobes; j += 32) {
         const float cd = probe_dist[(size_t)q * nprobes + j];
         probe_A[(size_t)q * nprobes + j] = cd - n2;
         mx = fmaxf(mx, fabsf(cd));
     }
-    qn2[q] = n2;
-    amax[q] = mx + n2;                                  // >= |A| and also covers the coarse distance's own rounding
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+        qn2[q] = n2;
+        amax[q] = mx + n2;                              // >= |A| and also covers the coarse distance's own rounding
+    }
 }
 
 // flags[q] = 1 when the approximate shortlist cannot be proven to contain the exact top-k.
@@ -251,7 +266,7 @@ void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uin
                         float *probe_A, float *qn2, float *amax, cudaStream_t st)
 {
     if (B == 0) return;
-    probe_terms_kernel<<<(B + 63) / 64, 64, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, qn2, amax);
+    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, qn2, amax);
     LGPU_CUDA(cudaGetLastError());
 }
 
