@@ -126,6 +126,22 @@ def test_search_refine(metric):
     _check_search(ix, queries(rng, 17, 48), k=10, nprobes=3, refine_factor=5)
 
 
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_search_two_pass_filter_verify(metric, monkeypatch):
+    """LGPU_TWO_PASS=1: approximate scan with per-query tables + exact re-score + exact fix-up of the
+    unproven queries must return exactly what the exact path returns (incl. ties -> fix-up)."""
+    monkeypatch.setenv("LGPU_TWO_PASS", "1")
+    rng = np.random.default_rng(21)
+    ix = random_index(rng, dim=64, nlist=24, m=8, metric=metric, n=9000)
+    _check_search(ix, queries(rng, 40, 64), k=10, nprobes=6)
+    _check_search(ix, queries(rng, 40, 64), k=40, nprobes=6)
+    ct = ix.codes_t.copy()                       # identical codes -> every distance ties -> fix-up pass
+    a, b = int(ix.part_offsets[3]), int(ix.part_offsets[4])
+    blk = ct[a * 8:b * 8].reshape(8, b - a); blk[:] = blk[:, :1]
+    ix.codes_t = ct
+    _check_search(ix, queries(rng, 12, 64), k=10, nprobes=24)
+
+
 def test_search_config2_shape_subset():
     """BASELINE config 2's geometry (d=768, m=96, nprobes=20, k=10) at 1/8 of its rows."""
     rng = np.random.default_rng(9)
