@@ -63,6 +63,7 @@ struct Workspace {
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
+    DevBuf timing;
     DevBuf tq, sbound, probe_A, amax;   // two-pass scan: per-query tables, bounds, per-probe scalars
     Workspace()
     {
@@ -312,6 +313,13 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
     sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
     sc.dist_out = ws->dist_out.as<float>();
+    static const bool scan_timing = getenv("LGPU_SCAN_TIMING") != nullptr;
+    if (scan_timing && prof) {
+        ws->scalars.ensure(64);
+        ws->timing.ensure(16 * 8);
+        LGPU_CUDA(cudaMemsetAsync(ws->timing.p, 0, 16 * 8, st));
+        sc.timing = ws->timing.as<unsigned long long>();
+    }
     // ---- two-pass form (tables.cu): approximate scan with per-QUERY tables as a filter, exact
     // re-score of the shortlist, exact redo of the queries whose shortlist cannot be proven ----
     const uint32_t kp2 = sp.k <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * sp.k + 32);
@@ -424,6 +432,13 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
         unsigned long long rows = 0;
         LGPU_CUDA(cudaMemcpy(&rows, ws->scalars.as<char>() + 16, 8, cudaMemcpyDeviceToHost));
         g_scanned_bytes = (uint64_t)rows * ix->m;
+        if (getenv("LGPU_SCAN_TIMING") && ws->timing.p) {
+            unsigned long long t[16];
+            LGPU_CUDA(cudaMemcpy(t, ws->timing.p, sizeof(t), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[scan timing] tiles %llu | producer warp-cycles: total %llu waitEMPTY %llu barPROD %llu | "
+                            "consumer warp-cycles: total %llu waitFULL %llu | tile-fetch cycles %llu\n",
+                    t[6], t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
     }
 }
 

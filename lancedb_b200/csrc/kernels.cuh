@@ -49,6 +49,7 @@ struct ScanArgs {
     const float *probe_A;         // [B*nprobes] |q - c_p|^2 - |q|^2
     const float *row_R;           // [nrows] 2 * codeword(row) . c_p
     const uint64_t *part_off;     // [nlist+1]
+    unsigned long long *timing;   // optional [16] stall accounting (LGPU_SCAN_TIMING=1)
 };
 bool scan_dsub_supported(uint32_t dsub);
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);

@@ -39,6 +39,27 @@ namespace lgpu {
 
 namespace {
 
+// Optional in-kernel stall accounting (LGPU_SCAN_TIMING=1): lane 0 of every warp accumulates clock64()
+// deltas per region into a.timing[]: 0 producer total, 1 producer wait-EMPTY, 2 producer barrier,
+// 3 consumer total, 4 consumer wait-FULL, 5 tile fetch (thread 0), 6 tiles, 7 producer warps, 8 consumer warps
+// Compiled in only with -DLGPU_SCAN_TIMING_BUILD=1 (it costs registers); see profiles/r01_scan_stalls.txt.
+#ifndef LGPU_SCAN_TIMING_BUILD
+#define LGPU_SCAN_TIMING_BUILD 0
+#endif
+struct Tm {
+    unsigned long long t0;
+    __device__ __forceinline__ void start(const ScanArgs &a)
+    {
+        if constexpr (LGPU_SCAN_TIMING_BUILD) { if (a.timing) t0 = clock64(); }
+    }
+    __device__ __forceinline__ void stop(const ScanArgs &a, int slot)
+    {
+        if constexpr (LGPU_SCAN_TIMING_BUILD) {
+            if (a.timing && (threadIdx.x & 31) == 0) atomicAdd(a.timing + slot, (unsigned long long)(clock64() - t0));
+        }
+    }
+};
+
 constexpr int BAR_FULL = 1;    // named barriers 1..3: chunk buffer b is built
 constexpr int BAR_EMPTY = 4;   // named barriers 4..6: chunk buffer b may be overwritten
 
@@ -169,7 +190,7 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
     for (uint32_t ch = 0; ch <= nch; ch++) {
         const int b = ch % 3;
         if (ch + 1 < nch) load_resid(ch + 1);
-        if (ch >= 2) bar_sync(BAR_EMPTY + b, NT);   // consumers are done with iteration ch-2
+        if (ch >= 2) { Tm tm; tm.start(a); bar_sync(BAR_EMPTY + b, NT); tm.stop(a, 1); }   // consumers done with iteration ch-2
         if (ch == 0 && tid < 64)       // "chunk -1": lagging lanes read code 0 of buffer 2 in iteration 0
             reinterpret_cast<float *>(lut + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
         if (ch == nch) {               // "chunk nch": zero row for the lanes that ran out of sub-vectors
@@ -265,7 +286,7 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
         }
         bar_arrive(BAR_FULL + b, NT);
         if (ch + 1 < nch) store_resid(ch + 1);
-        if (ch < nch) bar_sync(BAR_PROD, PT);      // residual chunk ch+1 visible; chunk ch's reads done
+        if (ch < nch) { Tm tm; tm.start(a); bar_sync(BAR_PROD, PT); tm.stop(a, 2); }   // residual chunk ch+1 visible
     }
 }
 
@@ -362,7 +383,7 @@ __device__ __forceinline__ void consume_tile(const ScanArgs &a, uint32_t p, int 
                 wn[r] = valid[r] ? __ldg(cs + (size_t)(it + 1) * npad + row) : make_uint2(0u, 0u);
             }
         }
-        bar_sync(BAR_FULL + (int)(it % 3), NT);
+        { Tm tm; tm.start(a); bar_sync(BAR_FULL + (int)(it % 3), NT); tm.stop(a, 4); }
         const uint32_t base_cur = (it % 3) * SCAN_LUT_BYTES;
         const uint32_t base_prev = ((it + 2) % 3) * SCAN_LUT_BYTES;
 #pragma unroll
@@ -488,10 +509,14 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
     if (tid < PW * 32) {
         if constexpr (PREG != CREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREG));
         for (;;) {
+            Tm tf; tf.start(a);
             TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, s_A, tid);
+            if (tid == 0) { tf.stop(a, 5); if constexpr (LGPU_SCAN_TIMING_BUILD) { if (a.timing && !ti.done) atomicAdd(a.timing + 6, 1ull); } }
             if (ti.done) break;
+            Tm tt; tt.start(a);
             if constexpr (DSUB == 0) produce_tile_copy<PW, NT>(a, ti.ng, s_q, tid);
             else produce_tile<DSUB, PW, NT>(a, ti.p, ti.ng, s_q, tid);
+            tt.stop(a, 0);
         }
     } else {
         if constexpr (PREG != CREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
@@ -500,6 +525,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
             TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, s_A, tid);
             if (ti.done) break;
             const int R = (int)((ti.nrows + CT - 1) / CT);     // uniform per tile; rounded up to even
+            Tm tt; tt.start(a);
 #define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ti.p, ti.ng, ti.row0, ti.nrows, s_out, s_A, ct)
             if (R <= 2) LGPU_CONSUME(2);
             else if (R <= 4) LGPU_CONSUME(4);
@@ -509,6 +535,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
                 else if constexpr (RMAX > 8) { if (R <= 10) LGPU_CONSUME(10); else LGPU_CONSUME(12); }
             }
 #undef LGPU_CONSUME
+            tt.stop(a, 3);
         }
     }
 }
