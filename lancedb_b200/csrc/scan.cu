@@ -133,6 +133,31 @@ __device__ __forceinline__ float l2_tree8_packed(const uint64_t r[4], const uint
     return __fadd_rn(u0, u1);
 }
 
+// Four table entries (the 4 queries of a half against one codeword) level by level, so that every
+// packed op has 3..15 independent neighbours instead of a 6-deep dependent chain per entry.
+__device__ __forceinline__ float4 l2_tree8_packed_x4(const uint64_t (&r)[4][4], const uint64_t (&c)[4], uint64_t zero)
+{
+    uint64_t d[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) d[j][e] = sub2(r[j][e], c[e]);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) d[j][e] = sq2(d[j][e], zero);
+    uint64_t t[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { t[j][0] = add2(d[j][0], d[j][2]); t[j][1] = add2(d[j][1], d[j][3]); }
+    uint64_t u[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) u[j] = add2(t[j][0], t[j][1]);
+    float lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) upk2(u[j], lo[j], hi[j]);
+    return make_float4(__fadd_rn(lo[0], hi[0]), __fadd_rn(lo[1], hi[1]), __fadd_rn(lo[2], hi[2]), __fadd_rn(lo[3], hi[3]));
+}
+
 // ------------------------------------------------------------------ producer side
 constexpr int BAR_PROD = 7;    // named barrier 7: producer-only (residual chunk hand-over)
 
@@ -235,10 +260,7 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
                                 if (l2) {
                                     uint64_t pc[4] = {pk2(cur[u][0].x, cur[u][0].y), pk2(cur[u][0].z, cur[u][0].w),
                                                       pk2(cur[u][1].x, cur[u][1].y), pk2(cur[u][1].z, cur[u][1].w)};
-                                    out.x = l2_tree8_packed(pr[0], pc, a.fzero2);
-                                    out.y = l2_tree8_packed(pr[1], pc, a.fzero2);
-                                    out.z = l2_tree8_packed(pr[2], pc, a.fzero2);
-                                    out.w = l2_tree8_packed(pr[3], pc, a.fzero2);
+                                    out = l2_tree8_packed_x4(pr, pc, a.fzero2);
                                 } else {
                                     float cv[8] = {cur[u][0].x, cur[u][0].y, cur[u][0].z, cur[u][0].w,
                                                    cur[u][1].x, cur[u][1].y, cur[u][1].z, cur[u][1].w};
@@ -571,7 +593,7 @@ void launch_one<0, 8, 8, 6, 128, 128>(const ScanArgs &a, int grid, cudaStream_t 
 template <int DSUB>
 void launch_variant(const ScanArgs &a, int grid, cudaStream_t st)
 {
-    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 96, 224>(a, grid, st);
+    if (a.rows_tile == SCAN_ROWS_TILE_MID) launch_one<DSUB, 12, 4, 12, 104, 200>(a, grid, st);
     else launch_one<DSUB, 8, 8, 8, 96, 160>(a, grid, st);
 }
 
