@@ -313,6 +313,8 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
     sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
     sc.dist_out = ws->dist_out.as<float>();
+    static const bool scalar_table = getenv("LGPU_SCALAR_TABLE") != nullptr;
+    sc.scalar_table = scalar_table ? 1 : 0;
     static const bool scan_timing = getenv("LGPU_SCAN_TIMING") != nullptr;
     if (scan_timing && prof) {
         ws->scalars.ensure(64);

@@ -50,6 +50,7 @@ struct ScanArgs {
     const float *row_R;           // [nrows] 2 * codeword(row) . c_p
     const uint64_t *part_off;     // [nlist+1]
     unsigned long long *timing;   // optional [16] stall accounting (LGPU_SCAN_TIMING=1)
+    int scalar_table;             // 1: scalar FADD/FMUL table build instead of packed f32x2 (A/B timing)
 };
 bool scan_dsub_supported(uint32_t dsub);
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);

@@ -158,6 +158,24 @@ __device__ __forceinline__ float4 l2_tree8_packed_x4(const uint64_t (&r)[4][4], 
     return make_float4(__fadd_rn(lo[0], hi[0]), __fadd_rn(lo[1], hi[1]), __fadd_rn(lo[2], hi[2]), __fadd_rn(lo[3], hi[3]));
 }
 
+// scalar FADD/FMUL variant of the same four entries (selected with LGPU_SCALAR_TABLE=1 for A/B timing)
+__device__ __forceinline__ float4 l2_tree8_scalar_x4(const uint64_t (&r)[4][4], const uint64_t (&c)[4])
+{
+    float cv[8], o[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) upk2(c[e], cv[2 * e], cv[2 * e + 1]);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float rv[8], sq[8];
+#pragma unroll
+        for (int e = 0; e < 4; e++) upk2(r[j][e], rv[2 * e], rv[2 * e + 1]);
+#pragma unroll
+        for (int e = 0; e < 8; e++) { float d = __fsub_rn(rv[e], cv[e]); sq[e] = __fmul_rn(d, d); }
+        o[j] = reduce_sum_x8(sq);
+    }
+    return make_float4(o[0], o[1], o[2], o[3]);
+}
+
 // ------------------------------------------------------------------ producer side
 constexpr int BAR_PROD = 7;    // named barrier 7: producer-only (residual chunk hand-over)
 
@@ -260,7 +278,7 @@ __device__ __forceinline__ void produce_tile(const ScanArgs &a, uint32_t p, int 
                                 if (l2) {
                                     uint64_t pc[4] = {pk2(cur[u][0].x, cur[u][0].y), pk2(cur[u][0].z, cur[u][0].w),
                                                       pk2(cur[u][1].x, cur[u][1].y), pk2(cur[u][1].z, cur[u][1].w)};
-                                    out = l2_tree8_packed_x4(pr, pc, a.fzero2);
+                                    out = a.scalar_table ? l2_tree8_scalar_x4(pr, pc) : l2_tree8_packed_x4(pr, pc, a.fzero2);
                                 } else {
                                     float cv[8] = {cur[u][0].x, cur[u][0].y, cur[u][0].z, cur[u][0].w,
                                                    cur[u][1].x, cur[u][1].y, cur[u][1].z, cur[u][1].w};
