@@ -158,6 +158,17 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic():
+    """dram__bytes_read+write per launch of the scan kernel from the committed ncu --set full capture
+    (profiles/): a profiler number, so it is read from the profile, never measured in this run."""
+    try:
+        cands = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_scan_traffic.json"))
+        with open(os.path.join(ROOT, "profiles", cands[-1])) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def cpu_baseline(cfg, ix, queries, seconds=12.0):
     """The oracle (port of the lance CPU path) on all host cores, bounded sample."""
     import oracle
@@ -369,7 +380,8 @@ def main():
             "recall_at_k": recall,
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "scan_kernel<8>", "kernel_ms": scan_avg,
+                         "traffic": profiled_traffic(), "kernel": "scan_kernel<8,...> (fused PQ table build + code scan)",
+                         "kernel_ms": scan_avg,
                          "algorithmic_bytes_per_launch": code_bytes, "peak_source": peak_src,
                          "compulsory_bytes_per_launch": int(full_ix.codes_t.size)},
         }
