@@ -217,6 +217,58 @@ static void tc_topk_l2(Workspace *ws, cudaStream_t st, int num_sms, const float 
     launch_select(sc, st);
 }
 
+// Large-N variant of tc_topk_l2 (flat search): a tensor-core pass over a row sample fixes, per query, a
+// score threshold that provably admits every true top-k row; the pass over all rows then runs with the
+// filtering epilogue (no dense score matrix), the few admitted rows are re-scored exactly, and queries whose
+// candidate list overflowed are redone by the exact kernels.
+static void tc_topk_l2_filtered(Workspace *ws, cudaStream_t st, int num_sms, const float *Q, uint32_t B, const float *X,
+                                const void *Xb, const float *xnorm2, float xmax, uint64_t N, uint32_t d,
+                                const uint64_t *col_ids, uint32_t k, uint64_t *out_ids, float *out_dist,
+                                uint32_t *out_cnt, float *Dbuf, uint64_t ld)
+{
+    const uint64_t Ns = std::min<uint64_t>(N, std::max<uint64_t>(65536, N / 8));
+    const uint64_t lds = (Ns + 3) & ~3ull;               // Dbuf is [B][ld >= lds]
+    const uint32_t cap = 1024;
+    ws->qb.ensure((size_t)B * d * 2); ws->qn2.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
+    ws->t_ids.ensure((size_t)B * cap * 8); ws->t_dist.ensure((size_t)B * std::max<uint32_t>(k, 32) * 4);
+    ws->t_pos.ensure((size_t)B * cap * 8); ws->t_cnt.ensure((size_t)B * 4); ws->t_exact.ensure((size_t)B * cap * 4);
+    ws->probe_A.ensure((size_t)B * 4);                   // thr[q]
+    ws->amax.ensure((size_t)B * 4);                      // candidate counters
+    ws->sbound.ensure((size_t)B * std::max<uint32_t>(k, 32) * 8);   // sample ids (unused)
+    launch_to_bf16(Q, B, d, ws->qb.p, ws->qn2.as<float>(), st);
+    // 1. sample pass: dense scores of the first Ns rows, k-th best per query -> threshold
+    launch_gemm_dist(ws->qb.p, Xb, xnorm2, B, Ns, d, Dbuf, lds, num_sms, st);
+    SelectArgs sa{};
+    sa.mode = 1; sa.dense = Dbuf; sa.ncols = Ns; sa.row_stride = lds; sa.B = B; sa.k = k;
+    sa.out_ids = ws->sbound.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>(); sa.out_count = ws->t_cnt.as<uint32_t>();
+    launch_select(sa, st);
+    launch_sample_threshold(ws->t_dist.as<float>(), ws->t_cnt.as<uint32_t>(), ws->qn2.as<float>(), xmax, d, B, k,
+                            ws->probe_A.as<float>(), st);
+    // 2. full pass with the filtering epilogue
+    LGPU_CUDA(cudaMemsetAsync(ws->amax.p, 0, (size_t)B * 4, st));
+    LGPU_CUDA(cudaMemsetAsync(ws->t_pos.p, 0xff, (size_t)B * cap * 8, st));
+    LGPU_CUDA(cudaMemsetAsync(ws->t_ids.p, 0xff, (size_t)B * cap * 8, st));
+    GemmFilter flt{};
+    flt.thr = ws->probe_A.as<float>(); flt.count = ws->amax.as<uint32_t>(); flt.cand_pos = ws->t_pos.as<uint64_t>();
+    flt.cand_ids = ws->t_ids.as<uint64_t>(); flt.col_ids = col_ids; flt.cap = cap;
+    launch_gemm_dist(ws->qb.p, Xb, xnorm2, B, N, d, nullptr, 0, num_sms, st, &flt);
+    launch_overflow_flags(ws->amax.as<uint32_t>(), cap, B, ws->flags.as<uint32_t>(), st);
+    // 3. exact re-score of the admitted rows, final top-k
+    launch_pair_distance(Q, X, ws->t_pos.as<uint64_t>(), B, cap, d, LGPU_L2, ws->t_exact.as<float>(), st);
+    SelectArgs sb{};
+    sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
+    sb.ncols = cap; sb.inner = cap; sb.row_stride = cap; sb.outer_stride = 0;
+    sb.B = B; sb.k = k; sb.out_ids = out_ids; sb.out_dist = out_dist; sb.out_count = out_cnt;
+    launch_select(sb, st);
+    // 4. fix-up of overflowed queries (no-ops otherwise)
+    launch_dist_matrix(Q, X, B, N, d, 0, nullptr, nullptr, Dbuf, ld, st, ws->flags.as<uint32_t>());
+    SelectArgs sc{};
+    sc.mode = 1; sc.dense = Dbuf; sc.ncols = N; sc.row_stride = ld; sc.col_ids = col_ids;
+    sc.B = B; sc.k = k; sc.out_ids = out_ids; sc.out_dist = out_dist; sc.out_count = out_cnt;
+    sc.only = ws->flags.as<uint32_t>();
+    launch_select(sc, st);
+}
+
 void check_params(const lgpu_search_params *p)
 {
     LGPU_REQUIRE(p != nullptr, "search params are null");
@@ -472,9 +524,16 @@ void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metri
         }
         const uint32_t kp = (uint32_t)std::min<uint64_t>(N, std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(8 * sp.k, 256)));
         if (fl->has_tc && tc_enabled() && metric == LGPU_L2 && !sp.has_lower && !sp.has_upper && b >= 8 && N >= 4096) {
-            tc_topk_l2(ws, st, fl->num_sms, q, b, fl->vectors.as<float>(), fl->vec_b.p, fl->vec_n2.as<float>(),
-                       fl->vec_max, N, fl->dim, fl->has_ids ? fl->row_ids.as<uint64_t>() : nullptr, sp.k, kp,
-                       d_ids + (size_t)q0 * sp.k, d_dist + (size_t)q0 * sp.k, d_cnt + q0, ws->D.as<float>(), ld);
+            if (N >= 262144 && !getenv("LGPU_FLAT_DENSE"))
+                tc_topk_l2_filtered(ws, st, fl->num_sms, q, b, fl->vectors.as<float>(), fl->vec_b.p,
+                                    fl->vec_n2.as<float>(), fl->vec_max, N, fl->dim,
+                                    fl->has_ids ? fl->row_ids.as<uint64_t>() : nullptr, sp.k,
+                                    d_ids + (size_t)q0 * sp.k, d_dist + (size_t)q0 * sp.k, d_cnt + q0,
+                                    ws->D.as<float>(), ld);
+            else
+                tc_topk_l2(ws, st, fl->num_sms, q, b, fl->vectors.as<float>(), fl->vec_b.p, fl->vec_n2.as<float>(),
+                           fl->vec_max, N, fl->dim, fl->has_ids ? fl->row_ids.as<uint64_t>() : nullptr, sp.k, kp,
+                           d_ids + (size_t)q0 * sp.k, d_dist + (size_t)q0 * sp.k, d_cnt + q0, ws->D.as<float>(), ld);
             continue;
         }
         launch_dist_matrix(q, fl->vectors.as<float>(), b, N, fl->dim, metric == LGPU_L2 ? 0 : (metric == LGPU_DOT ? 1 : 2),

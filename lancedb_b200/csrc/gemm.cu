@@ -115,7 +115,7 @@ constexpr uint32_t G_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                  const float *__restrict__ xnorm2, float *__restrict__ out, uint64_t ld_out, uint32_t B, uint64_t N,
-                 uint32_t num_kb)
+                 uint32_t num_kb, GemmFilter flt)
 {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // SWIZZLE_128B needs 1024 B alignment
@@ -212,7 +212,26 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (q < B) {
+                if (q < B && flt.thr) {
+                    // filtering epilogue: nothing dense is written; scores not above the per-query threshold
+                    // are appended to the query's candidate list (rare: ~1e-4 of the columns)
+                    const uint64_t xb = x0 + c0;
+                    const float thr = flt.thr[q];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const uint64_t x = xb + j;
+                        if (x < N) {
+                            const float sc = __ldg(xnorm2 + x) - 2.0f * __uint_as_float(r[j]);
+                            if (sc <= thr) {
+                                const uint32_t slot = atomicAdd(flt.count + q, 1u);
+                                if (slot < flt.cap) {
+                                    flt.cand_pos[(size_t)q * flt.cap + slot] = x;
+                                    flt.cand_ids[(size_t)q * flt.cap + slot] = flt.col_ids ? flt.col_ids[x] : x;
+                                }
+                            }
+                        }
+                    }
+                } else if (q < B) {
                     const uint64_t xb = x0 + c0;
                     if (xb + 32 <= N && ((ld_out & 3) == 0)) {
 #pragma unroll
@@ -320,7 +339,45 @@ __global__ void band_check_kernel(const float *__restrict__ approx, const uint32
     flags[q] = f;
 }
 
+// thr[q] = (k-th smallest approximate score of the sample) + 2 E_q, or +inf when the sample holds < k rows;
+// every true top-k row of the full set has a score <= thr[q] (E_q as in band_check_kernel)
+__global__ void sample_threshold_kernel(const float *__restrict__ approx, const uint32_t *__restrict__ cnt,
+                                        const float *__restrict__ qnorm2, float xmax, uint32_t d, uint32_t B, uint32_t k,
+                                        float *__restrict__ thr)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    float t = __int_as_float(0x7f800000);
+    if (cnt[q] >= k) {
+        const float qn = sqrtf(qnorm2[q]);
+        const float s = qn + xmax;
+        const float E = 0.0078125f * 1.00390625f * qn * xmax + 4.0f * (float)d * 5.9604645e-8f * s * s;
+        t = approx[(size_t)q * k + k - 1] + 2.0f * E;
+    }
+    thr[q] = t;
+}
+__global__ void overflow_flags_kernel(const uint32_t *__restrict__ count, uint32_t cap, uint32_t B, uint32_t *__restrict__ flags)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < B) flags[q] = count[q] > cap ? 1u : 0u;
+}
+
 }  // namespace
+
+void launch_sample_threshold(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
+                             uint32_t B, uint32_t k, float *thr, cudaStream_t st)
+{
+    if (B == 0) return;
+    sample_threshold_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, qnorm2, xmax, d, B, k, thr);
+    LGPU_CUDA(cudaGetLastError());
+}
+
+void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint32_t *flags, cudaStream_t st)
+{
+    if (B == 0) return;
+    overflow_flags_kernel<<<(B + 127) / 128, 128, 0, st>>>(count, cap, B, flags);
+    LGPU_CUDA(cudaGetLastError());
+}
 
 void launch_band_check(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st)
@@ -341,7 +398,7 @@ void launch_to_bf16(const float *X, uint64_t n, uint32_t d, void *Xb, float *nor
 }
 
 void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint32_t B, uint64_t N, uint32_t d,
-                      float *out, uint64_t ld_out, int num_sms, cudaStream_t st)
+                      float *out, uint64_t ld_out, int num_sms, cudaStream_t st, const GemmFilter *filter)
 {
     if (B == 0 || N == 0) return;
     LGPU_REQUIRE(gemm_shape_supported(d), "tensor-core path needs a dimension that is a multiple of 8");
@@ -350,7 +407,9 @@ void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint3
     LGPU_CUDA(cudaFuncSetAttribute(gemm_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
     const uint64_t tiles = (uint64_t)((B + GM - 1) / GM) * ((N + GN - 1) / GN);
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)num_sms);
-    gemm_dist_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK);
+    GemmFilter flt{};
+    if (filter) flt = *filter;
+    gemm_dist_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK, flt);
     LGPU_CUDA(cudaGetLastError());
 }
 

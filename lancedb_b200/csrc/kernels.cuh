@@ -129,8 +129,21 @@ bool gemm_shape_supported(uint32_t d);
 // X f32 [n][d] -> bf16 [n][d]; norm2[n] = |x|^2 (f32) if norm2 != nullptr
 void launch_to_bf16(const float *X, uint64_t n, uint32_t d, void *Xb, float *norm2, cudaStream_t st);
 // out[q][x] = xnorm2[x] - 2 * bf16(Q[q]) . bf16(X[x])   (tcgen05 + TMA), q < B, x < N
+// optional filtering epilogue: instead of writing the dense score matrix, append the columns whose score
+// is <= thr[q] to the query's candidate list (count may exceed cap: those appends are dropped)
+struct GemmFilter {
+    const float *thr;             // [B]; nullptr = dense output
+    uint32_t *count;              // [B], zeroed by the caller
+    uint64_t *cand_pos;           // [B][cap] column (storage row) of each candidate
+    uint64_t *cand_ids;           // [B][cap] its id (col_ids[x] or x)
+    const uint64_t *col_ids;      // optional
+    uint32_t cap;
+};
 void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint32_t B, uint64_t N, uint32_t d,
-                      float *out, uint64_t ld_out, int num_sms, cudaStream_t st);
+                      float *out, uint64_t ld_out, int num_sms, cudaStream_t st, const GemmFilter *filter = nullptr);
+void launch_sample_threshold(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
+                             uint32_t B, uint32_t k, float *thr, cudaStream_t st);
+void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint32_t *flags, cudaStream_t st);
 // flags[q] = 1 when the approximate shortlist of query q cannot be proven to contain the exact top-k:
 // approx[q][0..kp) ascending, cnt[q] entries valid; proven iff cnt < kp or approx[kp-1] > approx[k-1] + 2E_q,
 // E_q = 2^-7 (1+2^-8) |q| xmax + 4 d 2^-24 (|q| + xmax)^2

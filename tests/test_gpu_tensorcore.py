@@ -44,6 +44,23 @@ def test_flat_tensorcore_path_bit_exact(n, dim, B, k):
     assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
 
 
+def test_flat_tensorcore_filtered_epilogue_large_n():
+    """N >= 256k takes the sampled-threshold + filtering-epilogue path (no dense score matrix)"""
+    rng = np.random.default_rng(31)
+    n, dim = 300_000, 64
+    v = queries(rng, n, dim)
+    v[200_000] = v[7]; v[299_999] = v[7]                  # ties across the sampled and unsampled parts
+    q = queries(rng, 24, dim)
+    q[0] = v[7]
+    fl = _native.GpuFlat(v)
+    for k in (10, 40):
+        gi, gd, gc = fl.search(q, k=k)
+        oi, od, oc = oracle.flat_search(v, q, k=k, nthreads=8)
+        assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    fl.close()
+
+
 def test_flat_tensorcore_clustered_fallback():
     """near-duplicate rows make the error band overflow the shortlist -> exact fix-up path"""
     rng = np.random.default_rng(5)
