@@ -217,18 +217,29 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     // are appended to the query's candidate list (rare: ~1e-4 of the columns)
                     const uint64_t xb = x0 + c0;
                     const float thr = flt.thr[q];
+                    auto admit = [&](uint64_t x) {
+                        const uint32_t slot = atomicAdd(flt.count + q, 1u);
+                        if (slot < flt.cap) {
+                            flt.cand_pos[(size_t)q * flt.cap + slot] = x;
+                            flt.cand_ids[(size_t)q * flt.cap + slot] = flt.col_ids ? flt.col_ids[x] : x;
+                        }
+                    };
+                    if (xb + 32 <= N) {
+                        unsigned hit = 0;                                  // bit j: column xb+j passes
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const uint64_t x = xb + j;
-                        if (x < N) {
-                            const float sc = __ldg(xnorm2 + x) - 2.0f * __uint_as_float(r[j]);
-                            if (sc <= thr) {
-                                const uint32_t slot = atomicAdd(flt.count + q, 1u);
-                                if (slot < flt.cap) {
-                                    flt.cand_pos[(size_t)q * flt.cap + slot] = x;
-                                    flt.cand_ids[(size_t)q * flt.cap + slot] = flt.col_ids ? flt.col_ids[x] : x;
-                                }
-                            }
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 xn = __ldg(reinterpret_cast<const float4 *>(xnorm2 + xb + j));
+                            hit |= (xn.x - 2.0f * __uint_as_float(r[j]) <= thr ? 1u : 0u) << j;
+                            hit |= (xn.y - 2.0f * __uint_as_float(r[j + 1]) <= thr ? 1u : 0u) << (j + 1);
+                            hit |= (xn.z - 2.0f * __uint_as_float(r[j + 2]) <= thr ? 1u : 0u) << (j + 2);
+                            hit |= (xn.w - 2.0f * __uint_as_float(r[j + 3]) <= thr ? 1u : 0u) << (j + 3);
+                        }
+                        while (hit) { const int j = __ffs(hit) - 1; hit &= hit - 1; admit(xb + j); }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const uint64_t x = xb + j;
+                            if (x < N && __ldg(xnorm2 + x) - 2.0f * __uint_as_float(r[j]) <= thr) admit(x);
                         }
                     }
                 } else if (q < B) {
