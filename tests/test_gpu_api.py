@@ -1,0 +1,73 @@
+"""The reference-facing Python surface end to end on the GPU: `connect().create_table().search()...`
+with the reference's own doctest inputs (python/python/lancedb/table.py:3587-3603,
+query.py:1555-1571) and an IVF_PQ table checked against the oracle through the same builder calls."""
+import numpy as np
+import pytest
+
+import lancedb_b200 as lancedb
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def test_table_search_doctest_l2():
+    db = lancedb.connect("memory://")
+    data = [{"original_width": 100, "caption": "bar", "vector": [0.1, 2.3, 4.5]},
+            {"original_width": 2000, "caption": "foo", "vector": [0.5, 3.4, 1.3]},
+            {"original_width": 3000, "caption": "test", "vector": [0.3, 6.2, 2.6]}]
+    table = db.create_table("my_table", data)
+    out = table.search([0.4, 1.4, 2.4]).select(["caption", "original_width", "vector"]).limit(3).to_arrow()
+    assert out.schema.names == ["caption", "original_width", "vector", "_distance"]
+    assert str(out.schema.field("_distance").type) == "float"
+    rows = out.to_pylist()
+    assert [r["caption"] for r in rows] == ["foo", "bar", "test"]
+    assert f"{rows[0]['_distance']:.6f}" == "5.220000" and f"{rows[2]['_distance']:.6f}" == "23.089996"
+
+
+def test_table_search_doctest_cosine():
+    db = lancedb.connect("memory://")
+    data = [{"vector": [1.1, 1.2], "b": 2}, {"vector": [0.5, 1.3], "b": 4},
+            {"vector": [0.4, 0.4], "b": 6}, {"vector": [0.4, 0.4], "b": 10}]
+    table = db.create_table("my_table", data=data)
+    df = table.search([0.4, 0.4]).distance_type("cosine").select(["b", "vector"]).limit(3).to_pandas()
+    assert list(df["b"]) == [6, 10, 2]
+    assert [f"{d:.6f}" for d in df["_distance"]] == ["0.000000", "0.000000", "0.000944"]
+
+
+def test_exact_match_distance_zero_and_ordering():
+    # python/python/tests/test_db.py:198-199, test_query.py:562-570
+    db = lancedb.connect("memory://")
+    t = db.create_table("t", [{"vector": [1.0, 2.0], "id": 1}, {"vector": [3.0, 4.0], "id": 2}])
+    rows = t.search([1.0, 2.0]).to_list()
+    assert rows[0]["id"] == 1 and rows[0]["_distance"] == 0.0
+    assert [r["id"] for r in t.search([0.0, 0.0]).to_list()] == [1, 2]
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_ivf_pq_table_vs_oracle(metric):
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((6000, 64)).astype(np.float32)
+    db = lancedb.connect("memory://")
+    t = db.create_table("v", {"vector": x, "id": np.arange(6000)})
+    t.create_index(metric=metric, num_partitions=16, num_sub_vectors=8, max_iterations=4)
+    q = rng.standard_normal((5, 64)).astype(np.float32)
+    orc = oracle.OracleIndex.from_data(t._index_data["vector"])
+    oi, od, oc = orc.search(q, k=12, nprobes=4)          # top_k = limit + offset
+    for i in range(5):
+        out = t.search(q[i]).distance_type(metric).nprobes(4).limit(10).offset(2).with_row_id(True).to_arrow()
+        assert out["_rowid"].to_pylist() == [int(v) for v in oi[i, 2:12]]
+        assert np.array_equal(np.asarray(out["_distance"].to_pylist(), np.float32), od[i, 2:12])
+        assert out["id"].to_pylist() == out["_rowid"].to_pylist()
+    # refine_factor re-ranks with exact distances (rust/lancedb/src/query.rs:1302-1332)
+    out = t.search(q[0]).distance_type(metric).nprobes(4).refine_factor(3).limit(5).to_arrow()
+    ri, rd, rc = orc.search(q[:1], k=5, nprobes=4, refine_factor=3)
+    assert np.array_equal(np.asarray(out["_distance"].to_pylist(), np.float32), rd[0])
+    # bypass_vector_index -> exact flat search
+    flat = t.search(q[0]).distance_type(metric).bypass_vector_index().limit(5).to_arrow()
+    fi, fd, fc = oracle.flat_search(x, q[:1], k=5, metric=metric)
+    assert flat["id"].to_pylist() == [int(v) for v in fi[0]]
+    # multi-vector query: one result block per query vector, tagged with query_index
+    multi = t.search(q[:3]).distance_type(metric).nprobes(4).limit(4).to_arrow()
+    assert multi["query_index"].to_pylist() == [0] * 4 + [1] * 4 + [2] * 4
+    with pytest.raises(ValueError, match="minimum_nprobes must be greater than 0"):
+        t.search(q[0]).nprobes(0).to_arrow()
