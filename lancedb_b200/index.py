@@ -180,6 +180,17 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
     x = torch.as_tensor(vectors, dtype=torch.float32)
     if device is not None:
         x = x.to(device)
+    if x.device.type == "cpu" and torch.get_num_threads() > 16:
+        # many-core hosts with a small CPU quota: a 100+ thread OpenMP team spins instead of working
+        prev = torch.get_num_threads()
+        torch.set_num_threads(16)
+        try:
+            return train_ivf_pq(x, num_partitions=num_partitions, num_sub_vectors=num_sub_vectors,
+                                distance_type=distance_type, sample_rate=sample_rate, max_iterations=max_iterations,
+                                row_ids=row_ids, keep_vectors=keep_vectors, seed=seed, device=None,
+                                encode_chunk=encode_chunk)
+        finally:
+            torch.set_num_threads(prev)
     n, dim = x.shape
     nlist = int(num_partitions or suggested_num_partitions(n))
     m = int(num_sub_vectors or suggested_num_sub_vectors(dim))

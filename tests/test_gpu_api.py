@@ -49,7 +49,7 @@ def test_ivf_pq_table_vs_oracle(metric):
     x = rng.standard_normal((6000, 64)).astype(np.float32)
     db = lancedb.connect("memory://")
     t = db.create_table("v", {"vector": x, "id": np.arange(6000)})
-    t.create_index(metric=metric, num_partitions=16, num_sub_vectors=8, max_iterations=4)
+    t.create_index(metric=metric, num_partitions=16, num_sub_vectors=8, max_iterations=4, accelerator="cuda")
     q = rng.standard_normal((5, 64)).astype(np.float32)
     orc = oracle.OracleIndex.from_data(t._index_data["vector"])
     oi, od, oc = orc.search(q, k=12, nprobes=4)          # top_k = limit + offset
