@@ -476,47 +476,55 @@ __device__ __forceinline__ void consume_tile(const ScanArgs &a, uint32_t p, int 
 
 // Per-tile bookkeeping shared by both roles (every thread of the CTA runs it, so the two
 // __syncthreads line up across the role-specific loops).
-// Tile descriptors are fetched one tile ahead by a single consumer thread (while its warp would be
-// waiting for the first table chunk anyway) into a double-buffered shared slot, so the atomic, the
-// binary search over tile_off and the dependent loads of the query list are off the critical path.
-struct TileSlot {
-    uint32_t t;                 // 0xffffffff: no more tiles
+struct TileInfo {
     uint32_t p, row0, nrows;
     int ng;
-    uint32_t q[SCAN_G];
-    float A[SCAN_G];
-    uint64_t out[SCAN_G];
+    bool done;
 };
 
-__device__ __forceinline__ void fetch_tile(const ScanArgs &a, uint32_t total, TileSlot *slot)
+template <int NT>
+__device__ __forceinline__ TileInfo next_tile(const ScanArgs &a, uint32_t total, uint32_t *s_tile, uint32_t *s_p,
+                                              uint32_t *s_q, uint64_t *s_out, float *s_A, int tid)
 {
-    const uint32_t t = atomicAdd(a.tile_counter, 1u);
-    if (t >= total) { slot->t = 0xffffffffu; return; }
-    uint32_t lo = 0, hi = a.nlist - 1;              // smallest p with tile_off[p+1] > t
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (a.tile_off[mid + 1] > t) hi = mid; else lo = mid + 1;
+    TileInfo ti;
+    __syncthreads();                            // previous tile fully drained
+    if (tid == 0) {
+        uint32_t t = atomicAdd(a.tile_counter, 1u);
+        *s_tile = t;
+        if (t < total) {                        // smallest p with tile_off[p+1] > t
+            uint32_t lo = 0, hi = a.nlist - 1;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (a.tile_off[mid + 1] > t) hi = mid; else lo = mid + 1;
+            }
+            *s_p = lo;
+        }
     }
-    const uint32_t p = lo;
+    __syncthreads();
+    const uint32_t t = *s_tile;
+    ti.done = t >= total;
+    if (ti.done) { ti.p = 0; ti.row0 = 0; ti.nrows = 0; ti.ng = 0; return ti; }
+    const uint32_t p = *s_p;
     const uint32_t n_p = a.part_n[p];
     const uint32_t nrb = scan_nrb(n_p, a.rows_tile), rbr = scan_rb_rows(n_p, nrb);
     const uint32_t local = t - a.tile_off[p];
     const uint32_t grp = local / nrb, rb = local - grp * nrb;
-    const int ng = (int)min((uint32_t)SCAN_G, a.part_cnt[p] - grp * SCAN_G);
-    const uint32_t row0 = rb * rbr;
-    slot->p = p; slot->ng = ng; slot->row0 = row0;
-    slot->nrows = row0 < n_p ? min(rbr, n_p - row0) : 0;
-    for (int g = 0; g < SCAN_G; g++) {
-        if (g < ng) {
-            const uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + g];
-            slot->q[g] = e / a.nprobes;
-            slot->out[g] = a.seg_off[e];
-            slot->A[g] = a.tq ? a.probe_A[e] : 0.f;
+    ti.p = p;
+    ti.ng = (int)min((uint32_t)SCAN_G, a.part_cnt[p] - grp * SCAN_G);
+    ti.row0 = rb * rbr;
+    ti.nrows = ti.row0 < n_p ? min(rbr, n_p - ti.row0) : 0;
+    if (tid < SCAN_G) {
+        if (tid < ti.ng) {
+            uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + tid];
+            s_q[tid] = e / a.nprobes;
+            s_out[tid] = a.seg_off[e];
+            if (a.tq) s_A[tid] = a.probe_A[e];
         } else {
-            slot->q[g] = 0xffffffffu;
+            s_q[tid] = 0xffffffffu;
         }
     }
-    slot->t = t;
+    __syncthreads();
+    return ti;
 }
 
 // PW producer warps + CW consumer warps (both multiples of 4: setmaxnreg works on
@@ -530,38 +538,35 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
     static_assert(PW % 4 == 0 && CW % 4 == 0, "roles must be whole warpgroups");
     static_assert(PW * 32 * PREG + CW * 32 * CREG <= 65536, "register budget");
     // dynamic smem: 3 x 64 KB table ring, then 2 x [8 g][8 s][DSUB] residual chunks
-    __shared__ TileSlot s_slot[2];
+    __shared__ uint32_t s_tile, s_p;
+    __shared__ uint32_t s_q[SCAN_G];
+    __shared__ uint64_t s_out[SCAN_G];
+    __shared__ float s_A[SCAN_G];
 
     const int tid = threadIdx.x;
     const uint32_t total = *a.total_tiles;
-    constexpr int FETCHER = PW * 32;                 // first consumer thread
-    if (tid == FETCHER) fetch_tile(a, total, &s_slot[0]);
-    __syncthreads();
 
     if (tid < PW * 32) {
         if constexpr (PREG != CREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREG));
-        for (int cur = 0;; cur ^= 1) {
-            const TileSlot &ts = s_slot[cur];
-            if (ts.t == 0xffffffffu) break;
+        for (;;) {
+            Tm tf; tf.start(a);
+            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, s_A, tid);
+            if (tid == 0) { tf.stop(a, 5); if constexpr (LGPU_SCAN_TIMING_BUILD) { if (a.timing && !ti.done) atomicAdd(a.timing + 6, 1ull); } }
+            if (ti.done) break;
             Tm tt; tt.start(a);
-            if constexpr (DSUB == 0) produce_tile_copy<PW, NT>(a, ts.ng, ts.q, tid);
-            else produce_tile<DSUB, PW, NT>(a, ts.p, ts.ng, ts.q, tid);
+            if constexpr (DSUB == 0) produce_tile_copy<PW, NT>(a, ti.ng, s_q, tid);
+            else produce_tile<DSUB, PW, NT>(a, ti.p, ti.ng, s_q, tid);
             tt.stop(a, 0);
-            __syncthreads();                         // tile drained; next descriptor visible
         }
     } else {
         if constexpr (PREG != CREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREG));
         const int ct = tid - PW * 32;
-        for (int cur = 0;; cur ^= 1) {
-            const TileSlot &ts = s_slot[cur];
-            if (ts.t == 0xffffffffu) break;
-            if (tid == FETCHER) {
-                fetch_tile(a, total, &s_slot[cur ^ 1]);
-                if constexpr (LGPU_SCAN_TIMING_BUILD) { if (a.timing) atomicAdd(a.timing + 6, 1ull); }
-            }
-            const int R = (int)((ts.nrows + CT - 1) / CT);     // uniform per tile; rounded up to even
+        for (;;) {
+            TileInfo ti = next_tile<NT>(a, total, &s_tile, &s_p, s_q, s_out, s_A, tid);
+            if (ti.done) break;
+            const int R = (int)((ti.nrows + CT - 1) / CT);     // uniform per tile; rounded up to even
             Tm tt; tt.start(a);
-#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ts.p, ts.ng, ts.row0, ts.nrows, ts.out, ts.A, ct)
+#define LGPU_CONSUME(RR) consume_tile<RR, CT, NT>(a, ti.p, ti.ng, ti.row0, ti.nrows, s_out, s_A, ct)
             if (R <= 2) LGPU_CONSUME(2);
             else if (R <= 4) LGPU_CONSUME(4);
             else if (R <= 6 || RMAX <= 6) LGPU_CONSUME(6);
@@ -571,7 +576,6 @@ __global__ void __launch_bounds__((PW + CW) * 32, 1) scan_kernel(ScanArgs a)
             }
 #undef LGPU_CONSUME
             tt.stop(a, 3);
-            __syncthreads();
         }
     }
 }
