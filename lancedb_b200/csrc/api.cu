@@ -307,7 +307,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         ws->D.ensure((size_t)B * ldc * 4);
         // the bf16 error band around the nprobes-th centroid has to fit in the shortlist, so take 3x
         // nprobes (>= 64) candidates; below ~8M (query, centroid) pairs the exact kernel is as fast
-        const uint32_t kp = std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(128, 3 * nprobes));   // <= 128 selects in registers
+        const uint32_t kp = std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(64, 3 * nprobes));
         const bool big = (uint64_t)B * nlist >= ((uint64_t)1 << 23) || getenv("LGPU_FORCE_TC_COARSE");
         if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes && big) {
             // tcgen05 GEMM shortlist + exact re-score (bit-identical probe sets, see gemm.cu)
