@@ -224,11 +224,11 @@ static void tc_topk_l2(Workspace *ws, cudaStream_t st, int num_sms, const float 
 static void tc_topk_l2_filtered(Workspace *ws, cudaStream_t st, int num_sms, const float *Q, uint32_t B, const float *X,
                                 const void *Xb, const float *xnorm2, float xmax, uint64_t N, uint32_t d,
                                 const uint64_t *col_ids, uint32_t k, uint64_t *out_ids, float *out_dist,
-                                uint32_t *out_cnt, float *Dbuf, uint64_t ld)
+                                uint32_t *out_cnt, float *Dbuf, uint64_t ld, uint64_t min_sample = 65536,
+                                uint32_t cap = 1024)
 {
-    const uint64_t Ns = std::min<uint64_t>(N, std::max<uint64_t>(65536, N / 8));
+    const uint64_t Ns = std::min<uint64_t>(N, std::max<uint64_t>(min_sample, N / 8));
     const uint64_t lds = (Ns + 3) & ~3ull;               // Dbuf is [B][ld >= lds]
-    const uint32_t cap = 1024;
     ws->qb.ensure((size_t)B * d * 2); ws->qn2.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
     ws->t_ids.ensure((size_t)B * cap * 8); ws->t_dist.ensure((size_t)B * std::max<uint32_t>(k, 32) * 4);
     ws->t_pos.ensure((size_t)B * cap * 8); ws->t_cnt.ensure((size_t)B * 4); ws->t_exact.ensure((size_t)B * cap * 4);
@@ -312,10 +312,17 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes && big) {
             // tcgen05 GEMM shortlist + exact re-score (bit-identical probe sets, see gemm.cu)
             mark();
-            tc_topk_l2(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
-                       ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes, std::min(kp, nlist),
-                       ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(), ws->probe_cnt.as<uint32_t>(),
-                       ws->D.as<float>(), ldc);
+            if (nlist >= 4096 && nprobes <= 64 && !getenv("LGPU_COARSE_DENSE"))
+                // sampled threshold + filtering epilogue (as in the flat path): no 64-wide block select
+                tc_topk_l2_filtered(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
+                                    ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes,
+                                    ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(),
+                                    ws->probe_cnt.as<uint32_t>(), ws->D.as<float>(), ldc, 1024, 512);
+            else
+                tc_topk_l2(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
+                           ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes, std::min(kp, nlist),
+                           ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(), ws->probe_cnt.as<uint32_t>(),
+                           ws->D.as<float>(), ldc);
         } else {
             launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, ix->metric == LGPU_DOT ? 1 : 0,
                                nullptr, nullptr, ws->D.as<float>(), ldc, st);

@@ -61,6 +61,23 @@ def test_flat_tensorcore_filtered_epilogue_large_n():
     fl.close()
 
 
+def test_coarse_filtered_path_large_nlist(monkeypatch):
+    """nlist >= 4096: sampled threshold + filtering epilogue picks the probes; result must equal the oracle"""
+    monkeypatch.setenv("LGPU_FORCE_TC_COARSE", "1")
+    rng = np.random.default_rng(17)
+    sizes = np.full(4200, 3, np.int64); sizes[::7] = 0
+    ix = random_index(rng, dim=64, nlist=4200, m=8, sizes=sizes)
+    q = queries(rng, 40, 64)
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    for nprobes in (20, 50):
+        gi, gd, gc = gpu.search(q, k=10, nprobes=nprobes)
+        oi, od, oc = orc.search(q, k=10, nprobes=nprobes, nthreads=8)
+        assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    gpu.close()
+
+
 def test_flat_tensorcore_clustered_fallback():
     """near-duplicate rows make the error band overflow the shortlist -> exact fix-up path"""
     rng = np.random.default_rng(5)
