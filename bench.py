@@ -376,7 +376,9 @@ def main():
             "dtype": "f32", "data": DATA_DESC,
             "config": workload_config(cfg, args, world, par),
             "clocks": clocks,
-            "gpu_launches": args.steps * 7,   # dist_matrix, select(probes), 3 group kernels, scan, select(top-k)
+            # to_bf16, gemm (sample), select, threshold, gemm (filtered), overflow flags, pair distance, select,
+            # dist_matrix + select fix-ups, 3 group kernels, scan, select(top-k)
+            "gpu_launches": args.steps * 15,
             "recall_at_k": recall,
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -306,13 +306,14 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         const uint64_t ldc = (nlist + 3u) & ~3u;
         ws->D.ensure((size_t)B * ldc * 4);
         // the bf16 error band around the nprobes-th centroid has to fit in the shortlist, so take 3x
-        // nprobes (>= 64) candidates; below ~8M (query, centroid) pairs the exact kernel is as fast
+        // nprobes (>= 64) candidates (dense variant) or admit by threshold (filtered variant)
         const uint32_t kp = std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(64, 3 * nprobes));
-        const bool big = (uint64_t)B * nlist >= ((uint64_t)1 << 23) || getenv("LGPU_FORCE_TC_COARSE");
+        // from ~1M (query, centroid) pairs the tensor-core shortlist wins (C2: 0.16 vs 0.19 ms)
+        const bool big = (uint64_t)B * nlist >= ((uint64_t)1 << 20) || getenv("LGPU_FORCE_TC_COARSE");
         if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes && big) {
             // tcgen05 GEMM shortlist + exact re-score (bit-identical probe sets, see gemm.cu)
             mark();
-            if (nlist >= 4096 && nprobes <= 64 && !getenv("LGPU_COARSE_DENSE"))
+            if (nlist >= 1024 && nprobes <= 64 && !getenv("LGPU_COARSE_DENSE"))
                 // sampled threshold + filtering epilogue (as in the flat path): no 64-wide block select
                 tc_topk_l2_filtered(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
                                     ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes,
