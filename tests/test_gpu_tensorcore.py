@@ -78,6 +78,21 @@ def test_coarse_filtered_path_large_nlist(monkeypatch):
     gpu.close()
 
 
+def test_coarse_default_path_c2_shape():
+    """B x nlist >= 1M with nlist >= 1024 (BASELINE config 2's coarse shape) takes the tensor-core
+    shortlist by default; probes and final results must equal the oracle."""
+    rng = np.random.default_rng(23)
+    sizes = rng.integers(0, 9, 1024).astype(np.int64)
+    ix = random_index(rng, dim=64, nlist=1024, m=8, sizes=sizes)
+    q = queries(rng, 1100, 64)
+    gpu = _native.GpuIvfPq(ix)
+    gi, gd, gc = gpu.search(q, k=10, nprobes=20)
+    oi, od, oc = oracle.OracleIndex.from_data(ix).search(q, k=10, nprobes=20, nthreads=8)
+    gpu.close()
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
 def test_flat_tensorcore_clustered_fallback():
     """near-duplicate rows make the error band overflow the shortlist -> exact fix-up path"""
     rng = np.random.default_rng(5)
