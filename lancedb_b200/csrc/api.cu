@@ -39,12 +39,15 @@ static size_t workspace_budget()
     return v;
 }
 
+static thread_local uint64_t g_alloc_epoch = 0;   // bumped by every workspace (re)allocation on this thread
+
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     void ensure(size_t n)
     {
         if (n <= bytes) return;
+        g_alloc_epoch++;
         if (p) { cudaFree(p); p = nullptr; bytes = 0; }
         size_t want = n + n / 8;
         LGPU_CUDA(cudaMalloc(&p, want));
@@ -64,6 +67,10 @@ struct Workspace {
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
     DevBuf timing;
+    // CUDA graph of one host-buffer search (lgpu_search): the ~15 launches of a batch replayed as one
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_key[4] = {0, 0, 0, 0};
+    int graph_state = 0;                // 0: next call runs eagerly (warm-up), 1: capture, 2: replay, -1: disabled
     DevBuf tq, sbound, probe_A, amax;   // two-pass scan: per-query tables, bounds, per-probe scalars
     Workspace()
     {
@@ -73,6 +80,7 @@ struct Workspace {
     }
     ~Workspace()
     {
+        if (graph) cudaGraphExecDestroy(graph);
         if (stream) cudaStreamDestroy(stream);
         if (done) cudaEventDestroy(done);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
@@ -578,23 +586,87 @@ void require_device(int device)
 }
 
 // host-buffer wrapper: stage in, run, stage out, synchronise
+static bool graphs_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LGPU_NO_GRAPH"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
+// host-buffer wrapper: stage in, run, stage out, synchronise.  `key` identifies the launch sequence
+// (shapes + parameters): the second call with the same key is captured into a CUDA graph and later calls
+// replay it, which removes ~15 launch latencies from the synchronous end-to-end path.  Any workspace
+// (re)allocation, profiling mode, or a failed capture falls back to eager launches.
 template <class Run>
 void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t dim, uint32_t k, uint64_t *out_ids,
-               float *out_dist, uint32_t *out_count, Run &&run)
+               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], Run &&run)
 {
     WsLease lease(pool, nullptr, false);
     Workspace *ws = lease.ws;
     cudaStream_t st = lease.st;
+    const uint64_t epoch0 = g_alloc_epoch;
     ws->q.ensure(std::max<size_t>((size_t)B * dim, 1) * 4);
     ws->out_ids.ensure(std::max<size_t>((size_t)B * k, 1) * 8);
     ws->out_dist.ensure(std::max<size_t>((size_t)B * k, 1) * 4);
     ws->out_count.ensure(std::max<size_t>(B, 1) * 4);
     LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
-    run(ws, st, ws->q.as<float>(), ws->out_ids.as<uint64_t>(), ws->out_dist.as<float>(), ws->out_count.as<uint32_t>());
+    auto eager = [&] {
+        run(ws, st, ws->q.as<float>(), ws->out_ids.as<uint64_t>(), ws->out_dist.as<float>(), ws->out_count.as<uint32_t>());
+    };
+    const bool same = memcmp(key, ws->graph_key, sizeof(key)) == 0;
+    if (!graphs_enabled() || profiling_enabled() || ws->graph_state < 0) {
+        eager();
+    } else if (!same) {                                     // new shape: warm up (allocations), capture next time
+        if (ws->graph) { cudaGraphExecDestroy(ws->graph); ws->graph = nullptr; }
+        memcpy(ws->graph_key, key, sizeof(key));
+        ws->graph_state = 0;
+        eager();
+        if (g_alloc_epoch == epoch0 || true) ws->graph_state = 1;
+    } else if (ws->graph_state == 2 && g_alloc_epoch == epoch0) {
+        LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
+    } else if (ws->graph_state == 1) {
+        bool ok = false;
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            try {
+                eager();
+                ok = cudaStreamEndCapture(st, &g) == cudaSuccess && g != nullptr && g_alloc_epoch == epoch0;
+            } catch (const Failure &) {
+                cudaStreamEndCapture(st, &g);
+                ok = false;
+            }
+        }
+        if (ok && cudaGraphInstantiate(&ws->graph, g, 0) == cudaSuccess) {
+            ws->graph_state = 2;
+            cudaGraphDestroy(g);
+            LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
+        } else {                                            // never try again with this workspace
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            ws->graph = nullptr;
+            ws->graph_state = -1;
+            LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
+            eager();
+        }
+    } else {                                                // state 2 but buffers moved: re-warm
+        if (ws->graph) { cudaGraphExecDestroy(ws->graph); ws->graph = nullptr; }
+        ws->graph_state = 1;
+        eager();
+    }
     LGPU_CUDA(cudaMemcpyAsync(out_ids, ws->out_ids.p, (size_t)B * k * 8, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaMemcpyAsync(out_dist, ws->out_dist.p, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaMemcpyAsync(out_count, ws->out_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaStreamSynchronize(st));
+}
+
+static inline void make_key(uint64_t (&key)[4], uint64_t tag, uint32_t B, const lgpu_search_params &p)
+{
+    uint32_t lo, hi;
+    memcpy(&lo, &p.lower, 4); memcpy(&hi, &p.upper, 4);
+    key[0] = tag ^ ((uint64_t)B << 32);
+    key[1] = (uint64_t)p.k | ((uint64_t)p.nprobes << 32);
+    key[2] = (uint64_t)p.refine_factor | ((uint64_t)(p.has_lower ? 1 : 0) << 32) | ((uint64_t)(p.has_upper ? 1 : 0) << 33);
+    key[3] = (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
 }  // namespace
@@ -791,7 +863,9 @@ int lgpu_search(lgpu_index *ix, const float *queries, uint32_t B, const lgpu_sea
         check_ivf_call(ix, queries, B, params, out_ids, out_dist, out_count);
         if (B == 0) return;
         require_device(ix->device);
-        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count,
+        uint64_t key[4];
+        make_key(key, 0x1f5ull, B, *params);
+        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key,
                   [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
                       ivf_search_device(ix, ws, st, dq, B, *params, di, dd, dc);
                   });
@@ -881,7 +955,9 @@ int lgpu_flat_search(lgpu_flat *fl, int metric, const float *queries, uint32_t B
         check_flat_call(fl, metric, queries, B, params, out_ids, out_dist, out_count);
         if (B == 0) return;
         require_device(fl->device);
-        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count,
+        uint64_t key[4];
+        make_key(key, 0xf1a7ull + (uint64_t)metric, B, *params);
+        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count, key,
                   [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
                       flat_search_device(fl, ws, st, metric, dq, B, *params, di, dd, dc);
                   });
