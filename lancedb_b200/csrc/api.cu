@@ -62,7 +62,7 @@ struct Workspace {
     cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
     cudaEvent_t ev[8] = {};
     DevBuf q, qn, xnorm, D, probes, probe_dist, probe_cnt;
-    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars;
+    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars, tile_desc;
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
@@ -109,6 +109,7 @@ using namespace lgpu;
 struct lgpu_index {
     int device = 0, num_sms = 0;
     uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0, rows_tile = SCAN_ROWS_TILE_MID;
+    uint32_t max_nrb = 1;          // row blocks of the largest partition (bounds the tile count)
     int metric = 0;
     uint64_t nrows = 0, device_bytes = 0;
     DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
@@ -164,6 +165,13 @@ static bool two_pass_enabled()
 {
     const char *e = getenv("LGPU_TWO_PASS");
     return e && e[0] == '1';
+}
+
+// LGPU_SCAN_V1=1 selects the round-1 scan kernel (scan.cu, per-tile drain) instead of the streaming one
+static bool scan_v2_enabled()
+{
+    const char *e = getenv("LGPU_SCAN_V1");
+    return !(e && e[0] == '1');
 }
 
 static bool tc_enabled()
@@ -365,6 +373,15 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     ga.qlist = ws->qlist.as<uint32_t>();
     ga.total_tiles = ws->scalars.as<uint32_t>(); ga.tile_counter = ws->scalars.as<uint32_t>() + 1;
     ga.scanned_rows = reinterpret_cast<unsigned long long *>(ws->scalars.as<char>() + 16);
+    // streaming scan kernel (scan2.cu): tile descriptors, sized by a host bound on the tile count
+    // sum_p ceil(cnt_p / 8) * nrb_p <= (slots / 8 + #probed partitions) * max_p nrb_p
+    const bool scan_v2 = scan_v2_enabled() && ix->rows_tile == SCAN_ROWS_TILE_MID;
+    if (scan_v2) {
+        uint64_t max_tiles = ((uint64_t)slots / SCAN_G + std::min<uint64_t>(nlist, slots) + 1) * ix->max_nrb;
+        LGPU_REQUIRE(max_tiles < (1ull << 31), "batch too large for one scan launch");
+        ws->tile_desc.ensure((size_t)max_tiles * sizeof(TileDesc));
+        ga.tile_desc = ws->tile_desc.as<TileDesc>(); ga.max_tiles = (uint32_t)max_tiles;
+    }
     launch_group(ga, st);
     mark();
     // ---- K2+K3: fused distance-table build + code scan ----
@@ -381,6 +398,11 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
     sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
     sc.dist_out = ws->dist_out.as<float>();
+    sc.tile_desc = ga.tile_desc;
+    auto run_exact_scan = [&]() {
+        if (scan_v2) launch_scan2(sc, ix->dsub, ix->num_sms, st);
+        else launch_scan(sc, ix->dsub, ix->num_sms, st);
+    };
     static const bool scalar_table = getenv("LGPU_SCALAR_TABLE") != nullptr;
     sc.scalar_table = scalar_table ? 1 : 0;
     static const bool scan_timing = getenv("LGPU_SCAN_TIMING") != nullptr;
@@ -433,7 +455,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         ga.only = ws->flags.as<uint32_t>();
         launch_group(ga, st);
         sc.tq = nullptr;
-        launch_scan(sc, ix->dsub, ix->num_sms, st);
+        run_exact_scan();
         SelectArgs sf = sa;
         sf.k = sp.k; sf.out_ids = d_ids; sf.out_dist = d_dist; sf.out_count = d_cnt; sf.out_pos = nullptr;
         sf.only = ws->flags.as<uint32_t>();
@@ -441,7 +463,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         mark(); mark();
         return;
     }
-    launch_scan(sc, ix->dsub, ix->num_sms, st);
+    run_exact_scan();
     mark();
     if (!d_ids) { mark(); mark(); return; }     // debug: distances only
     // ---- K4: top-k ----
@@ -589,7 +611,7 @@ void require_device(int device)
 static bool graphs_enabled()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("LGPU_NO_GRAPH"); v = (e && e[0] == '1') ? 0 : 1; }
+    if (v < 0) { const char *e = getenv("LGPU_GRAPH"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
 
@@ -621,7 +643,7 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
         memcpy(ws->graph_key, key, sizeof(key));
         ws->graph_state = 0;
         eager();
-        if (g_alloc_epoch == epoch0 || true) ws->graph_state = 1;
+        ws->graph_state = 1;
     } else if (ws->graph_state == 2 && g_alloc_epoch == epoch0) {
         LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
     } else if (ws->graph_state == 1) {
@@ -745,6 +767,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
                 if (v == SCAN_ROWS_TILE_MID || v == SCAN_ROWS_TILE_LARGE) ix->rows_tile = v;
             }
         }
+        for (uint32_t p = 0; p < nlist; p++) ix->max_nrb = std::max(ix->max_nrb, scan_nrb(part_n[p], ix->rows_tile));
         std::sort(pads.begin(), pads.end(), std::greater<uint64_t>());
         ix->pad_prefix.assign(nlist + 1, 0);
         for (uint32_t p = 0; p < nlist; p++) ix->pad_prefix[p + 1] = ix->pad_prefix[p] + pads[p];

@@ -107,6 +107,40 @@ __global__ void group_fill_kernel(GroupArgs a)
     if (a.slot_pos[slot] != 0xffffffffu) a.qlist[a.qlist_off[p] + a.slot_pos[slot]] = slot;
 }
 
+// 8 threads per tile (one per query slot of the group): tile t -> (partition, query group, row block),
+// the same arithmetic scan.cu::next_tile does on the fly.  Tiles are numbered partition-major.
+__global__ void tile_desc_kernel(GroupArgs a)
+{
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = gid / SCAN_G, g = gid % SCAN_G;
+    const uint32_t total = *a.total_tiles;
+    if (t >= total || t >= a.max_tiles) return;
+    uint32_t lo = 0, hi = a.nlist - 1;          // smallest p with tile_off[p+1] > t
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (a.tile_off[mid + 1] > t) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t p = lo;
+    const uint32_t n_p = a.part_n[p];
+    const uint32_t nrb = scan_nrb(n_p, a.rows_tile), rbr = scan_rb_rows(n_p, nrb);
+    const uint32_t local = t - a.tile_off[p];
+    const uint32_t grp = local / nrb, rb = local - grp * nrb;
+    const uint32_t ng = min((uint32_t)SCAN_G, a.part_cnt[p] - grp * SCAN_G);
+    const uint32_t row0 = rb * rbr;
+    TileDesc *d = a.tile_desc + t;
+    if (g == 0) {
+        d->p = p; d->row0 = row0; d->nrows = row0 < n_p ? min(rbr, n_p - row0) : 0; d->ng = ng;
+    }
+    if (g < ng) {
+        const uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + g];
+        d->q[g] = e / a.nprobes;
+        d->out[g] = a.seg_off[e];
+    } else {
+        d->q[g] = 0xffffffffu;
+        d->out[g] = 0;
+    }
+}
+
 }  // namespace
 
 void launch_group(const GroupArgs &a, cudaStream_t st)
@@ -118,6 +152,10 @@ void launch_group(const GroupArgs &a, cudaStream_t st)
     group_scan_kernel<<<1, 1024, 0, st>>>(a);
     uint32_t slots = a.B * a.nprobes;
     group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a);
+    if (a.tile_desc && a.max_tiles) {
+        uint64_t threads = (uint64_t)a.max_tiles * SCAN_G;
+        tile_desc_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+    }
     LGPU_CUDA(cudaGetLastError());
 }
 

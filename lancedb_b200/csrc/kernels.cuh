@@ -22,6 +22,16 @@ __host__ __device__ __forceinline__ uint32_t scan_rb_rows(uint32_t n, uint32_t n
     return nrb ? (((n + nrb - 1) / nrb + 31u) & ~31u) : 0u;
 }
 
+// One scan tile, precomputed by the regroup step (group.cu) so the persistent scan CTAs fetch a tile with a
+// single 112-byte read: partition p, rows [row0, row0+nrows), ng (1..8) queries q[] whose distances go to
+// dist_out + out[g].  ng == 0 marks "no tile" inside the kernel's shared-memory copy.
+struct alignas(16) TileDesc {
+    uint32_t p, row0, nrows, ng;
+    uint32_t q[SCAN_G];
+    uint64_t out[SCAN_G];
+};
+static_assert(sizeof(TileDesc) == 112, "TileDesc layout");
+
 struct ScanArgs {
     // index (device)
     const float *centroids;       // [nlist][dim]
@@ -44,6 +54,7 @@ struct ScanArgs {
     const uint32_t *total_tiles;  // [1]
     uint32_t *tile_counter;       // [1], zeroed before launch
     float *dist_out;
+    const TileDesc *tile_desc;    // [total_tiles] (streaming kernel, scan2.cu)
     // approximate pass (tables.cu); tq == nullptr selects the exact kernel
     const float *tq;              // [B][nch][256][8] per-query tables |q_i - codebook_i[c]|^2
     const float *probe_A;         // [B*nprobes] |q - c_p|^2 - |q|^2
@@ -54,6 +65,9 @@ struct ScanArgs {
 };
 bool scan_dsub_supported(uint32_t dsub);
 void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
+// streaming variant (scan2.cu): tiles flow through the table ring without a per-tile drain; exact pass only,
+// rows_tile == SCAN_ROWS_TILE_MID, needs a.tile_desc
+void launch_scan2(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
 
 // ---------------- batch preparation (grouping probes by partition) ----------------
 struct GroupArgs {
@@ -72,6 +86,8 @@ struct GroupArgs {
     uint32_t *tile_counter;       // [1]
     unsigned long long *scanned_rows;  // [1] sum over probe slots of n_p (roofline bytes / m)
     const uint32_t *only;         // optional [B]: regroup only the flagged queries (fix-up pass)
+    TileDesc *tile_desc;          // optional [max_tiles] tile descriptors for the streaming scan kernel
+    uint32_t max_tiles;           // capacity of tile_desc (host bound on the tile count)
 };
 void launch_group(const GroupArgs &a, cudaStream_t st);
 

@@ -1,0 +1,470 @@
+// scan2.cu -- K2+K3, streaming form: the same arithmetic and the same shared-memory table ring as
+// scan.cu (bit-identical results; see that file for the layout, the skewed code stream and the
+// reference citations [lance, recalled; SURVEY.md 8a rows a4-a7]), re-pipelined after the ncu stall
+// profile of round 1 (profiles/r01_scan_stalls.txt):
+//
+//   * no per-tile drain.  scan.cu ends every tile with a CTA-wide barrier (fetch the next tile, refill the
+//     pipeline): the table builders idle ~16 % of the time while the scanners finish.  Here the stage
+//     counter runs on across tiles -- the all-zero "stage nch" of tile n doubles as the "stage -1" of
+//     tile n+1 -- and tile descriptors (precomputed by group.cu::tile_desc_kernel) are claimed two tiles
+//     ahead by producer warp 0 into a 4-slot shared ring, so neither role ever waits for a fetch.
+//   * 8 builder warps + 8 scanner warps; the scanners are split by query half (warps 0-3: queries 0-3,
+//     warps 4-7: queries 4-7 of the tile).  A scanner thread carries 12 rows x 4 queries of accumulators
+//     (48 registers instead of 96), which leaves room to keep a dozen LDS.128 in flight, and there are two
+//     scanner warps per scheduler instead of one.
+//   * the table build is straight-line code: 16 (or 8) tasks per warp and chunk, no bounds checks, the
+//     metric and the half count are template parameters, codebook entries are prefetched three tasks
+//     ahead across chunk and tile boundaries (the codebook does not depend on the tile).
+//   * tiles with <= 4 queries use a 4-codes-per-warp mapping (HALVES = 1): half the build work instead of
+//     idle lanes.
+#include "kernels.cuh"
+#include "scan_common.cuh"
+
+namespace lgpu {
+
+namespace {
+
+constexpr int S2_PW = 8, S2_CW = 8;                 // builder / scanner warps
+constexpr int S2_PT = S2_PW * 32, S2_NT = (S2_PW + S2_CW) * 32;
+constexpr int S2_CT = 128;                          // scanner threads per query half
+constexpr int S2_RMAX = 12;                         // rows per scanner thread: 128 * 12 = SCAN_ROWS_TILE_MID
+constexpr int S2_PREG = 104, S2_CREG = 152;         // 256 * 104 + 256 * 152 = 65536 registers
+constexpr int S2_SLOTS = 4;                         // tile-descriptor ring
+constexpr int S2_SLOT_BYTES = 128;
+constexpr int S2_PF = 3;                            // codebook prefetch distance (tasks)
+static_assert(SCAN_ROWS_TILE_MID == S2_CT * S2_RMAX, "rows_tile");
+static_assert(S2_PT * S2_PREG + S2_CW * 32 * S2_CREG <= 65536, "register budget");
+
+__device__ __forceinline__ int ring_next(int b) { return b == 2 ? 0 : b + 1; }
+
+// ---------------------------------------------------------------- shared-memory carve-up
+template <int DSUB>
+struct Smem {
+    static constexpr int RB = SCAN_G * 8 * DSUB;                     // floats per residual chunk [g][s][e]
+    static constexpr size_t LUT = 0;
+    static constexpr size_t RBUF = 3 * (size_t)SCAN_LUT_BYTES;
+    static constexpr size_t TILES = RBUF + 2 * (size_t)RB * sizeof(float);
+    static constexpr size_t TOTAL = TILES + S2_SLOTS * S2_SLOT_BYTES;
+};
+
+__device__ __forceinline__ const TileDesc *slot_ptr(const unsigned char *tiles, uint32_t n)
+{
+    return reinterpret_cast<const TileDesc *>(tiles + (n & (S2_SLOTS - 1)) * S2_SLOT_BYTES);
+}
+
+// ---------------------------------------------------------------- builder (producer) side
+template <int DSUB>
+struct Resid {
+    static constexpr int RB = Smem<DSUB>::RB;
+    static constexpr int RPT = (RB + S2_PT - 1) / S2_PT;
+    float v[RPT];
+    // global loads of residual chunk `ch` of tile T (q - centroid, or q for dot) into registers
+    template <bool DOT>
+    __device__ __forceinline__ void load(const ScanArgs &a, const TileDesc *T, uint32_t ch, int tid)
+    {
+        const uint32_t p = T->p;
+        const int ng = (int)T->ng;
+        const float *cenp = a.centroids + (size_t)p * a.dim;
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            const int idx = tid + u * S2_PT;
+            float r = 0.f;
+            if (idx < RB) {
+                const int g = idx / (8 * DSUB), rem = idx - g * (8 * DSUB);
+                const int ss = rem / DSUB, e = rem - ss * DSUB;
+                const uint32_t i = ch * 8 + ss;
+                if (g < ng && i < a.m) {
+                    const uint32_t dimi = i * DSUB + e;
+                    const float qv = __ldg(a.queries + (size_t)T->q[g] * a.dim + dimi);
+                    r = DOT ? qv : __fsub_rn(qv, __ldg(cenp + dimi));
+                }
+            }
+            v[u] = r;
+        }
+    }
+    __device__ __forceinline__ void store(float *dst, int tid) const
+    {
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            const int idx = tid + u * S2_PT;
+            if (idx < RB) dst[idx] = v[u];
+        }
+    }
+};
+
+// Codebook entries of the next S2_PF tasks, carried across chunk / tile boundaries (DSUB == 8 only).
+struct CbRing {
+    float4 v[S2_PF + 1][2];
+};
+
+// address of the codebook entry of task k in chunk ch: [ch][c][s][8], c = CPT * (pw + 8 k) + csel
+template <int CPT>
+__device__ __forceinline__ const float4 *cb_task_ptr(const ScanArgs &a, uint32_t ch, int pw, int lane, int k)
+{
+    const int s = lane & 7;
+    const int csel = (CPT == 2) ? (lane >> 4) : (lane >> 3);
+    const int c = CPT * (pw + S2_PW * k) + csel;
+    return reinterpret_cast<const float4 *>(a.cb_tiled + (((size_t)ch * 256 + c) * 8 + s) * 8);
+}
+
+// Build one 8-sub-space chunk of the distance table into ring buffer `b`.
+//   HALVES == 2: lane -> (s = lane & 7, h = (lane >> 3) & 1, cc = lane >> 4); a warp task covers 2 codes
+//                x 8 sub-spaces x both query halves; 16 tasks per warp.
+//   HALVES == 1: lane -> (s = lane & 7, cq = lane >> 3); a warp task covers 4 codes x 8 sub-spaces for
+//                queries 0-3; 8 tasks per warp.
+// `ring` holds the codebook entries of tasks 0..PF-1 on entry and those of the first PF tasks of chunk
+// `ch_next` (mapping `cpt_next`) on exit.
+template <int DSUB, bool DOT, int HALVES>
+__device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int b, int rslot, CbRing &ring,
+                                            uint32_t ch_next, int cpt_next, int pw, int lane)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];      // declared here so every access is a plain
+    unsigned char *const lut = smem + Smem<DSUB>::LUT;           // shared-space LDS/STS
+    const float *const rsrc_chunk = reinterpret_cast<const float *>(smem + Smem<DSUB>::RBUF) + rslot * Smem<DSUB>::RB;
+    constexpr int CPT = HALVES == 2 ? 2 : 4;
+    constexpr int NTASK = 256 / CPT / S2_PW;                   // 16 or 8
+    static_assert(NTASK % (S2_PF + 1) == 0, "the prefetch ring must keep its phase across chunks");
+    const int s = lane & 7;
+    const int h = HALVES == 2 ? ((lane >> 3) & 1) : 0;
+    const int csel = HALVES == 2 ? (lane >> 4) : (lane >> 3);
+    const bool sub_ok = (ch * 8 + s) < a.m;
+    const float *rsrc = rsrc_chunk + ((4 * h) * 8 + s) * DSUB;                // + j * 8 * DSUB per query
+    unsigned char *dst = lut + b * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16 + (CPT * pw + csel) * 128;
+    constexpr int DST_STRIDE = CPT * S2_PW * 128;                              // bytes between tasks
+
+    if constexpr (DSUB == 8) {
+        uint64_t pr[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float4 lo = *reinterpret_cast<const float4 *>(rsrc + j * 64);
+            const float4 hi = *reinterpret_cast<const float4 *>(rsrc + j * 64 + 4);
+            pr[j][0] = pk2(lo.x, lo.y); pr[j][1] = pk2(lo.z, lo.w);
+            pr[j][2] = pk2(hi.x, hi.y); pr[j][3] = pk2(hi.z, hi.w);
+        }
+        const float4 *cb_here = cb_task_ptr<CPT>(a, ch, pw, lane, 0);
+        constexpr int CB_STRIDE = CPT * S2_PW * 8 * 8 / 4;                     // float4 between tasks
+        const float4 *cb_nx = (cpt_next == 2) ? cb_task_ptr<2>(a, ch_next, pw, lane, 0)
+                                              : cb_task_ptr<4>(a, ch_next, pw, lane, 0);
+        const int nx_stride = cpt_next * S2_PW * 8 * 8 / 4;
+#pragma unroll
+        for (int k = 0; k < NTASK; k++) {
+            // issue the load of task k + PF (this chunk, or the head of the next one)
+            {
+                constexpr int RS = S2_PF + 1;
+                const int slot = (k + S2_PF) % RS;
+                if (k + S2_PF < NTASK) {
+                    const float4 *src = cb_here + (size_t)(k + S2_PF) * CB_STRIDE;
+                    ring.v[slot][0] = __ldg(src); ring.v[slot][1] = __ldg(src + 1);
+                } else {
+                    const float4 *src = cb_nx + (size_t)(k + S2_PF - NTASK) * nx_stride;
+                    ring.v[slot][0] = __ldg(src); ring.v[slot][1] = __ldg(src + 1);
+                }
+            }
+            const float4 c0 = ring.v[k % (S2_PF + 1)][0], c1 = ring.v[k % (S2_PF + 1)][1];
+            float4 out;
+            if constexpr (!DOT) {
+                const uint64_t pc[4] = {pk2(c0.x, c0.y), pk2(c0.z, c0.w), pk2(c1.x, c1.y), pk2(c1.z, c1.w)};
+                out = l2_tree8_packed_x4(pr, pc, a.fzero2);      // zero-padded codebook & residual => +0 past m
+            } else {
+                const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float rr[8];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) upk2(pr[j][e], rr[2 * e], rr[2 * e + 1]);
+                    o[j] = sub_ok ? subvec_dot_dist<8>(rr, cv) : 0.f;
+                }
+                out = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            *reinterpret_cast<float4 *>(dst + k * DST_STRIDE) = out;
+        }
+    } else {
+        (void)ring; (void)ch_next; (void)cpt_next;
+        const float *cbp = a.cb_tiled + (((size_t)ch * 256 + CPT * pw + csel) * 8 + s) * DSUB;
+        for (int k = 0; k < NTASK; k++) {
+            float cbv[DSUB], rr[DSUB], o[4] = {0.f, 0.f, 0.f, 0.f};
+            load_vec<DSUB>(cbv, cbp + (size_t)k * CPT * S2_PW * 8 * DSUB);
+            if (sub_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+#pragma unroll
+                    for (int e = 0; e < DSUB; e++) rr[e] = rsrc[j * 8 * DSUB + e];
+                    o[j] = DOT ? subvec_dot_dist<DSUB>(rr, cbv) : subvec_l2<DSUB>(rr, cbv);
+                }
+            }
+            *reinterpret_cast<float4 *>(dst + k * DST_STRIDE) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+template <int DSUB, bool DOT>
+__device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total, int tid)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *const lut = smem + Smem<DSUB>::LUT;
+    float *const rbuf = reinterpret_cast<float *>(smem + Smem<DSUB>::RBUF);
+    unsigned char *const tiles = smem + Smem<DSUB>::TILES;
+    constexpr int RB = Smem<DSUB>::RB;
+    const int lane = tid & 31, pw = tid >> 5;
+    const uint32_t nch = a.nch;
+
+    Resid<DSUB> res;
+    CbRing ring;
+    {   // first tile: residual chunk 0 and the head of the codebook prefetch ring
+        const TileDesc *T0 = slot_ptr(tiles, 0);
+        if (T0->ng) {
+            res.template load<DOT>(a, T0, 0, tid);
+            res.store(rbuf, tid);
+            if constexpr (DSUB == 8) {
+                const bool two = T0->ng > 4;
+#pragma unroll
+                for (int k = 0; k < S2_PF; k++) {
+                    const float4 *src = two ? cb_task_ptr<2>(a, 0, pw, lane, k) : cb_task_ptr<4>(a, 0, pw, lane, k);
+                    ring.v[k][0] = __ldg(src); ring.v[k][1] = __ldg(src + 1);
+                }
+            }
+        }
+    }
+    bar_sync(BAR_PROD, S2_PT);
+
+    int b = 0;                 // ring buffer of the current stage
+    uint32_t gs = 0;           // stages issued so far (only "< 2" matters)
+    for (uint32_t n = 0;; n++) {
+        const TileDesc *T = slot_ptr(tiles, n);
+        const int ng = (int)T->ng;
+        if (ng == 0) break;
+        const TileDesc *Tn = slot_ptr(tiles, n + 1);
+        const int ng_next = (int)Tn->ng;
+        uint32_t t_claim = 0, t_word = 0;
+        for (uint32_t ch = 0; ch <= nch; ch++) {
+            // --- tile look-ahead (warp 0): claim at stage 0, read the descriptor at stage 1 ---
+            if (pw == 0) {
+                if (ch == 0) {
+                    if (lane == 0) t_claim = atomicAdd(a.tile_counter, 1u);
+                    t_claim = __shfl_sync(0xffffffffu, t_claim, 0);
+                } else if (ch == 1) {
+                    t_word = 0;
+                    if (lane < (int)(sizeof(TileDesc) / 4) && t_claim < total)
+                        t_word = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t_claim) + lane);
+                }
+            }
+            // --- residual prefetch: next chunk of this tile, or chunk 0 of the next tile ---
+            const bool res_here = ch + 1 < nch;
+            const bool res_next = (ch == nch) && ng_next != 0;
+            if (res_here) res.template load<DOT>(a, T, ch + 1, tid);
+            else if (res_next) res.template load<DOT>(a, Tn, 0, tid);
+
+            if (gs >= 2) bar_sync(BAR_EMPTY + b, S2_NT);          // scanners are done with stage gs-2
+            if (ch == nch) {                                       // all-zero row for the lagging lanes
+                if (tid < 64)
+                    reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+            } else {
+                const uint32_t ch_next = ch + 1 < nch ? ch + 1 : 0;
+                const int cpt_next = ch + 1 < nch ? (ng > 4 ? 2 : 4) : (ng_next > 4 ? 2 : 4);
+                if (ng > 4) build_chunk<DSUB, DOT, 2>(a, ch, b, (int)(ch & 1), ring, ch_next, cpt_next, pw, lane);
+                else build_chunk<DSUB, DOT, 1>(a, ch, b, (int)(ch & 1), ring, ch_next, cpt_next, pw, lane);
+            }
+            if (pw == 0 && ch == 1 && lane < (int)(sizeof(TileDesc) / 4))   // publish tile n+2 before FULL(stage 1)
+                reinterpret_cast<uint32_t *>(const_cast<TileDesc *>(slot_ptr(tiles, n + 2)))[lane] = t_word;
+            bar_arrive(BAR_FULL + b, S2_NT);
+            if (res_here) res.store(rbuf + ((ch + 1) & 1) * RB, tid);
+            else if (res_next) res.store(rbuf, tid);
+            bar_sync(BAR_PROD, S2_PT);
+            b = ring_next(b);
+            gs++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scanner (consumer) side
+// R rows per thread (row = row0 + ct + r * 128), the 4 queries of half h.  R == 0: this half has no
+// queries in the tile; the thread only keeps the barrier protocol going.
+template <int DSUB, int R>
+__device__ __forceinline__ int consume_tile(const ScanArgs &a, const TileDesc *T, bool next_exists, int b, int h,
+                                            int ct)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const unsigned char *const lut_half = smem + Smem<DSUB>::LUT + h * SCAN_LUT_HALF;
+    const uint32_t nch = a.nch;
+    const uint32_t p = T->p, row0 = T->row0, nrows = T->nrows;
+    const int ng = (int)T->ng;
+    const int sig = ct & 7;                               // this lane's skew (== row % 8)
+    const uint32_t n_p = a.part_n[p], npad = a.part_npad[p];
+    const uint2 *cs = reinterpret_cast<const uint2 *>(a.codes + a.code_base[p]);   // [nch+1][npad]
+
+    constexpr int RR = R > 0 ? R : 1;
+    float acc[RR][4];
+    bool valid[RR];
+    uint2 wn[RR];
+#pragma unroll
+    for (int r = 0; r < RR; r++) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) acc[r][g] = 0.f;
+        const uint32_t row = row0 + ct + r * S2_CT;
+        valid[r] = R > 0 && row < row0 + nrows && row < n_p;
+        wn[r] = valid[r] ? __ldg(cs + row) : make_uint2(0u, 0u);
+    }
+
+    for (uint32_t it = 0; it <= nch; it++) {
+        uint2 w[RR];
+#pragma unroll
+        for (int r = 0; r < RR; r++) w[r] = wn[r];
+        if (R > 0 && it < nch) {                           // prefetch the next block of code bytes
+#pragma unroll
+            for (int r = 0; r < RR; r++) {
+                const uint32_t row = row0 + ct + r * S2_CT;
+                wn[r] = valid[r] ? __ldg(cs + (size_t)(it + 1) * npad + row) : make_uint2(0u, 0u);
+            }
+        }
+        bar_sync(BAR_FULL + b, S2_NT);
+        const int bp = b == 0 ? 2 : b - 1;                 // buffer of the previous stage
+        if (R > 0) {
+            const uint32_t base_cur = (uint32_t)b * SCAN_LUT_BYTES;
+            const uint32_t base_prev = (uint32_t)bp * SCAN_LUT_BYTES;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const uint32_t off = ((e < sig) ? base_prev : base_cur) + (((e - sig) & 7) << 4);
+#pragma unroll
+                for (int r = 0; r < RR; r++) {
+                    const uint32_t word = (e < 4) ? w[r].x : w[r].y;
+                    const uint32_t c = (word >> (8 * (e & 3))) & 0xffu;
+                    const float4 v = *reinterpret_cast<const float4 *>(lut_half + off + (c << 7));
+                    acc[r][0] = __fadd_rn(acc[r][0], v.x);
+                    acc[r][1] = __fadd_rn(acc[r][1], v.y);
+                    acc[r][2] = __fadd_rn(acc[r][2], v.z);
+                    acc[r][3] = __fadd_rn(acc[r][3], v.w);
+                }
+            }
+        }
+        // the previous stage's buffer is free again; the builders wait for it iff they still have a stage
+        // (this tile's or the next tile's) to put there
+        if (it + 2 <= nch || next_exists) bar_arrive(BAR_EMPTY + bp, S2_NT);
+        b = ring_next(b);
+    }
+
+    // ---- epilogue: metric post-processing, one f32 per (row, query) to HBM ----
+    if (R > 0) {
+        const float mcorr = (float)(a.m - 1);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int g = 4 * h + j;
+            if (g < ng) {
+                float *out = a.dist_out + T->out[g];
+#pragma unroll
+                for (int r = 0; r < RR; r++) {
+                    if (valid[r]) {
+                        float v = acc[r][j];
+                        if (a.metric == LGPU_COSINE) v = __fmul_rn(v, 0.5f);
+                        else if (a.metric == LGPU_DOT) v = __fsub_rn(v, mcorr);
+                        out[row0 + ct + r * S2_CT] = v;
+                    }
+                }
+            }
+        }
+    }
+    return b;
+}
+
+template <int DSUB>
+__device__ __forceinline__ void consumer_loop(const ScanArgs &a, int tid)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const unsigned char *const tiles = smem + Smem<DSUB>::TILES;
+    const int cidx = tid - S2_PT;
+    const int h = cidx >> 7, ct = cidx & (S2_CT - 1);
+    int b = 0;
+    for (uint32_t n = 0;; n++) {
+        const TileDesc *T = slot_ptr(tiles, n);
+        const int ng = (int)T->ng;
+        if (ng == 0) break;
+        const bool next_exists = slot_ptr(tiles, n + 1)->ng != 0;
+        const int R = 4 * h < ng ? (int)((T->nrows + S2_CT - 1) / S2_CT) : 0;      // uniform per half
+#define LGPU_CONSUME(RR) b = consume_tile<DSUB, RR>(a, T, next_exists, b, h, ct)
+        if (R == 0) LGPU_CONSUME(0);
+        else if (R <= 2) LGPU_CONSUME(2);
+        else if (R <= 4) LGPU_CONSUME(4);
+        else if (R <= 6) LGPU_CONSUME(6);
+        else if (R <= 8) LGPU_CONSUME(8);
+        else if (R <= 10) LGPU_CONSUME(10);
+        else LGPU_CONSUME(12);
+#undef LGPU_CONSUME
+    }
+}
+
+// ---------------------------------------------------------------- kernel
+template <int DSUB, bool DOT>
+__global__ void __launch_bounds__(S2_NT, 1) scan2_kernel(ScanArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const uint32_t total = *a.total_tiles;
+    unsigned char *const tiles = smem + Smem<DSUB>::TILES;
+
+    // "stage -1" of the first tile: zero code-0 row in ring buffer 2 (both halves)
+    if (tid < 64)
+        reinterpret_cast<float *>(smem + 2 * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
+    // tiles 0 and 1 of this CTA
+    if (tid < 32) {
+        uint32_t t0 = 0, t1 = 0;
+        if (tid == 0) { t0 = atomicAdd(a.tile_counter, 1u); t1 = atomicAdd(a.tile_counter, 1u); }
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        t1 = __shfl_sync(0xffffffffu, t1, 0);
+        if (tid < (int)(sizeof(TileDesc) / 4)) {
+            uint32_t w0 = 0, w1 = 0;
+            if (t0 < total) w0 = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t0) + tid);
+            if (t1 < total) w1 = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t1) + tid);
+            reinterpret_cast<uint32_t *>(tiles)[tid] = w0;
+            reinterpret_cast<uint32_t *>(tiles + S2_SLOT_BYTES)[tid] = w1;
+        }
+    }
+    __syncthreads();
+
+    if (tid < S2_PT) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S2_PREG));
+        producer_loop<DSUB, DOT>(a, total, tid);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S2_CREG));
+        consumer_loop<DSUB>(a, tid);
+    }
+}
+
+template <int DSUB, bool DOT>
+void launch2(const ScanArgs &a, int grid, cudaStream_t st)
+{
+    constexpr size_t smem = Smem<DSUB>::TOTAL;
+    auto kern = scan2_kernel<DSUB, DOT>;
+    LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, S2_NT, smem, st>>>(a);
+    LGPU_CUDA(cudaGetLastError());
+}
+
+template <int DSUB>
+void launch2_metric(const ScanArgs &a, int grid, cudaStream_t st)
+{
+    if (a.metric == LGPU_DOT) launch2<DSUB, true>(a, grid, st);
+    else launch2<DSUB, false>(a, grid, st);
+}
+
+}  // namespace
+
+void launch_scan2(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st)
+{
+    if (a.tq || !a.tile_desc || a.rows_tile != SCAN_ROWS_TILE_MID) {
+        set_error("internal: streaming scan needs tile descriptors, rows_tile 1536 and the exact pass");
+        throw Failure{LGPU_RUNTIME};
+    }
+    switch (dsub) {
+    case 1: launch2_metric<1>(a, grid, st); break;
+    case 2: launch2_metric<2>(a, grid, st); break;
+    case 4: launch2_metric<4>(a, grid, st); break;
+    case 8: launch2_metric<8>(a, grid, st); break;
+    case 16: launch2_metric<16>(a, grid, st); break;
+    case 32: launch2_metric<32>(a, grid, st); break;
+    default:
+        set_error("unsupported PQ sub-vector length (dim/num_sub_vectors must be 1,2,4,8,16 or 32)");
+        throw Failure{LGPU_INVALID_INPUT};
+    }
+}
+
+}  // namespace lgpu

@@ -71,3 +71,40 @@ def test_ivf_pq_table_vs_oracle(metric):
     assert multi["query_index"].to_pylist() == [0] * 4 + [1] * 4 + [2] * 4
     with pytest.raises(ValueError, match="minimum_nprobes must be greater than 0"):
         t.search(q[0]).nprobes(0).to_arrow()
+
+
+_GRAPH_SCRIPT = r"""
+import sys, numpy as np
+sys.path.insert(0, {root!r})
+from tests.util import random_index, queries
+from lancedb_b200._native import GpuIvfPq, GpuFlat
+rng = np.random.default_rng(5)
+ix = random_index(rng, dim=64, nlist=24, m=8, n=6000, with_vectors=True)
+g = GpuIvfPq(ix)
+f = GpuFlat(ix.vectors, ix.row_ids)
+out = []
+for rep in range(4):                       # call 1 eager, call 2 captured, calls 3-4 replayed
+    q = queries(np.random.default_rng(100 + rep), 33, 64)
+    ids, dist, cnt = g.search(q, k=7, nprobes=5)
+    fi, fd, fc = f.search(q, k=7, metric="l2")
+    out.append((ids.copy(), dist.copy(), cnt.copy(), fi.copy(), fd.copy()))
+ids, dist, cnt = g.search(queries(np.random.default_rng(9), 17, 64), k=3, nprobes=24)   # new key
+np.savez({dst!r}, **{{f"a{{i}}_{{j}}": a for i, t in enumerate(out) for j, a in enumerate(t)}}, last_ids=ids, last_dist=dist)
+"""
+
+
+def test_graph_replay_matches_eager(tmp_path):
+    """LGPU_GRAPH=1 (capture on the 2nd call of a shape, replay afterwards) returns exactly what the
+    eager launch sequence returns, for fresh query contents on every replay."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("0", "1"):
+        dst = str(tmp_path / f"g{mode}.npz")
+        env = dict(os.environ, LGPU_GRAPH=mode)
+        subprocess.run([sys.executable, "-c", _GRAPH_SCRIPT.format(root=root, dst=dst)], check=True, env=env,
+                       timeout=300)
+        res[mode] = np.load(dst)
+    assert set(res["0"].files) == set(res["1"].files)
+    for name in res["0"].files:
+        assert np.array_equal(res["0"][name], res["1"][name]), name

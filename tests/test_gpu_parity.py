@@ -200,3 +200,30 @@ def test_error_contract():
     bad = random_index(rng, dim=30, nlist=2, m=2, n=10)      # dsub = 15
     with pytest.raises(ValueError, match="sub-vector length"):
         _native.GpuIvfPq(bad)
+
+
+@pytest.mark.parametrize("metric,dim,m", [("l2", 768, 96), ("dot", 64, 8), ("cosine", 80, 10), ("l2", 64, 2)])
+def test_round1_scan_kernel_still_matches(metric, dim, m, monkeypatch):
+    """LGPU_SCAN_V1=1 keeps the per-tile-drain kernel (scan.cu) selectable; both it and the default
+    streaming kernel (scan2.cu) must reproduce the oracle bit for bit (many tiles per CTA, mixed
+    group sizes 1..8, multi-block partitions)."""
+    rng = np.random.default_rng(21)
+    sizes = [0, 5, 1500, 1537, 3100, 40, 977, 200, 128, 129, 64, 1, 700, 0, 1024, 333]
+    ix = random_index(rng, dim=dim, nlist=len(sizes), m=m, metric=metric, sizes=sizes)
+    q = queries(rng, 77, dim)
+    out = {}
+    for v1 in ("0", "1"):
+        monkeypatch.setenv("LGPU_SCAN_V1", v1)
+        out[v1] = _check_search(ix, q, k=10, nprobes=6)
+    for a, b in zip(out["0"], out["1"]):
+        assert np.array_equal(a, b)
+
+
+def test_streaming_scan_many_tiles_per_cta():
+    """More tiles than CTAs (each persistent CTA streams tens of tiles through the table ring) with
+    group sizes from 1 to 8 and both table-build mappings alternating."""
+    rng = np.random.default_rng(22)
+    nlist = 600
+    sizes = rng.integers(1, 400, size=nlist)
+    ix = random_index(rng, dim=32, nlist=nlist, m=4, sizes=sizes)
+    _check_search(ix, queries(rng, 700, 32), k=5, nprobes=9)
