@@ -31,7 +31,7 @@ constexpr int S2_RMAX = 12;                         // rows per scanner thread: 
 constexpr int S2_PREG = 104, S2_CREG = 152;         // 256 * 104 + 256 * 152 = 65536 registers
 constexpr int S2_SLOTS = 4;                         // tile-descriptor ring
 constexpr int S2_SLOT_BYTES = 128;
-constexpr int S2_PF = 3;                            // codebook prefetch distance (tasks)
+constexpr int S2_STAGE_BYTES = 3072;                // per builder warp: 6 x 512 B (2-code tasks) or 3 x 1 KB
 static_assert(SCAN_ROWS_TILE_MID == S2_CT * S2_RMAX, "rows_tile");
 static_assert(S2_PT * S2_PREG + S2_CW * 32 * S2_CREG <= 65536, "register budget");
 
@@ -44,7 +44,8 @@ struct Smem {
     static constexpr size_t LUT = 0;
     static constexpr size_t RBUF = 3 * (size_t)SCAN_LUT_BYTES;
     static constexpr size_t TILES = RBUF + 2 * (size_t)RB * sizeof(float);
-    static constexpr size_t TOTAL = TILES + S2_SLOTS * S2_SLOT_BYTES;
+    static constexpr size_t STAGE = TILES + S2_SLOTS * S2_SLOT_BYTES;    // codebook staging rings (DSUB == 8)
+    static constexpr size_t TOTAL = STAGE + (DSUB == 8 ? S2_PW * S2_STAGE_BYTES : 0);
 };
 
 __device__ __forceinline__ const TileDesc *slot_ptr(const unsigned char *tiles, uint32_t n)
@@ -57,8 +58,9 @@ template <int DSUB>
 struct Resid {
     static constexpr int RB = Smem<DSUB>::RB;
     static constexpr int RPT = (RB + S2_PT - 1) / S2_PT;
-    float v[RPT];
-    // global loads of residual chunk `ch` of tile T (q - centroid, or q for dot) into registers
+    float vq[RPT], vc[RPT];
+    // global loads for residual chunk `ch` of tile T into registers; the subtraction (q - centroid, or
+    // q - 0 for dot) happens in store(), a whole build stage later, so the loads are never waited on here
     template <bool DOT>
     __device__ __forceinline__ void load(const ScanArgs &a, const TileDesc *T, uint32_t ch, int tid)
     {
@@ -68,18 +70,18 @@ struct Resid {
 #pragma unroll
         for (int u = 0; u < RPT; u++) {
             const int idx = tid + u * S2_PT;
-            float r = 0.f;
+            float rq = 0.f, rc = 0.f;
             if (idx < RB) {
                 const int g = idx / (8 * DSUB), rem = idx - g * (8 * DSUB);
                 const int ss = rem / DSUB, e = rem - ss * DSUB;
                 const uint32_t i = ch * 8 + ss;
                 if (g < ng && i < a.m) {
                     const uint32_t dimi = i * DSUB + e;
-                    const float qv = __ldg(a.queries + (size_t)T->q[g] * a.dim + dimi);
-                    r = DOT ? qv : __fsub_rn(qv, __ldg(cenp + dimi));
+                    rq = __ldg(a.queries + (size_t)T->q[g] * a.dim + dimi);
+                    if (!DOT) rc = __ldg(cenp + dimi);
                 }
             }
-            v[u] = r;
+            vq[u] = rq; vc[u] = rc;
         }
     }
     __device__ __forceinline__ void store(float *dst, int tid) const
@@ -87,24 +89,62 @@ struct Resid {
 #pragma unroll
         for (int u = 0; u < RPT; u++) {
             const int idx = tid + u * S2_PT;
-            if (idx < RB) dst[idx] = v[u];
+            if (idx < RB) dst[idx] = __fsub_rn(vq[u], vc[u]);
         }
     }
 };
 
-// Codebook entries of the next S2_PF tasks, carried across chunk / tile boundaries (DSUB == 8 only).
-struct CbRing {
-    float4 v[S2_PF + 1][2];
+// ---- codebook staging (DSUB == 8).  A builder warp's task needs CPT codes x 8 sub-spaces x 32 B of the
+// codebook chunk = CPT * 256 contiguous bytes.  Instead of loading them into registers a few tasks ahead
+// (round 1: the L2 round trip was the builders' largest stall), each warp streams them with cp.async
+// (LDGSTS, 16 B per lane) into a private ring of D = 3072 / (CPT * 256) slots, D tasks ahead, and reads
+// its (code, sub-space) entry back with two LDS.128 one task ahead.  16-byte unit u of a code's 256 B
+// is stored at unit u ^ ((u >> 3) & 1) so that the eight lanes of a quarter-warp (sub-spaces 0..7, 32 B
+// apart) hit eight different bank groups.
+struct CbStage {
+    uint32_t base;      // shared-space address of this warp's ring
+    uint32_t so;        // byte offset of the slot holding the task whose entry is in `cur`
+    float4 cur[2];      // codebook entry (this lane's code, sub-space) of the current task
 };
 
-// address of the codebook entry of task k in chunk ch: [ch][c][s][8], c = CPT * (pw + 8 k) + csel
-template <int CPT>
-__device__ __forceinline__ const float4 *cb_task_ptr(const ScanArgs &a, uint32_t ch, int pw, int lane, int k)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
-    const int s = lane & 7;
-    const int csel = (CPT == 2) ? (lane >> 4) : (lane >> 3);
-    const int c = CPT * (pw + S2_PW * k) + csel;
-    return reinterpret_cast<const float4 *>(a.cb_tiled + (((size_t)ch * 256 + c) * 8 + s) * 8);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t stage_swz(int lane) { return (uint32_t)((lane ^ ((lane >> 3) & 1)) << 4); }
+
+// issue the copy of task k of chunk ch (CPT codes) into the slot at byte offset `so`
+template <int CPT>
+__device__ __forceinline__ void stage_issue(const ScanArgs &a, const CbStage &cs, uint32_t so, uint32_t ch, int k,
+                                            int pw, int lane)
+{
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(a.cb_tiled) +
+                               ((size_t)ch * 256 + CPT * (pw + S2_PW * k)) * 256 + lane * 16;
+    const uint32_t dst = cs.base + so + stage_swz(lane);
+    cp_async16(dst, src);
+    if constexpr (CPT == 4) cp_async16(dst + 512, src + 512);
+}
+
+// start of a tile: tasks 0..D-1 of chunk 0 in flight, ring phase reset
+template <int CPT>
+__device__ __forceinline__ void stage_start(const ScanArgs &a, CbStage &cs, int pw, int lane)
+{
+    constexpr int SLOT = CPT * 256, D = S2_STAGE_BYTES / SLOT;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        stage_issue<CPT>(a, cs, k * SLOT, 0, k, pw, lane);
+        cp_async_commit();
+    }
+    cs.so = 0;
 }
 
 // Build one 8-sub-space chunk of the distance table into ring buffer `b`.
@@ -115,15 +155,14 @@ __device__ __forceinline__ const float4 *cb_task_ptr(const ScanArgs &a, uint32_t
 // `ring` holds the codebook entries of tasks 0..PF-1 on entry and those of the first PF tasks of chunk
 // `ch_next` (mapping `cpt_next`) on exit.
 template <int DSUB, bool DOT, int HALVES>
-__device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int b, int rslot, CbRing &ring,
-                                            uint32_t ch_next, int cpt_next, int pw, int lane)
+__device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int b, int rslot, CbStage &cs,
+                                            bool has_next, int pw, int lane)
 {
     extern __shared__ __align__(1024) unsigned char smem[];      // declared here so every access is a plain
     unsigned char *const lut = smem + Smem<DSUB>::LUT;           // shared-space LDS/STS
     const float *const rsrc_chunk = reinterpret_cast<const float *>(smem + Smem<DSUB>::RBUF) + rslot * Smem<DSUB>::RB;
     constexpr int CPT = HALVES == 2 ? 2 : 4;
     constexpr int NTASK = 256 / CPT / S2_PW;                   // 16 or 8
-    static_assert(NTASK % (S2_PF + 1) == 0, "the prefetch ring must keep its phase across chunks");
     const int s = lane & 7;
     const int h = HALVES == 2 ? ((lane >> 3) & 1) : 0;
     const int csel = HALVES == 2 ? (lane >> 4) : (lane >> 3);
@@ -133,6 +172,8 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
     constexpr int DST_STRIDE = CPT * S2_PW * 128;                              // bytes between tasks
 
     if constexpr (DSUB == 8) {
+        constexpr int SLOT = CPT * 256, D = S2_STAGE_BYTES / SLOT;             // 6 or 3 tasks in flight
+        static_assert(D >= 2 && D <= NTASK, "staging depth");
         uint64_t pr[4][4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -141,26 +182,25 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
             pr[j][0] = pk2(lo.x, lo.y); pr[j][1] = pk2(lo.z, lo.w);
             pr[j][2] = pk2(hi.x, hi.y); pr[j][3] = pk2(hi.z, hi.w);
         }
-        const float4 *cb_here = cb_task_ptr<CPT>(a, ch, pw, lane, 0);
-        constexpr int CB_STRIDE = CPT * S2_PW * 8 * 8 / 4;                     // float4 between tasks
-        const float4 *cb_nx = (cpt_next == 2) ? cb_task_ptr<2>(a, ch_next, pw, lane, 0)
-                                              : cb_task_ptr<4>(a, ch_next, pw, lane, 0);
-        const int nx_stride = cpt_next * S2_PW * 8 * 8 / 4;
+        // this lane's entry inside a slot: code csel, sub-space s, swizzled 16-byte units 2s and 2s+1
+        const uint32_t ent = cs.base + (uint32_t)csel * 256 + (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
+        if (ch == 0) {                          // first task of the tile: its copy is the oldest of D groups
+            cp_async_wait<D - 1>();
+            __syncwarp();
+            cs.cur[0] = lds128(ent + cs.so); cs.cur[1] = lds128((ent + cs.so) ^ 16u);
+        }
 #pragma unroll
         for (int k = 0; k < NTASK; k++) {
-            // issue the load of task k + PF (this chunk, or the head of the next one)
-            {
-                constexpr int RS = S2_PF + 1;
-                const int slot = (k + S2_PF) % RS;
-                if (k + S2_PF < NTASK) {
-                    const float4 *src = cb_here + (size_t)(k + S2_PF) * CB_STRIDE;
-                    ring.v[slot][0] = __ldg(src); ring.v[slot][1] = __ldg(src + 1);
-                } else {
-                    const float4 *src = cb_nx + (size_t)(k + S2_PF - NTASK) * nx_stride;
-                    ring.v[slot][0] = __ldg(src); ring.v[slot][1] = __ldg(src + 1);
-                }
-            }
-            const float4 c0 = ring.v[k % (S2_PF + 1)][0], c1 = ring.v[k % (S2_PF + 1)][1];
+            // entry of task k is in cs.cur, its slot (cs.so) is free: refill it with task k + D
+            cp_async_wait<D - 2>();             // task k+1 has landed (this lane's part) ...
+            __syncwarp();                       // ... and every lane's part; also orders last LDS before the refill
+            if (k + D < NTASK) stage_issue<CPT>(a, cs, cs.so, ch, k + D, pw, lane);
+            else if (has_next) stage_issue<CPT>(a, cs, cs.so, ch + 1, k + D - NTASK, pw, lane);
+            cp_async_commit();                  // (possibly empty: keeps the group count per task at one)
+            const uint32_t so_next = cs.so + SLOT == S2_STAGE_BYTES ? 0u : cs.so + SLOT;
+            float4 n0 = cs.cur[0], n1 = cs.cur[1];
+            if (k + 1 < NTASK || has_next) { n0 = lds128(ent + so_next); n1 = lds128((ent + so_next) ^ 16u); }
+            const float4 c0 = cs.cur[0], c1 = cs.cur[1];
             float4 out;
             if constexpr (!DOT) {
                 const uint64_t pc[4] = {pk2(c0.x, c0.y), pk2(c0.z, c0.w), pk2(c1.x, c1.y), pk2(c1.z, c1.w)};
@@ -178,9 +218,10 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
                 out = make_float4(o[0], o[1], o[2], o[3]);
             }
             *reinterpret_cast<float4 *>(dst + k * DST_STRIDE) = out;
+            cs.cur[0] = n0; cs.cur[1] = n1; cs.so = so_next;
         }
     } else {
-        (void)ring; (void)ch_next; (void)cpt_next;
+        (void)cs; (void)has_next;
         const float *cbp = a.cb_tiled + (((size_t)ch * 256 + CPT * pw + csel) * 8 + s) * DSUB;
         for (int k = 0; k < NTASK; k++) {
             float cbv[DSUB], rr[DSUB], o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -210,20 +251,18 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
     const uint32_t nch = a.nch;
 
     Resid<DSUB> res;
-    CbRing ring;
-    {   // first tile: residual chunk 0 and the head of the codebook prefetch ring
+    CbStage cs;
+    cs.base = (uint32_t)__cvta_generic_to_shared(smem + Smem<DSUB>::STAGE) + (uint32_t)pw * S2_STAGE_BYTES;
+    cs.so = 0;
+    cs.cur[0] = cs.cur[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    {   // first tile: residual chunk 0 and the first codebook copies
         const TileDesc *T0 = slot_ptr(tiles, 0);
         if (T0->ng) {
+            if constexpr (DSUB == 8) {
+                if (T0->ng > 4) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
+            }
             res.template load<DOT>(a, T0, 0, tid);
             res.store(rbuf, tid);
-            if constexpr (DSUB == 8) {
-                const bool two = T0->ng > 4;
-#pragma unroll
-                for (int k = 0; k < S2_PF; k++) {
-                    const float4 *src = two ? cb_task_ptr<2>(a, 0, pw, lane, k) : cb_task_ptr<4>(a, 0, pw, lane, k);
-                    ring.v[k][0] = __ldg(src); ring.v[k][1] = __ldg(src + 1);
-                }
-            }
         }
     }
     bar_sync(BAR_PROD, S2_PT);
@@ -253,17 +292,21 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
             const bool res_here = ch + 1 < nch;
             const bool res_next = (ch == nch) && ng_next != 0;
             if (res_here) res.template load<DOT>(a, T, ch + 1, tid);
-            else if (res_next) res.template load<DOT>(a, Tn, 0, tid);
+            else if (res_next) {
+                res.template load<DOT>(a, Tn, 0, tid);
+                if constexpr (DSUB == 8) {      // this stage builds nothing: start the next tile's codebook copies
+                    if (ng_next > 4) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
+                }
+            }
 
             if (gs >= 2) bar_sync(BAR_EMPTY + b, S2_NT);          // scanners are done with stage gs-2
             if (ch == nch) {                                       // all-zero row for the lagging lanes
                 if (tid < 64)
                     reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
             } else {
-                const uint32_t ch_next = ch + 1 < nch ? ch + 1 : 0;
-                const int cpt_next = ch + 1 < nch ? (ng > 4 ? 2 : 4) : (ng_next > 4 ? 2 : 4);
-                if (ng > 4) build_chunk<DSUB, DOT, 2>(a, ch, b, (int)(ch & 1), ring, ch_next, cpt_next, pw, lane);
-                else build_chunk<DSUB, DOT, 1>(a, ch, b, (int)(ch & 1), ring, ch_next, cpt_next, pw, lane);
+                const bool has_next = ch + 1 < nch;
+                if (ng > 4) build_chunk<DSUB, DOT, 2>(a, ch, b, (int)(ch & 1), cs, has_next, pw, lane);
+                else build_chunk<DSUB, DOT, 1>(a, ch, b, (int)(ch & 1), cs, has_next, pw, lane);
             }
             if (pw == 0 && ch == 1 && lane < (int)(sizeof(TileDesc) / 4))   // publish tile n+2 before FULL(stage 1)
                 reinterpret_cast<uint32_t *>(const_cast<TileDesc *>(slot_ptr(tiles, n + 2)))[lane] = t_word;
