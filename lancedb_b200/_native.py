@@ -62,11 +62,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("LGPU_LIB_PATH") or LIB_PATH      # kernel A/B builds (csrc/Makefile OUT=...)
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(lancedb_b200 has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, u32, i32 = C.c_void_p, C.c_uint32, C.c_int
     lib.lgpu_last_error.restype = C.c_char_p
     lib.lgpu_abi_version.restype = u32

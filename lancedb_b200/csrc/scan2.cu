@@ -28,7 +28,16 @@ constexpr int S2_PW = 8, S2_CW = 8;                 // builder / scanner warps
 constexpr int S2_PT = S2_PW * 32, S2_NT = (S2_PW + S2_CW) * 32;
 constexpr int S2_CT = 128;                          // scanner threads per query half
 constexpr int S2_RMAX = 12;                         // rows per scanner thread: 128 * 12 = SCAN_ROWS_TILE_MID
-constexpr int S2_PREG = 104, S2_CREG = 152;         // 256 * 104 + 256 * 152 = 65536 registers
+#ifndef S2_PREG_V
+#define S2_PREG_V 104
+#endif
+#ifndef S2_CREG_V
+#define S2_CREG_V 152
+#endif
+#ifndef S2_LDS_AHEAD
+#define S2_LDS_AHEAD 1                              // codebook entries are read back 1 or 2 tasks ahead
+#endif
+constexpr int S2_PREG = S2_PREG_V, S2_CREG = S2_CREG_V;   // 256 * 104 + 256 * 152 = 65536 registers
 constexpr int S2_SLOTS = 4;                         // tile-descriptor ring
 constexpr int S2_SLOT_BYTES = 128;
 constexpr int S2_STAGE_BYTES = 3072;                // per builder warp: 6 x 512 B (2-code tasks) or 3 x 1 KB
@@ -89,7 +98,14 @@ struct Resid {
 #pragma unroll
         for (int u = 0; u < RPT; u++) {
             const int idx = tid + u * S2_PT;
-            if (idx < RB) dst[idx] = __fsub_rn(vq[u], vc[u]);
+            if (idx < RB) {
+                int at = idx;
+                if constexpr (DSUB == 8) {      // 16-byte unit u -> u ^ ((u >> 3) & 1): conflict-free LDS.128 reads
+                    const int unit = idx >> 2;
+                    at = ((unit ^ ((unit >> 3) & 1)) << 2) | (idx & 3);
+                }
+                dst[at] = __fsub_rn(vq[u], vc[u]);
+            }
         }
     }
 };
@@ -105,6 +121,7 @@ struct CbStage {
     uint32_t base;      // shared-space address of this warp's ring
     uint32_t so;        // byte offset of the slot holding the task whose entry is in `cur`
     float4 cur[2];      // codebook entry (this lane's code, sub-space) of the current task
+    float4 nx1[2];      // ... of the task after it (S2_LDS_AHEAD == 2)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
@@ -147,6 +164,30 @@ __device__ __forceinline__ void stage_start(const ScanArgs &a, CbStage &cs, int 
     cs.so = 0;
 }
 
+// The residuals of this lane's sub-space for its 4 queries (DSUB == 8), packed for the f32x2 ops.  Loaded by the
+// builder loop *before* it waits for the ring buffer, so the LDS latency hides behind the barrier.
+struct ResidRegs {
+    uint64_t pr[4][4];
+};
+template <int DSUB>
+__device__ __forceinline__ void load_resid_regs(ResidRegs &rr, int rslot, bool two_halves, int lane)
+{
+    if constexpr (DSUB == 8) {
+        extern __shared__ __align__(1024) unsigned char smem[];
+        const int s = lane & 7;
+        const int h = two_halves ? ((lane >> 3) & 1) : 0;
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem + Smem<DSUB>::RBUF) +
+                              (uint32_t)rslot * Smem<DSUB>::RB * 4 + (uint32_t)(4 * h) * 256 +
+                              (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float4 lo = lds128(base + j * 256), hi = lds128((base + j * 256) ^ 16u);
+            rr.pr[j][0] = pk2(lo.x, lo.y); rr.pr[j][1] = pk2(lo.z, lo.w);
+            rr.pr[j][2] = pk2(hi.x, hi.y); rr.pr[j][3] = pk2(hi.z, hi.w);
+        }
+    }
+}
+
 // Build one 8-sub-space chunk of the distance table into ring buffer `b`.
 //   HALVES == 2: lane -> (s = lane & 7, h = (lane >> 3) & 1, cc = lane >> 4); a warp task covers 2 codes
 //                x 8 sub-spaces x both query halves; 16 tasks per warp.
@@ -156,7 +197,7 @@ __device__ __forceinline__ void stage_start(const ScanArgs &a, CbStage &cs, int 
 // `ch_next` (mapping `cpt_next`) on exit.
 template <int DSUB, bool DOT, int HALVES>
 __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int b, int rslot, CbStage &cs,
-                                            bool has_next, int pw, int lane)
+                                            const ResidRegs &rr, bool has_next, int pw, int lane)
 {
     extern __shared__ __align__(1024) unsigned char smem[];      // declared here so every access is a plain
     unsigned char *const lut = smem + Smem<DSUB>::LUT;           // shared-space LDS/STS
@@ -174,32 +215,37 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
     if constexpr (DSUB == 8) {
         constexpr int SLOT = CPT * 256, D = S2_STAGE_BYTES / SLOT;             // 6 or 3 tasks in flight
         static_assert(D >= 2 && D <= NTASK, "staging depth");
-        uint64_t pr[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float4 lo = *reinterpret_cast<const float4 *>(rsrc + j * 64);
-            const float4 hi = *reinterpret_cast<const float4 *>(rsrc + j * 64 + 4);
-            pr[j][0] = pk2(lo.x, lo.y); pr[j][1] = pk2(lo.z, lo.w);
-            pr[j][2] = pk2(hi.x, hi.y); pr[j][3] = pk2(hi.z, hi.w);
-        }
+        const uint64_t (&pr)[4][4] = rr.pr;
         // this lane's entry inside a slot: code csel, sub-space s, swizzled 16-byte units 2s and 2s+1
         const uint32_t ent = cs.base + (uint32_t)csel * 256 + (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
-        if (ch == 0) {                          // first task of the tile: its copy is the oldest of D groups
-            cp_async_wait<D - 1>();
+        constexpr int AH = S2_LDS_AHEAD;
+        static_assert(AH == 1 || AH == 2, "read-back distance");
+        static_assert(D - 1 - AH >= 0, "staging depth vs read-back distance");
+        if (ch == 0) {                          // first task(s) of the tile: the oldest of D copy groups
+            cp_async_wait<D - AH>();
             __syncwarp();
             cs.cur[0] = lds128(ent + cs.so); cs.cur[1] = lds128((ent + cs.so) ^ 16u);
+            if constexpr (AH == 2) {
+                const uint32_t s1 = cs.so + SLOT == S2_STAGE_BYTES ? 0u : cs.so + SLOT;
+                cs.nx1[0] = lds128(ent + s1); cs.nx1[1] = lds128((ent + s1) ^ 16u);
+            }
         }
 #pragma unroll
         for (int k = 0; k < NTASK; k++) {
             // entry of task k is in cs.cur, its slot (cs.so) is free: refill it with task k + D
-            cp_async_wait<D - 2>();             // task k+1 has landed (this lane's part) ...
+            cp_async_wait<D - 1 - AH>();        // task k+AH has landed (this lane's part) ...
             __syncwarp();                       // ... and every lane's part; also orders last LDS before the refill
             if (k + D < NTASK) stage_issue<CPT>(a, cs, cs.so, ch, k + D, pw, lane);
             else if (has_next) stage_issue<CPT>(a, cs, cs.so, ch + 1, k + D - NTASK, pw, lane);
             cp_async_commit();                  // (possibly empty: keeps the group count per task at one)
             const uint32_t so_next = cs.so + SLOT == S2_STAGE_BYTES ? 0u : cs.so + SLOT;
             float4 n0 = cs.cur[0], n1 = cs.cur[1];
-            if (k + 1 < NTASK || has_next) { n0 = lds128(ent + so_next); n1 = lds128((ent + so_next) ^ 16u); }
+            if constexpr (AH == 1) {
+                if (k + 1 < NTASK || has_next) { n0 = lds128(ent + so_next); n1 = lds128((ent + so_next) ^ 16u); }
+            } else {
+                const uint32_t so_2 = so_next + SLOT == S2_STAGE_BYTES ? 0u : so_next + SLOT;
+                if (k + 2 < NTASK || has_next) { n0 = lds128(ent + so_2); n1 = lds128((ent + so_2) ^ 16u); }
+            }
             const float4 c0 = cs.cur[0], c1 = cs.cur[1];
             float4 out;
             if constexpr (!DOT) {
@@ -218,10 +264,12 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
                 out = make_float4(o[0], o[1], o[2], o[3]);
             }
             *reinterpret_cast<float4 *>(dst + k * DST_STRIDE) = out;
-            cs.cur[0] = n0; cs.cur[1] = n1; cs.so = so_next;
+            if constexpr (AH == 1) { cs.cur[0] = n0; cs.cur[1] = n1; }
+            else { cs.cur[0] = cs.nx1[0]; cs.cur[1] = cs.nx1[1]; cs.nx1[0] = n0; cs.nx1[1] = n1; }
+            cs.so = so_next;
         }
     } else {
-        (void)cs; (void)has_next;
+        (void)cs; (void)has_next; (void)rr;
         const float *cbp = a.cb_tiled + (((size_t)ch * 256 + CPT * pw + csel) * 8 + s) * DSUB;
         for (int k = 0; k < NTASK; k++) {
             float cbv[DSUB], rr[DSUB], o[4] = {0.f, 0.f, 0.f, 0.f};
@@ -254,7 +302,7 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
     CbStage cs;
     cs.base = (uint32_t)__cvta_generic_to_shared(smem + Smem<DSUB>::STAGE) + (uint32_t)pw * S2_STAGE_BYTES;
     cs.so = 0;
-    cs.cur[0] = cs.cur[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cs.cur[0] = cs.cur[1] = cs.nx1[0] = cs.nx1[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     {   // first tile: residual chunk 0 and the first codebook copies
         const TileDesc *T0 = slot_ptr(tiles, 0);
         if (T0->ng) {
@@ -299,14 +347,16 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
                 }
             }
 
+            ResidRegs rr;
+            if (ch < nch) load_resid_regs<DSUB>(rr, (int)(ch & 1), ng > 4, lane);
             if (gs >= 2) bar_sync(BAR_EMPTY + b, S2_NT);          // scanners are done with stage gs-2
             if (ch == nch) {                                       // all-zero row for the lagging lanes
                 if (tid < 64)
                     reinterpret_cast<float *>(lut + b * SCAN_LUT_BYTES + (tid >> 5) * SCAN_LUT_HALF)[tid & 31] = 0.f;
             } else {
                 const bool has_next = ch + 1 < nch;
-                if (ng > 4) build_chunk<DSUB, DOT, 2>(a, ch, b, (int)(ch & 1), cs, has_next, pw, lane);
-                else build_chunk<DSUB, DOT, 1>(a, ch, b, (int)(ch & 1), cs, has_next, pw, lane);
+                if (ng > 4) build_chunk<DSUB, DOT, 2>(a, ch, b, (int)(ch & 1), cs, rr, has_next, pw, lane);
+                else build_chunk<DSUB, DOT, 1>(a, ch, b, (int)(ch & 1), cs, rr, has_next, pw, lane);
             }
             if (pw == 0 && ch == 1 && lane < (int)(sizeof(TileDesc) / 4))   // publish tile n+2 before FULL(stage 1)
                 reinterpret_cast<uint32_t *>(const_cast<TileDesc *>(slot_ptr(tiles, n + 2)))[lane] = t_word;
