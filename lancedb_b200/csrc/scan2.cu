@@ -28,16 +28,19 @@ constexpr int S2_PW = 8, S2_CW = 8;                 // builder / scanner warps
 constexpr int S2_PT = S2_PW * 32, S2_NT = (S2_PW + S2_CW) * 32;
 constexpr int S2_CT = 128;                          // scanner threads per query half
 constexpr int S2_RMAX = 12;                         // rows per scanner thread: 128 * 12 = SCAN_ROWS_TILE_MID
+// registers per builder / scanner thread.  Measured on B200 (C2, scan stage ms per batch): 104/152 0.867,
+// 112/144 0.830, 120/136 0.823, 128/128 0.810, 136/120 0.820, 144/112 0.870 -- the builders schedule better
+// with more registers until the scanners start to spill.
 #ifndef S2_PREG_V
-#define S2_PREG_V 104
+#define S2_PREG_V 128
 #endif
 #ifndef S2_CREG_V
-#define S2_CREG_V 152
+#define S2_CREG_V 128
 #endif
 #ifndef S2_LDS_AHEAD
 #define S2_LDS_AHEAD 1                              // codebook entries are read back 1 or 2 tasks ahead
 #endif
-constexpr int S2_PREG = S2_PREG_V, S2_CREG = S2_CREG_V;   // 256 * 104 + 256 * 152 = 65536 registers
+constexpr int S2_PREG = S2_PREG_V, S2_CREG = S2_CREG_V;   // 256 * PREG + 256 * CREG <= 65536 registers
 constexpr int S2_SLOTS = 4;                         // tile-descriptor ring
 constexpr int S2_SLOT_BYTES = 128;
 constexpr int S2_STAGE_BYTES = 3072;                // per builder warp: 6 x 512 B (2-code tasks) or 3 x 1 KB
@@ -514,10 +517,12 @@ __global__ void __launch_bounds__(S2_NT, 1) scan2_kernel(ScanArgs a)
     __syncthreads();
 
     if (tid < S2_PT) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S2_PREG));
+        if constexpr (S2_PREG < S2_CREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S2_PREG));
+        else if constexpr (S2_PREG > S2_CREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S2_PREG));
         producer_loop<DSUB, DOT>(a, total, tid);
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S2_CREG));
+        if constexpr (S2_PREG < S2_CREG) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S2_CREG));
+        else if constexpr (S2_PREG > S2_CREG) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S2_CREG));
         consumer_loop<DSUB>(a, tid);
     }
 }
