@@ -292,13 +292,23 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
             }
         }
     };
-    // one warp-iteration = 256 consecutive values of `src` starting at r0 (n values in total): two float4 per lane.
-    // load256 only issues the loads; process256 offers the 8 values.  Row ids are fetched only for values that
-    // beat the current k-th best, and for all 8 values of the iteration at once (one exposed latency instead
-    // of up to eight); iterations in which no lane has such a value cost one ballot.
-    auto load256 = [&](const float *src, uint64_t r0, uint64_t n, bool vec, float4 &ta, float4 &tb) {
+    auto offer4 = [&](const float4 t, uint64_t n_left, uint64_t idbase, const uint64_t *idsrc, uint64_t posbase) {
+        const float v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            float f = v[u];
+            if (f == 0.f) f = 0.f;                          // -0 and +0 tie
+            const uint32_t key = f32_key(f);
+            const bool pass = (uint64_t)u < n_left && in_range(f) && key <= tau_k;
+            uint64_t id = 0;
+            if (pass) id = idsrc ? idsrc[idbase + u] : idbase + u;
+            offer(pass, key, id, posbase + u);
+        }
+    };
+    // one warp-iteration = 256 consecutive values of `src` starting at r0 (n values in total)
+    auto scan256 = [&](const float *src, uint64_t r0, uint64_t n, bool vec, uint64_t idbase, const uint64_t *idsrc) {
         const uint64_t ra = r0 + (uint64_t)lane * 4, rb = ra + 128;
-        ta = make_float4(0.f, 0.f, 0.f, 0.f); tb = ta;
+        float4 ta = make_float4(0.f, 0.f, 0.f, 0.f), tb = ta;
         if (vec) {
             if (ra < n) ta = *reinterpret_cast<const float4 *>(src + ra);   // rows padded to 4 floats
             if (rb < n) tb = *reinterpret_cast<const float4 *>(src + rb);
@@ -310,68 +320,21 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
                 if (rb + u < n) pb[u] = src[rb + u];
             }
         }
-    };
-    auto process256 = [&](const float4 ta, const float4 tb, uint64_t r0, uint64_t n, uint64_t idbase,
-                          const uint64_t *idsrc) {
-        const uint64_t ra = r0 + (uint64_t)lane * 4;
-        const float v[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-        uint32_t key[8];
-        uint64_t id[8];
-        bool pass[8], anyp = false;
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            float f = v[u];
-            if (f == 0.f) f = 0.f;                          // -0 and +0 tie
-            key[u] = f32_key(f);
-            const uint64_t r = ra + (u < 4 ? u : 124 + u);  // ra + u, or rb + (u - 4) with rb = ra + 128
-            pass[u] = r < n && in_range(f) && key[u] <= tau_k;
-            id[u] = 0;
-            if (pass[u]) id[u] = idsrc ? idsrc[idbase + r] : idbase + r;
-            anyp |= pass[u];
-        }
-        if (__ballot_sync(0xffffffffu, anyp) == 0) return;
-#pragma unroll
-        for (int u = 0; u < 8; u++) offer(pass[u], key[u], id[u], idbase + ra + (u < 4 ? u : 124 + u));
-    };
-    auto scan256 = [&](const float *src, uint64_t r0, uint64_t n, bool vec, uint64_t idbase, const uint64_t *idsrc) {
-        float4 ta, tb;
-        load256(src, r0, n, vec, ta, tb);
-        process256(ta, tb, r0, n, idbase, idsrc);
+        offer4(ta, ra < n ? n - ra : 0, idbase + ra, idsrc, idbase + ra);
+        offer4(tb, rb < n ? n - rb : 0, idbase + rb, idsrc, idbase + rb);
     };
 
     if (a.mode == 0) {
-        // per-probe metadata is fetched 32 probes at a time (one per lane) and broadcast, so the dependent
-        // probes -> part_n / seg_off chain is paid once, not per partition; the values of this warp's next
-        // 256-block are in flight while the previous block is offered
-        uint32_t itc = 0;                                   // block counter across segments
-        bool have = false;
-        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
-        uint64_t p_r0 = 0, p_n = 0, p_base = 0;
-        for (uint32_t j0 = 0; j0 < a.nprobes; j0 += 32) {
-            uint32_t my_n = 0;
-            uint64_t my_off = 0, my_base = 0;
-            if (j0 + lane < a.nprobes) {
-                const uint32_t slot = q * a.nprobes + j0 + lane;
-                const uint32_t p = (uint32_t)a.probes[slot];
-                my_n = a.part_n[p];
-                my_off = a.seg_off[slot];
-                my_base = a.part_off[p];
-            }
-            const uint32_t jn = min(32u, a.nprobes - j0);
-            for (uint32_t jj = 0; jj < jn; jj++) {
-                const uint32_t n = __shfl_sync(0xffffffffu, my_n, jj);
-                const float *src = a.dist + __shfl_sync(0xffffffffu, my_off, jj);
-                const uint64_t rowbase = __shfl_sync(0xffffffffu, my_base, jj);
-                for (uint32_t r0 = 0; r0 < n; r0 += 256, itc++) {
-                    if ((itc & (SELW_WARPS - 1)) != (uint32_t)w) continue;
-                    float4 ta, tb;
-                    load256(src, r0, n, true, ta, tb);
-                    if (have) process256(pa, pb, p_r0, p_n, p_base, a.row_ids);
-                    pa = ta; pb = tb; p_r0 = r0; p_n = n; p_base = rowbase; have = true;
-                }
-            }
+        uint32_t itc = 0;                                   // iteration counter across segments
+        for (uint32_t j = 0; j < a.nprobes; j++) {
+            const uint32_t slot = q * a.nprobes + j;
+            const uint32_t p = (uint32_t)a.probes[slot];
+            const uint32_t n = a.part_n[p];
+            const float *src = a.dist + a.seg_off[slot];
+            const uint64_t rowbase = a.part_off[p];
+            for (uint32_t r0 = 0; r0 < n; r0 += 256, itc++)
+                if ((itc & (SELW_WARPS - 1)) == (uint32_t)w) scan256(src, r0, n, true, rowbase, a.row_ids);
         }
-        if (have) process256(pa, pb, p_r0, p_n, p_base, a.row_ids);
     } else if (a.mode == 1) {
         const float *src = a.dense + (size_t)q * a.row_stride;
         const bool aligned = ((a.row_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dense) & 15) == 0);
