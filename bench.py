@@ -378,11 +378,11 @@ def main():
             "clocks": clocks,
             # to_bf16, gemm (sample), select, threshold, gemm (filtered), overflow flags, pair distance, select,
             # dist_matrix + select fix-ups, 3 group kernels, scan, select(top-k)
-            "gpu_launches": args.steps * 15,
+            "gpu_launches": args.steps * 16,
             "recall_at_k": recall,
             "stage_ms": stage,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(), "kernel": "scan_kernel<8,...> (fused PQ table build + code scan)",
+                         "traffic": profiled_traffic(), "kernel": "scan2_kernel<8,false> (fused PQ table build + code scan, streaming)",
                          "kernel_ms": scan_avg,
                          "algorithmic_bytes_per_launch": code_bytes, "peak_source": peak_src,
                          "compulsory_bytes_per_launch": int(full_ix.codes_t.size)},
