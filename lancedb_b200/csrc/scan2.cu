@@ -37,6 +37,9 @@ constexpr int S2_RMAX = 12;                         // rows per scanner thread: 
 #ifndef S2_CREG_V
 #define S2_CREG_V 128
 #endif
+#ifndef S2_BOTH_HALVES
+#define S2_BOTH_HALVES 0                            // 1: a builder lane computes its (code, sub-space) entry for all 8
+#endif                                              //    queries (codebook entry read once), DSUB == 8 only
 #ifndef S2_LDS_AHEAD
 #define S2_LDS_AHEAD 1                              // codebook entries are read back 1 or 2 tasks ahead
 #endif
@@ -170,7 +173,7 @@ __device__ __forceinline__ void stage_start(const ScanArgs &a, CbStage &cs, int 
 // The residuals of this lane's sub-space for its 4 queries (DSUB == 8), packed for the f32x2 ops.  Loaded by the
 // builder loop *before* it waits for the ring buffer, so the LDS latency hides behind the barrier.
 struct ResidRegs {
-    uint64_t pr[4][4];
+    uint64_t pr[2][4][4];       // [half][query][dim pair]; only pr[0] is used unless S2_BOTH_HALVES
 };
 template <int DSUB>
 __device__ __forceinline__ void load_resid_regs(ResidRegs &rr, int rslot, bool two_halves, int lane)
@@ -178,15 +181,20 @@ __device__ __forceinline__ void load_resid_regs(ResidRegs &rr, int rslot, bool t
     if constexpr (DSUB == 8) {
         extern __shared__ __align__(1024) unsigned char smem[];
         const int s = lane & 7;
-        const int h = two_halves ? ((lane >> 3) & 1) : 0;
+        const int h = (two_halves && !S2_BOTH_HALVES) ? ((lane >> 3) & 1) : 0;
         const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem + Smem<DSUB>::RBUF) +
                               (uint32_t)rslot * Smem<DSUB>::RB * 4 + (uint32_t)(4 * h) * 256 +
                               (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float4 lo = lds128(base + j * 256), hi = lds128((base + j * 256) ^ 16u);
-            rr.pr[j][0] = pk2(lo.x, lo.y); rr.pr[j][1] = pk2(lo.z, lo.w);
-            rr.pr[j][2] = pk2(hi.x, hi.y); rr.pr[j][3] = pk2(hi.z, hi.w);
+        for (int hh = 0; hh < (S2_BOTH_HALVES ? 2 : 1); hh++) {
+            if (hh == 1 && !two_halves) break;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t at = base + (hh * 4 + j) * 256;
+                const float4 lo = lds128(at), hi = lds128(at ^ 16u);
+                rr.pr[hh][j][0] = pk2(lo.x, lo.y); rr.pr[hh][j][1] = pk2(lo.z, lo.w);
+                rr.pr[hh][j][2] = pk2(hi.x, hi.y); rr.pr[hh][j][3] = pk2(hi.z, hi.w);
+            }
         }
     }
 }
@@ -205,11 +213,12 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
     extern __shared__ __align__(1024) unsigned char smem[];      // declared here so every access is a plain
     unsigned char *const lut = smem + Smem<DSUB>::LUT;           // shared-space LDS/STS
     const float *const rsrc_chunk = reinterpret_cast<const float *>(smem + Smem<DSUB>::RBUF) + rslot * Smem<DSUB>::RB;
-    constexpr int CPT = HALVES == 2 ? 2 : 4;
+    constexpr bool BOTH = S2_BOTH_HALVES && DSUB == 8 && HALVES == 2;   // both query halves per lane
+    constexpr int CPT = (HALVES == 2 && !BOTH) ? 2 : 4;
     constexpr int NTASK = 256 / CPT / S2_PW;                   // 16 or 8
     const int s = lane & 7;
-    const int h = HALVES == 2 ? ((lane >> 3) & 1) : 0;
-    const int csel = HALVES == 2 ? (lane >> 4) : (lane >> 3);
+    const int h = (HALVES == 2 && !BOTH) ? ((lane >> 3) & 1) : 0;
+    const int csel = (HALVES == 2 && !BOTH) ? (lane >> 4) : (lane >> 3);
     const bool sub_ok = (ch * 8 + s) < a.m;
     const float *rsrc = rsrc_chunk + ((4 * h) * 8 + s) * DSUB;                // + j * 8 * DSUB per query
     unsigned char *dst = lut + b * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16 + (CPT * pw + csel) * 128;
@@ -218,7 +227,7 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
     if constexpr (DSUB == 8) {
         constexpr int SLOT = CPT * 256, D = S2_STAGE_BYTES / SLOT;             // 6 or 3 tasks in flight
         static_assert(D >= 2 && D <= NTASK, "staging depth");
-        const uint64_t (&pr)[4][4] = rr.pr;
+        const uint64_t (&pr)[4][4] = rr.pr[0];
         // this lane's entry inside a slot: code csel, sub-space s, swizzled 16-byte units 2s and 2s+1
         const uint32_t ent = cs.base + (uint32_t)csel * 256 + (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
         constexpr int AH = S2_LDS_AHEAD;
@@ -267,6 +276,25 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
                 out = make_float4(o[0], o[1], o[2], o[3]);
             }
             *reinterpret_cast<float4 *>(dst + k * DST_STRIDE) = out;
+            if constexpr (BOTH) {               // same codebook entry against queries 4-7
+                float4 out1;
+                if constexpr (!DOT) {
+                    const uint64_t pc[4] = {pk2(c0.x, c0.y), pk2(c0.z, c0.w), pk2(c1.x, c1.y), pk2(c1.z, c1.w)};
+                    out1 = l2_tree8_packed_x4(rr.pr[1], pc, a.fzero2);
+                } else {
+                    const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float r8[8];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) upk2(rr.pr[1][j][e], r8[2 * e], r8[2 * e + 1]);
+                        o[j] = sub_ok ? subvec_dot_dist<8>(r8, cv) : 0.f;
+                    }
+                    out1 = make_float4(o[0], o[1], o[2], o[3]);
+                }
+                *reinterpret_cast<float4 *>(dst + k * DST_STRIDE + SCAN_LUT_HALF) = out1;
+            }
             if constexpr (AH == 1) { cs.cur[0] = n0; cs.cur[1] = n1; }
             else { cs.cur[0] = cs.nx1[0]; cs.cur[1] = cs.nx1[1]; cs.nx1[0] = n0; cs.nx1[1] = n1; }
             cs.so = so_next;
@@ -310,7 +338,7 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
         const TileDesc *T0 = slot_ptr(tiles, 0);
         if (T0->ng) {
             if constexpr (DSUB == 8) {
-                if (T0->ng > 4) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
+                if (T0->ng > 4 && !S2_BOTH_HALVES) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
             }
             res.template load<DOT>(a, T0, 0, tid);
             res.store(rbuf, tid);
@@ -346,7 +374,7 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
             else if (res_next) {
                 res.template load<DOT>(a, Tn, 0, tid);
                 if constexpr (DSUB == 8) {      // this stage builds nothing: start the next tile's codebook copies
-                    if (ng_next > 4) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
+                    if (ng_next > 4 && !S2_BOTH_HALVES) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
                 }
             }
 

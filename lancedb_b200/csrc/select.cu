@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
 // iteration (two float4 loads in flight) and only the ones not worse than the warp's
 // current k-th best are inserted (ballot loop).  After warm-up almost nothing passes, so
 // a query costs ~1 compare per candidate.  The four queues are merged through shared memory.
-constexpr int SELW_WARPS = 4;
+#ifndef SELW_WARPS_V
+#define SELW_WARPS_V 4
+#endif
+constexpr int SELW_WARPS = SELW_WARPS_V;       // power of two
 
 template <bool POS, int NQ>
 __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs a)
