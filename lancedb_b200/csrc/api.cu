@@ -267,10 +267,12 @@ static void tc_topk_l2_filtered(Workspace *ws, cudaStream_t st, int num_sms, con
     GemmFilter flt{};
     flt.thr = ws->probe_A.as<float>(); flt.count = ws->amax.as<uint32_t>(); flt.cand_pos = ws->t_pos.as<uint64_t>();
     flt.cand_ids = ws->t_ids.as<uint64_t>(); flt.col_ids = col_ids; flt.cap = cap;
-    launch_gemm_dist(ws->qb.p, Xb, xnorm2, B, N, d, nullptr, 0, num_sms, st, &flt);
+    if (Ns == N) launch_filter_dense(Dbuf, lds, B, N, flt, st);      // the sample pass already scored every row
+    else launch_gemm_dist(ws->qb.p, Xb, xnorm2, B, N, d, nullptr, 0, num_sms, st, &flt);
     launch_overflow_flags(ws->amax.as<uint32_t>(), cap, B, ws->flags.as<uint32_t>(), st);
-    // 3. exact re-score of the admitted rows, final top-k
-    launch_pair_distance(Q, X, ws->t_pos.as<uint64_t>(), B, cap, d, LGPU_L2, ws->t_exact.as<float>(), st);
+    // 3. exact re-score of the admitted rows (lists are filled from slot 0), final top-k
+    launch_pair_distance_counted(Q, X, ws->t_pos.as<uint64_t>(), ws->amax.as<uint32_t>(), B, cap, d, LGPU_L2,
+                                 ws->t_exact.as<float>(), st);
     SelectArgs sb{};
     sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
     sb.ncols = cap; sb.inner = cap; sb.row_stride = cap; sb.outer_stride = 0;

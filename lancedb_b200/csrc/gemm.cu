@@ -408,6 +408,33 @@ void launch_to_bf16(const float *X, uint64_t n, uint32_t d, void *Xb, float *nor
     LGPU_CUDA(cudaGetLastError());
 }
 
+// The filtering epilogue applied to an already written dense score matrix D[B][ld] (same scores, same
+// `<= thr` test, same candidate lists up to order): used when the threshold sample was the whole matrix, so
+// a second tensor-core pass would only recompute what D already holds.
+__global__ void filter_dense_kernel(const float *__restrict__ D, uint64_t ld, uint64_t N, GemmFilter flt)
+{
+    const uint32_t q = blockIdx.y;
+    const float thr = flt.thr[q];
+    const float *row = D + (size_t)q * ld;
+    for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < N; x += (uint64_t)gridDim.x * blockDim.x) {
+        if (row[x] <= thr) {
+            const uint32_t slot = atomicAdd(flt.count + q, 1u);
+            if (slot < flt.cap) {
+                flt.cand_pos[(size_t)q * flt.cap + slot] = x;
+                flt.cand_ids[(size_t)q * flt.cap + slot] = flt.col_ids ? flt.col_ids[x] : x;
+            }
+        }
+    }
+}
+
+void launch_filter_dense(const float *D, uint64_t ld, uint32_t B, uint64_t N, const GemmFilter &flt, cudaStream_t st)
+{
+    if (B == 0 || N == 0) return;
+    dim3 grid((unsigned)std::min<uint64_t>((N + 1023) / 1024, 64), B);
+    filter_dense_kernel<<<grid, 256, 0, st>>>(D, ld, N, flt);
+    LGPU_CUDA(cudaGetLastError());
+}
+
 void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint32_t B, uint64_t N, uint32_t d,
                       float *out, uint64_t ld_out, int num_sms, cudaStream_t st, const GemmFilter *filter)
 {

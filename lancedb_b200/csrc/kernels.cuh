@@ -107,6 +107,10 @@ void launch_normalize(const float *X, uint32_t B, uint32_t d, float *out, cudaSt
 void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, uint32_t B, uint32_t nc,
                           uint32_t d, int metric, float *out, cudaStream_t st);
 
+// the same for candidate lists filled from slot 0: only slots < min(cnt[q], nc) are computed / written
+void launch_pair_distance_counted(const float *Q, const float *V, const uint64_t *pos, const uint32_t *cnt,
+                                  uint32_t B, uint32_t nc, uint32_t d, int metric, float *out, cudaStream_t st);
+
 // ---------------- top-k select (K4) ------------------------------------------------
 constexpr uint32_t SELECT_KMAX = 2048;
 struct SelectArgs {
@@ -157,6 +161,8 @@ struct GemmFilter {
 };
 void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint32_t B, uint64_t N, uint32_t d,
                       float *out, uint64_t ld_out, int num_sms, cudaStream_t st, const GemmFilter *filter = nullptr);
+// filtering epilogue on an existing dense score matrix D[B][ld] (see gemm.cu)
+void launch_filter_dense(const float *D, uint64_t ld, uint32_t B, uint64_t N, const GemmFilter &flt, cudaStream_t st);
 void launch_sample_threshold(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
                              uint32_t B, uint32_t k, float *thr, cudaStream_t st);
 void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint32_t *flags, cudaStream_t st);
