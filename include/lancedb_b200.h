@@ -119,6 +119,17 @@ int lgpu_search(lgpu_index *ix, const float *queries, uint32_t B,
                 const lgpu_search_params *params,
                 uint64_t *out_ids, float *out_dist, uint32_t *out_count);
 
+/* Prefiltered search: the reference's default filter mode ("filtering will be performed
+ * before the vector search", rust/lancedb/src/query.rs:489-507; the row-id allow-list the
+ * scalar filter produced is what lance hands to the ANN nodes as a pre-filter [lance,
+ * recalled]).  `allow` is a host bitmap over row ids: bit (r & 31) of word r >> 5 set = row
+ * id r may be returned; ids >= allow_bits are excluded.  Excluded rows are dropped before the
+ * top-k (and before refine), so up to k allowed rows come back from the probed partitions. */
+int lgpu_search_filtered(lgpu_index *ix, const float *queries, uint32_t B,
+                         const lgpu_search_params *params,
+                         const uint32_t *allow, uint64_t allow_bits,
+                         uint64_t *out_ids, float *out_dist, uint32_t *out_count);
+
 /* Same, all five buffers in DEVICE memory of the index's device; enqueued on
  * `cuda_stream` (a cudaStream_t, may be 0) and NOT synchronised on return. */
 int lgpu_search_device(lgpu_index *ix, const float *d_queries, uint32_t B,
@@ -142,6 +153,11 @@ void lgpu_flat_close(lgpu_flat *fl);
 int  lgpu_flat_search(lgpu_flat *fl, int metric, const float *queries, uint32_t B,
                       const lgpu_search_params *params,
                       uint64_t *out_ids, float *out_dist, uint32_t *out_count);
+/* flat search under a row-id allow-list (same bitmap as lgpu_search_filtered) */
+int  lgpu_flat_search_filtered(lgpu_flat *fl, int metric, const float *queries, uint32_t B,
+                               const lgpu_search_params *params,
+                               const uint32_t *allow, uint64_t allow_bits,
+                               uint64_t *out_ids, float *out_dist, uint32_t *out_count);
 int  lgpu_flat_search_device(lgpu_flat *fl, int metric, const float *d_queries, uint32_t B,
                              const lgpu_search_params *params,
                              uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,

@@ -24,8 +24,8 @@ ABI_VERSION = 1
 EXPORTS = [
     "lgpu_last_error", "lgpu_abi_version", "lgpu_device_count",
     "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
-    "lgpu_search", "lgpu_search_device", "lgpu_merge_topk_device",
-    "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_device",
+    "lgpu_search", "lgpu_search_filtered", "lgpu_search_device", "lgpu_merge_topk_device",
+    "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
     "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
 ]
 
@@ -78,12 +78,14 @@ def load():
     lib.lgpu_index_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.lgpu_last_scanned_code_bytes.argtypes = [C.POINTER(C.c_uint64)]
     lib.lgpu_search.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
+    lib.lgpu_search_filtered.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_search_device.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
     lib.lgpu_merge_topk_device.argtypes = [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]
     lib.lgpu_flat_open.argtypes = [vp, C.c_uint64, u32, vp, i32, C.POINTER(vp)]
     lib.lgpu_flat_close.argtypes = [vp]
     lib.lgpu_flat_close.restype = None
     lib.lgpu_flat_search.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
+    lib.lgpu_flat_search_filtered.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_flat_search_device.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
     lib.lgpu_debug_coarse.argtypes = [vp, vp, u32, u32, vp, vp]
     lib.lgpu_debug_partition_distances.argtypes = [vp, vp, u32, vp]
@@ -161,13 +163,21 @@ class GpuIvfPq:
         check(load().lgpu_index_device_bytes(self._h, C.byref(b)))
         return b.value
 
-    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None):
-        """Host-buffer search: returns (ids [B,k] u64, dist [B,k] f32, count [B] u32)."""
+    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, allow=None, allow_bits=0):
+        """Host-buffer search: returns (ids [B,k] u64, dist [B,k] f32, count [B] u32).
+        `allow` (u32 bitmap over row ids, `allow_bits` bits) = prefilter allow-list."""
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
         B = q.shape[0]
         ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
         p = make_params(k, nprobes, refine_factor, lower, upper)
-        check(load().lgpu_search(self._h, _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist), _ptr(cnt)))
+        if allow is None:
+            check(load().lgpu_search(self._h, _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist), _ptr(cnt)))
+        else:
+            bm = np.ascontiguousarray(allow, np.uint32)
+            if bm.size * 32 < allow_bits:
+                raise ValueError("allow bitmap shorter than allow_bits")
+            check(load().lgpu_search_filtered(self._h, _ptr(q), B, C.byref(p), _ptr(bm), int(allow_bits), _ptr(ids),
+                                              _ptr(dist), _ptr(cnt)))
         return ids, dist, cnt
 
     def search_into(self, q: np.ndarray, p: SearchParams, ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray):
@@ -213,14 +223,38 @@ class GpuFlat:
 
     __del__ = close
 
-    def search(self, queries, k=10, metric="l2", lower=None, upper=None):
+    def search(self, queries, k=10, metric="l2", lower=None, upper=None, allow=None, allow_bits=0):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
         B = q.shape[0]
         ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
         p = make_params(k, 0, 0, lower, upper)
-        check(load().lgpu_flat_search(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist),
-                                      _ptr(cnt)))
+        if allow is None:
+            check(load().lgpu_flat_search(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist),
+                                          _ptr(cnt)))
+        else:
+            bm = np.ascontiguousarray(allow, np.uint32)
+            if bm.size * 32 < allow_bits:
+                raise ValueError("allow bitmap shorter than allow_bits")
+            check(load().lgpu_flat_search_filtered(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(bm),
+                                                   int(allow_bits), _ptr(ids), _ptr(dist), _ptr(cnt)))
         return ids, dist, cnt
+
+
+def allow_bitmap(row_ids, nbits: int) -> np.ndarray:
+    """Row-id allow-list -> the u32 bitmap lgpu_search_filtered takes (bit r & 31 of word r >> 5)."""
+    bm = np.zeros((int(nbits) + 31) // 32, np.uint32)
+    r = np.asarray(row_ids, np.uint64)
+    r = r[r < nbits]
+    np.bitwise_or.at(bm, (r >> np.uint64(5)).astype(np.int64), np.uint32(1) << (r & np.uint64(31)).astype(np.uint32))
+    return bm
+
+
+def mask_bitmap(mask) -> np.ndarray:
+    """Boolean mask over row ids 0..n-1 -> u32 bitmap."""
+    m = np.asarray(mask, bool)
+    pad = (-m.size) % 32
+    bits = np.packbits(np.concatenate([m, np.zeros(pad, bool)]), bitorder="little")
+    return np.ascontiguousarray(bits).view(np.uint32)
 
     def search_device(self, metric: str, d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int, d_cnt: int,
                       stream: int = 0):

@@ -62,7 +62,7 @@ struct Workspace {
     cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
     cudaEvent_t ev[8] = {};
     DevBuf q, qn, xnorm, D, probes, probe_dist, probe_cnt;
-    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars, tile_desc;
+    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars, tile_desc, allow;
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
@@ -161,6 +161,12 @@ struct WsLease {
 // The two-pass (filter + verify) scan is bit-identical to the exact path but, as measured on B200
 // (C2 workload: 1.73 ms vs 1.54 ms per 1024-query batch), not yet faster, so it is
 // opt-in: LGPU_TWO_PASS=1.
+// prefilter: device bitmap over row ids (nullptr = no filter)
+struct RowFilter {
+    const uint32_t *bits = nullptr;
+    uint64_t nbits = 0;
+};
+
 static bool two_pass_enabled()
 {
     const char *e = getenv("LGPU_TWO_PASS");
@@ -270,9 +276,9 @@ static void tc_topk_l2_filtered(Workspace *ws, cudaStream_t st, int num_sms, con
     if (Ns == N) launch_filter_dense(Dbuf, lds, B, N, flt, st);      // the sample pass already scored every row
     else launch_gemm_dist(ws->qb.p, Xb, xnorm2, B, N, d, nullptr, 0, num_sms, st, &flt);
     launch_overflow_flags(ws->amax.as<uint32_t>(), cap, B, ws->flags.as<uint32_t>(), st);
-    // 3. exact re-score of the admitted rows (lists are filled from slot 0), final top-k
-    launch_pair_distance_counted(Q, X, ws->t_pos.as<uint64_t>(), ws->amax.as<uint32_t>(), B, cap, d, LGPU_L2,
-                                 ws->t_exact.as<float>(), st);
+    // 3. exact re-score of the admitted rows, final top-k.  (Launch shapes that skip the empty slots -- a loop
+    // over the filled slots, 32- or 64-slot CTAs -- measured no faster at C2 and slower at C4 / C5 shapes.)
+    launch_pair_distance(Q, X, ws->t_pos.as<uint64_t>(), B, cap, d, LGPU_L2, ws->t_exact.as<float>(), st);
     SelectArgs sb{};
     sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
     sb.ncols = cap; sb.inner = cap; sb.row_stride = cap; sb.outer_stride = 0;
@@ -299,7 +305,7 @@ void check_params(const lgpu_search_params *p)
 // one sub-batch of an IVF_PQ search, everything device-side on `st`
 void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *d_q, uint32_t B,
                    const lgpu_search_params &sp, uint32_t nprobes, uint64_t *d_ids, float *d_dist,
-                   uint32_t *d_cnt, bool prof, const uint64_t *forced_probes = nullptr)
+                   uint32_t *d_cnt, bool prof, const uint64_t *forced_probes = nullptr, RowFilter rf = RowFilter())
 {
     const uint32_t dim = ix->dim, nlist = ix->nlist;
     const uint32_t slots = B * nprobes;
@@ -418,7 +424,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     // re-score of the shortlist, exact redo of the queries whose shortlist cannot be proven ----
     const uint32_t kp2 = sp.k <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * sp.k + 32);
     const bool two_pass = ix->has_tables && two_pass_enabled() && ix->metric != LGPU_DOT && !sp.has_lower &&
-                          !sp.has_upper && sp.refine_factor == 0 && !forced_probes && d_ids && kp2 > sp.k;
+                          !sp.has_upper && sp.refine_factor == 0 && !forced_probes && d_ids && kp2 > sp.k && !rf.bits;
     if (two_pass) {
         const size_t tq_floats = (size_t)ix->nch * 256 * 8;
         ws->tq.ensure((size_t)B * tq_floats * 4); ws->sbound.ensure((size_t)B * 4);
@@ -474,6 +480,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sa.nprobes = nprobes; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
     sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B;
     sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
+    sa.allow = rf.bits; sa.allow_bits = rf.nbits;          // prefilter: rows are dropped before the top-k
     if (sp.refine_factor == 0) {
         sa.k = sp.k; sa.out_ids = d_ids; sa.out_dist = d_dist; sa.out_count = d_cnt;
         launch_select(sa, st);
@@ -509,7 +516,8 @@ uint32_t ivf_sub_batch_size(lgpu_index *ix, uint32_t B, uint32_t nprobes)
 }
 
 void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *d_q, uint32_t B,
-                       const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt)
+                       const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt,
+                       RowFilter rf = RowFilter())
 {
     const uint32_t nprobes = std::min<uint32_t>(std::max<uint32_t>(sp.nprobes, 1), ix->nlist);
     const uint32_t bs = ivf_sub_batch_size(ix, B, nprobes);
@@ -517,7 +525,7 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
     for (uint32_t q0 = 0; q0 < B; q0 += bs) {
         uint32_t b = std::min(bs, B - q0);
         ivf_sub_batch(ix, ws, st, d_q + (size_t)q0 * ix->dim, b, sp, nprobes, d_ids + (size_t)q0 * sp.k,
-                      d_dist + (size_t)q0 * sp.k, d_cnt + q0, prof && q0 == 0);
+                      d_dist + (size_t)q0 * sp.k, d_cnt + q0, prof && q0 == 0, nullptr, rf);
     }
     if (prof) {
         LGPU_CUDA(cudaStreamSynchronize(st));
@@ -537,7 +545,8 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
 }
 
 void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metric, const float *d_q, uint32_t B,
-                        const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt)
+                        const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt,
+                        RowFilter rf = RowFilter())
 {
     const uint64_t N = fl->nrows;
     const uint64_t ld = (N + 3) & ~3ull;
@@ -563,7 +572,9 @@ void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metri
             xn = ws->xnorm.as<float>();
         }
         const uint32_t kp = (uint32_t)std::min<uint64_t>(N, std::min<uint32_t>(SELECT_KMAX, std::max<uint32_t>(8 * sp.k, 256)));
-        if (fl->has_tc && tc_enabled() && metric == LGPU_L2 && !sp.has_lower && !sp.has_upper && b >= 8 && N >= 4096) {
+        // (a prefilter goes through the exact kernels: the shortlist thresholds are fixed on unfiltered rows)
+        if (fl->has_tc && tc_enabled() && metric == LGPU_L2 && !sp.has_lower && !sp.has_upper && b >= 8 && N >= 4096 &&
+            !rf.bits) {
             if (N >= 262144 && !getenv("LGPU_FLAT_DENSE"))
                 tc_topk_l2_filtered(ws, st, fl->num_sms, q, b, fl->vectors.as<float>(), fl->vec_b.p,
                                     fl->vec_n2.as<float>(), fl->vec_max, N, fl->dim,
@@ -584,6 +595,7 @@ void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metri
         sa.B = b; sa.k = sp.k;
         sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
         sa.out_ids = d_ids + (size_t)q0 * sp.k; sa.out_dist = d_dist + (size_t)q0 * sp.k; sa.out_count = d_cnt + q0;
+        sa.allow = rf.bits; sa.allow_bits = rf.nbits;
         launch_select(sa, st);
     }
 }
@@ -623,7 +635,7 @@ static bool graphs_enabled()
 // (re)allocation, profiling mode, or a failed capture falls back to eager launches.
 template <class Run>
 void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t dim, uint32_t k, uint64_t *out_ids,
-               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], Run &&run)
+               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], Run &&run, bool allow_graph = true)
 {
     WsLease lease(pool, nullptr, false);
     Workspace *ws = lease.ws;
@@ -638,7 +650,7 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
         run(ws, st, ws->q.as<float>(), ws->out_ids.as<uint64_t>(), ws->out_dist.as<float>(), ws->out_count.as<uint32_t>());
     };
     const bool same = memcmp(key, ws->graph_key, sizeof(key)) == 0;
-    if (!graphs_enabled() || profiling_enabled() || ws->graph_state < 0) {
+    if (!allow_graph || !graphs_enabled() || profiling_enabled() || ws->graph_state < 0) {
         eager();
     } else if (!same) {                                     // new shape: warm up (allocations), capture next time
         if (ws->graph) { cudaGraphExecDestroy(ws->graph); ws->graph = nullptr; }
@@ -897,6 +909,29 @@ int lgpu_search(lgpu_index *ix, const float *queries, uint32_t B, const lgpu_sea
     });
 }
 
+int lgpu_search_filtered(lgpu_index *ix, const float *queries, uint32_t B, const lgpu_search_params *params,
+                         const uint32_t *allow, uint64_t allow_bits, uint64_t *out_ids, float *out_dist,
+                         uint32_t *out_count)
+{
+    return guarded([&] {
+        check_ivf_call(ix, queries, B, params, out_ids, out_dist, out_count);
+        LGPU_REQUIRE(allow != nullptr || allow_bits == 0, "allow bitmap is null");
+        if (B == 0) return;
+        require_device(ix->device);
+        uint64_t key[4];
+        make_key(key, 0x1f6ull, B, *params);
+        key[0] ^= allow_bits << 8;
+        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
+                      const size_t words = (size_t)((allow_bits + 31) / 32);
+                      ws->allow.ensure(std::max<size_t>(words, 1) * 4);
+                      if (words) LGPU_CUDA(cudaMemcpyAsync(ws->allow.p, allow, words * 4, cudaMemcpyHostToDevice, st));
+                      RowFilter rf; rf.bits = ws->allow.as<uint32_t>(); rf.nbits = allow_bits;
+                      ivf_search_device(ix, ws, st, dq, B, *params, di, dd, dc, rf);
+                  }, false);
+    });
+}
+
 int lgpu_search_device(lgpu_index *ix, const float *d_queries, uint32_t B, const lgpu_search_params *params,
                        uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count, void *cuda_stream)
 {
@@ -986,6 +1021,28 @@ int lgpu_flat_search(lgpu_flat *fl, int metric, const float *queries, uint32_t B
                   [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
                       flat_search_device(fl, ws, st, metric, dq, B, *params, di, dd, dc);
                   });
+    });
+}
+
+int lgpu_flat_search_filtered(lgpu_flat *fl, int metric, const float *queries, uint32_t B,
+                              const lgpu_search_params *params, const uint32_t *allow, uint64_t allow_bits,
+                              uint64_t *out_ids, float *out_dist, uint32_t *out_count)
+{
+    return guarded([&] {
+        check_flat_call(fl, metric, queries, B, params, out_ids, out_dist, out_count);
+        LGPU_REQUIRE(allow != nullptr || allow_bits == 0, "allow bitmap is null");
+        if (B == 0) return;
+        require_device(fl->device);
+        uint64_t key[4];
+        make_key(key, 0xf1b7ull + (uint64_t)metric, B, *params);
+        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count, key,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
+                      const size_t words = (size_t)((allow_bits + 31) / 32);
+                      ws->allow.ensure(std::max<size_t>(words, 1) * 4);
+                      if (words) LGPU_CUDA(cudaMemcpyAsync(ws->allow.p, allow, words * 4, cudaMemcpyHostToDevice, st));
+                      RowFilter rf; rf.bits = ws->allow.as<uint32_t>(); rf.nbits = allow_bits;
+                      flat_search_device(fl, ws, st, metric, dq, B, *params, di, dd, dc, rf);
+                  }, false);
     });
 }
 

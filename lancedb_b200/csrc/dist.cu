@@ -194,42 +194,6 @@ __global__ void pair_distance_kernel(const float *__restrict__ Q, const float *_
     if (hl == 0) out[pair] = v;
 }
 
-// Same result as pair_distance_kernel for candidate lists that are filled from slot 0 (cnt[q] entries,
-// possibly above nc when appends were dropped): one CTA per query loops over the filled slots only, instead
-// of one half-warp per (query, slot) -- the lists are mostly empty, and launching B * nc / 16 CTAs that exit
-// at once cost more than the distances themselves (C2 coarse step: 47 us for ~60 filled slots of 512).
-// grid = (nc / 64 slot blocks, B): a CTA of 16 half-warps owns 64 slots, CTAs past the fill count exit on
-// one load, and long lists (flat search: ~150 of 1024) still spread over several CTAs.
-// Slots >= cnt[q] are left untouched: their ids are UINT64_MAX and the selector ignores them.
-__global__ void pair_distance_counted_kernel(const float *__restrict__ Q, const float *__restrict__ V,
-                                             const uint64_t *__restrict__ pos, const uint32_t *__restrict__ cnt,
-                                             uint32_t nc, uint32_t d, int metric, float *__restrict__ out)
-{
-    const uint32_t q = blockIdx.y;
-    const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
-    const unsigned hmask = 0xffffu << hbase;
-    const uint32_t c0 = blockIdx.x * 64u;
-    const uint32_t n = min(min(cnt[q], nc), c0 + 64u);
-    if (c0 >= n) return;
-    const float *x = Q + (size_t)q * d;
-    for (uint32_t c = c0 + (threadIdx.x >> 4); c < n; c += blockDim.x >> 4) {
-        const uint64_t pair = (uint64_t)q * nc + c;
-        const uint64_t ps = pos[pair];
-        if (ps == UINT64_MAX) { if (hl == 0) out[pair] = CUDART_INF_F; continue; }
-        const float *y = V + ps * d;
-        float v;
-        if (metric == LGPU_L2) v = halfwarp_l2(x, y, d, hl, hmask, hbase);
-        else if (metric == LGPU_DOT) v = __fsub_rn(1.0f, halfwarp_dot(x, y, d, hl, hmask, hbase));
-        else {
-            float xn = sqrtf(halfwarp_dot(x, x, d, hl, hmask, hbase));
-            float yy = halfwarp_dot(y, y, d, hl, hmask, hbase);
-            float xy = halfwarp_dot(x, y, d, hl, hmask, hbase);
-            v = __fsub_rn(1.0f, __fdiv_rn(__fdiv_rn(xy, xn), sqrtf(yy)));
-        }
-        if (hl == 0) out[pair] = v;
-    }
-}
-
 }  // namespace
 
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
@@ -266,15 +230,6 @@ void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, u
     if (B == 0 || nc == 0) return;
     uint64_t threads = (uint64_t)B * nc * 16;
     pair_distance_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Q, V, pos, B, nc, d, metric, out);
-    LGPU_CUDA(cudaGetLastError());
-}
-
-void launch_pair_distance_counted(const float *Q, const float *V, const uint64_t *pos, const uint32_t *cnt,
-                                  uint32_t B, uint32_t nc, uint32_t d, int metric, float *out, cudaStream_t st)
-{
-    if (B == 0 || nc == 0) return;
-    dim3 grid((nc + 63) / 64, B);
-    pair_distance_counted_kernel<<<grid, 256, 0, st>>>(Q, V, pos, cnt, nc, d, metric, out);
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -107,10 +107,6 @@ void launch_normalize(const float *X, uint32_t B, uint32_t d, float *out, cudaSt
 void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, uint32_t B, uint32_t nc,
                           uint32_t d, int metric, float *out, cudaStream_t st);
 
-// the same for candidate lists filled from slot 0: only slots < min(cnt[q], nc) are computed / written
-void launch_pair_distance_counted(const float *Q, const float *V, const uint64_t *pos, const uint32_t *cnt,
-                                  uint32_t B, uint32_t nc, uint32_t d, int metric, float *out, cudaStream_t st);
-
 // ---------------- top-k select (K4) ------------------------------------------------
 constexpr uint32_t SELECT_KMAX = 2048;
 struct SelectArgs {
@@ -141,6 +137,10 @@ struct SelectArgs {
     uint32_t *out_count;          // [B]
     uint64_t *out_pos;            // optional [B][k] storage position (mode 0) / column (mode 1)
     const uint32_t *only;         // optional [B]: queries whose flag is 0 are left untouched
+    // prefilter (query.rs:489-507): optional row-id allow-list bitmap; a candidate whose id has bit 0 (or is
+    // >= allow_bits) is dropped before it can enter the top-k
+    const uint32_t *allow;
+    uint64_t allow_bits;
 };
 void launch_select(const SelectArgs &a, cudaStream_t st);
 

@@ -59,6 +59,11 @@ __device__ void bitonic_sort(Stage s, uint32_t n2)
     }
 }
 
+__device__ __forceinline__ bool allow_bit(const SelectArgs &a, uint64_t id)
+{
+    return id < a.allow_bits && ((a.allow[id >> 5] >> (id & 31)) & 1u);
+}
+
 template <bool POS>
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint32_t cap, uint32_t trigger)
 {
@@ -106,6 +111,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
             if (f == 0.f) f = 0.f;                           // -0 and +0 tie
             uint32_t key = f32_key(f);
             bool pass = ok[u] && in_range(f) && key <= tau;
+            uint64_t id = 0;
+            if (pass) {
+                id = idsrc ? idsrc[idbase + u] : idbase + u;
+                if (a.allow) pass = allow_bit(a, id);
+            }
             unsigned mask = __ballot_sync(0xffffffffu, pass);
             if (mask) {
                 uint32_t base = 0;
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
                 if (pass) {
                     uint32_t slot = base + __popc(mask & ((1u << lane) - 1));
                     st.keys[slot] = key;
-                    st.ids[slot] = idsrc ? idsrc[idbase + u] : idbase + u;
+                    st.ids[slot] = id;
                     if (POS) st.pos[slot] = posbase + u;
                 }
             }
@@ -188,6 +198,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
                 if (f == 0.f) f = 0.f;
                 uint32_t key = f32_key(f);
                 bool pass = ok[u] && in_range(f) && key <= tau;
+                if (pass && a.allow) pass = allow_bit(a, idv[u]);
                 unsigned mask = __ballot_sync(0xffffffffu, pass);
                 if (mask) {
                     uint32_t base = 0;
@@ -302,9 +313,12 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
             float f = v[u];
             if (f == 0.f) f = 0.f;                          // -0 and +0 tie
             const uint32_t key = f32_key(f);
-            const bool pass = (uint64_t)u < n_left && in_range(f) && key <= tau_k;
+            bool pass = (uint64_t)u < n_left && in_range(f) && key <= tau_k;
             uint64_t id = 0;
-            if (pass) id = idsrc ? idsrc[idbase + u] : idbase + u;
+            if (pass) {
+                id = idsrc ? idsrc[idbase + u] : idbase + u;
+                if (a.allow) pass = allow_bit(a, id);
+            }
             offer(pass, key, id, posbase + u);
         }
     };
@@ -358,6 +372,7 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
                 if (f == 0.f) f = 0.f;
                 key = f32_key(f);
                 pass = id != UINT64_MAX && in_range(f) && key <= tau_k;
+                if (pass && a.allow) pass = allow_bit(a, id);
                 if (POS && a.cand_pos) pos = a.cand_pos[addr];
             }
             offer(pass, key, id, pos);

@@ -6,8 +6,10 @@ and the request it lowers to, `VectorQueryRequest`
 (/root/reference/rust/lancedb/src/query.rs:1066-1114): limit 10, nprobes 20 (min == max),
 no refine, L2.  Everything below `to_arrow()` runs on the GPU through the C ABI; only the
 `Take` of the non-vector columns for the k result rows happens in
-pyarrow on the host.  Filters (`where`), FTS and rerankers are outside the hot path and
-raise NotImplementedError.
+pyarrow on the host.  `where(...)` filters: the predicate is evaluated on the host (filter.py) and its
+row-id allow-list goes to the GPU as a bitmap (prefilter, the default, `lgpu_search_filtered`) or is
+applied to the k results (postfilter).  FTS and rerankers are outside the hot path and raise
+NotImplementedError.
 """
 from __future__ import annotations
 
@@ -15,6 +17,8 @@ from typing import List, Optional, Union
 
 import numpy as np
 import pyarrow as pa
+
+from . import filter as _filter
 
 DEFAULT_TOP_K = 10          # rust/lancedb/src/query.rs:36
 DEFAULT_NPROBES = 20        # rust/lancedb/src/query.rs:1097-1113
@@ -44,6 +48,8 @@ class LanceVectorQueryBuilder:
         self._columns: Optional[List[str]] = None
         self._with_row_id = False
         self._use_index = True
+        self._where: Optional[str] = None
+        self._postfilter = False
 
     # ---- setters (same names as the reference) ----
     def metric(self, metric: str) -> "LanceVectorQueryBuilder":
@@ -99,8 +105,21 @@ class LanceVectorQueryBuilder:
         self._use_index = False
         return self
 
-    def where(self, *a, **k):
-        raise NotImplementedError("filters (prefilter/postfilter) are outside the GPU hot path (SURVEY.md 8f-3)")
+    def where(self, where: str, prefilter: Optional[bool] = None) -> "LanceVectorQueryBuilder":
+        """SQL predicate over the table's columns; calling it again ANDs the filters
+        (python/python/lancedb/query.py:1864-1892).  prefilter (default): rows are excluded before the
+        vector search; prefilter=False: the filter is applied to the search's results, which can
+        then be fewer than `limit` (rust/lancedb/src/query.rs:489-507)."""
+        if not isinstance(where, str):
+            raise NotImplementedError("only SQL string filters are supported (no Expr objects)")
+        self._where = _filter.combine(self._where, where)
+        if prefilter is not None:
+            self._postfilter = not prefilter
+        return self
+
+    def postfilter(self) -> "LanceVectorQueryBuilder":
+        self._postfilter = True
+        return self
 
     def rerank(self, *a, **k):
         raise NotImplementedError("rerankers are out of scope")
@@ -126,15 +145,23 @@ class LanceVectorQueryBuilder:
         if self._query.shape[1] != t._dim(self._vector_column):
             raise ValueError(
                 f"No vector column found to match with the query vector dimension: {self._query.shape[1]}")
+        mask = None
+        if self._where is not None:
+            mask = _filter.evaluate(t._data, self._where)          # row id == row position
         ids, dist, cnt = t._vector_search(
             self._query, column=self._vector_column, k=k, nprobes=nprobes,
             refine_factor=self._refine_factor, distance_type=self._distance_type,
-            lower=self._lower_bound, upper=self._upper_bound, use_index=self._use_index)
+            lower=self._lower_bound, upper=self._upper_bound, use_index=self._use_index,
+            allow_mask=None if (mask is None or self._postfilter) else mask)
         out = []
         for qi in range(self._query.shape[0]):
             n = int(cnt[qi])
-            sel_ids = ids[qi, self._offset:n][:lim]
-            sel_dist = dist[qi, self._offset:n][:lim]
+            row_ids, row_dist = ids[qi, :n], dist[qi, :n]
+            if mask is not None and self._postfilter:              # filter the vector search's results
+                keep = mask[row_ids.astype(np.int64)]
+                row_ids, row_dist = row_ids[keep], row_dist[keep]
+            sel_ids = row_ids[self._offset:][:lim]
+            sel_dist = row_dist[self._offset:][:lim]
             tbl = t._take(sel_ids, self._columns)
             tbl = tbl.append_column("_distance", pa.array(sel_dist, pa.float32()))
             if self._with_row_id:

@@ -33,7 +33,26 @@ class _Params(C.Structure):
     _fields_ = [
         ("k", C.c_uint32), ("nprobes", C.c_uint32), ("refine_factor", C.c_uint32),
         ("has_lower", C.c_int), ("has_upper", C.c_int), ("lower", C.c_float), ("upper", C.c_float),
+        ("allow", C.c_void_p), ("allow_bits", C.c_uint64),
     ]
+
+
+def allow_bitmap(row_ids, nbits: int) -> np.ndarray:
+    """Row-id allow-list -> u32 bitmap of `nbits` bits (the form orc_params.allow / the C ABI take)."""
+    bm = np.zeros((int(nbits) + 31) // 32, np.uint32)
+    r = np.asarray(row_ids, np.uint64)
+    r = r[r < nbits]
+    np.bitwise_or.at(bm, (r >> np.uint64(5)).astype(np.int64), (np.uint32(1) << (r & np.uint64(31)).astype(np.uint32)))
+    return bm
+
+
+def _params(k, nprobes, refine_factor, lower, upper, allow=None, allow_bits=0):
+    p = _Params(k, nprobes, refine_factor, lower is not None, upper is not None,
+                0.0 if lower is None else lower, 0.0 if upper is None else upper, None, 0)
+    if allow is not None:
+        p.allow = allow.ctypes.data
+        p.allow_bits = int(allow_bits)
+    return p
 
 
 def build(force: bool = False) -> str:
@@ -163,11 +182,12 @@ class OracleIndex:
         load().orc_partition_distances(C.byref(self.c), _ptr(q), int(part), _ptr(out))
         return out
 
-    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, nthreads=1):
+    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, nthreads=1,
+               allow=None, allow_bits=0):
         q = _f32(queries).reshape(-1, self.dim)
         B = q.shape[0]
-        p = _Params(k, nprobes, refine_factor, lower is not None, upper is not None,
-                    0.0 if lower is None else lower, 0.0 if upper is None else upper)
+        allow = None if allow is None else np.ascontiguousarray(allow, np.uint32)
+        p = _params(k, nprobes, refine_factor, lower, upper, allow, allow_bits)
         ids = np.empty((B, k), np.uint64)
         dist = np.empty((B, k), np.float32)
         cnt = np.empty(B, np.uint32)
@@ -178,14 +198,15 @@ class OracleIndex:
         return ids, dist, cnt
 
 
-def flat_search(vectors, queries, k=10, metric="l2", row_ids=None, lower=None, upper=None, nthreads=1):
+def flat_search(vectors, queries, k=10, metric="l2", row_ids=None, lower=None, upper=None, nthreads=1,
+                allow=None, allow_bits=0):
     v = _f32(vectors)
     n, dim = v.shape
     q = _f32(queries).reshape(-1, dim)
     B = q.shape[0]
     rid = np.ascontiguousarray(row_ids, dtype=np.uint64) if row_ids is not None else None
-    p = _Params(k, 0, 0, lower is not None, upper is not None,
-                0.0 if lower is None else lower, 0.0 if upper is None else upper)
+    allow = None if allow is None else np.ascontiguousarray(allow, np.uint32)
+    p = _params(k, 0, 0, lower, upper, allow, allow_bits)
     ids = np.empty((B, k), np.uint64)
     dist = np.empty((B, k), np.float32)
     cnt = np.empty(B, np.uint32)

@@ -189,6 +189,12 @@ static int cand_cmp(const void *pa, const void *pb)
     return 0;
 }
 
+static inline int allowed(const orc_params *p, uint64_t id)
+{
+    if (!p->allow) return 1;
+    return id < p->allow_bits && ((p->allow[id >> 5] >> (id & 31)) & 1u);
+}
+
 static inline int in_range(const orc_params *p, float d)
 {
     if (d != d) return 0;                      /* FilterExec: _distance IS NOT NULL */
@@ -341,7 +347,8 @@ static void *ivf_worker(void *arg)
             if (n == 0) continue;
             partition_distances(ix, qn, part, resid, lut, dists);
             for (size_t r = 0; r < n; r++)
-                if (in_range(p, dists[r])) heap_offer(&h, dists[r], ix->row_ids[off + r], off + r);
+                if (in_range(p, dists[r]) && allowed(p, ix->row_ids[off + r]))
+                    heap_offer(&h, dists[r], ix->row_ids[off + r], off + r);
         }
         if (p->refine_factor && ix->vectors) {
             /* refine (rust/lancedb/src/query.rs:1302-1332): exact distance of the
@@ -402,7 +409,8 @@ static void *flat_worker(void *arg)
         h.n = 0;
         for (uint64_t r = 0; r < job->n; r++) {
             float d = orc_distance_f32(job->metric, q, job->vectors + r * job->dim, job->dim);
-            if (in_range(p, d)) heap_offer(&h, d, job->row_ids ? job->row_ids[r] : r, r);
+            uint64_t id = job->row_ids ? job->row_ids[r] : r;
+            if (in_range(p, d) && allowed(p, id)) heap_offer(&h, d, id, r);
         }
         emit(p, &h, job->out_ids + (size_t)qi * p->k, job->out_dist + (size_t)qi * p->k,
              job->out_count + qi);

@@ -67,6 +67,12 @@ typedef struct {
     uint32_t refine_factor;  /* 0 = none */
     int      has_lower, has_upper;
     float    lower, upper;   /* distance range [lower, upper) */
+    /* prefilter (rust/lancedb/src/query.rs:489-507, the default filter mode): row-id allow-list as a
+     * bitmap, bit r of word r/32 = row id r may be returned; ids >= allow_bits are excluded.
+     * NULL = no filter.  Rows are dropped before the top-k, so k allowed rows come back if the probed
+     * partitions hold that many. */
+    const uint32_t *allow;
+    uint64_t allow_bits;
 } orc_params;
 
 /* IvfModel::find_partitions [lance, recalled]: all-centroid distances, then the

@@ -108,3 +108,41 @@ def test_graph_replay_matches_eager(tmp_path):
     assert set(res["0"].files) == set(res["1"].files)
     for name in res["0"].files:
         assert np.array_equal(res["0"][name], res["1"][name]), name
+
+
+def test_query_builder_with_prefilter_and_postfilter():
+    """python/python/tests/test_query.py:911-986: where() prefilters by default, prefilter=False filters
+    the vector search's results (possibly to nothing), repeated where() calls AND."""
+    db = lancedb.connect("memory://")
+    t = db.create_table("t", [{"vector": [1.0, 2.0], "id": 1, "b": 5}, {"vector": [3.0, 4.0], "id": 2, "b": 20},
+                              {"vector": [5.0, 6.0], "id": 3, "b": 7}, {"vector": [0.5, 0.1], "id": 4, "b": 9}])
+    rs = t.search([0, 0]).where("id = 2").to_list()
+    assert len(rs) == 1 and rs[0]["id"] == 2 and rs[0]["vector"] == [3.0, 4.0]
+    df = t.search([0, 0]).where("id = 2", prefilter=True).limit(1).to_pandas()
+    assert df["id"].values[0] == 2
+    df = t.search([0, 0]).where("id = 2", prefilter=False).limit(1).to_pandas()
+    assert len(df) == 0                                   # the nearest row is id 4; the filter drops it
+    assert len(t.search([0, 0]).where("id = 2").postfilter().limit(1).to_list()) == 0
+    rs = t.search([0, 0]).where("id >= 1").where("b < 10").limit(10).to_list()
+    assert [r["id"] for r in rs] == [4, 1, 3]
+    assert t.search([0, 0]).where("id < 0").to_list() == []
+    with pytest.raises(ValueError):
+        t.search([0, 0]).where("nosuchcolumn = 1").to_list()
+
+
+def test_ivf_pq_table_prefilter_vs_oracle():
+    rng = np.random.default_rng(17)
+    n, dim = 4000, 32
+    vec = rng.standard_normal((n, dim)).astype(np.float32)
+    db = lancedb.connect("memory://")
+    t = db.create_table("t", {"vector": list(vec), "id": np.arange(n), "grp": np.arange(n) % 7})
+    t.create_index(metric="l2", num_partitions=16, num_sub_vectors=8, accelerator="cuda")
+    q = rng.standard_normal(dim).astype(np.float32)
+    out = t.search(q).where("grp = 3 AND id >= 100").nprobes(8).limit(10).with_row_id(True).to_arrow()
+    data = t._index_data["vector"]
+    mask = (np.arange(n) % 7 == 3) & (np.arange(n) >= 100)
+    oi, od, oc = oracle.OracleIndex.from_data(data).search(q, k=10, nprobes=8, allow=oracle.allow_bitmap(
+        np.nonzero(mask)[0], n), allow_bits=n)
+    assert out["_rowid"].to_pylist() == oi[0, :oc[0]].tolist()
+    assert np.array_equal(np.asarray(out["_distance"]).view(np.uint32), od[0, :oc[0]].view(np.uint32))
+    assert all(g == 3 for g in out["grp"].to_pylist())

@@ -227,3 +227,54 @@ def test_streaming_scan_many_tiles_per_cta():
     sizes = rng.integers(1, 400, size=nlist)
     ix = random_index(rng, dim=32, nlist=nlist, m=4, sizes=sizes)
     _check_search(ix, queries(rng, 700, 32), k=5, nprobes=9)
+
+
+# ---------------------------------------------------------------- prefilter (row-id allow-list)
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+@pytest.mark.parametrize("frac", [0.5, 0.02])
+def test_prefiltered_ivf_search(metric, frac):
+    """lgpu_search_filtered against the oracle with the same bitmap: dense and selective allow-lists,
+    ids beyond allow_bits excluded, k larger than some queries' allowed candidates."""
+    rng = np.random.default_rng(31)
+    ix = random_index(rng, dim=64, nlist=24, m=8, metric=metric, n=9000)
+    n = int(ix.part_offsets[-1])
+    nbits = n - 37                                      # the last 37 row ids fall outside the bitmap
+    mask = rng.random(nbits) < frac
+    bm = _native.mask_bitmap(mask)
+    assert np.array_equal(bm, oracle.allow_bitmap(np.nonzero(mask)[0], nbits))
+    gi, gd, gc = _check_search(ix, queries(rng, 41, 64), k=25, nprobes=6, allow=bm, allow_bits=nbits)
+    for i in range(41):
+        got = gi[i, :gc[i]].astype(np.int64)
+        assert (got < nbits).all() and mask[got].all()
+    if frac < 0.1:
+        assert (gc < 25).any()                          # selective filter: fewer than k allowed rows probed
+
+
+def test_prefiltered_ivf_with_refine_and_range():
+    rng = np.random.default_rng(32)
+    ix = random_index(rng, dim=32, nlist=10, m=4, n=5000, with_vectors=True)
+    mask = rng.random(5000) < 0.3
+    bm = _native.mask_bitmap(mask)
+    _check_search(ix, queries(rng, 19, 32), k=8, nprobes=5, refine_factor=3, allow=bm, allow_bits=5000)
+    _check_search(ix, queries(rng, 19, 32), k=8, nprobes=5, lower=1.0, upper=40.0, allow=bm, allow_bits=5000)
+    empty = np.zeros_like(bm)
+    gi, gd, gc = _check_search(ix, queries(rng, 5, 32), k=8, nprobes=5, allow=empty, allow_bits=5000)
+    assert (gc == 0).all() and (gi == np.iinfo(np.uint64).max).all()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_prefiltered_flat_search(metric):
+    rng = np.random.default_rng(33)
+    n, dim = 6000, 48                                   # n >= 4096: the unfiltered call would take the tensor-core path
+    v = rng.standard_normal((n, dim)).astype(np.float32)
+    ids = rng.permutation(n).astype(np.uint64)
+    q = rng.standard_normal((33, dim)).astype(np.float32)
+    mask = rng.random(n) < 0.1
+    bm = _native.mask_bitmap(mask)
+    fl = _native.GpuFlat(v, ids)
+    gi, gd, gc = fl.search(q, k=12, metric=metric, allow=bm, allow_bits=n)
+    fl.close()
+    oi, od, oc = oracle.flat_search(v, q, k=12, metric=metric, row_ids=ids, allow=bm, allow_bits=n, nthreads=8)
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert mask[gi[gc > 0][:, 0].astype(np.int64)].all()

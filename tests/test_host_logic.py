@@ -62,8 +62,10 @@ def test_builder_validation_errors():
         LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").limit(0)
     with pytest.raises(ValueError, match="maximum_nprobes"):
         LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").minimum_nprobes(10).maximum_nprobes(5).to_arrow()
+    b = LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").where("a > 1").where("a < 5", prefilter=False)
+    assert b._where == "(a > 1) AND (a < 5)" and b._postfilter        # test_query.py:600-604
     with pytest.raises(NotImplementedError):
-        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").where("a > 1")
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").where(object())
 
 
 def test_index_parameter_defaults():
@@ -143,3 +145,65 @@ def test_sharded_search_pattern_world2_gloo(tmp_path):
     port = _free_port()
     mp.spawn(_rank_main, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+# ---------------------------------------------------------------- where() filters (host side)
+def test_filter_evaluator_matches_reference_test_predicates():
+    """The predicate forms the reference's tests pass to .where() (python/python/tests/test_query.py:
+    284-308, 600-604, 911-986, 1024) evaluated on the host; NULL predicates exclude the row."""
+    import pyarrow as pa
+    from lancedb_b200 import filter as F
+    t = pa.table({"id": [1, 2, 3, 4, None], "b": [5.0, 15.0, 2.5, None, 9.0], "name": ["aa", "ab", "ca", None, "zz"]})
+    cases = {
+        "id = 2": [0, 1, 0, 0, 0], "id >= 2": [0, 1, 1, 1, 0], "b < 10": [1, 0, 1, 0, 1],
+        "(id >= 1) AND (id < 2)": [1, 0, 0, 0, 0], "id < 0": [0, 0, 0, 0, 0],
+        "id IN (1, 3) OR name LIKE 'z%'": [1, 0, 1, 0, 1], "NOT id = 2": [1, 0, 1, 1, 0],
+        "b IS NULL": [0, 0, 0, 1, 0], "id IS NOT NULL and b BETWEEN 2 AND 9": [1, 0, 1, 0, 0],
+        "name = 'ab'": [0, 1, 0, 0, 0], "id NOT IN (1, 2)": [0, 0, 1, 1, 0],
+    }
+    for w, want in cases.items():
+        assert F.evaluate(t, w).astype(int).tolist() == want, w
+    assert F.combine(None, "id >= 1") == "id >= 1"
+    assert F.combine("id >= 1", "id < 2") == "(id >= 1) AND (id < 2)"       # test_query.py:600-604
+    for bad in ("id ==== 2", "nosuchcolumn = 1", "id = ", ""):
+        with pytest.raises(ValueError):
+            F.evaluate(t, bad)
+
+
+def test_allow_bitmaps_agree():
+    from lancedb_b200 import _native
+    import oracle
+    rng = np.random.default_rng(5)
+    for n in (1, 31, 32, 33, 1000):
+        mask = rng.random(n) < 0.3
+        a = _native.mask_bitmap(mask)
+        b = _native.allow_bitmap(np.nonzero(mask)[0], n)
+        c = oracle.allow_bitmap(np.nonzero(mask)[0], n)
+        assert a.dtype == np.uint32 and a.size == (n + 31) // 32
+        assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_oracle_prefilter_semantics():
+    """Prefilter = rows dropped before the top-k: the filtered result equals the unfiltered search over
+    only the allowed rows (flat), and every returned id is allowed (IVF_PQ)."""
+    import oracle
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(6)
+    v = rng.standard_normal((300, 16)).astype(np.float32)
+    q = rng.standard_normal((5, 16)).astype(np.float32)
+    allowed = np.sort(rng.choice(300, 40, replace=False)).astype(np.uint64)
+    bm = oracle.allow_bitmap(allowed, 300)
+    fi, fd, fc = oracle.flat_search(v, q, k=7, allow=bm, allow_bits=300)
+    si, sd, sc = oracle.flat_search(v[allowed], q, k=7, row_ids=allowed)
+    assert np.array_equal(fi, si) and np.array_equal(fd, sd) and np.array_equal(fc, sc)
+    ix = random_index(rng, dim=32, nlist=8, m=4, n=2000)
+    orc = oracle.OracleIndex.from_data(ix)
+    allowed = rng.choice(2000, 150, replace=False).astype(np.uint64)
+    bm = oracle.allow_bitmap(allowed, 2000)
+    ids, dist, cnt = orc.search(queries(rng, 9, 32), k=10, nprobes=8, allow=bm, allow_bits=2000)
+    ok = set(allowed.tolist())
+    for i in range(9):
+        assert cnt[i] == 10 and all(int(x) in ok for x in ids[i, :cnt[i]])
+    # ids beyond allow_bits are excluded
+    ids2, _, cnt2 = orc.search(queries(rng, 3, 32), k=10, nprobes=8, allow=oracle.allow_bitmap(np.arange(64), 64), allow_bits=64)
+    assert all(int(x) < 64 for i in range(3) for x in ids2[i, :cnt2[i]])
