@@ -208,14 +208,14 @@ def run_reference(args, cfg):
     dt = time.perf_counter() - t0
     qps = B * args.steps / dt
     sample = f"{B} queries per step (the full batch), oracle/oracle.c, {cores} threads"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "ANN queries/sec (IVF_PQ)", "value": qps, "unit": "queries/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA_DESC,
         "config": workload_config(cfg, args, 1, "cpu"),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def workload_config(cfg, args, world, par):
@@ -227,7 +227,29 @@ def workload_config(cfg, args, world, par):
             "l2_flush": "512 MiB write between steps (untimed); each step uses a different query batch"}
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner to
+    fd 1 when NCCL_DEBUG is set in the environment) write there too, so fd 1 points at stderr until
+    _emit() prints the line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -392,7 +414,7 @@ def main():
                           "d2h_bytes_per_step": B * k * 12 + B * 4}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(cfg, full_ix, qn.reshape(-1, dim))
-        print(json.dumps(out), flush=True)
+        _emit(out)
     gpu.close()
     if world > 1:
         dist.destroy_process_group()
