@@ -37,12 +37,6 @@ constexpr int S2_RMAX = 12;                         // rows per scanner thread: 
 #ifndef S2_CREG_V
 #define S2_CREG_V 128
 #endif
-#ifndef S2_BOTH_HALVES
-#define S2_BOTH_HALVES 0                            // 1: a builder lane computes its (code, sub-space) entry for all 8
-#endif                                              //    queries (codebook entry read once), DSUB == 8 only
-#ifndef S2_LDS_AHEAD
-#define S2_LDS_AHEAD 1                              // codebook entries are read back 1 or 2 tasks ahead
-#endif
 constexpr int S2_PREG = S2_PREG_V, S2_CREG = S2_CREG_V;   // 256 * PREG + 256 * CREG <= 65536 registers
 constexpr int S2_SLOTS = 4;                         // tile-descriptor ring
 constexpr int S2_SLOT_BYTES = 128;
@@ -127,7 +121,6 @@ struct CbStage {
     uint32_t base;      // shared-space address of this warp's ring
     uint32_t so;        // byte offset of the slot holding the task whose entry is in `cur`
     float4 cur[2];      // codebook entry (this lane's code, sub-space) of the current task
-    float4 nx1[2];      // ... of the task after it (S2_LDS_AHEAD == 2)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
@@ -173,7 +166,7 @@ __device__ __forceinline__ void stage_start(const ScanArgs &a, CbStage &cs, int 
 // The residuals of this lane's sub-space for its 4 queries (DSUB == 8), packed for the f32x2 ops.  Loaded by the
 // builder loop *before* it waits for the ring buffer, so the LDS latency hides behind the barrier.
 struct ResidRegs {
-    uint64_t pr[2][4][4];       // [half][query][dim pair]; only pr[0] is used unless S2_BOTH_HALVES
+    uint64_t pr[4][4];          // [query][dim pair]
 };
 template <int DSUB>
 __device__ __forceinline__ void load_resid_regs(ResidRegs &rr, int rslot, bool two_halves, int lane)
@@ -181,20 +174,16 @@ __device__ __forceinline__ void load_resid_regs(ResidRegs &rr, int rslot, bool t
     if constexpr (DSUB == 8) {
         extern __shared__ __align__(1024) unsigned char smem[];
         const int s = lane & 7;
-        const int h = (two_halves && !S2_BOTH_HALVES) ? ((lane >> 3) & 1) : 0;
+        const int h = two_halves ? ((lane >> 3) & 1) : 0;
         const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem + Smem<DSUB>::RBUF) +
                               (uint32_t)rslot * Smem<DSUB>::RB * 4 + (uint32_t)(4 * h) * 256 +
                               (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
 #pragma unroll
-        for (int hh = 0; hh < (S2_BOTH_HALVES ? 2 : 1); hh++) {
-            if (hh == 1 && !two_halves) break;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t at = base + (hh * 4 + j) * 256;
-                const float4 lo = lds128(at), hi = lds128(at ^ 16u);
-                rr.pr[hh][j][0] = pk2(lo.x, lo.y); rr.pr[hh][j][1] = pk2(lo.z, lo.w);
-                rr.pr[hh][j][2] = pk2(hi.x, hi.y); rr.pr[hh][j][3] = pk2(hi.z, hi.w);
-            }
+        for (int j = 0; j < 4; j++) {
+            const uint32_t at = base + j * 256;
+            const float4 lo = lds128(at), hi = lds128(at ^ 16u);
+            rr.pr[j][0] = pk2(lo.x, lo.y); rr.pr[j][1] = pk2(lo.z, lo.w);
+            rr.pr[j][2] = pk2(hi.x, hi.y); rr.pr[j][3] = pk2(hi.z, hi.w);
         }
     }
 }
@@ -213,12 +202,11 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
     extern __shared__ __align__(1024) unsigned char smem[];      // declared here so every access is a plain
     unsigned char *const lut = smem + Smem<DSUB>::LUT;           // shared-space LDS/STS
     const float *const rsrc_chunk = reinterpret_cast<const float *>(smem + Smem<DSUB>::RBUF) + rslot * Smem<DSUB>::RB;
-    constexpr bool BOTH = S2_BOTH_HALVES && DSUB == 8 && HALVES == 2;   // both query halves per lane
-    constexpr int CPT = (HALVES == 2 && !BOTH) ? 2 : 4;
+    constexpr int CPT = HALVES == 2 ? 2 : 4;
     constexpr int NTASK = 256 / CPT / S2_PW;                   // 16 or 8
     const int s = lane & 7;
-    const int h = (HALVES == 2 && !BOTH) ? ((lane >> 3) & 1) : 0;
-    const int csel = (HALVES == 2 && !BOTH) ? (lane >> 4) : (lane >> 3);
+    const int h = HALVES == 2 ? ((lane >> 3) & 1) : 0;
+    const int csel = HALVES == 2 ? (lane >> 4) : (lane >> 3);
     const bool sub_ok = (ch * 8 + s) < a.m;
     const float *rsrc = rsrc_chunk + ((4 * h) * 8 + s) * DSUB;                // + j * 8 * DSUB per query
     unsigned char *dst = lut + b * SCAN_LUT_BYTES + h * SCAN_LUT_HALF + s * 16 + (CPT * pw + csel) * 128;
@@ -227,37 +215,25 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
     if constexpr (DSUB == 8) {
         constexpr int SLOT = CPT * 256, D = S2_STAGE_BYTES / SLOT;             // 6 or 3 tasks in flight
         static_assert(D >= 2 && D <= NTASK, "staging depth");
-        const uint64_t (&pr)[4][4] = rr.pr[0];
+        const uint64_t (&pr)[4][4] = rr.pr;
         // this lane's entry inside a slot: code csel, sub-space s, swizzled 16-byte units 2s and 2s+1
         const uint32_t ent = cs.base + (uint32_t)csel * 256 + (uint32_t)(((2 * s) ^ (s >> 2)) << 4);
-        constexpr int AH = S2_LDS_AHEAD;
-        static_assert(AH == 1 || AH == 2, "read-back distance");
-        static_assert(D - 1 - AH >= 0, "staging depth vs read-back distance");
-        if (ch == 0) {                          // first task(s) of the tile: the oldest of D copy groups
-            cp_async_wait<D - AH>();
+        if (ch == 0) {                          // first task of the tile: its copy is the oldest of D groups
+            cp_async_wait<D - 1>();
             __syncwarp();
             cs.cur[0] = lds128(ent + cs.so); cs.cur[1] = lds128((ent + cs.so) ^ 16u);
-            if constexpr (AH == 2) {
-                const uint32_t s1 = cs.so + SLOT == S2_STAGE_BYTES ? 0u : cs.so + SLOT;
-                cs.nx1[0] = lds128(ent + s1); cs.nx1[1] = lds128((ent + s1) ^ 16u);
-            }
         }
 #pragma unroll
         for (int k = 0; k < NTASK; k++) {
             // entry of task k is in cs.cur, its slot (cs.so) is free: refill it with task k + D
-            cp_async_wait<D - 1 - AH>();        // task k+AH has landed (this lane's part) ...
+            cp_async_wait<D - 2>();             // task k+1 has landed (this lane's part) ...
             __syncwarp();                       // ... and every lane's part; also orders last LDS before the refill
             if (k + D < NTASK) stage_issue<CPT>(a, cs, cs.so, ch, k + D, pw, lane);
             else if (has_next) stage_issue<CPT>(a, cs, cs.so, ch + 1, k + D - NTASK, pw, lane);
             cp_async_commit();                  // (possibly empty: keeps the group count per task at one)
             const uint32_t so_next = cs.so + SLOT == S2_STAGE_BYTES ? 0u : cs.so + SLOT;
             float4 n0 = cs.cur[0], n1 = cs.cur[1];
-            if constexpr (AH == 1) {
-                if (k + 1 < NTASK || has_next) { n0 = lds128(ent + so_next); n1 = lds128((ent + so_next) ^ 16u); }
-            } else {
-                const uint32_t so_2 = so_next + SLOT == S2_STAGE_BYTES ? 0u : so_next + SLOT;
-                if (k + 2 < NTASK || has_next) { n0 = lds128(ent + so_2); n1 = lds128((ent + so_2) ^ 16u); }
-            }
+            if (k + 1 < NTASK || has_next) { n0 = lds128(ent + so_next); n1 = lds128((ent + so_next) ^ 16u); }
             const float4 c0 = cs.cur[0], c1 = cs.cur[1];
             float4 out;
             if constexpr (!DOT) {
@@ -276,27 +252,7 @@ __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int 
                 out = make_float4(o[0], o[1], o[2], o[3]);
             }
             *reinterpret_cast<float4 *>(dst + k * DST_STRIDE) = out;
-            if constexpr (BOTH) {               // same codebook entry against queries 4-7
-                float4 out1;
-                if constexpr (!DOT) {
-                    const uint64_t pc[4] = {pk2(c0.x, c0.y), pk2(c0.z, c0.w), pk2(c1.x, c1.y), pk2(c1.z, c1.w)};
-                    out1 = l2_tree8_packed_x4(rr.pr[1], pc, a.fzero2);
-                } else {
-                    const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                    float o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float r8[8];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) upk2(rr.pr[1][j][e], r8[2 * e], r8[2 * e + 1]);
-                        o[j] = sub_ok ? subvec_dot_dist<8>(r8, cv) : 0.f;
-                    }
-                    out1 = make_float4(o[0], o[1], o[2], o[3]);
-                }
-                *reinterpret_cast<float4 *>(dst + k * DST_STRIDE + SCAN_LUT_HALF) = out1;
-            }
-            if constexpr (AH == 1) { cs.cur[0] = n0; cs.cur[1] = n1; }
-            else { cs.cur[0] = cs.nx1[0]; cs.cur[1] = cs.nx1[1]; cs.nx1[0] = n0; cs.nx1[1] = n1; }
+            cs.cur[0] = n0; cs.cur[1] = n1;
             cs.so = so_next;
         }
     } else {
@@ -333,12 +289,12 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
     CbStage cs;
     cs.base = (uint32_t)__cvta_generic_to_shared(smem + Smem<DSUB>::STAGE) + (uint32_t)pw * S2_STAGE_BYTES;
     cs.so = 0;
-    cs.cur[0] = cs.cur[1] = cs.nx1[0] = cs.nx1[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cs.cur[0] = cs.cur[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     {   // first tile: residual chunk 0 and the first codebook copies
         const TileDesc *T0 = slot_ptr(tiles, 0);
         if (T0->ng) {
             if constexpr (DSUB == 8) {
-                if (T0->ng > 4 && !S2_BOTH_HALVES) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
+                if (T0->ng > 4) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
             }
             res.template load<DOT>(a, T0, 0, tid);
             res.store(rbuf, tid);
@@ -374,7 +330,7 @@ __device__ __forceinline__ void producer_loop(const ScanArgs &a, uint32_t total,
             else if (res_next) {
                 res.template load<DOT>(a, Tn, 0, tid);
                 if constexpr (DSUB == 8) {      // this stage builds nothing: start the next tile's codebook copies
-                    if (ng_next > 4 && !S2_BOTH_HALVES) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
+                    if (ng_next > 4) stage_start<2>(a, cs, pw, lane); else stage_start<4>(a, cs, pw, lane);
                 }
             }
 
