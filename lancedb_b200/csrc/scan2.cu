@@ -13,8 +13,8 @@
 //     (48 registers instead of 96), which leaves room to keep a dozen LDS.128 in flight, and there are two
 //     scanner warps per scheduler instead of one.
 //   * the table build is straight-line code: 16 (or 8) tasks per warp and chunk, no bounds checks, the
-//     metric and the half count are template parameters, codebook entries are prefetched three tasks
-//     ahead across chunk and tile boundaries (the codebook does not depend on the tile).
+//     metric and the half count are template parameters; each builder warp streams the codebook entries of
+//     its tasks through a private cp.async ring, six tasks ahead, across chunk boundaries (CbStage below).
 //   * tiles with <= 4 queries use a 4-codes-per-warp mapping (HALVES = 1): half the build work instead of
 //     idle lanes.
 #include "kernels.cuh"
@@ -193,8 +193,9 @@ __device__ __forceinline__ void load_resid_regs(ResidRegs &rr, int rslot, bool t
 //                x 8 sub-spaces x both query halves; 16 tasks per warp.
 //   HALVES == 1: lane -> (s = lane & 7, cq = lane >> 3); a warp task covers 4 codes x 8 sub-spaces for
 //                queries 0-3; 8 tasks per warp.
-// `ring` holds the codebook entries of tasks 0..PF-1 on entry and those of the first PF tasks of chunk
-// `ch_next` (mapping `cpt_next`) on exit.
+// DSUB == 8: on entry `cs` has the copies of this chunk's first D tasks in flight (or landed) and, from the
+// second chunk of a tile on, the entry of task 0 in cs.cur; `has_next` = the tile has another chunk, whose
+// first D tasks are issued from here.  `rr` = this lane's residuals (load_resid_regs).
 template <int DSUB, bool DOT, int HALVES>
 __device__ __forceinline__ void build_chunk(const ScanArgs &a, uint32_t ch, int b, int rslot, CbStage &cs,
                                             const ResidRegs &rr, bool has_next, int pw, int lane)

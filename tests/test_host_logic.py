@@ -207,3 +207,23 @@ def test_oracle_prefilter_semantics():
     # ids beyond allow_bits are excluded
     ids2, _, cnt2 = orc.search(queries(rng, 3, 32), k=10, nprobes=8, allow=oracle.allow_bitmap(np.arange(64), 64), allow_bits=64)
     assert all(int(x) < 64 for i in range(3) for x in ids2[i, :cnt2[i]])
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """bench.py --impl reference (the CPU arm the driver times next to ours) on the tiny workload: exactly one
+    line on stdout, the contract's keys, `impl: reference`, and a cpu_baseline that describes this run."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NCCL_DEBUG="VERSION")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "tiny",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["steps"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
