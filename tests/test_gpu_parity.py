@@ -278,3 +278,14 @@ def test_prefiltered_flat_search(metric):
     assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
     assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
     assert mask[gi[gc > 0][:, 0].astype(np.int64)].all()
+
+
+@pytest.mark.parametrize("metric", ["l2", "dot"])
+def test_streaming_scan_many_tiles_dsub8(metric):
+    """The dsub == 8 build path (cp.async codebook staging, both table-build mappings) with ~7 tiles per
+    persistent CTA and three table chunks per tile (m = 20: the last chunk is half padding)."""
+    rng = np.random.default_rng(23)
+    nlist = 300
+    sizes = rng.integers(1, 260, size=nlist)
+    ix = random_index(rng, dim=160, nlist=nlist, m=20, metric=metric, sizes=sizes)
+    _check_search(ix, queries(rng, 500, 160), k=10, nprobes=12)
