@@ -145,6 +145,20 @@ int lgpu_merge_topk_device(int device, uint32_t nlists, uint32_t B, uint32_t k,
                            uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
                            void *cuda_stream);
 
+/* ---- index build passes (reference: IVF_PQ build through lance, parameters at
+ * rust/lancedb/src/table/create_index.rs:283-303, rust/lancedb/src/index/vector.rs:246-319; "GPU support in
+ * building vector index", python/python/lancedb/table.py:2883-2937).  k-means training stays with the caller;
+ * these are the two passes over every row, bit-consistent with the search kernels.  All pointers are HOST
+ * memory; vectors are raw rows (normalised internally for LGPU_COSINE). ------------------------------- */
+/* out_parts[r] = the partition find_partitions(vectors[r], nprobes = 1) returns */
+int lgpu_ivf_assign(const float *centroids, uint32_t nlist, uint32_t dim, int metric,
+                    const float *vectors, uint64_t n, int device, uint32_t *out_parts);
+/* out_codes[r][i] (row-major [n][m]) = the codeword of sub-space i with the smallest distance-table entry
+ * for row r's residual (row - centroid[parts[r]]; the row itself for LGPU_DOT); ties go to the lowest code */
+int lgpu_pq_encode(const float *centroids, const float *codebook, uint32_t nlist, uint32_t dim, uint32_t m,
+                   int metric, const float *vectors, const uint32_t *parts, uint64_t n, int device,
+                   unsigned char *out_codes);
+
 /* ---- flat / brute force (LanceRead -> KNNVectorDistance -> TopK) --------- */
 int  lgpu_flat_open(const float *vectors, uint64_t nrows, uint32_t dim,
                     const uint64_t *row_ids /* NULL => 0..nrows-1 */, int device,

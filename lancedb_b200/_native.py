@@ -26,6 +26,7 @@ EXPORTS = [
     "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
     "lgpu_search", "lgpu_search_filtered", "lgpu_search_device", "lgpu_merge_topk_device",
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
+    "lgpu_ivf_assign", "lgpu_pq_encode",
     "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
 ]
 
@@ -84,6 +85,8 @@ def load():
     lib.lgpu_flat_open.argtypes = [vp, C.c_uint64, u32, vp, i32, C.POINTER(vp)]
     lib.lgpu_flat_close.argtypes = [vp]
     lib.lgpu_flat_close.restype = None
+    lib.lgpu_ivf_assign.argtypes = [vp, u32, u32, i32, vp, C.c_uint64, i32, vp]
+    lib.lgpu_pq_encode.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp, C.c_uint64, i32, vp]
     lib.lgpu_flat_search.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
     lib.lgpu_flat_search_filtered.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_flat_search_device.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
@@ -238,6 +241,25 @@ class GpuFlat:
             check(load().lgpu_flat_search_filtered(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(bm),
                                                    int(allow_bits), _ptr(ids), _ptr(dist), _ptr(cnt)))
         return ids, dist, cnt
+
+
+def ivf_assign(centroids, vectors, metric: str = "l2", device: int = 0) -> np.ndarray:
+    """Partition of every row = find_partitions(row, nprobes=1) with the search path's exact kernels."""
+    c = np.ascontiguousarray(centroids, np.float32); v = np.ascontiguousarray(vectors, np.float32)
+    out = np.empty(v.shape[0], np.uint32)
+    check(load().lgpu_ivf_assign(_ptr(c), c.shape[0], c.shape[1], METRICS[metric], _ptr(v), v.shape[0], device, _ptr(out)))
+    return out
+
+
+def pq_encode(centroids, codebook, vectors, parts, metric: str = "l2", device: int = 0) -> np.ndarray:
+    """8-bit PQ codes [n, m] of raw rows given their partitions (residual PQ for l2/cosine)."""
+    c = np.ascontiguousarray(centroids, np.float32); cb = np.ascontiguousarray(codebook, np.float32)
+    v = np.ascontiguousarray(vectors, np.float32); p = np.ascontiguousarray(parts, np.uint32)
+    m = cb.shape[0]
+    out = np.empty((v.shape[0], m), np.uint8)
+    check(load().lgpu_pq_encode(_ptr(c), _ptr(cb), c.shape[0], c.shape[1], m, METRICS[metric], _ptr(v), _ptr(p),
+                                v.shape[0], device, _ptr(out)))
+    return out
 
 
 def allow_bitmap(row_ids, nbits: int) -> np.ndarray:

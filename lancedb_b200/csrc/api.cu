@@ -1136,4 +1136,81 @@ int lgpu_debug_partition_distances(lgpu_index *ix, const float *query, uint32_t 
     });
 }
 
+// ---- index build passes (build.cu): host buffers in, host buffers out, chunked over rows ----
+int lgpu_ivf_assign(const float *centroids, uint32_t nlist, uint32_t dim, int metric, const float *vectors,
+                    uint64_t n, int device, uint32_t *out_parts)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(centroids && nlist > 0 && dim > 0, "null centroids / empty shape");
+        LGPU_REQUIRE(metric == LGPU_L2 || metric == LGPU_COSINE || metric == LGPU_DOT, "unknown distance type");
+        LGPU_REQUIRE(n == 0 || (vectors && out_parts), "null vectors / output");
+        if (n == 0) return;
+        require_device(device);
+        cudaStream_t st = nullptr;
+        const uint64_t ld = (nlist + 3ull) & ~3ull;
+        const uint64_t CH = std::max<uint64_t>(256, std::min<uint64_t>(65536, ((uint64_t)1 << 28) / (ld * 4)));
+        DevBuf cent, x, xn, D, ids, dist, cnt;
+        cent.ensure((size_t)nlist * dim * 4);
+        LGPU_CUDA(cudaMemcpyAsync(cent.p, centroids, (size_t)nlist * dim * 4, cudaMemcpyHostToDevice, st));
+        x.ensure((size_t)CH * dim * 4); D.ensure((size_t)CH * ld * 4);
+        ids.ensure((size_t)CH * 8); dist.ensure((size_t)CH * 4); cnt.ensure((size_t)CH * 4);
+        if (metric == LGPU_COSINE) xn.ensure((size_t)CH * dim * 4);
+        std::vector<uint64_t> h_ids(CH);
+        for (uint64_t r0 = 0; r0 < n; r0 += CH) {
+            const uint32_t b = (uint32_t)std::min<uint64_t>(CH, n - r0);
+            LGPU_CUDA(cudaMemcpyAsync(x.p, vectors + r0 * dim, (size_t)b * dim * 4, cudaMemcpyHostToDevice, st));
+            const float *q = x.as<float>();
+            if (metric == LGPU_COSINE) { launch_normalize(q, b, dim, xn.as<float>(), st); q = xn.as<float>(); }
+            // the search path's own coarse step (find_partitions with nprobes = 1)
+            launch_dist_matrix(q, cent.as<float>(), b, nlist, dim, metric == LGPU_DOT ? 1 : 0, nullptr, nullptr,
+                               D.as<float>(), ld, st);
+            SelectArgs sa{};
+            sa.mode = 1; sa.dense = D.as<float>(); sa.ncols = nlist; sa.row_stride = ld; sa.B = b; sa.k = 1;
+            sa.out_ids = ids.as<uint64_t>(); sa.out_dist = dist.as<float>(); sa.out_count = cnt.as<uint32_t>();
+            launch_select(sa, st);
+            LGPU_CUDA(cudaMemcpyAsync(h_ids.data(), ids.p, (size_t)b * 8, cudaMemcpyDeviceToHost, st));
+            LGPU_CUDA(cudaStreamSynchronize(st));
+            for (uint32_t i = 0; i < b; i++) {
+                LGPU_REQUIRE(h_ids[i] < nlist, "a vector has no finite centroid distance (NaN input?)");
+                out_parts[r0 + i] = (uint32_t)h_ids[i];
+            }
+        }
+    });
+}
+
+int lgpu_pq_encode(const float *centroids, const float *codebook, uint32_t nlist, uint32_t dim, uint32_t m,
+                   int metric, const float *vectors, const uint32_t *parts, uint64_t n, int device,
+                   unsigned char *out_codes)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(centroids && codebook && nlist > 0 && dim > 0 && m > 0, "null index array / empty shape");
+        LGPU_REQUIRE(dim % m == 0 && scan_dsub_supported(dim / m),
+                     "unsupported PQ sub-vector length (dim/num_sub_vectors must be 1,2,4,8,16 or 32)");
+        LGPU_REQUIRE(metric == LGPU_L2 || metric == LGPU_COSINE || metric == LGPU_DOT, "unknown distance type");
+        LGPU_REQUIRE(n == 0 || (vectors && parts && out_codes), "null vectors / partitions / output");
+        if (n == 0) return;
+        for (uint64_t r = 0; r < n; r++) LGPU_REQUIRE(parts[r] < nlist, "partition id out of range");
+        require_device(device);
+        cudaStream_t st = nullptr;
+        const uint64_t CH = 65536;
+        DevBuf cent, cb, x, xn, p, codes;
+        cent.ensure((size_t)nlist * dim * 4); cb.ensure((size_t)m * 256 * (dim / m) * 4);
+        LGPU_CUDA(cudaMemcpyAsync(cent.p, centroids, (size_t)nlist * dim * 4, cudaMemcpyHostToDevice, st));
+        LGPU_CUDA(cudaMemcpyAsync(cb.p, codebook, (size_t)m * 256 * (dim / m) * 4, cudaMemcpyHostToDevice, st));
+        x.ensure((size_t)CH * dim * 4); p.ensure((size_t)CH * 4); codes.ensure((size_t)CH * m);
+        if (metric == LGPU_COSINE) xn.ensure((size_t)CH * dim * 4);
+        for (uint64_t r0 = 0; r0 < n; r0 += CH) {
+            const uint32_t b = (uint32_t)std::min<uint64_t>(CH, n - r0);
+            LGPU_CUDA(cudaMemcpyAsync(x.p, vectors + r0 * dim, (size_t)b * dim * 4, cudaMemcpyHostToDevice, st));
+            LGPU_CUDA(cudaMemcpyAsync(p.p, parts + r0, (size_t)b * 4, cudaMemcpyHostToDevice, st));
+            const float *q = x.as<float>();
+            if (metric == LGPU_COSINE) { launch_normalize(q, b, dim, xn.as<float>(), st); q = xn.as<float>(); }
+            launch_pq_encode(q, p.as<uint32_t>(), cent.as<float>(), cb.as<float>(), b, dim, m, metric,
+                             codes.as<unsigned char>(), st);
+            LGPU_CUDA(cudaMemcpyAsync(out_codes + r0 * m, codes.p, (size_t)b * m, cudaMemcpyDeviceToHost, st));
+            LGPU_CUDA(cudaStreamSynchronize(st));
+        }
+    });
+}
+
 }  // extern "C"

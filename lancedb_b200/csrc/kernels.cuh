@@ -194,6 +194,11 @@ void launch_band_check2(const float *approx, const uint32_t *cnt, const float *s
                         const int *rmax_bits, float scale, uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags,
                         cudaStream_t st);
 
+// ---------------- index build (build.cu) ----------------------------------------------
+// codes[row][i] = argmin_c entry(row's residual sub-vector i, codebook_i[c]) (ties: lowest c); X normalised for cosine
+void launch_pq_encode(const float *X, const uint32_t *parts, const float *centroids, const float *codebook,
+                      uint64_t n, uint32_t dim, uint32_t m, int metric, unsigned char *codes, cudaStream_t st);
+
 // ---------------- index re-layout (open time) --------------------------------------
 void launch_retile_codes(const unsigned char *codes, int layout, const uint64_t *part_off, uint32_t nlist,
                          uint64_t nrows, uint32_t m, uint32_t nch, const uint64_t *code_base,

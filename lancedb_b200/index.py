@@ -168,10 +168,15 @@ def _batched_kmeans(x, k, iters, gen):
 def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vectors: Optional[int] = None,
                  distance_type: str = "l2", sample_rate: int = 256, max_iterations: int = 50,
                  row_ids: Optional[np.ndarray] = None, keep_vectors: bool = False, seed: int = 45,
-                 device: Optional[str] = None, encode_chunk: int = 1 << 16) -> IvfPqIndexData:
+                 device: Optional[str] = None, encode_chunk: int = 1 << 16,
+                 native_passes: bool = False) -> IvfPqIndexData:
     """Train IVF centroids + residual PQ codebooks and encode every row.
 
     vectors: [n, dim] float32 (numpy or torch).  Returns the plain-array index.
+    native_passes: run the two passes over every row (IVF assignment, PQ encoding) through the C ABI
+    (`lgpu_ivf_assign` / `lgpu_pq_encode`, csrc/build.cu) -- the search kernels' own arithmetic, so a row
+    always lands in the partition its own vector probes first -- instead of torch's GEMM-form argmin.
+    The k-means training loops stay in torch either way.
     """
     import torch
     metric = distance_type.lower()
@@ -188,7 +193,7 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
             return train_ivf_pq(x, num_partitions=num_partitions, num_sub_vectors=num_sub_vectors,
                                 distance_type=distance_type, sample_rate=sample_rate, max_iterations=max_iterations,
                                 row_ids=row_ids, keep_vectors=keep_vectors, seed=seed, device=None,
-                                encode_chunk=encode_chunk)
+                                encode_chunk=encode_chunk, native_passes=native_passes)
         finally:
             torch.set_num_threads(prev)
     n, dim = x.shape
@@ -205,7 +210,14 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
     ns = min(n, sample_rate * nlist)
     samp = x[torch.randperm(n, generator=gen, device="cpu")[:ns].to(x.device)] if ns < n else x
     centroids = _kmeans(samp, nlist, max_iterations, gen)
-    assign = _assign(x, centroids)
+    dev_index = x.device.index or 0 if x.device.type == "cuda" else 0
+    if native_passes:
+        from . import _native
+        raw_np = raw.detach().cpu().numpy()
+        assign = torch.as_tensor(_native.ivf_assign(centroids.cpu().numpy(), raw_np, metric, dev_index).astype(np.int64),
+                                 device=x.device)
+    else:
+        assign = _assign(x, centroids)
 
     # PQ codebooks: residuals for l2/cosine, raw vectors for dot
     nps = min(n, max(256, sample_rate) * 256)
@@ -216,7 +228,11 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
 
     cbn = (codebook * codebook).sum(2)                                     # [m, 256]
     codes = torch.empty((n, m), dtype=torch.uint8, device=x.device)
-    for s in range(0, n, encode_chunk):
+    if native_passes:
+        codes = torch.as_tensor(_native.pq_encode(centroids.cpu().numpy(), codebook.cpu().numpy(), raw_np,
+                                                  assign.cpu().numpy().astype(np.uint32), metric, dev_index),
+                                device=x.device)
+    for s in range(0, n if not native_passes else 0, encode_chunk):
         xs = x[s:s + encode_chunk]
         r = xs - centroids[assign[s:s + encode_chunk]] if metric != "dot" else xs
         r = r.reshape(-1, m, dsub).transpose(0, 1)                         # [m, c, dsub]

@@ -92,6 +92,10 @@ def load():
     lib.orc_pq_scan.argtypes = [vp, vp, C.c_size_t, C.c_uint32, vp]
     lib.orc_partition_distances.restype = None
     lib.orc_partition_distances.argtypes = [C.POINTER(_Index), vp, C.c_uint32, vp]
+    lib.orc_ivf_assign.argtypes = [C.POINTER(_Index), vp, C.c_uint64, vp]
+    lib.orc_ivf_assign.restype = None
+    lib.orc_pq_encode.argtypes = [C.POINTER(_Index), vp, vp, C.c_uint64, vp]
+    lib.orc_pq_encode.restype = None
     lib.orc_ivfpq_search.restype = C.c_int
     lib.orc_ivfpq_search.argtypes = [C.POINTER(_Index), vp, C.c_uint32, C.POINTER(_Params), vp, vp, vp, C.c_int]
     lib.orc_flat_search.restype = C.c_int
@@ -180,6 +184,19 @@ class OracleIndex:
         n = int(self.part_offsets[part + 1] - self.part_offsets[part])
         out = np.empty(n, np.float32)
         load().orc_partition_distances(C.byref(self.c), _ptr(q), int(part), _ptr(out))
+        return out
+
+    def ivf_assign(self, vectors):
+        v = _f32(vectors).reshape(-1, self.dim)
+        out = np.empty(v.shape[0], np.uint32)
+        load().orc_ivf_assign(C.byref(self.c), _ptr(v), v.shape[0], _ptr(out))
+        return out
+
+    def pq_encode(self, vectors, parts):
+        v = _f32(vectors).reshape(-1, self.dim)
+        p = np.ascontiguousarray(parts, np.uint32)
+        out = np.empty((v.shape[0], self.m), np.uint8)
+        load().orc_pq_encode(C.byref(self.c), _ptr(v), _ptr(p), v.shape[0], _ptr(out))
         return out
 
     def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, nthreads=1,

@@ -391,6 +391,50 @@ int orc_ivfpq_search(const orc_index *ix, const float *queries, uint32_t B,
 }
 
 /* ------------------------------------------------------------------------ */
+void orc_ivf_assign(const orc_index *ix, const float *vectors, uint64_t n, uint32_t *out_parts)
+{
+    float *qn = (float *)malloc(sizeof(float) * ix->dim);
+    for (uint64_t r = 0; r < n; r++) {
+        const float *x = vectors + r * ix->dim;
+        if (ix->metric == ORC_COSINE) orc_normalize_f32(x, ix->dim, qn);
+        else memcpy(qn, x, sizeof(float) * ix->dim);
+        orc_find_partitions(ix, qn, 1, out_parts + r, NULL, NULL);
+    }
+    free(qn);
+}
+
+void orc_pq_encode(const orc_index *ix, const float *vectors, const uint32_t *parts, uint64_t n,
+                   uint8_t *out_codes)
+{
+    uint32_t dim = ix->dim, m = ix->m, dsub = dim / m;
+    float *qn = (float *)malloc(sizeof(float) * dim * 2);
+    float *res = qn + dim;
+    for (uint64_t r = 0; r < n; r++) {
+        const float *x = vectors + r * dim;
+        if (ix->metric == ORC_COSINE) orc_normalize_f32(x, dim, qn);
+        else memcpy(qn, x, sizeof(float) * dim);
+        const float *rq = qn;
+        if (ix->metric != ORC_DOT) {
+            const float *c = ix->centroids + (size_t)parts[r] * dim;
+            for (uint32_t t = 0; t < dim; t++) res[t] = qn[t] - c[t];
+            rq = res;
+        }
+        for (uint32_t i = 0; i < m; i++) {
+            const float *sub = rq + (size_t)i * dsub;
+            const float *cb = ix->codebook + (size_t)i * 256 * dsub;
+            float best = 0.0f; int best_c = 0;
+            for (int j = 0; j < 256; j++) {
+                float d = ix->metric == ORC_DOT ? 1.0f - orc_dot_f32(sub, cb + (size_t)j * dsub, dsub)
+                                                : orc_l2_subvec(sub, cb + (size_t)j * dsub, dsub);
+                if (j == 0 || d < best) { best = d; best_c = j; }
+            }
+            out_codes[r * m + i] = (uint8_t)best_c;
+        }
+    }
+    free(qn);
+}
+
+/* ------------------------------------------------------------------------ */
 typedef struct {
     const float *vectors; uint64_t n; uint32_t dim; const uint64_t *row_ids; int metric;
     const float *queries; uint32_t q0, q1; const orc_params *p;

@@ -101,6 +101,14 @@ int orc_ivfpq_search(const orc_index *ix, const float *queries, uint32_t B,
 void orc_partition_distances(const orc_index *ix, const float *q, uint32_t part,
                              float *dists);
 
+/* Index-build passes [lance, recalled]: IVF assignment = find_partitions with nprobes 1 per row
+ * (rows normalised first for cosine); ProductQuantizer::transform = per sub-vector the codeword with the
+ * smallest distance-table entry (residual row - centroid for L2/cosine, the row for dot), ties to the
+ * lowest code.  vectors are raw rows; out_codes is row-major [n][m]. */
+void orc_ivf_assign(const orc_index *ix, const float *vectors, uint64_t n, uint32_t *out_parts);
+void orc_pq_encode(const orc_index *ix, const float *vectors, const uint32_t *parts, uint64_t n,
+                   uint8_t *out_codes);
+
 /* Flat KNN (KNNVectorDistance + TopK by (_distance,_rowid)). row_ids may be
  * NULL (then 0..n-1). */
 int orc_flat_search(const float *vectors, uint64_t n, uint32_t dim,

@@ -227,3 +227,23 @@ def test_bench_reference_arm_prints_one_json_line(tmp_path):
     assert d["impl"] == "reference" and d["steps"] == 2 and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_oracle_pq_encode_is_argmin_of_the_distance_table():
+    """orc_pq_encode picks, per sub-vector, the first minimum of the very table row orc_build_lut produces for
+    the row's residual; orc_ivf_assign is find_partitions with nprobes 1."""
+    import oracle
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(8)
+    for metric, dim, m in (("l2", 32, 4), ("cosine", 48, 3), ("dot", 16, 16)):
+        ix = random_index(rng, dim=dim, nlist=7, m=m, metric=metric, n=100)
+        orc = oracle.OracleIndex.from_data(ix)
+        v = queries(rng, 20, dim)
+        parts = orc.ivf_assign(v)
+        codes = orc.pq_encode(v, parts)
+        for r in range(20):
+            qn = oracle.normalize(v[r]) if metric == "cosine" else v[r]
+            assert parts[r] == orc.find_partitions(qn, 1)[0][0]
+            resid = qn if metric == "dot" else (qn - ix.centroids[parts[r]]).astype(np.float32)
+            lut = orc.build_lut(resid)
+            assert np.array_equal(codes[r], lut.argmin(axis=1).astype(np.uint8))
