@@ -112,7 +112,8 @@ class Table:
         data = train_ivf_pq(self._vectors(column), num_partitions=num_partitions,
                             num_sub_vectors=num_sub_vectors, distance_type=metric,
                             max_iterations=max_iterations, sample_rate=sample_rate,
-                            keep_vectors=True, device=dev)
+                            keep_vectors=True, device=dev,
+                            native_passes=dev is not None)      # accelerator: row passes through the C ABI (build.cu)
         self._attach_index(column, data)
 
     def _attach_index(self, column: str, data: IvfPqIndexData):
