@@ -123,3 +123,73 @@ def run(ntiles, nch, seed):
 def test_scan2_handover_protocol(ntiles, nch):
     for seed in range(25):
         run(ntiles, nch, seed)
+
+
+# ---------------------------------------------------------------- codebook staging ring (cp.async groups)
+def _staging_run(ntask, depth, nch, tiles, seed):
+    """One builder warp's cp.async ring as scan2.cu::build_chunk / stage_start drive it.  Copies complete in
+    commit order but at arbitrary times unless a wait_group forces them; a slot read must find its task
+    landed, and a slot may only be refilled after its previous task was read back into registers."""
+    rng = random.Random(seed)
+    nslots = depth
+    groups = []                                # committed groups, oldest first: [task or None, slot, landed]
+    slot_task = [None] * nslots                # task whose bytes are (being) written to the slot
+    slot_read = [True] * nslots                # has that task been read back?
+
+    def commit(task, slot):
+        if task is not None:
+            assert slot_read[slot], f"slot {slot} refilled before task {slot_task[slot]} was read"
+            slot_task[slot], slot_read[slot] = task, False
+        groups.append([task, slot, False])
+
+    def wait_group(n):                         # all but the newest n groups are complete
+        for g in groups[:max(0, len(groups) - n)]:
+            g[2] = True
+        for g in groups:                       # in-order completion at random times
+            if not g[2] and rng.random() < 0.3:
+                g[2] = True
+            elif not g[2]:
+                break
+
+    def read(task, slot):
+        assert slot_task[slot] == task, f"slot {slot} holds task {slot_task[slot]}, wanted {task}"
+        landed = [g for g in groups if g[0] == task]
+        assert landed and landed[-1][2], f"task {task} read before its copy landed"
+        slot_read[slot] = True
+
+    for t in range(tiles):
+        base = (t, 0, 0)
+        # stage_start: tasks 0..D-1 of chunk 0, ring phase reset
+        for k in range(depth):
+            commit((t, 0, k), k)
+        so = 0
+        for ch in range(nch):
+            has_next = ch + 1 < nch
+            if ch == 0:
+                wait_group(depth - 1)
+                read((t, 0, 0), so)
+            for k in range(ntask):
+                wait_group(depth - 2)
+                if k + depth < ntask:
+                    commit((t, ch, k + depth), so)
+                elif has_next:
+                    commit((t, ch + 1, k + depth - ntask), so)
+                else:
+                    commit(None, so)
+                so_next = 0 if so + 1 == nslots else so + 1
+                if k + 1 < ntask:
+                    read((t, ch, k + 1), so_next)
+                elif has_next:
+                    read((t, ch + 1, 0), so_next)
+                so = so_next
+        # every real copy of the tile has been consumed before the next stage_start overwrites the ring
+        assert all(slot_read), f"tile {t} left unread slots: {slot_task}"
+        for g in groups:
+            g[2] = True
+
+
+@pytest.mark.parametrize("ntask,depth", [(16, 6), (8, 3)])
+@pytest.mark.parametrize("nch", [1, 2, 3, 12])
+def test_scan2_codebook_staging_ring(ntask, depth, nch):
+    for seed in range(20):
+        _staging_run(ntask, depth, nch, tiles=3, seed=seed)
