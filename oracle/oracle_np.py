@@ -92,8 +92,33 @@ def pq_scan(lut, codes_t):
     return acc
 
 
-def ivfpq_search_one(ix, q, k, nprobes, lower=None, upper=None):
-    """ix: lancedb_b200.index.IvfPqIndexData; returns (ids, dists) sorted by (dist, id)"""
+def ivf_assign(ix, v):
+    """find_partitions(row, nprobes = 1) per row"""
+    out = np.empty(len(v), np.uint32)
+    for r, x in enumerate(np.asarray(v, f32)):
+        qn = normalize(x) if ix.metric == "cosine" else x
+        if ix.metric == "dot":
+            cd = np.array([f32(f32(1) - dot(qn, c)) for c in ix.centroids], f32)
+        else:
+            cd = np.array([l2(qn, c) for c in ix.centroids], f32)
+        out[r] = np.lexsort((np.arange(ix.nlist), cd))[0]
+    return out
+
+
+def pq_encode(ix, v, parts):
+    """ProductQuantizer::transform [lance, recalled]: first minimum of each distance-table row"""
+    dsub = ix.dim // ix.m
+    out = np.empty((len(v), ix.m), np.uint8)
+    for r, x in enumerate(np.asarray(v, f32)):
+        qn = normalize(x) if ix.metric == "cosine" else x
+        rq = qn if ix.metric == "dot" else (qn - ix.centroids[parts[r]]).astype(f32)
+        out[r] = build_lut(ix.codebook, rq, ix.metric).argmin(axis=1)
+    return out
+
+
+def ivfpq_search_one(ix, q, k, nprobes, lower=None, upper=None, allowed=None):
+    """ix: lancedb_b200.index.IvfPqIndexData; returns (ids, dists) sorted by (dist, id).
+    allowed: optional set of row ids (prefilter: other rows are dropped before the top-k)"""
     q = np.asarray(q, f32)
     qn = normalize(q) if ix.metric == "cosine" else q
     if ix.metric == "dot":
@@ -118,6 +143,8 @@ def ivfpq_search_one(ix, q, k, nprobes, lower=None, upper=None):
             if lower is not None and not d[r] >= f32(lower):
                 continue
             if upper is not None and not d[r] < f32(upper):
+                continue
+            if allowed is not None and int(ix.row_ids[a + r]) not in allowed:
                 continue
             cands.append((d[r], int(ix.row_ids[a + r])))
     cands.sort()

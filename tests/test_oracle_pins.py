@@ -104,6 +104,27 @@ def test_ivfpq_c_vs_numpy_mirror(metric):
     assert np.array_equal(ids, ids2) and np.array_equal(dist, dist2) and np.array_equal(cnt, cnt2)
 
 
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_prefilter_and_build_passes_c_vs_numpy_mirror(metric):
+    """The C oracle's prefilter, IVF assignment and PQ encoding against the independent NumPy statement."""
+    rng = np.random.default_rng(44)
+    x = rng.standard_normal((500, 32)).astype(np.float32)
+    ix = train_ivf_pq(x, num_partitions=5, num_sub_vectors=4, distance_type=metric, max_iterations=4)
+    oix = oracle.OracleIndex.from_data(ix)
+    q = rng.standard_normal((4, 32)).astype(np.float32)
+    allowed = sorted(int(a) for a in rng.choice(500, 60, replace=False))
+    bm = oracle.allow_bitmap(allowed, 500)
+    ids, dist, cnt = oix.search(q, k=9, nprobes=3, allow=bm, allow_bits=500)
+    for i in range(4):
+        wi, wd = oracle_np.ivfpq_search_one(ix, q[i], 9, 3, allowed=set(allowed))
+        assert cnt[i] == len(wi)
+        assert np.array_equal(ids[i, :cnt[i]], wi) and np.array_equal(dist[i, :cnt[i]], wd)
+    v = rng.standard_normal((12, 32)).astype(np.float32)
+    parts = oix.ivf_assign(v)
+    assert np.array_equal(parts, oracle_np.ivf_assign(ix, v))
+    assert np.array_equal(oix.pq_encode(v, parts), oracle_np.pq_encode(ix, v, parts))
+
+
 def test_ivfpq_multivector_relational():
     # test_query.py:791-850: same query twice gives same per-query distances
     # (the "2x" multivector sum is applied above the ANN path and is out of scope)
