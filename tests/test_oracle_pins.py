@@ -136,3 +136,34 @@ def test_ivfpq_multivector_relational():
     ids, dist, cnt = oix.search(np.stack([q, q]), k=10, nprobes=1)
     assert np.array_equal(ids[0], ids[1]) and np.array_equal(dist[0], dist[1])
     assert (dist[0] >= 0).all() and (dist[0] <= 2).all()
+
+
+def test_golden_reference_pins_file():
+    """tests/golden/reference_pins.json: the reference's own known-answers as data (with their source
+    locations); the oracle reproduces every one of them."""
+    import json, os
+    pins = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pins.json")))
+    p = pins["l2_doctest"]
+    ids, dist, cnt = oracle.flat_search(np.array(p["vectors"], np.float32), np.array(p["query"], np.float32), k=3)
+    caps = ["bar", "foo", "test"]                      # row order in the doctest's table
+    assert [caps[i] for i in ids[0]] == p["captions_in_order"]
+    assert [f"{d:.6f}" for d in dist[0]] == p["distances_6dp"]
+    p = pins["cosine_doctest"]
+    ids, dist, cnt = oracle.flat_search(np.array(p["vectors"], np.float32), np.array(p["query"], np.float32), k=3,
+                                        metric="cosine")
+    assert [p["b"][i] for i in ids[0]] == p["b_in_order"]       # (_distance, _rowid) tie-break: 6 before 10
+    assert [f"{d:.6f}" for d in dist[0]] == p["distances_6dp"]
+    v = np.array([[1.0, 2.0], [3.0, 4.0]], np.float32)
+    assert oracle.flat_search(v, v[0], k=1)[1][0, 0] == pins["exact_match"]["distance"]
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_golden_ivfpq_fixture_matches_oracle(metric):
+    """The committed oracle outputs (tests/golden/ivfpq_small.npz) are what oracle.c computes today: freezes the
+    restatement between rounds.  The GPU twin of this test is tests/test_gpu_parity.py::test_golden_ivfpq_fixture."""
+    from tests.util import load_golden, same_result
+    ix, q, cases, flat = load_golden(metric)
+    orc = oracle.OracleIndex.from_data(ix)
+    for name, (kw, want) in cases.items():
+        assert same_result(orc.search(q, **kw), want), name
+    assert same_result(oracle.flat_search(ix.vectors, q, k=7, metric=metric, row_ids=ix.row_ids), flat)

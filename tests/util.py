@@ -39,3 +39,33 @@ def random_index(rng, *, dim, nlist, m, metric="l2", sizes=None, n=None, with_ve
 
 def queries(rng, B, dim, scale=1.0):
     return (rng.standard_normal((B, dim)) * scale).astype(np.float32)
+
+
+GOLDEN_CASES = {"plain": dict(k=7, nprobes=3), "range": dict(k=7, nprobes=3, lower=2.0, upper=30.0),
+                "refine": dict(k=5, nprobes=3, refine_factor=3), "prefilter": dict(k=7, nprobes=4)}
+
+
+def load_golden(metric):
+    """tests/golden/ivfpq_small.npz (made by tests/golden/make_golden.py): index, queries, and per case the
+    search kwargs + the committed (ids, dist, cnt)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ivfpq_small.npz"))
+    g = lambda name: z[f"{metric}_{name}"]
+    ix = IvfPqIndexData(32, 8, 4, metric, g("centroids"), g("codebook"), g("part_offsets"), g("codes_t"), g("row_ids"),
+                        g("vectors"))
+    ix.validate()
+    cases = {}
+    for name, kw in GOLDEN_CASES.items():
+        kw = dict(kw)
+        if name == "prefilter":
+            kw.update(allow=g("allow"), allow_bits=600)
+        cases[name] = (kw, (g(f"{name}_ids"), g(f"{name}_dist"), g(f"{name}_cnt")))
+    flat = (g("flat_ids"), g("flat_dist"), g("flat_cnt"))
+    return ix, g("queries"), cases, flat
+
+
+def same_result(got, want):
+    gi, gd, gc = got
+    wi, wd, wc = want
+    return (np.array_equal(gc, wc) and np.array_equal(gi, wi)
+            and np.array_equal(np.asarray(gd, np.float32).view(np.uint32), np.asarray(wd, np.float32).view(np.uint32)))
