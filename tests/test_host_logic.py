@@ -247,3 +247,23 @@ def test_oracle_pq_encode_is_argmin_of_the_distance_table():
             resid = qn if metric == "dot" else (qn - ix.centroids[parts[r]]).astype(np.float32)
             lut = orc.build_lut(resid)
             assert np.array_equal(codes[r], lut.argmin(axis=1).astype(np.uint8))
+
+
+def test_full_size_property_checker_on_the_oracle():
+    """tests/test_gpu_zz_fullsize.py's property checker, run here with the oracle standing in for the CUDA
+    path on a reduced shape (it must hold for any correct implementation; on the GPU box it runs at the
+    BASELINE configs[1] size)."""
+    import oracle
+    from tests.test_gpu_zz_fullsize import check_properties
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(78)
+    ix = random_index(rng, dim=64, nlist=64, m=8, n=40000, shuffle_ids=False)
+    q = queries(rng, 256, 64)
+    cache = {}
+
+    def search(data, qq):
+        if id(data) not in cache:
+            cache[id(data)] = oracle.OracleIndex.from_data(data)
+        return cache[id(data)].search(qq, k=10, nprobes=20, nthreads=4)
+
+    check_properties(search, ix, q, 10, 20)
