@@ -59,12 +59,12 @@ def test_config2_full_size_properties():
 
     def search(data, qq):
         key = id(data)
-        if key not in handles:
-            handles[key] = _native.GpuIvfPq(data)
-        return handles[key].search(qq, k=C2["k"], nprobes=C2["nprobes"])
+        if key not in handles:                       # keep `data` referenced: a freed shard's id() could be reused
+            handles[key] = (data, _native.GpuIvfPq(data))
+        return handles[key][1].search(qq, k=C2["k"], nprobes=C2["nprobes"])
 
     try:
         check_properties(search, ix, q, C2["k"], C2["nprobes"])
     finally:
-        for h in handles.values():
+        for _, h in handles.values():
             h.close()

@@ -262,8 +262,8 @@ def test_full_size_property_checker_on_the_oracle():
     cache = {}
 
     def search(data, qq):
-        if id(data) not in cache:
-            cache[id(data)] = oracle.OracleIndex.from_data(data)
-        return cache[id(data)].search(qq, k=10, nprobes=20, nthreads=4)
+        if id(data) not in cache:                    # keep `data` referenced (id() of a freed shard could be reused)
+            cache[id(data)] = (data, oracle.OracleIndex.from_data(data))
+        return cache[id(data)][1].search(qq, k=10, nprobes=20, nthreads=4)
 
     check_properties(search, ix, q, 10, 20)
