@@ -289,17 +289,3 @@ def test_streaming_scan_many_tiles_dsub8(metric):
     sizes = rng.integers(1, 260, size=nlist)
     ix = random_index(rng, dim=160, nlist=nlist, m=20, metric=metric, sizes=sizes)
     _check_search(ix, queries(rng, 500, 160), k=10, nprobes=12)
-
-
-@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
-def test_golden_ivfpq_fixture(metric):
-    """The CUDA path reproduces the committed fixture (tests/golden/ivfpq_small.npz) byte for byte."""
-    from tests.util import load_golden, same_result
-    ix, q, cases, flat = load_golden(metric)
-    gpu = _native.GpuIvfPq(ix)
-    for name, (kw, want) in cases.items():
-        assert same_result(gpu.search(q, **kw), want), name
-    gpu.close()
-    fl = _native.GpuFlat(ix.vectors, ix.row_ids)
-    assert same_result(fl.search(q, k=7, metric=metric), flat)
-    fl.close()

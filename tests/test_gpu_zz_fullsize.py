@@ -1,8 +1,9 @@
 """BASELINE.json configs[1] at full size (1M x 768, nlist 1024, m 96, nprobes 20, k 10, batch 1024) on a
 synthetic (untrained) index: size-independent properties of the result -- sorted by (_distance, _rowid),
 k unique rows per query, idempotent, independent of the batch a query travels in, equal to the merge of a
-2-way partition-sharded search -- plus a bit-exact oracle spot-check on a few queries.  (File name sorts last
-on purpose: the small parity tests run first.)"""
+2-way partition-sharded search -- plus a bit-exact oracle spot-check on a few queries.  Also the committed
+golden fixture (tests/golden/ivfpq_small.npz) against the CUDA path.  (File name sorts last on purpose: the
+small parity tests run first.)"""
 import numpy as np
 import pytest
 
@@ -48,6 +49,21 @@ def check_properties(search, ix, q, k, nprobes, spot=6):
     oi, od, oc = orc.search(q[pick], k=k, nprobes=nprobes, nthreads=min(spot, 8))
     assert np.array_equal(oi, ids[pick]) and np.array_equal(od.view(np.uint32), dist[pick].view(np.uint32))
     assert np.array_equal(oc, cnt[pick])
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_golden_ivfpq_fixture(metric):
+    """The CUDA path reproduces the committed fixture (tests/golden/ivfpq_small.npz) byte for byte."""
+    from lancedb_b200 import _native
+    from tests.util import load_golden, same_result
+    ix, q, cases, flat = load_golden(metric)
+    gpu = _native.GpuIvfPq(ix)
+    for name, (kw, want) in cases.items():
+        assert same_result(gpu.search(q, **kw), want), name
+    gpu.close()
+    fl = _native.GpuFlat(ix.vectors, ix.row_ids)
+    assert same_result(fl.search(q, k=7, metric=metric), flat)
+    fl.close()
 
 
 def test_config2_full_size_properties():

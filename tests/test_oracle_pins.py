@@ -160,7 +160,7 @@ def test_golden_reference_pins_file():
 @pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
 def test_golden_ivfpq_fixture_matches_oracle(metric):
     """The committed oracle outputs (tests/golden/ivfpq_small.npz) are what oracle.c computes today: freezes the
-    restatement between rounds.  The GPU twin of this test is tests/test_gpu_parity.py::test_golden_ivfpq_fixture."""
+    restatement between rounds.  The GPU twin of this test is tests/test_gpu_zz_fullsize.py::test_golden_ivfpq_fixture."""
     from tests.util import load_golden, same_result
     ix, q, cases, flat = load_golden(metric)
     orc = oracle.OracleIndex.from_data(ix)
