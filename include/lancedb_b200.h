@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LGPU_ABI_VERSION 1
+#define LGPU_ABI_VERSION 2
 
 typedef enum {
     LGPU_OK = 0,
@@ -94,6 +94,12 @@ typedef struct {
     float    lower;
     float    upper;
     uint32_t flags;          /* reserved, 0 */
+    uint32_t max_nprobes;    /* maximum_nprobes (query.rs:1250-1275): under a prefilter, queries that found fewer
+                                than k rows in their `nprobes` nearest partitions are searched again over their
+                                max_nprobes nearest; 0 or <= nprobes = no widening */
+    uint32_t timeout_ms;     /* QueryExecutionOptions::timeout (query.rs:626-658, utils/mod.rs:328-393): the
+                                host-buffer entry points return LGPU_TIMEOUT, leaving the outputs untouched,
+                                when the results are not ready this many ms after the call started; 0 = none */
 } lgpu_search_params;
 
 /* ---- library ----------------------------------------------------------- */

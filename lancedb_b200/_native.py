@@ -19,7 +19,7 @@ _lib = None
 
 LGPU_OK, LGPU_INVALID_INPUT, LGPU_RUNTIME, LGPU_TIMEOUT, LGPU_OOM = 0, 1, 2, 3, 4
 METRICS = {"l2": 0, "euclidean": 0, "cosine": 1, "dot": 2}
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = [
     "lgpu_last_error", "lgpu_abi_version", "lgpu_device_count",
@@ -45,7 +45,7 @@ class SearchParams(C.Structure):
     _fields_ = [
         ("k", C.c_uint32), ("nprobes", C.c_uint32), ("refine_factor", C.c_uint32),
         ("has_lower", C.c_int32), ("has_upper", C.c_int32), ("lower", C.c_float), ("upper", C.c_float),
-        ("flags", C.c_uint32),
+        ("flags", C.c_uint32), ("max_nprobes", C.c_uint32), ("timeout_ms", C.c_uint32),
     ]
 
 
@@ -128,9 +128,11 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def make_params(k=10, nprobes=20, refine_factor=0, lower=None, upper=None) -> SearchParams:
+def make_params(k=10, nprobes=20, refine_factor=0, lower=None, upper=None, max_nprobes=0,
+                timeout_ms=0) -> SearchParams:
     return SearchParams(int(k), int(nprobes), int(refine_factor or 0), lower is not None, upper is not None,
-                        0.0 if lower is None else float(lower), 0.0 if upper is None else float(upper), 0)
+                        0.0 if lower is None else float(lower), 0.0 if upper is None else float(upper), 0,
+                        int(max_nprobes or 0), int(timeout_ms or 0))
 
 
 class GpuIvfPq:
@@ -166,13 +168,14 @@ class GpuIvfPq:
         check(load().lgpu_index_device_bytes(self._h, C.byref(b)))
         return b.value
 
-    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, allow=None, allow_bits=0):
+    def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, allow=None, allow_bits=0,
+               max_nprobes=0, timeout_ms=0):
         """Host-buffer search: returns (ids [B,k] u64, dist [B,k] f32, count [B] u32).
         `allow` (u32 bitmap over row ids, `allow_bits` bits) = prefilter allow-list."""
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
         B = q.shape[0]
         ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
-        p = make_params(k, nprobes, refine_factor, lower, upper)
+        p = make_params(k, nprobes, refine_factor, lower, upper, max_nprobes, timeout_ms)
         if allow is None:
             check(load().lgpu_search(self._h, _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist), _ptr(cnt)))
         else:
@@ -226,11 +229,11 @@ class GpuFlat:
 
     __del__ = close
 
-    def search(self, queries, k=10, metric="l2", lower=None, upper=None, allow=None, allow_bits=0):
+    def search(self, queries, k=10, metric="l2", lower=None, upper=None, allow=None, allow_bits=0, timeout_ms=0):
         q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
         B = q.shape[0]
         ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
-        p = make_params(k, 0, 0, lower, upper)
+        p = make_params(k, 0, 0, lower, upper, 0, timeout_ms)
         if allow is None:
             check(load().lgpu_flat_search(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist),
                                           _ptr(cnt)))
@@ -241,6 +244,18 @@ class GpuFlat:
             check(load().lgpu_flat_search_filtered(self._h, METRICS[metric], _ptr(q), B, C.byref(p), _ptr(bm),
                                                    int(allow_bits), _ptr(ids), _ptr(dist), _ptr(cnt)))
         return ids, dist, cnt
+
+    def search_into(self, metric: str, q: np.ndarray, p: SearchParams, ids: np.ndarray, dist: np.ndarray,
+                    cnt: np.ndarray):
+        """Host-buffer flat search into caller-owned (e.g. pinned) arrays; no allocation."""
+        check(load().lgpu_flat_search(self._h, METRICS[metric], q.ctypes.data, q.shape[0], C.byref(p),
+                                      ids.ctypes.data, dist.ctypes.data, cnt.ctypes.data))
+
+    def search_device(self, metric: str, d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int, d_cnt: int,
+                      stream: int = 0):
+        """Device-pointer flat search (raw addresses), enqueued on `stream`, not synchronised."""
+        check(load().lgpu_flat_search_device(self._h, METRICS[metric], d_q, B, C.byref(p), d_ids, d_dist, d_cnt,
+                                             stream))
 
 
 def ivf_assign(centroids, vectors, metric: str = "l2", device: int = 0) -> np.ndarray:
@@ -277,11 +292,6 @@ def mask_bitmap(mask) -> np.ndarray:
     pad = (-m.size) % 32
     bits = np.packbits(np.concatenate([m, np.zeros(pad, bool)]), bitorder="little")
     return np.ascontiguousarray(bits).view(np.uint32)
-
-    def search_device(self, metric: str, d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int, d_cnt: int,
-                      stream: int = 0):
-        check(load().lgpu_flat_search_device(self._h, METRICS[metric], d_q, B, C.byref(p), d_ids, d_dist, d_cnt,
-                                             stream))
 
 
 def merge_topk_device(device: int, nlists: int, B: int, k: int, d_ids: int, d_dist: int, d_out_ids: int,

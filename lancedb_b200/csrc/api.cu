@@ -9,11 +9,19 @@
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
+#include <unordered_set>
 #include <vector>
+
+#include <pthread.h>
+#include <unistd.h>
 
 namespace lgpu {
 
@@ -22,11 +30,17 @@ static thread_local float g_stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
 static thread_local uint64_t g_scanned_bytes = 0;
 void set_error(const std::string &msg) { g_err = msg; }
 
-static int g_profiling = -1;
+static std::atomic<int> g_profiling{-1};
 static bool profiling_enabled()
 {
-    if (g_profiling < 0) { const char *e = getenv("LGPU_PROFILE"); g_profiling = (e && e[0] == '1') ? 1 : 0; }
-    return g_profiling == 1;
+    int v = g_profiling.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char *e = getenv("LGPU_PROFILE");
+        int want = (e && e[0] == '1') ? 1 : 0;
+        g_profiling.compare_exchange_strong(v, want);     // lgpu_set_profiling may have won the race: keep its value
+        v = g_profiling.load(std::memory_order_relaxed);
+    }
+    return v == 1;
 }
 static size_t workspace_budget()
 {
@@ -39,7 +53,10 @@ static size_t workspace_budget()
     return v;
 }
 
-static thread_local uint64_t g_alloc_epoch = 0;   // bumped by every workspace (re)allocation on this thread
+// bumped by every device (re)allocation in the process.  A captured CUDA graph bakes workspace pointers in, so a
+// graph is only replayed while the epoch still equals the one recorded at capture (Workspace::graph_epoch): any
+// entry point, on any thread, that grows a buffer invalidates every captured graph (they re-capture on next use).
+static std::atomic<uint64_t> g_alloc_epoch{0};
 
 struct DevBuf {
     void *p = nullptr;
@@ -70,6 +87,7 @@ struct Workspace {
     // CUDA graph of one host-buffer search (lgpu_search): the ~15 launches of a batch replayed as one
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_key[4] = {0, 0, 0, 0};
+    uint64_t graph_epoch = 0;           // g_alloc_epoch when `graph` was captured
     int graph_state = 0;                // 0: next call runs eagerly (warm-up), 1: capture, 2: replay, -1: disabled
     DevBuf tq, sbound, probe_A, amax;   // two-pass scan: per-query tables, bounds, per-probe scalars
     Workspace()
@@ -106,7 +124,63 @@ struct WorkspacePool {
 
 using namespace lgpu;
 
+// ---- live-handle registry: every entry point resolves its handle through it, so a handle that was closed (or
+// that belongs to the parent of a fork()) is rejected instead of dereferenced, and close waits for the calls
+// still inside the handle (BaseTable is Send + Sync: rust/lancedb/src/table.rs:549; queries are re-executable
+// from any tokio worker: rust/lancedb/src/query.rs:954-955).
+namespace lgpu {
+static std::mutex g_live_mu;
+static std::condition_variable g_live_cv;
+static std::unordered_set<const void *> g_live;
+static std::atomic<bool> g_cuda_touched{false};   // this process has created a CUDA context through the library
+static std::atomic<bool> g_fork_poisoned{false};  // we are the child of a fork() taken after that
+// fork(): the reference rebuilds its tokio runtime in the child (python/src/runtime.rs:68-81); a CUDA context has
+// the same constraint and cannot be rebuilt, so the child drops every handle and refuses GPU work.
+static void atfork_prepare() { g_live_mu.lock(); }
+static void atfork_parent() { g_live_mu.unlock(); }
+static void atfork_child()
+{
+    g_live.clear();                                  // the parent's handles are not valid here (leaked, never freed)
+    if (g_cuda_touched.load()) g_fork_poisoned.store(true);
+    g_live_mu.unlock();
+}
+static void register_handle(const void *h)
+{
+    static std::once_flag once;
+    std::call_once(once, [] { pthread_atfork(atfork_prepare, atfork_parent, atfork_child); });
+    std::lock_guard<std::mutex> g(g_live_mu);
+    g_live.insert(h);
+}
+template <class H> struct HandleRef {
+    H *h;
+    HandleRef(H *p, const char *what) : h(nullptr)
+    {
+        std::lock_guard<std::mutex> g(g_live_mu);
+        if (!p || !g_live.count(p)) {
+            set_error(std::string(what) + " handle is null, closed, or was opened in another process (fork)");
+            throw Failure{LGPU_INVALID_INPUT};
+        }
+        p->refs.fetch_add(1);
+        h = p;
+    }
+    ~HandleRef()
+    {
+        if (h && h->refs.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(g_live_mu); g_live_cv.notify_all(); }
+    }
+    H *operator->() const { return h; }
+};
+// unregister and wait until no call is inside the handle any more; false = it was not a live handle
+template <class H> static bool retire_handle(H *p)
+{
+    std::unique_lock<std::mutex> g(g_live_mu);
+    if (!p || !g_live.erase(p)) return false;
+    g_live_cv.wait(g, [&] { return p->refs.load() == 0; });
+    return true;
+}
+}  // namespace lgpu
+
 struct lgpu_index {
+    std::atomic<int> refs{0};
     int device = 0, num_sms = 0;
     uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0, rows_tile = SCAN_ROWS_TILE_MID;
     uint32_t max_nrb = 1;          // row blocks of the largest partition (bounds the tile count)
@@ -125,6 +199,7 @@ struct lgpu_index {
 };
 
 struct lgpu_flat {
+    std::atomic<int> refs{0};
     int device = 0;
     uint64_t nrows = 0;
     uint32_t dim = 0;
@@ -157,6 +232,33 @@ struct WsLease {
     }
 };
 
+// Deadline of one call (QueryExecutionOptions::timeout -> TimeoutStream, rust/lancedb/src/utils/mod.rs:328-393,
+// used at rust/lancedb/src/query.rs:1452-1457).  Kernels cannot be cancelled, so the deadline is enforced where
+// the host waits: between sub-batches and before the results are copied back.  On expiry the call returns
+// LGPU_TIMEOUT without touching the caller's output buffers; work already enqueued drains into the workspace,
+// which stays fenced by its `done` event until then.
+struct Deadline {
+    bool armed = false;
+    std::chrono::steady_clock::time_point at;
+    explicit Deadline(uint32_t timeout_ms)
+    {
+        if (timeout_ms) { armed = true; at = std::chrono::steady_clock::now() + std::chrono::milliseconds(timeout_ms); }
+    }
+    bool expired() const { return armed && std::chrono::steady_clock::now() >= at; }
+    // wait for everything enqueued on `st` so far, or for the deadline
+    void wait(cudaStream_t st, cudaEvent_t ev) const
+    {
+        if (!armed) return;
+        LGPU_CUDA(cudaEventRecord(ev, st));
+        for (;;) {
+            cudaError_t e = cudaEventQuery(ev);
+            if (e == cudaSuccess) return;
+            if (e != cudaErrorNotReady) LGPU_CUDA(e);
+            if (expired()) { set_error("Query timeout"); throw Failure{LGPU_TIMEOUT}; }
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    }
+};
 
 // The two-pass (filter + verify) scan is bit-identical to the exact path but, as measured on B200
 // (C2 workload: 1.73 ms vs 1.54 ms per 1024-query batch), not yet faster, so it is
@@ -442,7 +544,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         mark();
         SelectArgs sa{};
         sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ga.seg_off; sa.probes = ga.probes;
-        sa.nprobes = nprobes; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
+        sa.nprobes = nprobes; sa.nlist = nlist; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
         sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B; sa.k = kp2;
         sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
         sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
@@ -477,7 +579,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     // ---- K4: top-k ----
     SelectArgs sa{};
     sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ga.seg_off; sa.probes = ga.probes;
-    sa.nprobes = nprobes; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
+    sa.nprobes = nprobes; sa.nlist = nlist; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
     sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B;
     sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
     sa.allow = rf.bits; sa.allow_bits = rf.nbits;          // prefilter: rows are dropped before the top-k
@@ -517,13 +619,14 @@ uint32_t ivf_sub_batch_size(lgpu_index *ix, uint32_t B, uint32_t nprobes)
 
 void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *d_q, uint32_t B,
                        const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt,
-                       RowFilter rf = RowFilter())
+                       RowFilter rf = RowFilter(), const Deadline *deadline = nullptr)
 {
     const uint32_t nprobes = std::min<uint32_t>(std::max<uint32_t>(sp.nprobes, 1), ix->nlist);
     const uint32_t bs = ivf_sub_batch_size(ix, B, nprobes);
     const bool prof = profiling_enabled();
     for (uint32_t q0 = 0; q0 < B; q0 += bs) {
         uint32_t b = std::min(bs, B - q0);
+        if (deadline && q0 > 0) deadline->wait(st, ws->ev[7]);      // the previous sub-batch, or LGPU_TIMEOUT
         ivf_sub_batch(ix, ws, st, d_q + (size_t)q0 * ix->dim, b, sp, nprobes, d_ids + (size_t)q0 * sp.k,
                       d_dist + (size_t)q0 * sp.k, d_cnt + q0, prof && q0 == 0, nullptr, rf);
     }
@@ -546,7 +649,7 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
 
 void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metric, const float *d_q, uint32_t B,
                         const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist, uint32_t *d_cnt,
-                        RowFilter rf = RowFilter())
+                        RowFilter rf = RowFilter(), const Deadline *deadline = nullptr)
 {
     const uint64_t N = fl->nrows;
     const uint64_t ld = (N + 3) & ~3ull;
@@ -563,6 +666,7 @@ void flat_search_device(lgpu_flat *fl, Workspace *ws, cudaStream_t st, int metri
     uint32_t bs = (uint32_t)std::max<size_t>(1, std::min<size_t>(workspace_budget() / per_q, B));
     for (uint32_t q0 = 0; q0 < B; q0 += bs) {
         uint32_t b = std::min(bs, B - q0);
+        if (deadline && q0 > 0) deadline->wait(st, ws->ev[7]);
         const float *q = d_q + (size_t)q0 * fl->dim;
         ws->D.ensure(std::max<size_t>((size_t)b * ld, 4) * 4);
         const float *xn = nullptr;
@@ -610,6 +714,11 @@ template <class F> int guarded(F &&f)
 
 void require_device(int device)
 {
+    if (g_fork_poisoned.load()) {
+        set_error("this process is a fork() of one that already used CUDA through lancedb_b200: the GPU context "
+                  "does not survive fork; open the index in a spawned process instead");
+        throw Failure{LGPU_RUNTIME};
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
@@ -619,38 +728,42 @@ void require_device(int device)
     }
     LGPU_REQUIRE(device >= 0 && device < n, "invalid CUDA device ordinal");
     LGPU_CUDA(cudaSetDevice(device));
+    g_cuda_touched.store(true);
 }
 
-// host-buffer wrapper: stage in, run, stage out, synchronise
+// CUDA-graph replay of the host-buffer entry points is on by default; LGPU_NO_GRAPH=1 disables it.
 static bool graphs_enabled()
 {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("LGPU_GRAPH"); v = (e && e[0] == '1') ? 1 : 0; }
+    if (v < 0) { const char *e = getenv("LGPU_NO_GRAPH"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
 }
 
 // host-buffer wrapper: stage in, run, stage out, synchronise.  `key` identifies the launch sequence
 // (shapes + parameters): the second call with the same key is captured into a CUDA graph and later calls
-// replay it, which removes ~15 launch latencies from the synchronous end-to-end path.  Any workspace
-// (re)allocation, profiling mode, or a failed capture falls back to eager launches.
+// replay it, which removes ~15 launch latencies from the synchronous end-to-end path.  Any device
+// (re)allocation anywhere in the process since the capture, profiling mode, or a failed capture falls back to
+// eager launches.
 template <class Run>
 void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t dim, uint32_t k, uint64_t *out_ids,
-               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], Run &&run, bool allow_graph = true)
+               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], uint32_t timeout_ms, Run &&run,
+               bool allow_graph = true)
 {
+    const Deadline deadline(timeout_ms);
     WsLease lease(pool, nullptr, false);
     Workspace *ws = lease.ws;
     cudaStream_t st = lease.st;
-    const uint64_t epoch0 = g_alloc_epoch;
     ws->q.ensure(std::max<size_t>((size_t)B * dim, 1) * 4);
     ws->out_ids.ensure(std::max<size_t>((size_t)B * k, 1) * 8);
     ws->out_dist.ensure(std::max<size_t>((size_t)B * k, 1) * 4);
     ws->out_count.ensure(std::max<size_t>(B, 1) * 4);
     LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
     auto eager = [&] {
-        run(ws, st, ws->q.as<float>(), ws->out_ids.as<uint64_t>(), ws->out_dist.as<float>(), ws->out_count.as<uint32_t>());
+        run(ws, st, ws->q.as<float>(), ws->out_ids.as<uint64_t>(), ws->out_dist.as<float>(), ws->out_count.as<uint32_t>(),
+            deadline);
     };
     const bool same = memcmp(key, ws->graph_key, sizeof(key)) == 0;
-    if (!allow_graph || !graphs_enabled() || profiling_enabled() || ws->graph_state < 0) {
+    if (!allow_graph || !graphs_enabled() || profiling_enabled() || ws->graph_state < 0 || deadline.armed) {
         eager();
     } else if (!same) {                                     // new shape: warm up (allocations), capture next time
         if (ws->graph) { cudaGraphExecDestroy(ws->graph); ws->graph = nullptr; }
@@ -658,15 +771,16 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
         ws->graph_state = 0;
         eager();
         ws->graph_state = 1;
-    } else if (ws->graph_state == 2 && g_alloc_epoch == epoch0) {
+    } else if (ws->graph_state == 2 && g_alloc_epoch.load() == ws->graph_epoch) {
         LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
     } else if (ws->graph_state == 1) {
         bool ok = false;
         cudaGraph_t g = nullptr;
+        const uint64_t epoch0 = g_alloc_epoch.load();
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             try {
                 eager();
-                ok = cudaStreamEndCapture(st, &g) == cudaSuccess && g != nullptr && g_alloc_epoch == epoch0;
+                ok = cudaStreamEndCapture(st, &g) == cudaSuccess && g != nullptr && g_alloc_epoch.load() == epoch0;
             } catch (const Failure &) {
                 cudaStreamEndCapture(st, &g);
                 ok = false;
@@ -674,8 +788,15 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
         }
         if (ok && cudaGraphInstantiate(&ws->graph, g, 0) == cudaSuccess) {
             ws->graph_state = 2;
+            ws->graph_epoch = epoch0;
             cudaGraphDestroy(g);
             LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
+        } else if (g_alloc_epoch.load() != epoch0) {        // a buffer moved during the capture: try again next call
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            ws->graph = nullptr;
+            LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
+            eager();
         } else {                                            // never try again with this workspace
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
@@ -684,11 +805,12 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
             LGPU_CUDA(cudaMemcpyAsync(ws->q.p, queries, (size_t)B * dim * 4, cudaMemcpyHostToDevice, st));
             eager();
         }
-    } else {                                                // state 2 but buffers moved: re-warm
+    } else {                                                // captured, but a buffer moved since: capture again
         if (ws->graph) { cudaGraphExecDestroy(ws->graph); ws->graph = nullptr; }
         ws->graph_state = 1;
         eager();
     }
+    deadline.wait(st, ws->ev[7]);
     LGPU_CUDA(cudaMemcpyAsync(out_ids, ws->out_ids.p, (size_t)B * k * 8, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaMemcpyAsync(out_dist, ws->out_dist.p, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaMemcpyAsync(out_count, ws->out_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
@@ -701,7 +823,8 @@ static inline void make_key(uint64_t (&key)[4], uint64_t tag, uint32_t B, const 
     memcpy(&lo, &p.lower, 4); memcpy(&hi, &p.upper, 4);
     key[0] = tag ^ ((uint64_t)B << 32);
     key[1] = (uint64_t)p.k | ((uint64_t)p.nprobes << 32);
-    key[2] = (uint64_t)p.refine_factor | ((uint64_t)(p.has_lower ? 1 : 0) << 32) | ((uint64_t)(p.has_upper ? 1 : 0) << 33);
+    key[2] = (uint64_t)p.refine_factor | ((uint64_t)(p.has_lower ? 1 : 0) << 32) | ((uint64_t)(p.has_upper ? 1 : 0) << 33) |
+             ((uint64_t)(p.max_nprobes & 0x3fffffu) << 34);
     key[3] = (uint64_t)lo | ((uint64_t)hi << 32);
 }
 
@@ -843,6 +966,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             LGPU_CUDA(cudaStreamSynchronize(st));
             ix->has_tables = true;
         }
+        register_handle(ix);
         *out = ix;
     });
     if (rc != LGPU_OK && ix) delete ix;
@@ -851,16 +975,17 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
 
 void lgpu_index_close(lgpu_index *ix)
 {
-    if (!ix) return;
+    if (!retire_handle(ix)) return;          // null, already closed, or a parent-process handle in a fork child
     cudaSetDevice(ix->device);
     cudaDeviceSynchronize();
     delete ix;
 }
 
-int lgpu_index_device_bytes(const lgpu_index *ix, uint64_t *bytes)
+int lgpu_index_device_bytes(const lgpu_index *ixh, uint64_t *bytes)
 {
     return guarded([&] {
-        LGPU_REQUIRE(ix && bytes, "null argument");
+        LGPU_REQUIRE(bytes, "null argument");
+        HandleRef<lgpu_index> ix(const_cast<lgpu_index *>(ixh), "index");
         *bytes = ix->device_bytes;
     });
 }
@@ -872,7 +997,7 @@ int lgpu_last_scanned_code_bytes(uint64_t *bytes)
 
 int lgpu_set_profiling(int enabled)
 {
-    g_profiling = enabled ? 1 : 0;
+    g_profiling.store(enabled ? 1 : 0);
     return LGPU_OK;
 }
 
@@ -884,7 +1009,6 @@ int lgpu_last_stage_ms(float *times)
 static void check_ivf_call(lgpu_index *ix, const void *q, uint32_t B, const lgpu_search_params *p,
                            const void *a, const void *b, const void *c)
 {
-    LGPU_REQUIRE(ix != nullptr, "index handle is null");
     check_params(p);
     LGPU_REQUIRE(p->nprobes >= 1, "minimum_nprobes must be greater than 0");
     LGPU_REQUIRE(p->nprobes <= SELECT_KMAX || p->nprobes >= ix->nlist, "nprobes above 2048 is not supported");
@@ -893,54 +1017,57 @@ static void check_ivf_call(lgpu_index *ix, const void *q, uint32_t B, const lgpu
                  "refine_factor needs the raw vectors: open the index with desc.vectors");
 }
 
-int lgpu_search(lgpu_index *ix, const float *queries, uint32_t B, const lgpu_search_params *params,
+int lgpu_search(lgpu_index *ixh, const float *queries, uint32_t B, const lgpu_search_params *params,
                 uint64_t *out_ids, float *out_dist, uint32_t *out_count)
 {
     return guarded([&] {
-        check_ivf_call(ix, queries, B, params, out_ids, out_dist, out_count);
+        HandleRef<lgpu_index> ix(ixh, "index");
+        check_ivf_call(ix.h, queries, B, params, out_ids, out_dist, out_count);
         if (B == 0) return;
         require_device(ix->device);
         uint64_t key[4];
         make_key(key, 0x1f5ull, B, *params);
-        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key,
-                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
-                      ivf_search_device(ix, ws, st, dq, B, *params, di, dd, dc);
-                  });
+        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key, params->timeout_ms,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc,
+                      const Deadline &dl) { ivf_search_device(ix.h, ws, st, dq, B, *params, di, dd, dc, RowFilter(), &dl); });
     });
 }
 
-int lgpu_search_filtered(lgpu_index *ix, const float *queries, uint32_t B, const lgpu_search_params *params,
+int lgpu_search_filtered(lgpu_index *ixh, const float *queries, uint32_t B, const lgpu_search_params *params,
                          const uint32_t *allow, uint64_t allow_bits, uint64_t *out_ids, float *out_dist,
                          uint32_t *out_count)
 {
     return guarded([&] {
-        check_ivf_call(ix, queries, B, params, out_ids, out_dist, out_count);
+        HandleRef<lgpu_index> ix(ixh, "index");
+        check_ivf_call(ix.h, queries, B, params, out_ids, out_dist, out_count);
         LGPU_REQUIRE(allow != nullptr || allow_bits == 0, "allow bitmap is null");
         if (B == 0) return;
         require_device(ix->device);
         uint64_t key[4];
         make_key(key, 0x1f6ull, B, *params);
         key[0] ^= allow_bits << 8;
-        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key,
-                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
+        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key, params->timeout_ms,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc,
+                      const Deadline &dl) {
                       const size_t words = (size_t)((allow_bits + 31) / 32);
                       ws->allow.ensure(std::max<size_t>(words, 1) * 4);
                       if (words) LGPU_CUDA(cudaMemcpyAsync(ws->allow.p, allow, words * 4, cudaMemcpyHostToDevice, st));
                       RowFilter rf; rf.bits = ws->allow.as<uint32_t>(); rf.nbits = allow_bits;
-                      ivf_search_device(ix, ws, st, dq, B, *params, di, dd, dc, rf);
+                      ivf_search_device(ix.h, ws, st, dq, B, *params, di, dd, dc, rf, &dl);
                   }, false);
     });
 }
 
-int lgpu_search_device(lgpu_index *ix, const float *d_queries, uint32_t B, const lgpu_search_params *params,
+int lgpu_search_device(lgpu_index *ixh, const float *d_queries, uint32_t B, const lgpu_search_params *params,
                        uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count, void *cuda_stream)
 {
     return guarded([&] {
-        check_ivf_call(ix, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
+        HandleRef<lgpu_index> ix(ixh, "index");
+        check_ivf_call(ix.h, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
         if (B == 0) return;
         require_device(ix->device);
         WsLease lease(ix->pool, (cudaStream_t)cuda_stream, true);
-        ivf_search_device(ix, lease.ws, lease.st, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
+        ivf_search_device(ix.h, lease.ws, lease.st, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
     });
 }
 
@@ -985,6 +1112,7 @@ int lgpu_flat_open(const float *vectors, uint64_t nrows, uint32_t dim, const uin
             LGPU_CUDA(cudaMemcpy(fl->row_ids.p, row_ids, (size_t)nrows * 8, cudaMemcpyHostToDevice));
             fl->has_ids = true;
         }
+        register_handle(fl);
         *out = fl;
     });
     if (rc != LGPU_OK && fl) delete fl;
@@ -993,7 +1121,7 @@ int lgpu_flat_open(const float *vectors, uint64_t nrows, uint32_t dim, const uin
 
 void lgpu_flat_close(lgpu_flat *fl)
 {
-    if (!fl) return;
+    if (!retire_handle(fl)) return;
     cudaSetDevice(fl->device);
     cudaDeviceSynchronize();
     delete fl;
@@ -1002,68 +1130,71 @@ void lgpu_flat_close(lgpu_flat *fl)
 static void check_flat_call(lgpu_flat *fl, int metric, const void *q, uint32_t B, const lgpu_search_params *p,
                             const void *a, const void *b, const void *c)
 {
-    LGPU_REQUIRE(fl != nullptr, "flat handle is null");
     LGPU_REQUIRE(metric == LGPU_L2 || metric == LGPU_COSINE || metric == LGPU_DOT, "unknown distance type");
     check_params(p);
     LGPU_REQUIRE(B == 0 || (q && a && b && c), "null buffer");
 }
 
-int lgpu_flat_search(lgpu_flat *fl, int metric, const float *queries, uint32_t B, const lgpu_search_params *params,
+int lgpu_flat_search(lgpu_flat *flh, int metric, const float *queries, uint32_t B, const lgpu_search_params *params,
                      uint64_t *out_ids, float *out_dist, uint32_t *out_count)
 {
     return guarded([&] {
-        check_flat_call(fl, metric, queries, B, params, out_ids, out_dist, out_count);
+        HandleRef<lgpu_flat> fl(flh, "flat");
+        check_flat_call(fl.h, metric, queries, B, params, out_ids, out_dist, out_count);
         if (B == 0) return;
         require_device(fl->device);
         uint64_t key[4];
         make_key(key, 0xf1a7ull + (uint64_t)metric, B, *params);
-        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count, key,
-                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
-                      flat_search_device(fl, ws, st, metric, dq, B, *params, di, dd, dc);
-                  });
+        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count, key, params->timeout_ms,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc,
+                      const Deadline &dl) { flat_search_device(fl.h, ws, st, metric, dq, B, *params, di, dd, dc, RowFilter(), &dl); });
     });
 }
 
-int lgpu_flat_search_filtered(lgpu_flat *fl, int metric, const float *queries, uint32_t B,
+int lgpu_flat_search_filtered(lgpu_flat *flh, int metric, const float *queries, uint32_t B,
                               const lgpu_search_params *params, const uint32_t *allow, uint64_t allow_bits,
                               uint64_t *out_ids, float *out_dist, uint32_t *out_count)
 {
     return guarded([&] {
-        check_flat_call(fl, metric, queries, B, params, out_ids, out_dist, out_count);
+        HandleRef<lgpu_flat> fl(flh, "flat");
+        check_flat_call(fl.h, metric, queries, B, params, out_ids, out_dist, out_count);
         LGPU_REQUIRE(allow != nullptr || allow_bits == 0, "allow bitmap is null");
         if (B == 0) return;
         require_device(fl->device);
         uint64_t key[4];
         make_key(key, 0xf1b7ull + (uint64_t)metric, B, *params);
-        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count, key,
-                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc) {
+        host_call(fl->pool, queries, B, fl->dim, params->k, out_ids, out_dist, out_count, key, params->timeout_ms,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc,
+                      const Deadline &dl) {
                       const size_t words = (size_t)((allow_bits + 31) / 32);
                       ws->allow.ensure(std::max<size_t>(words, 1) * 4);
                       if (words) LGPU_CUDA(cudaMemcpyAsync(ws->allow.p, allow, words * 4, cudaMemcpyHostToDevice, st));
                       RowFilter rf; rf.bits = ws->allow.as<uint32_t>(); rf.nbits = allow_bits;
-                      flat_search_device(fl, ws, st, metric, dq, B, *params, di, dd, dc, rf);
+                      flat_search_device(fl.h, ws, st, metric, dq, B, *params, di, dd, dc, rf, &dl);
                   }, false);
     });
 }
 
-int lgpu_flat_search_device(lgpu_flat *fl, int metric, const float *d_queries, uint32_t B,
+int lgpu_flat_search_device(lgpu_flat *flh, int metric, const float *d_queries, uint32_t B,
                             const lgpu_search_params *params, uint64_t *d_out_ids, float *d_out_dist,
                             uint32_t *d_out_count, void *cuda_stream)
 {
     return guarded([&] {
-        check_flat_call(fl, metric, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
+        HandleRef<lgpu_flat> fl(flh, "flat");
+        check_flat_call(fl.h, metric, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
         if (B == 0) return;
         require_device(fl->device);
         WsLease lease(fl->pool, (cudaStream_t)cuda_stream, true);
-        flat_search_device(fl, lease.ws, lease.st, metric, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
+        flat_search_device(fl.h, lease.ws, lease.st, metric, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
     });
 }
 
-int lgpu_debug_coarse(lgpu_index *ix, const float *queries, uint32_t B, uint32_t nprobes, uint32_t *out_parts,
+int lgpu_debug_coarse(lgpu_index *ixh, const float *queries, uint32_t B, uint32_t nprobes, uint32_t *out_parts,
                       float *out_dists)
 {
     return guarded([&] {
-        LGPU_REQUIRE(ix && queries && out_parts && out_dists && B > 0 && nprobes > 0, "bad argument");
+        LGPU_REQUIRE(queries && out_parts && out_dists && B > 0 && nprobes > 0, "bad argument");
+        HandleRef<lgpu_index> ix(ixh, "index");
         require_device(ix->device);
         nprobes = std::min(nprobes, ix->nlist);
         WsLease lease(ix->pool, nullptr, false);
@@ -1116,10 +1247,11 @@ int lgpu_debug_gemm(const float *Q, const float *X, uint32_t B, uint64_t N, uint
     });
 }
 
-int lgpu_debug_partition_distances(lgpu_index *ix, const float *query, uint32_t part, float *out)
+int lgpu_debug_partition_distances(lgpu_index *ixh, const float *query, uint32_t part, float *out)
 {
     return guarded([&] {
-        LGPU_REQUIRE(ix && query && out, "null argument");
+        LGPU_REQUIRE(query && out, "null argument");
+        HandleRef<lgpu_index> ix(ixh, "index");
         LGPU_REQUIRE(part < ix->nlist, "partition out of range");
         require_device(ix->device);
         WsLease lease(ix->pool, nullptr, false);
@@ -1129,7 +1261,7 @@ int lgpu_debug_partition_distances(lgpu_index *ix, const float *query, uint32_t 
         uint64_t forced = part;
         lgpu_search_params sp{};
         sp.k = 1; sp.nprobes = 1;
-        ivf_sub_batch(ix, ws, st, ws->q.as<float>(), 1, sp, 1, nullptr, nullptr, nullptr, false, &forced);
+        ivf_sub_batch(ix.h, ws, st, ws->q.as<float>(), 1, sp, 1, nullptr, nullptr, nullptr, false, &forced);
         uint32_t n = ix->h_part_n[part];
         if (n) LGPU_CUDA(cudaMemcpyAsync(out, ws->dist_out.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         LGPU_CUDA(cudaStreamSynchronize(st));

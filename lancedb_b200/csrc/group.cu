@@ -22,9 +22,13 @@ __global__ void group_count_kernel(GroupArgs a)
     uint64_t off = 0, rows = 0;
     for (uint32_t j = 0; j < a.nprobes; j++) {
         uint32_t slot = q * a.nprobes + j;
-        uint32_t p = (uint32_t)a.probes[slot];
-        uint32_t n = a.part_n[p];
-        a.slot_pos[slot] = take ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
+        // a query with fewer than nprobes finite centroid distances (NaN / Inf input, zero cosine query)
+        // leaves UINT64_MAX in its unused probe slots: those behave as empty partitions
+        const uint64_t pp = a.probes[slot];
+        const bool valid = pp < a.nlist;
+        uint32_t p = valid ? (uint32_t)pp : 0u;
+        uint32_t n = valid ? a.part_n[p] : 0u;
+        a.slot_pos[slot] = (take && valid) ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
         a.seg_local[slot] = off;
         off += pad4(n);
         rows += n;
@@ -102,9 +106,9 @@ __global__ void group_fill_kernel(GroupArgs a)
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.B * a.nprobes) return;
     uint32_t q = slot / a.nprobes;
-    uint32_t p = (uint32_t)a.probes[slot];
     a.seg_off[slot] = a.qtot[q] + a.seg_local[slot];
-    if (a.slot_pos[slot] != 0xffffffffu) a.qlist[a.qlist_off[p] + a.slot_pos[slot]] = slot;
+    if (a.slot_pos[slot] != 0xffffffffu)           // (implies a valid partition id, see group_count_kernel)
+        a.qlist[a.qlist_off[(uint32_t)a.probes[slot]] + a.slot_pos[slot]] = slot;
 }
 
 // 8 threads per tile (one per query slot of the group): tile t -> (partition, query group, row block),

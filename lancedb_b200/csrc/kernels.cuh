@@ -116,7 +116,7 @@ struct SelectArgs {
     const float *dist;            // dist_out
     const uint64_t *seg_off;      // [B*nprobes]
     const uint64_t *probes;       // [B*nprobes]
-    uint32_t nprobes;
+    uint32_t nprobes, nlist;      // probe ids >= nlist are unused slots
     const uint32_t *part_n;
     const uint64_t *part_off;     // [nlist+1] storage row offsets
     const uint64_t *row_ids;      // [nrows]

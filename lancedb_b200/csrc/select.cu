@@ -134,7 +134,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
     if (a.mode == 0) {
         for (uint32_t j = 0; j < a.nprobes; j++) {
             const uint32_t slot = q * a.nprobes + j;
-            const uint32_t p = (uint32_t)a.probes[slot];
+            const uint64_t pp = a.probes[slot];
+            if (pp >= a.nlist) continue;                   // unused probe slot (fewer than nprobes finite distances)
+            const uint32_t p = (uint32_t)pp;
             const uint32_t n = a.part_n[p];
             const float *src = a.dist + a.seg_off[slot];
             const uint64_t rowbase = a.part_off[p];
@@ -345,7 +347,9 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
         uint32_t itc = 0;                                   // iteration counter across segments
         for (uint32_t j = 0; j < a.nprobes; j++) {
             const uint32_t slot = q * a.nprobes + j;
-            const uint32_t p = (uint32_t)a.probes[slot];
+            const uint64_t pp = a.probes[slot];
+            if (pp >= a.nlist) continue;                   // unused probe slot (fewer than nprobes finite distances)
+            const uint32_t p = (uint32_t)pp;
             const uint32_t n = a.part_n[p];
             const float *src = a.dist + a.seg_off[slot];
             const uint64_t rowbase = a.part_off[p];

@@ -136,13 +136,15 @@ def _kmeans(x, k, iters, gen, chunk=1 << 16):
     return c
 
 
-def _assign(x, c, chunk=1 << 16):
+def _assign(x, c, chunk=1 << 16, metric="l2"):
+    """Partition of every row, ranked like the search's coarse step: L2 for l2/cosine, 1 - x.c for dot."""
     import torch
     n = x.shape[0]
     out = torch.empty(n, dtype=torch.long, device=x.device)
     cn = (c * c).sum(1)
     for s in range(0, n, chunk):
-        out[s:s + chunk] = (cn[None, :] - 2.0 * (x[s:s + chunk] @ c.T)).argmin(1)
+        xc = x[s:s + chunk] @ c.T
+        out[s:s + chunk] = (-xc).argmin(1) if metric == "dot" else (cn[None, :] - 2.0 * xc).argmin(1)
     return out
 
 
@@ -217,7 +219,7 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
         assign = torch.as_tensor(_native.ivf_assign(centroids.cpu().numpy(), raw_np, metric, dev_index).astype(np.int64),
                                  device=x.device)
     else:
-        assign = _assign(x, centroids)
+        assign = _assign(x, centroids, metric=metric)
 
     # PQ codebooks: residuals for l2/cosine, raw vectors for dot
     nps = min(n, max(256, sample_rate) * 256)

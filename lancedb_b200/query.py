@@ -136,11 +136,23 @@ class LanceVectorQueryBuilder:
         if max_np != 0 and max_np < min_np:
             raise ValueError("maximum_nprobes must be greater than or equal to minimum_nprobes")
         # with no filter every probed partition yields rows, so min == effective probes;
-        # maximum_nprobes only matters for filtered queries (query.py:1676-1692)
-        return k, lim, min_np
+        # maximum_nprobes only matters for filtered queries (query.py:1676-1692, query.rs:1250-1275):
+        # 0 = "search as many partitions as needed" -> every partition
+        return k, lim, min_np, (max_np if max_np != 0 else (1 << 30))
+
+    @staticmethod
+    def _timeout_ms(timeout) -> int:
+        """QueryExecutionOptions.timeout (datetime.timedelta or seconds) -> ms for the C ABI; None/0 = none."""
+        if timeout is None:
+            return 0
+        sec = timeout.total_seconds() if hasattr(timeout, "total_seconds") else float(timeout)
+        if sec <= 0:
+            raise ValueError("timeout must be positive")
+        return max(1, int(round(sec * 1000.0)))
 
     def to_arrow(self, *, timeout=None) -> pa.Table:
-        k, lim, nprobes = self._resolve()
+        k, lim, nprobes, max_nprobes = self._resolve()
+        timeout_ms = self._timeout_ms(timeout)
         t = self._table
         if self._query.shape[1] != t._dim(self._vector_column):
             raise ValueError(
@@ -152,7 +164,8 @@ class LanceVectorQueryBuilder:
             self._query, column=self._vector_column, k=k, nprobes=nprobes,
             refine_factor=self._refine_factor, distance_type=self._distance_type,
             lower=self._lower_bound, upper=self._upper_bound, use_index=self._use_index,
-            allow_mask=None if (mask is None or self._postfilter) else mask)
+            allow_mask=None if (mask is None or self._postfilter) else mask,
+            max_nprobes=max_nprobes, timeout_ms=timeout_ms)
         out = []
         for qi in range(self._query.shape[0]):
             n = int(cnt[qi])
@@ -172,11 +185,12 @@ class LanceVectorQueryBuilder:
         return pa.concat_tables(out) if len(out) > 1 else out[0]
 
     def to_batches(self, max_batch_length: Optional[int] = None, *, timeout=None):
-        return pa.RecordBatchReader.from_batches(
-            self.to_arrow().schema, self.to_arrow().to_batches(max_chunksize=max_batch_length or 1024))
+        """MaxBatchLengthStream (rust/lancedb/src/utils/mod.rs:395): the result re-chunked to <= 1024 rows."""
+        tbl = self.to_arrow(timeout=timeout)
+        return pa.RecordBatchReader.from_batches(tbl.schema, tbl.to_batches(max_chunksize=max_batch_length or 1024))
 
-    def to_pandas(self, **kw):
-        return self.to_arrow().to_pandas(**kw)
+    def to_pandas(self, *, timeout=None, **kw):
+        return self.to_arrow(timeout=timeout).to_pandas(**kw)
 
-    def to_list(self) -> list:
-        return self.to_arrow().to_pylist()
+    def to_list(self, *, timeout=None) -> list:
+        return self.to_arrow(timeout=timeout).to_pylist()

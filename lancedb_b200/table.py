@@ -150,7 +150,7 @@ class Table:
         return LanceVectorQueryBuilder(self, query, column)
 
     def _vector_search(self, queries: np.ndarray, *, column, k, nprobes, refine_factor, distance_type,
-                       lower, upper, use_index, allow_mask=None):
+                       lower, upper, use_index, allow_mask=None, max_nprobes=0, timeout_ms=0):
         allow, allow_bits = None, 0
         if allow_mask is not None:                 # prefilter: row-id allow-list as the C ABI's bitmap
             allow, allow_bits = _native.mask_bitmap(allow_mask), int(len(allow_mask))
@@ -160,14 +160,16 @@ class Table:
                 # the reference documents this as invalid results; be explicit instead
                 raise ValueError(f"distance_type {distance_type!r} does not match the index's {idx.metric!r}")
             return idx.search(queries, k=k, nprobes=nprobes, refine_factor=refine_factor or 0,
-                              lower=lower, upper=upper, allow=allow, allow_bits=allow_bits)
+                              lower=lower, upper=upper, allow=allow, allow_bits=allow_bits,
+                              max_nprobes=max_nprobes if allow is not None else 0, timeout_ms=timeout_ms)
         fl = self._flat.get(column)
         if fl is None:
             fl = self._flat[column] = _native.GpuFlat(self._vectors(column), device=self._device)
         metric = distance_type or "l2"
         if metric not in ("l2", "cosine", "dot"):
             raise ValueError(f"unsupported distance type {metric!r}")
-        return fl.search(queries, k=k, metric=metric, lower=lower, upper=upper, allow=allow, allow_bits=allow_bits)
+        return fl.search(queries, k=k, metric=metric, lower=lower, upper=upper, allow=allow, allow_bits=allow_bits,
+                         timeout_ms=timeout_ms)
 
     def _take(self, row_ids: np.ndarray, columns: Optional[List[str]]) -> pa.Table:
         t = self._data if columns is None else self._data.select(columns)

@@ -30,10 +30,10 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = _native.load()
-    assert lib.lgpu_abi_version() == 1
-    # must match the C layout: 8 x 4-byte fields, u64, 6 pointers / 8 x 4-byte fields
+    assert lib.lgpu_abi_version() == 2
+    # must match the C layout: 8 x 4-byte fields, u64, 6 pointers / 10 x 4-byte fields
     assert ctypes.sizeof(_native.IndexDesc) == 32 + 8 + 6 * 8
-    assert ctypes.sizeof(_native.SearchParams) == 32
+    assert ctypes.sizeof(_native.SearchParams) == 40
 
 
 def test_no_cpu_fallback_without_gpu():
