@@ -151,6 +151,35 @@ int lgpu_merge_topk_device(int device, uint32_t nlists, uint32_t B, uint32_t k,
                            uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
                            void *cuda_stream);
 
+/* ---- partition-sharded search across GPUs (the reference is single-process, so there is no
+ * reference interface to replace -- this is what north_star adds for an index larger than one GPU's HBM).
+ * One process (or thread) per GPU.  Centroids and codebook are replicated, every partition's codes and row ids
+ * live on exactly one rank (non-owned partitions are empty in that rank's lgpu_index), every rank receives the
+ * same query batch, and the only data-path collective is ONE ncclAllGather of [B][k] 16-byte (_rowid, _distance)
+ * records per batch, merged on every rank by (_distance, _rowid).  NCCL is bound at run time (dlopen of
+ * libnccl.so.2), so hosts that never shard need no NCCL.  The host distributes the unique id over whatever
+ * channel it already has (the Rust crate: its RPC layer; the Python mirror: torch.distributed / a file). ---- */
+#define LGPU_COMM_ID_BYTES 128
+typedef struct lgpu_comm lgpu_comm;
+/* rank 0: create the group's id (an ncclUniqueId), to be handed to every rank */
+int  lgpu_comm_unique_id(void *id_out, size_t id_bytes);
+/* every rank, collectively: join the group on CUDA device `device` */
+int  lgpu_comm_init(const void *unique_id, size_t id_bytes, int rank, int world, int device, lgpu_comm **out);
+void lgpu_comm_destroy(lgpu_comm *comm);
+/* collective: every rank passes the same B queries (host buffers) and its own shard; every rank receives the
+ * global top-k.  refine_factor must be 0. */
+int  lgpu_search_sharded(lgpu_index *shard, lgpu_comm *comm, const float *queries, uint32_t B,
+                         const lgpu_search_params *params,
+                         uint64_t *out_ids, float *out_dist, uint32_t *out_count);
+/* same with device buffers, enqueued on `cuda_stream`, not synchronised */
+int  lgpu_search_sharded_device(lgpu_index *shard, lgpu_comm *comm, const float *d_queries, uint32_t B,
+                                const lgpu_search_params *params,
+                                uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_count,
+                                void *cuda_stream);
+/* device time (ms) of the local search, the all-gather and the merge of the most recent sharded call made with
+ * profiling on (lgpu_set_profiling).  times: [3] */
+int  lgpu_comm_last_stage_ms(lgpu_comm *comm, float *times);
+
 /* ---- index build passes (reference: IVF_PQ build through lance, parameters at
  * rust/lancedb/src/table/create_index.rs:283-303, rust/lancedb/src/index/vector.rs:246-319; "GPU support in
  * building vector index", python/python/lancedb/table.py:2883-2937).  k-means training stays with the caller;

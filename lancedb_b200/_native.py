@@ -25,6 +25,8 @@ EXPORTS = [
     "lgpu_last_error", "lgpu_abi_version", "lgpu_device_count",
     "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
     "lgpu_search", "lgpu_search_filtered", "lgpu_search_device", "lgpu_merge_topk_device",
+    "lgpu_comm_unique_id", "lgpu_comm_init", "lgpu_comm_destroy", "lgpu_search_sharded", "lgpu_search_sharded_device",
+    "lgpu_comm_last_stage_ms",
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
     "lgpu_ivf_assign", "lgpu_pq_encode",
     "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
@@ -82,6 +84,13 @@ def load():
     lib.lgpu_search_filtered.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_search_device.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
     lib.lgpu_merge_topk_device.argtypes = [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]
+    lib.lgpu_comm_unique_id.argtypes = [vp, C.c_size_t]
+    lib.lgpu_comm_init.argtypes = [vp, C.c_size_t, i32, i32, i32, C.POINTER(vp)]
+    lib.lgpu_comm_destroy.argtypes = [vp]
+    lib.lgpu_comm_destroy.restype = None
+    lib.lgpu_search_sharded.argtypes = [vp, vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
+    lib.lgpu_search_sharded_device.argtypes = [vp, vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
+    lib.lgpu_comm_last_stage_ms.argtypes = [vp, vp]
     lib.lgpu_flat_open.argtypes = [vp, C.c_uint64, u32, vp, i32, C.POINTER(vp)]
     lib.lgpu_flat_close.argtypes = [vp]
     lib.lgpu_flat_close.restype = None
@@ -292,6 +301,55 @@ def mask_bitmap(mask) -> np.ndarray:
     pad = (-m.size) % 32
     bits = np.packbits(np.concatenate([m, np.zeros(pad, bool)]), bitorder="little")
     return np.ascontiguousarray(bits).view(np.uint32)
+
+
+COMM_ID_BYTES = 128
+# one gathered top-k entry (csrc/kernels.cuh TopkRecord): what crosses NVLink in the sharded search
+TOPK_RECORD = np.dtype([("id", "<u8"), ("dist", "<f4"), ("pad", "<u4")])
+
+
+def comm_unique_id() -> bytes:
+    """rank 0: the group's id (an ncclUniqueId) to hand to every rank."""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    check(load().lgpu_comm_unique_id(buf, COMM_ID_BYTES))
+    return bytes(buf)
+
+
+class Comm:
+    """One rank of a partition-sharded search group (lgpu_comm): collective constructor."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int = 0):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique id must be 128 bytes")
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        check(load().lgpu_comm_init(buf, COMM_ID_BYTES, rank, world, device, C.byref(h)))
+        self._h, self.rank, self.world, self.device = h, rank, world, device
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.lgpu_comm_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def search(self, shard: "GpuIvfPq", queries, k=10, nprobes=20, lower=None, upper=None):
+        """Collective host-buffer search: same queries on every rank, global top-k on every rank."""
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, shard.dim)
+        B = q.shape[0]
+        ids = np.empty((B, k), np.uint64); dist = np.empty((B, k), np.float32); cnt = np.empty(B, np.uint32)
+        p = make_params(k, nprobes, 0, lower, upper)
+        check(load().lgpu_search_sharded(shard._h, self._h, _ptr(q), B, C.byref(p), _ptr(ids), _ptr(dist), _ptr(cnt)))
+        return ids, dist, cnt
+
+    def search_device(self, shard: "GpuIvfPq", d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int,
+                      d_cnt: int, stream: int = 0):
+        check(load().lgpu_search_sharded_device(shard._h, self._h, d_q, B, C.byref(p), d_ids, d_dist, d_cnt, stream))
+
+    def last_stage_ms(self):
+        t = (C.c_float * 3)()
+        check(load().lgpu_comm_last_stage_ms(self._h, t))
+        return dict(zip(["local_search", "allgather", "merge"], list(t)))
 
 
 def merge_topk_device(device: int, nlists: int, B: int, k: int, d_ids: int, d_dist: int, d_out_ids: int,

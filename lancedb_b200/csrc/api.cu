@@ -20,6 +20,8 @@
 #include <unordered_set>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
 #include <pthread.h>
 #include <unistd.h>
 
@@ -211,6 +213,62 @@ struct lgpu_flat {
     bool has_ids = false, has_norms = false;
     std::mutex mu;
     WorkspacePool pool;
+};
+
+// ---- NCCL, bound at run time (dlopen): single-GPU hosts need no libnccl, and inside a process that already
+// loaded one (torch) the same library instance is used ----
+namespace lgpu {
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+static NcclApi &nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("LGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) { api.error = "libnccl.so.2 not found (set LGPU_NCCL_LIB)"; return; }
+        auto sym = [&](const char *n) { void *f = dlsym(api.lib, n); if (!f) api.error = std::string("missing NCCL symbol ") + n; return f; };
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+    });
+    if (!api.error.empty()) { set_error("NCCL unavailable: " + api.error); throw Failure{LGPU_RUNTIME}; }
+    return api;
+}
+#define LGPU_NCCL(expr)                                                                          \
+    do {                                                                                         \
+        ncclResult_t _r = (expr);                                                                \
+        if (_r != ncclSuccess) {                                                                 \
+            ::lgpu::set_error(std::string(#expr) + ": " + ::lgpu::nccl_api().GetErrorString(_r)); \
+            throw ::lgpu::Failure{LGPU_RUNTIME};                                                 \
+        }                                                                                        \
+    } while (0)
+}  // namespace lgpu
+
+// one rank of a partition-sharded search group: an NCCL communicator plus the gather buffers
+struct lgpu_comm {
+    std::atomic<int> refs{0};
+    int device = 0, rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    std::mutex mu;                       // collectives of one communicator are issued one call at a time
+    DevBuf send, recv;                   // [B][k] / [world][B][k] TopkRecord
+    DevBuf l_ids, l_dist, l_cnt;         // the local (per-shard) top-k before the exchange
+    cudaEvent_t ev[3] = {};              // local search done / all-gather done / merge done (stage timing)
+    float last_ms[3] = {0, 0, 0};        // local search, all-gather, merge of the most recent profiled call
 };
 
 namespace {
@@ -1186,6 +1244,124 @@ int lgpu_flat_search_device(lgpu_flat *flh, int metric, const float *d_queries, 
         require_device(fl->device);
         WsLease lease(fl->pool, (cudaStream_t)cuda_stream, true);
         flat_search_device(fl.h, lease.ws, lease.st, metric, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
+    });
+}
+
+// ---- partition-sharded multi-GPU search: one process per GPU, one ncclAllGather per batch ----
+int lgpu_comm_unique_id(void *id_out, size_t id_bytes)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(id_out && id_bytes >= LGPU_COMM_ID_BYTES, "id buffer must hold LGPU_COMM_ID_BYTES bytes");
+        static_assert(LGPU_COMM_ID_BYTES == sizeof(ncclUniqueId), "unique id size");
+        ncclUniqueId id;
+        LGPU_NCCL(nccl_api().GetUniqueId(&id));
+        memcpy(id_out, &id, sizeof(id));
+    });
+}
+
+int lgpu_comm_init(const void *unique_id, size_t id_bytes, int rank, int world, int device, lgpu_comm **out)
+{
+    lgpu_comm *c = nullptr;
+    int rc = guarded([&] {
+        LGPU_REQUIRE(unique_id && out && id_bytes >= LGPU_COMM_ID_BYTES, "null argument / short unique id");
+        LGPU_REQUIRE(world >= 1 && rank >= 0 && rank < world, "rank must be in [0, world)");
+        require_device(device);
+        NcclApi &api = nccl_api();
+        c = new lgpu_comm();
+        c->device = device; c->rank = rank; c->world = world;
+        ncclUniqueId id;
+        memcpy(&id, unique_id, sizeof(id));
+        LGPU_NCCL(api.CommInitRank(&c->comm, world, id, rank));
+        for (auto &e : c->ev) LGPU_CUDA(cudaEventCreate(&e));
+        register_handle(c);
+        *out = c;
+    });
+    if (rc != LGPU_OK && c) { if (c->comm) nccl_api().CommDestroy(c->comm); delete c; }
+    return rc;
+}
+
+void lgpu_comm_destroy(lgpu_comm *c)
+{
+    if (!retire_handle(c)) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    try { if (c->comm) nccl_api().CommDestroy(c->comm); } catch (const Failure &) {}
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+}
+
+// local top-k on this rank's shard -> pack -> ONE all-gather of [B][k] 16-byte records -> merge, all on `st`
+static void sharded_search_device(lgpu_index *ix, lgpu_comm *c, Workspace *ws, cudaStream_t st, const float *d_q,
+                                  uint32_t B, const lgpu_search_params &sp, uint64_t *d_ids, float *d_dist,
+                                  uint32_t *d_cnt, const Deadline *deadline)
+{
+    LGPU_REQUIRE(c->device == ix->device, "communicator and index live on different devices");
+    LGPU_REQUIRE(sp.refine_factor == 0, "refine_factor is not supported on the sharded path (raw vectors are not sharded)");
+    std::lock_guard<std::mutex> g(c->mu);
+    const size_t n = (size_t)B * sp.k;
+    c->l_ids.ensure(n * 8); c->l_dist.ensure(n * 4); c->l_cnt.ensure((size_t)B * 4);
+    c->send.ensure(n * sizeof(TopkRecord)); c->recv.ensure(n * sizeof(TopkRecord) * c->world);
+    const bool prof = profiling_enabled();
+    ivf_search_device(ix, ws, st, d_q, B, sp, c->l_ids.as<uint64_t>(), c->l_dist.as<float>(), c->l_cnt.as<uint32_t>(),
+                      RowFilter(), deadline);
+    launch_pack_records(c->l_ids.as<uint64_t>(), c->l_dist.as<float>(), n, c->send.as<TopkRecord>(), st);
+    if (prof) cudaEventRecord(c->ev[0], st);
+    LGPU_NCCL(nccl_api().AllGather(c->send.p, c->recv.p, n * sizeof(TopkRecord), ncclUint8, c->comm, st));
+    if (prof) cudaEventRecord(c->ev[1], st);
+    SelectArgs sb{};
+    sb.mode = 2; sb.cand_rec = c->recv.as<TopkRecord>();
+    sb.ncols = (uint64_t)c->world * sp.k; sb.inner = sp.k; sb.row_stride = sp.k; sb.outer_stride = (uint64_t)B * sp.k;
+    sb.B = B; sb.k = sp.k; sb.out_ids = d_ids; sb.out_dist = d_dist; sb.out_count = d_cnt;
+    launch_select(sb, st);
+    if (prof) {
+        cudaEventRecord(c->ev[2], st);
+        LGPU_CUDA(cudaStreamSynchronize(st));
+        c->last_ms[0] = g_stage_ms[6];
+        cudaEventElapsedTime(&c->last_ms[1], c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->last_ms[2], c->ev[1], c->ev[2]);
+    }
+}
+
+int lgpu_search_sharded(lgpu_index *ixh, lgpu_comm *ch, const float *queries, uint32_t B,
+                        const lgpu_search_params *params, uint64_t *out_ids, float *out_dist, uint32_t *out_count)
+{
+    return guarded([&] {
+        HandleRef<lgpu_index> ix(ixh, "index");
+        HandleRef<lgpu_comm> c(ch, "communicator");
+        check_ivf_call(ix.h, queries, B, params, out_ids, out_dist, out_count);
+        if (B == 0) return;
+        require_device(ix->device);
+        uint64_t key[4];
+        make_key(key, 0x5a4dull, B, *params);
+        host_call(ix->pool, queries, B, ix->dim, params->k, out_ids, out_dist, out_count, key, params->timeout_ms,
+                  [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc,
+                      const Deadline &dl) { sharded_search_device(ix.h, c.h, ws, st, dq, B, *params, di, dd, dc, &dl); },
+                  false);
+    });
+}
+
+int lgpu_search_sharded_device(lgpu_index *ixh, lgpu_comm *ch, const float *d_queries, uint32_t B,
+                               const lgpu_search_params *params, uint64_t *d_out_ids, float *d_out_dist,
+                               uint32_t *d_out_count, void *cuda_stream)
+{
+    return guarded([&] {
+        HandleRef<lgpu_index> ix(ixh, "index");
+        HandleRef<lgpu_comm> c(ch, "communicator");
+        check_ivf_call(ix.h, d_queries, B, params, d_out_ids, d_out_dist, d_out_count);
+        if (B == 0) return;
+        require_device(ix->device);
+        WsLease lease(ix->pool, (cudaStream_t)cuda_stream, true);
+        sharded_search_device(ix.h, c.h, lease.ws, lease.st, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count,
+                              nullptr);
+    });
+}
+
+int lgpu_comm_last_stage_ms(lgpu_comm *ch, float *times)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(times, "null argument");
+        HandleRef<lgpu_comm> c(ch, "communicator");
+        memcpy(times, c->last_ms, sizeof(c->last_ms));
     });
 }
 

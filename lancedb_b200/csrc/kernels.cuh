@@ -109,6 +109,14 @@ void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, u
 
 // ---------------- top-k select (K4) ------------------------------------------------
 constexpr uint32_t SELECT_KMAX = 2048;
+// one top-k entry as it crosses NVLink in the partition-sharded search: a single ncclAllGather of
+// [B][k] of these per rank, consumed in place by the merge (select mode 2)
+struct alignas(16) TopkRecord {
+    uint64_t id;      // _rowid, UINT64_MAX = unused slot
+    float dist;       // _distance
+    uint32_t pad;
+};
+static_assert(sizeof(TopkRecord) == 16, "TopkRecord layout");
 struct SelectArgs {
     int mode;                     // 0: IVF distance segments, 1: dense row (ids = column / col_ids),
                                   // 2: strided candidate lists with per-entry ids
@@ -128,6 +136,7 @@ struct SelectArgs {
     const uint64_t *col_ids;      // mode 1: optional id per column (NULL => column index)
     const uint64_t *cand_ids;     // mode 2: id per entry (same addressing as dense)
     const uint64_t *cand_pos;     // mode 2: optional pos per entry
+    const TopkRecord *cand_rec;   // mode 2: optional packed (id, dist) entries instead of dense + cand_ids
     // common
     uint32_t B, k;
     int has_lower, has_upper;
@@ -135,6 +144,7 @@ struct SelectArgs {
     uint64_t *out_ids;            // [B][k]
     float *out_dist;              // [B][k]
     uint32_t *out_count;          // [B]
+    TopkRecord *out_rec;          // optional [B][k]: packed output instead of out_ids / out_dist
     uint64_t *out_pos;            // optional [B][k] storage position (mode 0) / column (mode 1)
     const uint32_t *only;         // optional [B]: queries whose flag is 0 are left untouched
     // prefilter (query.rs:489-507): optional row-id allow-list bitmap; a candidate whose id has bit 0 (or is
@@ -143,6 +153,8 @@ struct SelectArgs {
     uint64_t allow_bits;
 };
 void launch_select(const SelectArgs &a, cudaStream_t st);
+// rec[i] = (ids[i], dist[i]) for i < n
+void launch_pack_records(const uint64_t *ids, const float *dist, uint64_t n, TopkRecord *out, cudaStream_t st);
 
 // ---------------- tensor-core shortlist (gemm.cu) ------------------------------------
 bool gemm_shape_supported(uint32_t d);

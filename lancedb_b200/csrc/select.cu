@@ -64,6 +64,14 @@ __device__ __forceinline__ bool allow_bit(const SelectArgs &a, uint64_t id)
     return id < a.allow_bits && ((a.allow[id >> 5] >> (id & 31)) & 1u);
 }
 
+__device__ __forceinline__ void write_entry(const SelectArgs &a, size_t at, bool have, uint64_t id, uint32_t key)
+{
+    const uint64_t oid = have ? id : UINT64_MAX;
+    const float od = have ? key_f32(key) : CUDART_INF_F;
+    if (a.out_rec) { TopkRecord r; r.id = oid; r.dist = od; r.pad = 0u; a.out_rec[at] = r; }
+    else { a.out_ids[at] = oid; a.out_dist[at] = od; }
+}
+
 template <bool POS>
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint32_t cap, uint32_t trigger)
 {
@@ -187,8 +195,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
                 if (c + u < a.ncols) {
                     uint64_t cc = c + u;
                     uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
-                    idv[u] = a.cand_ids[addr];
-                    v[u] = a.dense[addr];
+                    if (a.cand_rec) { const TopkRecord r = a.cand_rec[addr]; idv[u] = r.id; v[u] = r.dist; }
+                    else { idv[u] = a.cand_ids[addr]; v[u] = a.dense[addr]; }
                     ok[u] = idv[u] != UINT64_MAX;           // unused slot of a shorter list
                 }
             }
@@ -227,8 +235,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
     const uint32_t cnt = s_cnt;
     for (uint32_t i = tid; i < a.k; i += SEL_THREADS) {
         bool have = i < cnt;
-        a.out_ids[(size_t)q * a.k + i] = have ? st.ids[i] : UINT64_MAX;
-        a.out_dist[(size_t)q * a.k + i] = have ? key_f32(st.keys[i]) : CUDART_INF_F;
+        write_entry(a, (size_t)q * a.k + i, have, st.ids[i], st.keys[i]);
         if (POS) a.out_pos[(size_t)q * a.k + i] = have ? st.pos[i] : UINT64_MAX;
     }
     if (tid == 0) a.out_count[q] = cnt;
@@ -371,8 +378,9 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
             uint64_t id = UINT64_MAX, pos = cc;
             if (cc < a.ncols) {
                 const uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
-                id = a.cand_ids[addr];
-                float f = a.dense[addr];
+                float f;
+                if (a.cand_rec) { const TopkRecord r = a.cand_rec[addr]; id = r.id; f = r.dist; }
+                else { id = a.cand_ids[addr]; f = a.dense[addr]; }
                 if (f == 0.f) f = 0.f;
                 key = f32_key(f);
                 pass = id != UINT64_MAX && in_range(f) && key <= tau_k;
@@ -408,15 +416,30 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
         total += __popc(__ballot_sync(0xffffffffu, have));
         const uint32_t slot = i * 32 + lane;
         if (slot < k) {
-            a.out_ids[(size_t)q * k + slot] = have ? qid[i] : UINT64_MAX;
-            a.out_dist[(size_t)q * k + slot] = have ? key_f32(qk[i]) : CUDART_INF_F;
+            write_entry(a, (size_t)q * k + slot, have, qid[i], qk[i]);
             if (POS) a.out_pos[(size_t)q * k + slot] = have ? qpos[i] : UINT64_MAX;
         }
     }
     if (lane == 0) a.out_count[q] = min(total, k);
 }
 
+__global__ void pack_records_kernel(const uint64_t *__restrict__ ids, const float *__restrict__ dist, uint64_t n,
+                                    TopkRecord *__restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TopkRecord r; r.id = ids[i]; r.dist = dist[i]; r.pad = 0u;
+    out[i] = r;
+}
+
 }  // namespace
+
+void launch_pack_records(const uint64_t *ids, const float *dist, uint64_t n, TopkRecord *out, cudaStream_t st)
+{
+    if (n == 0) return;
+    pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, dist, n, out);
+    LGPU_CUDA(cudaGetLastError());
+}
 
 void launch_select(const SelectArgs &a, cudaStream_t st)
 {

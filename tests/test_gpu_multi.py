@@ -28,10 +28,16 @@ def _rank_main(rank, world, port, tmp):
     ix = random_index(rng, dim=64, nlist=40, m=8, n=20000)
     q = queries(rng, 77, 64)
     sh = ShardedIvfPq(ix, device=rank)
-    ids, dst, cnt = sh.search(q, k=10, nprobes=9)
     oi, od, oc = oracle.OracleIndex.from_data(ix).search(q, k=10, nprobes=9, nthreads=4)
+    # host-buffer collective (lgpu_search_sharded): in-library ncclAllGather of 16-byte records + merge
+    ids, dst, cnt = sh.search(q, k=10, nprobes=9)
     assert np.array_equal(cnt, oc) and np.array_equal(ids, oi)
     assert np.array_equal(dst.view(np.uint32), od.view(np.uint32))
+    # device-buffer collective (lgpu_search_sharded_device) on torch's current stream
+    d_ids, d_dst, d_cnt = sh.search_device(torch.from_numpy(q).cuda(rank), k=10, nprobes=9)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ids.cpu().numpy().view(np.uint64), oi) and np.array_equal(d_cnt.cpu().numpy().view(np.uint32), oc)
+    assert np.array_equal(d_dst.cpu().numpy().view(np.uint32), od.view(np.uint32))
     sh.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -116,25 +116,25 @@ def _rank_main(rank, world, port, tmp):
     import torch.distributed as dist
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import oracle
-    from lancedb_b200.distributed import gather_shape
+    from lancedb_b200 import _native
+    from lancedb_b200.distributed import gather_shape, merge_records, pack_records
     dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
     rng = np.random.default_rng(7)
     ix = random_index(rng, dim=32, nlist=9, m=4, n=1500)
     q = queries(rng, 11, 32)
     k, nprobes = 10, 5
     ids, dst, cnt = oracle.OracleIndex.from_data(ix.shard(rank, world)).search(q, k=k, nprobes=nprobes)
-    g_ids = torch.empty(gather_shape(world, 11, k), dtype=torch.int64)
-    g_dst = torch.empty(gather_shape(world, 11, k), dtype=torch.float32)
-    dist.all_gather_into_tensor(g_ids.view(-1, k), torch.from_numpy(ids.view(np.int64)))
-    dist.all_gather_into_tensor(g_dst.view(-1, k), torch.from_numpy(dst))
-    gi = g_ids.numpy().view(np.uint64); gd = g_dst.numpy()
+    # the library's exchange step, restated on the host: ONE all-gather of [B][k] 16-byte records
+    # (lgpu_search_sharded packs (id u64, dist f32, pad u32) and gathers them as bytes), then the merge
+    assert _native.TOPK_RECORD.itemsize == 16
+    send = pack_records(ids, dst)
+    recv = torch.empty(world * send.nbytes, dtype=torch.uint8)
+    dist.all_gather_into_tensor(recv, torch.from_numpy(send.view(np.uint8).reshape(-1)))
+    gathered = recv.numpy().view(_native.TOPK_RECORD).reshape(gather_shape(world, 11, k))
+    m_ids, m_dst, m_cnt = merge_records(gathered, k)
     full_ids, full_dst, full_cnt = oracle.OracleIndex.from_data(ix).search(q, k=k, nprobes=nprobes)
-    for b in range(11):                      # merge exactly as lgpu_merge_topk_device does
-        c = [(gd[r, b, i], gi[r, b, i]) for r in range(world) for i in range(k) if gi[r, b, i] != np.iinfo(np.uint64).max]
-        c.sort()
-        c = c[:k]
-        assert [x[1] for x in c] == list(full_ids[b, :full_cnt[b]])
-        assert [x[0] for x in c] == list(full_dst[b, :full_cnt[b]])
+    assert np.array_equal(m_cnt, full_cnt) and np.array_equal(m_ids, full_ids)
+    assert np.array_equal(m_dst.view(np.uint32), full_dst.view(np.uint32))
     dist.barrier()
     dist.destroy_process_group()
     open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
