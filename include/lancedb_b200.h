@@ -125,6 +125,17 @@ int lgpu_search(lgpu_index *ix, const float *queries, uint32_t B,
                 const lgpu_search_params *params,
                 uint64_t *out_ids, float *out_dist, uint32_t *out_count);
 
+/* Asynchronous form of lgpu_search (SURVEY.md 8b "Threading": today the Python binding parks the blocking call on
+ * spawn_blocking, python/src/runtime.rs:113-119).  Returns once the copies and kernels are enqueued on a private
+ * stream; every buffer must stay valid (and should be page-locked for the copies to overlap) until
+ * lgpu_ticket_wait returns.  Two or more tickets in flight pipeline: batch i+1's H2D overlaps batch i's kernels. */
+typedef struct lgpu_ticket lgpu_ticket;
+int lgpu_search_async(lgpu_index *ix, const float *queries, uint32_t B,
+                      const lgpu_search_params *params,
+                      uint64_t *out_ids, float *out_dist, uint32_t *out_count, lgpu_ticket **ticket);
+int lgpu_ticket_poll(lgpu_ticket *ticket, int *done);   /* *done = 1 when the results are in place */
+int lgpu_ticket_wait(lgpu_ticket *ticket);              /* blocks, frees the ticket, returns the call's status */
+
 /* Prefiltered search: the reference's default filter mode ("filtering will be performed
  * before the vector search", rust/lancedb/src/query.rs:489-507; the row-id allow-list the
  * scalar filter produced is what lance hands to the ANN nodes as a pre-filter [lance,
@@ -229,6 +240,8 @@ int lgpu_debug_gemm(const float *queries, const float *vectors, uint32_t B, uint
  * LGPU_PROFILE=1 in the environment: coarse, select-probes, group, scan, top-k,
  * refine, total.  times: [7] */
 int lgpu_last_stage_ms(float *times);
+/* kernels this process has launched through the library so far (eager launches and graph replays alike) */
+int lgpu_kernel_launch_count(uint64_t *count);
 /* switch per-stage CUDA-event timing (and the scanned-bytes counter) on/off for the
  * calling process; overrides LGPU_PROFILE.  While on, lgpu_search_device synchronises
  * the stream before returning. */

@@ -25,11 +25,13 @@ EXPORTS = [
     "lgpu_last_error", "lgpu_abi_version", "lgpu_device_count",
     "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
     "lgpu_search", "lgpu_search_filtered", "lgpu_search_device", "lgpu_merge_topk_device",
+    "lgpu_search_async", "lgpu_ticket_poll", "lgpu_ticket_wait",
     "lgpu_comm_unique_id", "lgpu_comm_init", "lgpu_comm_destroy", "lgpu_search_sharded", "lgpu_search_sharded_device",
     "lgpu_comm_last_stage_ms",
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
     "lgpu_ivf_assign", "lgpu_pq_encode",
     "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
+    "lgpu_kernel_launch_count",
 ]
 
 
@@ -81,6 +83,9 @@ def load():
     lib.lgpu_index_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     lib.lgpu_last_scanned_code_bytes.argtypes = [C.POINTER(C.c_uint64)]
     lib.lgpu_search.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
+    lib.lgpu_search_async.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, C.POINTER(vp)]
+    lib.lgpu_ticket_poll.argtypes = [vp, C.POINTER(C.c_int)]
+    lib.lgpu_ticket_wait.argtypes = [vp]
     lib.lgpu_search_filtered.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_search_device.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
     lib.lgpu_merge_topk_device.argtypes = [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]
@@ -104,6 +109,7 @@ def load():
     lib.lgpu_debug_gemm.argtypes = [vp, vp, u32, C.c_uint64, u32, i32, vp]
     lib.lgpu_last_stage_ms.argtypes = [vp]
     lib.lgpu_set_profiling.argtypes = [i32]
+    lib.lgpu_kernel_launch_count.argtypes = [C.POINTER(C.c_uint64)]
     for name in EXPORTS:
         getattr(lib, name)          # every declared symbol must be exported
     if lib.lgpu_abi_version() != ABI_VERSION:
@@ -199,6 +205,13 @@ class GpuIvfPq:
         """Host-buffer search into caller-owned (e.g. pinned) arrays; no allocation."""
         check(load().lgpu_search(self._h, q.ctypes.data, q.shape[0], C.byref(p), ids.ctypes.data,
                                  dist.ctypes.data, cnt.ctypes.data))
+
+    def search_async(self, q: np.ndarray, p: SearchParams, ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray):
+        """lgpu_search_async into caller-owned (pinned) arrays; returns a ticket for ticket_wait()."""
+        t = C.c_void_p()
+        check(load().lgpu_search_async(self._h, q.ctypes.data, q.shape[0], C.byref(p), ids.ctypes.data,
+                                       dist.ctypes.data, cnt.ctypes.data, C.byref(t)))
+        return t
 
     def search_device(self, d_q: int, B: int, p: SearchParams, d_ids: int, d_dist: int, d_cnt: int, stream: int = 0):
         """Device-pointer search (raw addresses), enqueued on `stream`, not synchronised."""
@@ -352,6 +365,16 @@ class Comm:
         return dict(zip(["local_search", "allgather", "merge"], list(t)))
 
 
+def ticket_wait(ticket) -> None:
+    check(load().lgpu_ticket_wait(ticket))
+
+
+def ticket_done(ticket) -> bool:
+    d = C.c_int(0)
+    check(load().lgpu_ticket_poll(ticket, C.byref(d)))
+    return bool(d.value)
+
+
 def merge_topk_device(device: int, nlists: int, B: int, k: int, d_ids: int, d_dist: int, d_out_ids: int,
                       d_out_dist: int, d_out_cnt: int, stream: int = 0):
     check(load().lgpu_merge_topk_device(device, nlists, B, k, d_ids, d_dist, d_out_ids, d_out_dist, d_out_cnt,
@@ -363,6 +386,12 @@ def debug_gemm(queries, vectors, device: int = 0) -> np.ndarray:
     out = np.empty((q.shape[0], x.shape[0]), np.float32)
     check(load().lgpu_debug_gemm(_ptr(q), _ptr(x), q.shape[0], x.shape[0], q.shape[1], device, _ptr(out)))
     return out
+
+
+def kernel_launch_count() -> int:
+    n = C.c_uint64(0)
+    check(load().lgpu_kernel_launch_count(C.byref(n)))
+    return n.value
 
 
 def set_profiling(enabled: bool) -> None:

@@ -32,6 +32,16 @@ static thread_local float g_stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
 static thread_local uint64_t g_scanned_bytes = 0;
 void set_error(const std::string &msg) { g_err = msg; }
 
+// every kernel the library launches (eagerly, into a stream capture, or through a graph replay) is counted
+static std::atomic<uint64_t> g_kernel_launches{0};
+static thread_local bool g_capturing = false;        // launches made while capturing are counted per replay instead
+static thread_local uint64_t g_captured_launches = 0;
+void count_launches(uint64_t n)
+{
+    if (g_capturing) g_captured_launches += n;
+    else g_kernel_launches.fetch_add(n, std::memory_order_relaxed);
+}
+
 static std::atomic<int> g_profiling{-1};
 static bool profiling_enabled()
 {
@@ -90,6 +100,7 @@ struct Workspace {
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_key[4] = {0, 0, 0, 0};
     uint64_t graph_epoch = 0;           // g_alloc_epoch when `graph` was captured
+    uint64_t graph_kernels = 0;         // kernel launches one replay stands for
     int graph_state = 0;                // 0: next call runs eagerly (warm-up), 1: capture, 2: replay, -1: disabled
     DevBuf tq, sbound, probe_A, amax;   // two-pass scan: per-query tables, bounds, per-probe scalars
     Workspace()
@@ -803,12 +814,10 @@ static bool graphs_enabled()
 // (re)allocation anywhere in the process since the capture, profiling mode, or a failed capture falls back to
 // eager launches.
 template <class Run>
-void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t dim, uint32_t k, uint64_t *out_ids,
-               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], uint32_t timeout_ms, Run &&run,
-               bool allow_graph = true)
+void host_submit(WsLease &lease, const Deadline &deadline, const float *queries, uint32_t B, uint32_t dim, uint32_t k,
+                 uint64_t *out_ids, float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], Run &&run,
+                 bool allow_graph, bool sync)
 {
-    const Deadline deadline(timeout_ms);
-    WsLease lease(pool, nullptr, false);
     Workspace *ws = lease.ws;
     cudaStream_t st = lease.st;
     ws->q.ensure(std::max<size_t>((size_t)B * dim, 1) * 4);
@@ -831,11 +840,13 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
         ws->graph_state = 1;
     } else if (ws->graph_state == 2 && g_alloc_epoch.load() == ws->graph_epoch) {
         LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
+        count_launches(ws->graph_kernels);
     } else if (ws->graph_state == 1) {
         bool ok = false;
         cudaGraph_t g = nullptr;
         const uint64_t epoch0 = g_alloc_epoch.load();
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            g_capturing = true; g_captured_launches = 0;
             try {
                 eager();
                 ok = cudaStreamEndCapture(st, &g) == cudaSuccess && g != nullptr && g_alloc_epoch.load() == epoch0;
@@ -843,12 +854,15 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
                 cudaStreamEndCapture(st, &g);
                 ok = false;
             }
+            g_capturing = false;
         }
         if (ok && cudaGraphInstantiate(&ws->graph, g, 0) == cudaSuccess) {
             ws->graph_state = 2;
             ws->graph_epoch = epoch0;
+            ws->graph_kernels = g_captured_launches;
             cudaGraphDestroy(g);
             LGPU_CUDA(cudaGraphLaunch(ws->graph, st));
+            count_launches(ws->graph_kernels);
         } else if (g_alloc_epoch.load() != epoch0) {        // a buffer moved during the capture: try again next call
             if (g) cudaGraphDestroy(g);
             cudaGetLastError();
@@ -868,11 +882,21 @@ void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t d
         ws->graph_state = 1;
         eager();
     }
-    deadline.wait(st, ws->ev[7]);
+    if (sync) deadline.wait(st, ws->ev[7]);
     LGPU_CUDA(cudaMemcpyAsync(out_ids, ws->out_ids.p, (size_t)B * k * 8, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaMemcpyAsync(out_dist, ws->out_dist.p, (size_t)B * k * 4, cudaMemcpyDeviceToHost, st));
     LGPU_CUDA(cudaMemcpyAsync(out_count, ws->out_count.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    LGPU_CUDA(cudaStreamSynchronize(st));
+    if (sync) LGPU_CUDA(cudaStreamSynchronize(st));
+}
+
+template <class Run>
+void host_call(WorkspacePool &pool, const float *queries, uint32_t B, uint32_t dim, uint32_t k, uint64_t *out_ids,
+               float *out_dist, uint32_t *out_count, const uint64_t (&key)[4], uint32_t timeout_ms, Run &&run,
+               bool allow_graph = true)
+{
+    const Deadline deadline(timeout_ms);
+    WsLease lease(pool, nullptr, false);
+    host_submit(lease, deadline, queries, B, dim, k, out_ids, out_dist, out_count, key, run, allow_graph, true);
 }
 
 static inline void make_key(uint64_t (&key)[4], uint64_t tag, uint32_t B, const lgpu_search_params &p)
@@ -1053,6 +1077,11 @@ int lgpu_last_scanned_code_bytes(uint64_t *bytes)
     return guarded([&] { LGPU_REQUIRE(bytes, "null argument"); *bytes = g_scanned_bytes; });
 }
 
+int lgpu_kernel_launch_count(uint64_t *count)
+{
+    return guarded([&] { LGPU_REQUIRE(count, "null argument"); *count = g_kernel_launches.load(); });
+}
+
 int lgpu_set_profiling(int enabled)
 {
     g_profiling.store(enabled ? 1 : 0);
@@ -1127,6 +1156,86 @@ int lgpu_search_device(lgpu_index *ixh, const float *d_queries, uint32_t B, cons
         WsLease lease(ix->pool, (cudaStream_t)cuda_stream, true);
         ivf_search_device(ix.h, lease.ws, lease.st, d_queries, B, *params, d_out_ids, d_out_dist, d_out_count);
     });
+}
+
+// ---- asynchronous completion (SURVEY.md 8b "Threading": a tokio worker must not be blocked for the length of a
+// search -- python/src/runtime.rs:113-119 uses spawn_blocking for that today).  lgpu_search_async stages the
+// queries, enqueues the search and the copy-back on a private stream and returns; lgpu_ticket_wait blocks until
+// the results are in the caller's buffers.  Two tickets in flight use two workspaces/streams, so batch i+1's
+// H2D overlaps batch i's kernels. ----
+struct lgpu_ticket {
+    HandleRef<lgpu_index> ix;
+    WsLease lease;
+    Deadline deadline;
+    cudaEvent_t done = nullptr;
+    lgpu_ticket(lgpu_index *h, uint32_t timeout_ms)
+        : ix(h, "index"), lease(ix->pool, nullptr, false), deadline(timeout_ms) {}
+    ~lgpu_ticket() { if (done) cudaEventDestroy(done); }
+};
+
+int lgpu_search_async(lgpu_index *ixh, const float *queries, uint32_t B, const lgpu_search_params *params,
+                      uint64_t *out_ids, float *out_dist, uint32_t *out_count, lgpu_ticket **ticket)
+{
+    lgpu_ticket *t = nullptr;
+    int rc = guarded([&] {
+        LGPU_REQUIRE(ticket != nullptr, "ticket is null");
+        LGPU_REQUIRE(params != nullptr, "search params are null");
+        {   // validate before taking a workspace
+            HandleRef<lgpu_index> ix(ixh, "index");
+            check_ivf_call(ix.h, queries, B, params, out_ids, out_dist, out_count);
+            require_device(ix->device);
+        }
+        t = new lgpu_ticket(ixh, params->timeout_ms);
+        LGPU_CUDA(cudaEventCreateWithFlags(&t->done, cudaEventDisableTiming));
+        if (B > 0) {
+            uint64_t key[4];
+            make_key(key, 0x1f5ull, B, *params);
+            lgpu_index *ix = t->ix.h;
+            const lgpu_search_params sp = *params;
+            host_submit(t->lease, t->deadline, queries, B, ix->dim, sp.k, out_ids, out_dist, out_count, key,
+                        [&](Workspace *ws, cudaStream_t st, const float *dq, uint64_t *di, float *dd, uint32_t *dc,
+                            const Deadline &) { ivf_search_device(ix, ws, st, dq, B, sp, di, dd, dc); },
+                        true, false);
+        }
+        LGPU_CUDA(cudaEventRecord(t->done, t->lease.st));
+        *ticket = t;
+    });
+    if (rc != LGPU_OK && t) { cudaStreamSynchronize(t->lease.st); delete t; }
+    return rc;
+}
+
+int lgpu_ticket_poll(lgpu_ticket *t, int *done)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(t && done, "null argument");
+        cudaError_t e = cudaEventQuery(t->done);
+        if (e != cudaSuccess && e != cudaErrorNotReady) LGPU_CUDA(e);
+        *done = e == cudaSuccess ? 1 : 0;
+    });
+}
+
+/* blocks until the call's results are in the caller's buffers, then frees the ticket.  With a timeout armed the
+ * status is LGPU_TIMEOUT when the deadline passed first -- the wait still runs to completion, because a DMA into
+ * the caller's buffers may not be left in flight. */
+int lgpu_ticket_wait(lgpu_ticket *t)
+{
+    if (!t) { set_error("ticket is null"); return LGPU_INVALID_INPUT; }
+    int rc = guarded([&] {
+        bool late = false;
+        if (t->deadline.armed) {
+            for (;;) {
+                cudaError_t e = cudaEventQuery(t->done);
+                if (e == cudaSuccess) break;
+                if (e != cudaErrorNotReady) LGPU_CUDA(e);
+                if (t->deadline.expired()) { late = true; break; }
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+            }
+        }
+        LGPU_CUDA(cudaEventSynchronize(t->done));
+        if (late) { set_error("Query timeout"); throw Failure{LGPU_TIMEOUT}; }
+    });
+    delete t;
+    return rc;
 }
 
 int lgpu_merge_topk_device(int device, uint32_t nlists, uint32_t B, uint32_t k, const uint64_t *d_ids,

@@ -62,7 +62,7 @@ void launch_pq_encode(const float *X, const uint32_t *parts, const float *centro
     if (n == 0) return;
     const uint32_t dsub = dim / m;
     dim3 grid((unsigned)((n + ENC_THREADS - 1) / ENC_THREADS), m);
-#define LGPU_ENC(D) pq_encode_kernel<D><<<grid, ENC_THREADS, 0, st>>>(X, parts, centroids, codebook, n, dim, m, metric, codes)
+#define LGPU_ENC(D) pq_encode_kernel<D><<<grid, ENC_THREADS, 0, st>>>(X, parts, centroids, codebook, n, dim, m, metric, codes), LGPU_COUNT_LAUNCH()
     switch (dsub) {
     case 1: LGPU_ENC(1); break;
     case 2: LGPU_ENC(2); break;

@@ -29,6 +29,10 @@ struct Failure { int status; };
         if (!(cond)) { ::lgpu::set_error(msg); throw ::lgpu::Failure{LGPU_INVALID_INPUT}; } \
     } while (0)
 
+// kernels launched by this process through the library (bench.py reports the count of its timed region)
+void count_launches(uint64_t n);
+#define LGPU_COUNT_LAUNCH() ::lgpu::count_launches(1)
+
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static inline uint64_t round_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b * b; }
 

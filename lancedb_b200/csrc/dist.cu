@@ -204,7 +204,7 @@ void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, 
     // the fix-up pass (`only`) is almost always a no-op: keep its CTA count small
     const uint64_t ct = (N + DM_C - 1) / DM_C;
     dim3 grid((unsigned)std::min<uint64_t>(ct, only ? 256 : ((uint64_t)1 << 30)), (B + DM_Q - 1) / DM_Q);
-    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only);
+    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -212,7 +212,7 @@ void launch_row_norms(const float *X, uint64_t n, uint32_t d, float *out, cudaSt
 {
     if (n == 0) return;
     uint64_t threads = n * 16;
-    row_norms_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, n, d, out);
+    row_norms_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, n, d, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -220,7 +220,7 @@ void launch_normalize(const float *X, uint32_t B, uint32_t d, float *out, cudaSt
 {
     if (B == 0) return;
     uint64_t threads = (uint64_t)B * 16;
-    normalize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, B, d, out);
+    normalize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, B, d, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -229,7 +229,7 @@ void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, u
 {
     if (B == 0 || nc == 0) return;
     uint64_t threads = (uint64_t)B * nc * 16;
-    pair_distance_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Q, V, pos, B, nc, d, metric, out);
+    pair_distance_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Q, V, pos, B, nc, d, metric, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -379,14 +379,14 @@ void launch_sample_threshold(const float *approx, const uint32_t *cnt, const flo
                              uint32_t B, uint32_t k, float *thr, cudaStream_t st)
 {
     if (B == 0) return;
-    sample_threshold_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, qnorm2, xmax, d, B, k, thr);
+    sample_threshold_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, qnorm2, xmax, d, B, k, thr); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
 void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint32_t *flags, cudaStream_t st)
 {
     if (B == 0) return;
-    overflow_flags_kernel<<<(B + 127) / 128, 128, 0, st>>>(count, cap, B, flags);
+    overflow_flags_kernel<<<(B + 127) / 128, 128, 0, st>>>(count, cap, B, flags); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -394,7 +394,7 @@ void launch_band_check(const float *approx, const uint32_t *cnt, const float *qn
                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st)
 {
     if (B == 0) return;
-    band_check_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, qnorm2, xmax, d, B, k, kp, flags);
+    band_check_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, qnorm2, xmax, d, B, k, kp, flags); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -404,7 +404,7 @@ void launch_to_bf16(const float *X, uint64_t n, uint32_t d, void *Xb, float *nor
 {
     if (n == 0) return;
     uint64_t threads = n * 32;
-    to_bf16_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, n, d, reinterpret_cast<__nv_bfloat16 *>(Xb), norm2);
+    to_bf16_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, n, d, reinterpret_cast<__nv_bfloat16 *>(Xb), norm2); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -431,7 +431,7 @@ void launch_filter_dense(const float *D, uint64_t ld, uint32_t B, uint64_t N, co
 {
     if (B == 0 || N == 0) return;
     dim3 grid((unsigned)std::min<uint64_t>((N + 1023) / 1024, 64), B);
-    filter_dense_kernel<<<grid, 256, 0, st>>>(D, ld, N, flt);
+    filter_dense_kernel<<<grid, 256, 0, st>>>(D, ld, N, flt); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -447,7 +447,7 @@ void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint3
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)num_sms);
     GemmFilter flt{};
     if (filter) flt = *filter;
-    gemm_dist_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK, flt);
+    gemm_dist_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK, flt); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

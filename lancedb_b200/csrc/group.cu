@@ -152,13 +152,13 @@ void launch_group(const GroupArgs &a, cudaStream_t st)
     if (a.B == 0) return;
     LGPU_CUDA(cudaMemsetAsync(a.part_cnt, 0, sizeof(uint32_t) * a.nlist, st));
     if (!a.only) LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
-    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a);
-    group_scan_kernel<<<1, 1024, 0, st>>>(a);
+    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+    group_scan_kernel<<<1, 1024, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     uint32_t slots = a.B * a.nprobes;
-    group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a);
+    group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     if (a.tile_desc && a.max_tiles) {
         uint64_t threads = (uint64_t)a.max_tiles * SCAN_G;
-        tile_desc_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a);
+        tile_desc_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     }
     LGPU_CUDA(cudaGetLastError());
 }

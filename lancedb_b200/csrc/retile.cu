@@ -75,7 +75,7 @@ void launch_retile_codes(const unsigned char *codes, int layout, const uint64_t 
     if (nrows == 0) return;
     uint64_t total = nrows * (nch + 1);
     retile_codes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(codes, layout, part_off, nlist, nrows, m,
-                                                                       nch, code_base, part_npad, out);
+                                                                       nch, code_base, part_npad, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -83,7 +83,7 @@ void launch_retile_codebook(const float *codebook, uint32_t m, uint32_t dsub, ui
                             cudaStream_t st)
 {
     uint64_t total = (uint64_t)nch * 256 * 8 * dsub;
-    retile_codebook_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(codebook, m, dsub, nch, out);
+    retile_codebook_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(codebook, m, dsub, nch, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -492,7 +492,7 @@ void launch_one(const ScanArgs &a, int grid, cudaStream_t st)
         set_error("internal: rows_tile does not match the scan kernel variant");
         throw Failure{LGPU_RUNTIME};
     }
-    kern<<<grid, (PW + CW) * 32, smem, st>>>(a);
+    kern<<<grid, (PW + CW) * 32, smem, st>>>(a); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -506,7 +506,7 @@ void launch_one<0, 8, 8, 6, 128, 128>(const ScanArgs &a, int grid, cudaStream_t 
         set_error("internal: rows_tile too large for the approximate scan variant");
         throw Failure{LGPU_RUNTIME};
     }
-    kern<<<grid, 512, smem, st>>>(a);
+    kern<<<grid, 512, smem, st>>>(a); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -518,7 +518,7 @@ void launch2(const ScanArgs &a, int grid, cudaStream_t st)
     constexpr size_t smem = Smem<DSUB>::TOTAL;
     auto kern = scan2_kernel<DSUB, DOT>;
     LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, S2_NT, smem, st>>>(a);
+    kern<<<grid, S2_NT, smem, st>>>(a); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -437,7 +437,7 @@ __global__ void pack_records_kernel(const uint64_t *__restrict__ ids, const floa
 void launch_pack_records(const uint64_t *ids, const float *dist, uint64_t n, TopkRecord *out, cudaStream_t st)
 {
     if (n == 0) return;
-    pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, dist, n, out);
+    pack_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ids, dist, n, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -450,7 +450,7 @@ void launch_select(const SelectArgs &a, cudaStream_t st)
     if (a.k <= 32) {
         const unsigned grid = a.B;
         const int nq = a.k <= 32 ? 1 : (a.k <= 64 ? 2 : 4);
-#define LGPU_SELW(P, N) select_warp_kernel<P, N><<<grid, SELW_WARPS * 32, 0, st>>>(a)
+#define LGPU_SELW(P, N) select_warp_kernel<P, N><<<grid, SELW_WARPS * 32, 0, st>>>(a), LGPU_COUNT_LAUNCH()
         if (a.out_pos) { if (nq == 1) LGPU_SELW(true, 1); else if (nq == 2) LGPU_SELW(true, 2); else LGPU_SELW(true, 4); }
         else { if (nq == 1) LGPU_SELW(false, 1); else if (nq == 2) LGPU_SELW(false, 2); else LGPU_SELW(false, 4); }
 #undef LGPU_SELW
@@ -464,10 +464,10 @@ void launch_select(const SelectArgs &a, cudaStream_t st)
     size_t smem = (size_t)cap * (pos ? 20 : 12);
     if (pos) {
         LGPU_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        select_kernel<true><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger);
+        select_kernel<true><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger); LGPU_COUNT_LAUNCH();
     } else {
         LGPU_CUDA(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        select_kernel<false><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger);
+        select_kernel<false><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger); LGPU_COUNT_LAUNCH();
     }
     LGPU_CUDA(cudaGetLastError());
 }

@@ -228,9 +228,9 @@ void launch_query_tables(const float *Q, const float *cb_tiled, uint32_t B, uint
     if (B == 0) return;
     const uint64_t total = (uint64_t)B * nch * 256 * 8;
     dispatch_dsub(dsub, [&](auto D) {
-        query_tables_kernel<decltype(D)::value><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, metric, T);
+        query_tables_kernel<decltype(D)::value><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, metric, T); LGPU_COUNT_LAUNCH();
     });
-    table_bound_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(T, B, nch, sbound);
+    table_bound_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(T, B, nch, sbound); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -243,7 +243,7 @@ void launch_row_const(const unsigned char *codes, const uint64_t *code_base, con
     if (nrows == 0) return;
     dispatch_dsub(dsub, [&](auto D) {
         row_const_kernel<decltype(D)::value><<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(
-            codes, code_base, part_npad, part_off, nlist, nrows, centroids, cb_tiled, dim, m, R, rmax_bits);
+            codes, code_base, part_npad, part_off, nlist, nrows, centroids, cb_tiled, dim, m, R, rmax_bits); LGPU_COUNT_LAUNCH();
     });
     LGPU_CUDA(cudaGetLastError());
 }
@@ -257,7 +257,7 @@ void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t
     const uint64_t total = (uint64_t)B * nc;
     dispatch_dsub(dsub, [&](auto D) {
         pq_rescore_kernel<decltype(D)::value><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
-            Q, pos, B, nc, codes, code_base, part_npad, part_off, nlist, centroids, cb_tiled, dim, m, metric, out);
+            Q, pos, B, nc, codes, code_base, part_npad, part_off, nlist, centroids, cb_tiled, dim, m, metric, out); LGPU_COUNT_LAUNCH();
     });
     LGPU_CUDA(cudaGetLastError());
 }
@@ -266,7 +266,7 @@ void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uin
                         float *probe_A, float *qn2, float *amax, cudaStream_t st)
 {
     if (B == 0) return;
-    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, qn2, amax);
+    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, qn2, amax); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -275,7 +275,7 @@ void launch_band_check2(const float *approx, const uint32_t *cnt, const float *s
                         cudaStream_t st)
 {
     if (B == 0) return;
-    band_check2_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, sbound, amax, rmax_bits, scale, B, k, kp, flags);
+    band_check2_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, sbound, amax, rmax_bits, scale, B, k, kp, flags); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
