@@ -94,14 +94,15 @@ np.savez({dst!r}, **{{f"a{{i}}_{{j}}": a for i, t in enumerate(out) for j, a in 
 
 
 def test_graph_replay_matches_eager(tmp_path):
-    """LGPU_GRAPH=1 (capture on the 2nd call of a shape, replay afterwards) returns exactly what the
-    eager launch sequence returns, for fresh query contents on every replay."""
+    """Graph replay (the default: capture on the 2nd call of a shape, replay afterwards; LGPU_NO_GRAPH=1
+    disables it) returns exactly what the eager launch sequence returns, for fresh query contents on every
+    replay."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = {}
     for mode in ("0", "1"):
         dst = str(tmp_path / f"g{mode}.npz")
-        env = dict(os.environ, LGPU_GRAPH=mode)
+        env = dict(os.environ, LGPU_NO_GRAPH="1" if mode == "0" else "0")
         subprocess.run([sys.executable, "-c", _GRAPH_SCRIPT.format(root=root, dst=dst)], check=True, env=env,
                        timeout=300)
         res[mode] = np.load(dst)
@@ -146,3 +147,150 @@ def test_ivf_pq_table_prefilter_vs_oracle():
     assert out["_rowid"].to_pylist() == oi[0, :oc[0]].tolist()
     assert np.array_equal(np.asarray(out["_distance"]).view(np.uint32), od[0, :oc[0]].view(np.uint32))
     assert all(g == 3 for g in out["grp"].to_pylist())
+
+
+# ---------------------------------------------------------------- boundary robustness (round 2)
+def test_nan_and_zero_queries_return_nothing_and_do_not_poison_the_context():
+    """A NaN / Inf query (any metric) or an all-zero cosine query has no finite centroid distance: fewer than
+    nprobes probes come back from the coarse step and the unused slots must behave as empty partitions --
+    count 0, no illegal address (group.cu read part_n[0xffffffff])."""
+    from lancedb_b200 import _native
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(31)
+    for metric in ("l2", "cosine", "dot"):
+        ix = random_index(rng, dim=64, nlist=12, m=8, metric=metric, n=3000)
+        gpu = _native.GpuIvfPq(ix)
+        q = queries(rng, 6, 64)
+        q[1, 3] = np.nan
+        q[4, :] = np.inf
+        if metric == "cosine":
+            q[2, :] = 0.0
+        gi, gd, gc = gpu.search(q, k=5, nprobes=4)
+        oi, od, oc = oracle.OracleIndex.from_data(ix).search(q, k=5, nprobes=4)
+        assert gc[1] == 0 and gc[4] == 0 and (metric != "cosine" or gc[2] == 0)
+        good = [0, 3, 5]
+        assert np.array_equal(gi[good], oi[good]) and np.array_equal(gc[good], oc[good])
+        assert np.array_equal(gd[good].view(np.uint32), od[good].view(np.uint32))
+        gi2, _, gc2 = gpu.search(q[:1], k=5, nprobes=4)          # the context is still healthy
+        assert np.array_equal(gi2[0], oi[0])
+        gpu.close()
+
+
+def test_closed_handle_is_rejected_not_dereferenced():
+    from lancedb_b200 import _native
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(32)
+    ix = random_index(rng, dim=32, nlist=4, m=4, n=500)
+    gpu = _native.GpuIvfPq(ix)
+    h = gpu._h
+    gpu.search(queries(rng, 2, 32), k=3, nprobes=2)
+    gpu.close()
+    gpu._h = h                                   # a stale handle value, as a buggy host might keep
+    with pytest.raises(ValueError, match="closed"):
+        gpu.search(queries(rng, 2, 32), k=3, nprobes=2)
+    gpu._h = None
+
+
+def test_close_waits_for_searches_in_flight():
+    """lgpu_index_close while other threads are inside lgpu_search must not free the index under them."""
+    import threading
+    from lancedb_b200 import _native
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(33)
+    ix = random_index(rng, dim=64, nlist=16, m=8, n=20000)
+    gpu = _native.GpuIvfPq(ix)
+    q = queries(rng, 64, 64)
+    want = gpu.search(q, k=10, nprobes=8)
+    errs, oks = [], []
+
+    def worker():
+        for _ in range(30):
+            try:
+                got = gpu.search(q, k=10, nprobes=8)
+                oks.append(np.array_equal(got[0], want[0]))
+            except ValueError as e:              # the handle was closed between two calls: the documented outcome
+                errs.append(str(e))
+                return
+    ths = [threading.Thread(target=worker) for _ in range(4)]
+    for t in ths:
+        t.start()
+    h = gpu._h
+    _native.load().lgpu_index_close(h)
+    for t in ths:
+        t.join()
+    gpu._h = None
+    assert all(oks) and all("closed" in e for e in errs)
+
+
+def test_timeout_status_and_builder_argument():
+    """QueryExecutionOptions.timeout (python/python/tests/test_query.py:1846,1957): an impossible deadline
+    maps to LGPU_TIMEOUT -> TimeoutError and leaves the outputs untouched; a generous one changes nothing."""
+    import datetime
+    from lancedb_b200 import _native
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(34)
+    ix = random_index(rng, dim=128, nlist=64, m=16, n=400000)
+    gpu = _native.GpuIvfPq(ix)
+    q = queries(rng, 512, 128)
+    want = gpu.search(q, k=10, nprobes=32)
+    got = gpu.search(q, k=10, nprobes=32, timeout_ms=60000)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    ids = np.full((512, 10), 7, np.uint64); dist = np.full((512, 10), -1.0, np.float32); cnt = np.full(512, 9, np.uint32)
+    p = _native.make_params(k=10, nprobes=32, timeout_ms=1)
+    big = np.ascontiguousarray(np.tile(q, (8, 1)))
+    ids8 = np.full((4096, 10), 7, np.uint64); dist8 = np.full((4096, 10), -1.0, np.float32); cnt8 = np.full(4096, 9, np.uint32)
+    with pytest.raises(TimeoutError, match="timeout"):
+        gpu.search_into(big, p, ids8, dist8, cnt8)          # 4096 x 32 probes cannot finish within 1 ms
+    assert (ids8 == 7).all() and (dist8 == -1.0).all() and (cnt8 == 9).all()
+    gpu.close()
+    db = lancedb.connect("memory://")
+    t = db.create_table("t", [{"vector": [1.0, 2.0], "id": 1}, {"vector": [3.0, 4.0], "id": 2}])
+    rows = t.search([1.0, 2.0]).to_list(timeout=datetime.timedelta(seconds=30))
+    assert rows[0]["id"] == 1
+    with pytest.raises(ValueError):
+        t.search([1.0, 2.0]).to_arrow(timeout=datetime.timedelta(seconds=-1))
+
+
+def test_async_tickets_pipeline_and_match_sync():
+    import torch
+    from lancedb_b200 import _native
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(35)
+    ix = random_index(rng, dim=64, nlist=32, m=8, n=30000)
+    gpu = _native.GpuIvfPq(ix)
+    p = _native.make_params(k=10, nprobes=6)
+    qs = [torch.from_numpy(queries(rng, 128, 64)).pin_memory().numpy() for _ in range(5)]
+    bufs = [(torch.empty(128, 10, dtype=torch.int64).pin_memory().numpy().view(np.uint64),
+             torch.empty(128, 10, dtype=torch.float32).pin_memory().numpy(),
+             torch.empty(128, dtype=torch.int32).pin_memory().numpy().view(np.uint32)) for _ in range(5)]
+    n0 = _native.kernel_launch_count()
+    tickets = [gpu.search_async(qs[i], p, *bufs[i]) for i in range(5)]     # five calls in flight
+    for t in tickets:
+        _native.ticket_wait(t)
+    assert _native.kernel_launch_count() > n0
+    for i in range(5):
+        want = gpu.search(qs[i], k=10, nprobes=6)
+        assert np.array_equal(bufs[i][0], want[0]) and np.array_equal(bufs[i][2], want[2])
+        assert np.array_equal(bufs[i][1].view(np.uint32), want[1].view(np.uint32))
+    gpu.close()
+
+
+def test_flat_search_device_matches_host_call():
+    """GpuFlat.search_device had fallen out of the class."""
+    import torch
+    from lancedb_b200 import _native
+    from tests.util import queries
+    rng = np.random.default_rng(36)
+    v = queries(rng, 9000, 64)
+    q = queries(rng, 16, 64)
+    fl = _native.GpuFlat(v)
+    want = fl.search(q, k=7, metric="l2")
+    dq = torch.from_numpy(q).cuda()
+    oi = torch.empty(16, 7, dtype=torch.int64, device="cuda"); od = torch.empty(16, 7, device="cuda")
+    oc = torch.empty(16, dtype=torch.int32, device="cuda")
+    fl.search_device("l2", dq.data_ptr(), 16, _native.make_params(k=7, nprobes=0), oi.data_ptr(), od.data_ptr(),
+                     oc.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(oi.cpu().numpy().view(np.uint64), want[0])
+    assert np.array_equal(od.cpu().numpy().view(np.uint32), want[1].view(np.uint32))
+    fl.close()
