@@ -95,14 +95,15 @@ struct Workspace {
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
-    DevBuf timing;
     // CUDA graph of one host-buffer search (lgpu_search): the ~15 launches of a batch replayed as one
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_key[4] = {0, 0, 0, 0};
     uint64_t graph_epoch = 0;           // g_alloc_epoch when `graph` was captured
     uint64_t graph_kernels = 0;         // kernel launches one replay stands for
     int graph_state = 0;                // 0: next call runs eagerly (warm-up), 1: capture, 2: replay, -1: disabled
-    DevBuf tq, sbound, probe_A, amax;   // two-pass scan: per-query tables, bounds, per-probe scalars
+    DevBuf sbound, probe_A, amax;       // tensor-core shortlists: thresholds / counters; filter scan: bounds, per-probe scalars
+    DevBuf qt, qt_mm, qt_step, qt_base, qt_bad;   // filter scan (scan3.cu): quantised per-query tables
+    DevBuf s_ids, s_lb, s_pos, s_cnt, s_exact;    // filter scan: shortlist by lower bound, exact re-score
     Workspace()
     {
         LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -195,12 +196,12 @@ template <class H> static bool retire_handle(H *p)
 struct lgpu_index {
     std::atomic<int> refs{0};
     int device = 0, num_sms = 0;
-    uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0, rows_tile = SCAN_ROWS_TILE_MID;
-    uint32_t max_nrb = 1;          // row blocks of the largest partition (bounds the tile count)
+    uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0;
+    uint32_t max_nrb = 1;          // row blocks (of 1536 rows) of the largest partition: bounds the tile count
     int metric = 0;
     uint64_t nrows = 0, device_bytes = 0;
     DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
-    DevBuf row_R, rmax_bits;            // two-pass scan: per-row constant 2 b.c and max |R| (tables.cu)
+    DevBuf row_R, rmax_bits;            // filter scan: per-row constant 2 b.c and max |R| (tables.cu)
     bool has_tables = false;
     DevBuf cent_b, cent_n2;             // bf16 centroids + |c|^2 for the tensor-core coarse step
     float cent_max = 0.f;
@@ -329,26 +330,18 @@ struct Deadline {
     }
 };
 
-// The two-pass (filter + verify) scan is bit-identical to the exact path but, as measured on B200
-// (C2 workload: 1.73 ms vs 1.54 ms per 1024-query batch), not yet faster, so it is
-// opt-in: LGPU_TWO_PASS=1.
 // prefilter: device bitmap over row ids (nullptr = no filter)
 struct RowFilter {
     const uint32_t *bits = nullptr;
     uint64_t nbits = 0;
 };
 
-static bool two_pass_enabled()
+// LGPU_EXACT_SCAN=1 sends every query through the exact kernel (scan2.cu) instead of filter + verify
+// (scan3.cu + tables.cu).  Results are bit-identical either way; the switch exists for A/B timing and tests.
+static bool exact_scan_forced()
 {
-    const char *e = getenv("LGPU_TWO_PASS");
+    const char *e = getenv("LGPU_EXACT_SCAN");
     return e && e[0] == '1';
-}
-
-// LGPU_SCAN_V1=1 selects the round-1 scan kernel (scan.cu, per-tile drain) instead of the streaming one
-static bool scan_v2_enabled()
-{
-    const char *e = getenv("LGPU_SCAN_V1");
-    return !(e && e[0] == '1');
 }
 
 static bool tc_enabled()
@@ -544,7 +537,6 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     ws->scalars.ensure(64);
     GroupArgs ga{};
     ga.probes = ws->probes.as<uint64_t>(); ga.B = B; ga.nprobes = nprobes; ga.nlist = nlist;
-    ga.rows_tile = ix->rows_tile;
     ga.part_n = ix->part_n.as<uint32_t>(); ga.part_cnt = ws->part_cnt.as<uint32_t>();
     ga.slot_pos = ws->slot_pos.as<uint32_t>(); ga.seg_local = ws->seg_local.as<uint64_t>();
     ga.qtot = ws->qtot.as<uint64_t>(); ga.seg_off = ws->seg_off.as<uint64_t>();
@@ -552,18 +544,24 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     ga.qlist = ws->qlist.as<uint32_t>();
     ga.total_tiles = ws->scalars.as<uint32_t>(); ga.tile_counter = ws->scalars.as<uint32_t>() + 1;
     ga.scanned_rows = reinterpret_cast<unsigned long long *>(ws->scalars.as<char>() + 16);
-    // streaming scan kernel (scan2.cu): tile descriptors, sized by a host bound on the tile count
+    // tile descriptors, sized by a host bound on the tile count (for 1536-row tiles; 3072-row tiles need fewer)
     // sum_p ceil(cnt_p / 8) * nrb_p <= (slots / 8 + #probed partitions) * max_p nrb_p
-    const bool scan_v2 = scan_v2_enabled() && ix->rows_tile == SCAN_ROWS_TILE_MID;
-    if (scan_v2) {
+    {
         uint64_t max_tiles = ((uint64_t)slots / SCAN_G + std::min<uint64_t>(nlist, slots) + 1) * ix->max_nrb;
         LGPU_REQUIRE(max_tiles < (1ull << 31), "batch too large for one scan launch");
         ws->tile_desc.ensure((size_t)max_tiles * sizeof(TileDesc));
         ga.tile_desc = ws->tile_desc.as<TileDesc>(); ga.max_tiles = (uint32_t)max_tiles;
     }
+    // the PQ top-`kk` of every query (kk = k, or k * refine_factor candidates for the exact re-rank)
+    const uint32_t kk = sp.refine_factor ? sp.k * sp.refine_factor : sp.k;
+    // ---- which scan: filter + verify (scan3.cu) unless the request needs every exact distance ----
+    const uint32_t kp = kk <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * kk + 32);
+    const bool filter_scan = ix->has_tables && !exact_scan_forced() && !sp.has_lower && !sp.has_upper && !forced_probes &&
+                             d_ids && kp > kk && ix->m <= 512;
+    ga.rows_tile = filter_scan ? SCAN3_ROWS_TILE : SCAN_ROWS_TILE_MID;
     launch_group(ga, st);
     mark();
-    // ---- K2+K3: fused distance-table build + code scan ----
+    // ---- K2+K3 ----
     uint32_t np_eff = std::min<uint32_t>(nprobes, nlist);
     size_t cap_floats = (size_t)B * ix->pad_prefix[np_eff];
     ws->dist_out.ensure(std::max<size_t>(cap_floats, 4) * 4);
@@ -572,108 +570,99 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sc.codes = ix->codes.as<unsigned char>(); sc.code_base = ix->code_base.as<uint64_t>();
     sc.part_n = ix->part_n.as<uint32_t>(); sc.part_npad = ix->part_npad.as<uint32_t>();
     sc.dim = dim; sc.m = ix->m; sc.nch = ix->nch; sc.metric = (uint32_t)ix->metric; sc.nlist = nlist;
-    sc.rows_tile = ix->rows_tile; sc.fzero2 = 0ull;
-    sc.queries = qsearch; sc.nprobes = nprobes;
-    sc.part_cnt = ga.part_cnt; sc.qlist_off = ga.qlist_off; sc.tile_off = ga.tile_off; sc.qlist = ga.qlist;
-    sc.seg_off = ga.seg_off; sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
+    sc.rows_tile = ga.rows_tile; sc.fzero2 = 0ull;
+    sc.queries = qsearch;
+    sc.total_tiles = ga.total_tiles; sc.tile_counter = ga.tile_counter;
     sc.dist_out = ws->dist_out.as<float>();
     sc.tile_desc = ga.tile_desc;
-    auto run_exact_scan = [&]() {
-        if (scan_v2) launch_scan2(sc, ix->dsub, ix->num_sms, st);
-        else launch_scan(sc, ix->dsub, ix->num_sms, st);
-    };
-    static const bool scalar_table = getenv("LGPU_SCALAR_TABLE") != nullptr;
-    sc.scalar_table = scalar_table ? 1 : 0;
-    static const bool scan_timing = getenv("LGPU_SCAN_TIMING") != nullptr;
-    if (scan_timing && prof) {
-        ws->scalars.ensure(64);
-        ws->timing.ensure(16 * 8);
-        LGPU_CUDA(cudaMemsetAsync(ws->timing.p, 0, 16 * 8, st));
-        sc.timing = ws->timing.as<unsigned long long>();
-    }
-    // ---- two-pass form (tables.cu): approximate scan with per-QUERY tables as a filter, exact
-    // re-score of the shortlist, exact redo of the queries whose shortlist cannot be proven ----
-    const uint32_t kp2 = sp.k <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * sp.k + 32);
-    const bool two_pass = ix->has_tables && two_pass_enabled() && ix->metric != LGPU_DOT && !sp.has_lower &&
-                          !sp.has_upper && sp.refine_factor == 0 && !forced_probes && d_ids && kp2 > sp.k && !rf.bits;
-    if (two_pass) {
-        const size_t tq_floats = (size_t)ix->nch * 256 * 8;
-        ws->tq.ensure((size_t)B * tq_floats * 4); ws->sbound.ensure((size_t)B * 4);
-        ws->probe_A.ensure((size_t)slots * 4); ws->qn2.ensure((size_t)B * 4); ws->amax.ensure((size_t)B * 4);
-        ws->flags.ensure((size_t)B * 4);
-        ws->t_ids.ensure((size_t)B * kp2 * 8); ws->t_dist.ensure((size_t)B * kp2 * 4);
-        ws->t_pos.ensure((size_t)B * kp2 * 8); ws->t_cnt.ensure((size_t)B * 4); ws->t_exact.ensure((size_t)B * kp2 * 4);
-        launch_query_tables(qsearch, ix->cb_tiled.as<float>(), B, dim, ix->m, ix->nch, ix->dsub, ix->metric,
-                            ws->tq.as<float>(), ws->sbound.as<float>(), st);
-        launch_probe_terms(ws->probe_dist.as<float>(), qsearch, B, nprobes, dim, ws->probe_A.as<float>(),
-                           ws->qn2.as<float>(), ws->amax.as<float>(), st);
-        sc.tq = ws->tq.as<float>(); sc.probe_A = ws->probe_A.as<float>(); sc.row_R = ix->row_R.as<float>();
-        sc.part_off = ix->part_off.as<uint64_t>();
-        launch_scan(sc, ix->dsub, ix->num_sms, st);
-        mark();
-        SelectArgs sa{};
-        sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ga.seg_off; sa.probes = ga.probes;
-        sa.nprobes = nprobes; sa.nlist = nlist; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
-        sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B; sa.k = kp2;
-        sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
-        sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
-        launch_select(sa, st);
-        launch_band_check2(ws->t_dist.as<float>(), ws->t_cnt.as<uint32_t>(), ws->sbound.as<float>(),
-                           ws->amax.as<float>(), ix->rmax_bits.as<int>(), ix->metric == LGPU_COSINE ? 0.5f : 1.0f,
-                           B, sp.k, kp2, ws->flags.as<uint32_t>(), st);
-        launch_pq_rescore(qsearch, ws->t_pos.as<uint64_t>(), B, kp2, ix->codes.as<unsigned char>(),
-                          ix->code_base.as<uint64_t>(), ix->part_npad.as<uint32_t>(), ix->part_off.as<uint64_t>(), nlist,
-                          ix->centroids.as<float>(), ix->cb_tiled.as<float>(), dim, ix->m, ix->dsub, ix->metric,
-                          ws->t_exact.as<float>(), st);
-        SelectArgs sb{};
-        sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
-        sb.ncols = kp2; sb.inner = kp2; sb.row_stride = kp2; sb.outer_stride = 0;
-        sb.B = B; sb.k = sp.k; sb.out_ids = d_ids; sb.out_dist = d_dist; sb.out_count = d_cnt;
-        launch_select(sb, st);
-        // fix-up (no work unless a query was flagged): regroup only the flagged queries, exact scan, exact top-k
-        ga.only = ws->flags.as<uint32_t>();
-        launch_group(ga, st);
-        sc.tq = nullptr;
-        run_exact_scan();
-        SelectArgs sf = sa;
-        sf.k = sp.k; sf.out_ids = d_ids; sf.out_dist = d_dist; sf.out_count = d_cnt; sf.out_pos = nullptr;
-        sf.only = ws->flags.as<uint32_t>();
-        launch_select(sf, st);
-        mark(); mark();
-        return;
-    }
-    run_exact_scan();
-    mark();
-    if (!d_ids) { mark(); mark(); return; }     // debug: distances only
-    // ---- K4: top-k ----
+    sc.part_off = ix->part_off.as<uint64_t>();
+
+    // K4 over the distance segments: the kk best by (_distance, _rowid), prefilter applied before the top-k
     SelectArgs sa{};
     sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ga.seg_off; sa.probes = ga.probes;
     sa.nprobes = nprobes; sa.nlist = nlist; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
     sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B;
-    sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
-    sa.allow = rf.bits; sa.allow_bits = rf.nbits;          // prefilter: rows are dropped before the top-k
-    if (sp.refine_factor == 0) {
-        sa.k = sp.k; sa.out_ids = d_ids; sa.out_dist = d_dist; sa.out_count = d_cnt;
-        launch_select(sa, st);
-        mark(); mark();
-        return;
+    sa.allow = rf.bits; sa.allow_bits = rf.nbits;
+    // where the PQ top-kk goes: straight to the caller, or to the refine stage's candidate lists
+    uint64_t *pq_ids = d_ids; float *pq_dist = d_dist; uint32_t *pq_cnt = d_cnt; uint64_t *pq_pos = nullptr;
+    if (sp.refine_factor) {
+        ws->t_ids.ensure((size_t)B * kk * 8); ws->t_dist.ensure((size_t)B * kk * 4);
+        ws->t_pos.ensure((size_t)B * kk * 8); ws->t_cnt.ensure((size_t)B * 4);
+        ws->t_exact.ensure((size_t)B * kk * 4);
+        pq_ids = ws->t_ids.as<uint64_t>(); pq_dist = ws->t_dist.as<float>(); pq_cnt = ws->t_cnt.as<uint32_t>();
+        pq_pos = ws->t_pos.as<uint64_t>();
     }
+
+    if (filter_scan) {
+        // per-query 16-bit tables, per-probe scalars
+        const bool dot = ix->metric == LGPU_DOT;
+        ws->qt.ensure((size_t)B * ix->nch * 256 * 16); ws->qt_mm.ensure((size_t)B * ix->nch * 8 * 8);
+        ws->qt_step.ensure((size_t)B * 4); ws->qt_base.ensure((size_t)B * 4); ws->qt_bad.ensure((size_t)B * 4);
+        ws->sbound.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
+        ws->s_ids.ensure((size_t)B * kp * 8); ws->s_lb.ensure((size_t)B * kp * 4); ws->s_pos.ensure((size_t)B * kp * 8);
+        ws->s_cnt.ensure((size_t)B * 4); ws->s_exact.ensure((size_t)B * kp * 4);
+        launch_query_tables_q16(qsearch, ix->cb_tiled.as<float>(), B, dim, ix->m, ix->nch, ix->dsub, ix->metric,
+                                ws->qt_mm.as<float>(), ws->qt.as<uint4>(), ws->qt_step.as<float>(), ws->qt_base.as<float>(),
+                                ws->sbound.as<float>(), ws->qt_bad.as<uint32_t>(), st);
+        if (!dot) {
+            ws->probe_A.ensure((size_t)slots * 4); ws->amax.ensure((size_t)B * 4);
+            launch_probe_terms(ws->probe_dist.as<float>(), qsearch, B, nprobes, dim, ws->probe_A.as<float>(),
+                               ws->amax.as<float>(), st);
+            sc.probe_A = ws->probe_A.as<float>(); sc.row_R = ix->row_R.as<float>();
+        }
+        sc.qt = ws->qt.as<uint4>(); sc.qt_step = ws->qt_step.as<float>(); sc.qt_base = ws->qt_base.as<float>();
+        launch_scan3(sc, ix->num_sms, st);
+        mark();
+        // shortlist: the kp smallest lower bounds (with their storage positions)
+        SelectArgs ss = sa;
+        ss.k = kp; ss.out_ids = ws->s_ids.as<uint64_t>(); ss.out_dist = ws->s_lb.as<float>();
+        ss.out_count = ws->s_cnt.as<uint32_t>(); ss.out_pos = ws->s_pos.as<uint64_t>();
+        launch_select(ss, st);
+        launch_band_check3(ws->s_lb.as<float>(), ws->s_cnt.as<uint32_t>(), ws->qt_step.as<float>(), ws->sbound.as<float>(),
+                           dot ? nullptr : ws->amax.as<float>(), dot ? nullptr : ix->rmax_bits.as<int>(),
+                           ws->qt_bad.as<uint32_t>(), ix->metric == LGPU_COSINE ? 0.5f : 1.0f, ix->m, B, kk, kp,
+                           ws->flags.as<uint32_t>(), st);
+        // exact PQ distances of the shortlist (oracle arithmetic), then the kk best of those
+        launch_pq_rescore(qsearch, ws->s_pos.as<uint64_t>(), B, kp, ix->codes.as<unsigned char>(),
+                          ix->code_base.as<uint64_t>(), ix->part_npad.as<uint32_t>(), ix->part_off.as<uint64_t>(), nlist,
+                          ix->centroids.as<float>(), ix->cb_tiled.as<float>(), dim, ix->m, ix->dsub, ix->metric,
+                          ws->s_exact.as<float>(), st);
+        SelectArgs sb{};
+        sb.mode = 2; sb.dense = ws->s_exact.as<float>(); sb.cand_ids = ws->s_ids.as<uint64_t>();
+        sb.cand_pos = ws->s_pos.as<uint64_t>();
+        sb.ncols = kp; sb.inner = kp; sb.row_stride = kp; sb.outer_stride = 0;
+        sb.B = B; sb.k = kk; sb.out_ids = pq_ids; sb.out_dist = pq_dist; sb.out_count = pq_cnt; sb.out_pos = pq_pos;
+        launch_select(sb, st);
+        // fix-up of the queries whose shortlist could not be proven (no tiles, hence no work, unless one is
+        // flagged): regroup them alone, exact scan, exact top-kk over their segments
+        ga.only = ws->flags.as<uint32_t>();
+        ga.rows_tile = SCAN_ROWS_TILE_MID;
+        launch_group(ga, st);
+        sc.rows_tile = SCAN_ROWS_TILE_MID;
+        launch_scan2(sc, ix->dsub, ix->num_sms, st);
+        SelectArgs sf = sa;
+        sf.k = kk; sf.out_ids = pq_ids; sf.out_dist = pq_dist; sf.out_count = pq_cnt; sf.out_pos = pq_pos;
+        sf.only = ws->flags.as<uint32_t>();
+        launch_select(sf, st);
+        mark();
+    } else {
+        launch_scan2(sc, ix->dsub, ix->num_sms, st);
+        mark();
+        if (!d_ids) { mark(); mark(); return; }     // debug: distances only
+        sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
+        sa.k = kk; sa.out_ids = pq_ids; sa.out_dist = pq_dist; sa.out_count = pq_cnt; sa.out_pos = pq_pos;
+        launch_select(sa, st);
+        mark();
+    }
+    if (sp.refine_factor == 0) { mark(); return; }
     // ---- refine (query.rs:1302-1332): exact distance of the k*rf candidates, re-sort ----
-    const uint32_t kk = sp.k * sp.refine_factor;
-    ws->t_ids.ensure((size_t)B * kk * 8); ws->t_dist.ensure((size_t)B * kk * 4);
-    ws->t_pos.ensure((size_t)B * kk * 8); ws->t_cnt.ensure((size_t)B * 4);
-    ws->t_exact.ensure((size_t)B * kk * 4);
-    sa.k = kk; sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
-    sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
-    launch_select(sa, st);
-    mark();
     launch_pair_distance(d_q, ix->vectors.as<float>(), ws->t_pos.as<uint64_t>(), B, kk, dim, ix->metric,
                          ws->t_exact.as<float>(), st);
-    SelectArgs sb{};
-    sb.mode = 2; sb.dense = ws->t_exact.as<float>(); sb.cand_ids = ws->t_ids.as<uint64_t>();
-    sb.ncols = kk; sb.inner = kk; sb.row_stride = kk; sb.outer_stride = 0;
-    sb.B = B; sb.k = sp.k; sb.out_ids = d_ids; sb.out_dist = d_dist; sb.out_count = d_cnt;
-    launch_select(sb, st);
+    SelectArgs sr{};
+    sr.mode = 2; sr.dense = ws->t_exact.as<float>(); sr.cand_ids = ws->t_ids.as<uint64_t>();
+    sr.ncols = kk; sr.inner = kk; sr.row_stride = kk; sr.outer_stride = 0;
+    sr.B = B; sr.k = sp.k; sr.out_ids = d_ids; sr.out_dist = d_dist; sr.out_count = d_cnt;
+    launch_select(sr, st);
     mark();
 }
 
@@ -682,6 +671,8 @@ uint32_t ivf_sub_batch_size(lgpu_index *ix, uint32_t B, uint32_t nprobes)
     uint32_t np_eff = std::min<uint32_t>(nprobes, ix->nlist);
     size_t per_q = std::max<size_t>(ix->pad_prefix[np_eff] * 4 + (size_t)ix->nlist * 4 + (size_t)ix->nch * 256 * 8 * 4, 4);
     size_t bs = workspace_budget() / per_q;
+    // tile descriptors address the distance segments with 32-bit float offsets
+    bs = std::min<size_t>(bs, (size_t)0xffffffffull / std::max<size_t>(ix->pad_prefix[np_eff], 1));
     bs = std::max<size_t>(1, std::min<size_t>(bs, 65535));
     return (uint32_t)std::min<size_t>(bs, B);
 }
@@ -706,13 +697,6 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
         unsigned long long rows = 0;
         LGPU_CUDA(cudaMemcpy(&rows, ws->scalars.as<char>() + 16, 8, cudaMemcpyDeviceToHost));
         g_scanned_bytes = (uint64_t)rows * ix->m;
-        if (getenv("LGPU_SCAN_TIMING") && ws->timing.p) {
-            unsigned long long t[16];
-            LGPU_CUDA(cudaMemcpy(t, ws->timing.p, sizeof(t), cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[scan timing] tiles %llu | producer warp-cycles: total %llu waitEMPTY %llu barPROD %llu | "
-                            "consumer warp-cycles: total %llu waitFULL %llu | tile-fetch cycles %llu\n",
-                    t[6], t[0], t[1], t[2], t[3], t[4], t[5]);
-        }
     }
 }
 
@@ -970,23 +954,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             pads[p] = (n + 3ull) & ~3ull;
         }
         ix->h_part_n = part_n;
-        {   // pick the scan kernel's warp-role split from the partition-size distribution:
-            // fewest row blocks for a (mean + 2 sigma) partition, ties to the producer-heavy split
-            double mean = 0, var = 0;
-            for (uint32_t p = 0; p < nlist; p++) mean += part_n[p];
-            mean /= nlist;
-            for (uint32_t p = 0; p < nlist; p++) var += (part_n[p] - mean) * (part_n[p] - mean);
-            double big = mean + 2.0 * std::sqrt(var / nlist);
-            uint32_t x = (uint32_t)std::max(1.0, big);
-            uint32_t nm = scan_nrb(x, SCAN_ROWS_TILE_MID), nl = scan_nrb(x, SCAN_ROWS_TILE_LARGE);
-            ix->rows_tile = nl < nm ? SCAN_ROWS_TILE_LARGE : SCAN_ROWS_TILE_MID;
-            if (ix->rows_tile > SCAN_ROWS_TILE_MID) ix->rows_tile = SCAN_ROWS_TILE_MID;   // the two-pass variant holds 1536 rows
-            if (const char *e = getenv("LGPU_SCAN_ROWS_TILE")) {
-                uint32_t v = (uint32_t)atoi(e);
-                if (v == SCAN_ROWS_TILE_MID || v == SCAN_ROWS_TILE_LARGE) ix->rows_tile = v;
-            }
-        }
-        for (uint32_t p = 0; p < nlist; p++) ix->max_nrb = std::max(ix->max_nrb, scan_nrb(part_n[p], ix->rows_tile));
+        for (uint32_t p = 0; p < nlist; p++) ix->max_nrb = std::max(ix->max_nrb, scan_nrb(part_n[p], SCAN_ROWS_TILE_MID));
         std::sort(pads.begin(), pads.end(), std::greater<uint64_t>());
         ix->pad_prefix.assign(nlist + 1, 0);
         for (uint32_t p = 0; p < nlist; p++) ix->pad_prefix[p + 1] = ix->pad_prefix[p] + pads[p];
@@ -1037,7 +1005,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             }
             LGPU_CUDA(cudaStreamSynchronize(st));
         }
-        if (d->metric != LGPU_DOT) {   // per-row constants of the two-pass scan (tables.cu)
+        if (d->metric != LGPU_DOT) {   // per-row constants of the filter scan (tables.cu)
             ix->row_R.ensure(std::max<size_t>((size_t)d->nrows * 4, 16));
             ix->rmax_bits.ensure(16);
             ix->device_bytes += ix->row_R.bytes;
@@ -1046,8 +1014,8 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
                              ix->cb_tiled.as<float>(), d->dim, d->m, ix->dsub, ix->row_R.as<float>(),
                              ix->rmax_bits.as<int>(), st);
             LGPU_CUDA(cudaStreamSynchronize(st));
-            ix->has_tables = true;
         }
+        ix->has_tables = true;
         register_handle(ix);
         *out = ix;
     });

@@ -112,7 +112,7 @@ __global__ void group_fill_kernel(GroupArgs a)
 }
 
 // 8 threads per tile (one per query slot of the group): tile t -> (partition, query group, row block),
-// the same arithmetic scan.cu::next_tile does on the fly.  Tiles are numbered partition-major.
+// Tiles are numbered partition-major.
 __global__ void tile_desc_kernel(GroupArgs a)
 {
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,9 +138,11 @@ __global__ void tile_desc_kernel(GroupArgs a)
     if (g < ng) {
         const uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + g];
         d->q[g] = e / a.nprobes;
-        d->out[g] = a.seg_off[e];
+        d->slot[g] = e;
+        d->out[g] = (uint32_t)a.seg_off[e];
     } else {
         d->q[g] = 0xffffffffu;
+        d->slot[g] = 0;
         d->out[g] = 0;
     }
 }

@@ -7,10 +7,9 @@ namespace lgpu {
 
 // ---------------- scan (K2+K3) geometry ------------------------------------------
 constexpr int SCAN_G = 8;                         // queries per tile
-// two warp-role splits of the 512-thread CTA (producer warps / consumer warps x 8 rows per thread)
-constexpr uint32_t SCAN_ROWS_TILE_MID = 4 * 32 * 12;    // 12 producer + 4 consumer warps x 12 rows: <= 1536 rows per tile
-constexpr uint32_t SCAN_ROWS_TILE_LARGE = 8 * 32 * 8;   //  8 producer + 8 consumer warps x  8 rows: <= 2048 rows per tile
-constexpr int SCAN_LUT_HALF = 32768;              // [256 c][8 s][4 g] f32
+constexpr uint32_t SCAN_ROWS_TILE_MID = 4 * 32 * 12;   // exact kernel (scan2.cu): 2 x 128 scanner threads x 12 rows
+constexpr uint32_t SCAN3_ROWS_TILE = 8 * 32 * 12;      // filter kernel (scan3.cu): 256 scanner threads x 12 rows
+constexpr int SCAN_LUT_HALF = 32768;              // exact kernel: [256 c][8 s][4 g] f32
 constexpr int SCAN_LUT_BYTES = 2 * SCAN_LUT_HALF; // [2 h] halves
 
 __host__ __device__ __forceinline__ uint32_t scan_nrb(uint32_t n, uint32_t rows_tile)
@@ -23,12 +22,13 @@ __host__ __device__ __forceinline__ uint32_t scan_rb_rows(uint32_t n, uint32_t n
 }
 
 // One scan tile, precomputed by the regroup step (group.cu) so the persistent scan CTAs fetch a tile with a
-// single 112-byte read: partition p, rows [row0, row0+nrows), ng (1..8) queries q[] whose distances go to
-// dist_out + out[g].  ng == 0 marks "no tile" inside the kernel's shared-memory copy.
+// single 112-byte read: partition p, rows [row0, row0+nrows), ng (1..8) queries q[] (probe slots slot[]) whose
+// distances go to dist_out + out[g].  ng == 0 marks "no tile" inside the kernel's shared-memory copy.
 struct alignas(16) TileDesc {
     uint32_t p, row0, nrows, ng;
     uint32_t q[SCAN_G];
-    uint64_t out[SCAN_G];
+    uint32_t slot[SCAN_G];        // probe slot (q * nprobes + j) of each query
+    uint32_t out[SCAN_G];         // offset (floats) of the slot's distance segment; sub-batches keep it < 2^32
 };
 static_assert(sizeof(TileDesc) == 112, "TileDesc layout");
 
@@ -36,38 +36,33 @@ struct ScanArgs {
     // index (device)
     const float *centroids;       // [nlist][dim]
     const float *cb_tiled;        // [nch][256][8][dsub]
-    const unsigned char *codes;   // skewed code streams, see index.cu
+    const unsigned char *codes;   // skewed code streams, see retile.cu
     const uint64_t *code_base;    // [nlist] byte offset of partition p's stream block
     const uint32_t *part_n;       // [nlist]
     const uint32_t *part_npad;    // [nlist] rows rounded up to 32
     uint32_t dim, m, nch, metric, nlist;
-    uint32_t rows_tile;           // SCAN_ROWS_TILE_MID or _LARGE (selects the kernel variant)
-    unsigned long long fzero2;    // packed (+0.f, +0.f); opaque to ptxas on purpose (scan.cu)
+    uint32_t rows_tile;           // SCAN_ROWS_TILE_MID (exact) or SCAN3_ROWS_TILE (filter)
+    unsigned long long fzero2;    // packed (+0.f, +0.f); opaque to ptxas on purpose (scan_common.cuh)
     // batch (device)
     const float *queries;         // [B][dim] (normalised for cosine)
-    uint32_t nprobes;
-    const uint32_t *part_cnt;     // [nlist] queries probing p
-    const uint32_t *qlist_off;    // [nlist] start of p's slice of qlist
-    const uint32_t *tile_off;     // [nlist+1]
-    const uint32_t *qlist;        // [B*nprobes] probe-slot ids (q*nprobes+j) grouped by partition
-    const uint64_t *seg_off;      // [B*nprobes] offset of the slot's distance segment
     const uint32_t *total_tiles;  // [1]
     uint32_t *tile_counter;       // [1], zeroed before launch
     float *dist_out;
-    const TileDesc *tile_desc;    // [total_tiles] (streaming kernel, scan2.cu)
-    // approximate pass (tables.cu); tq == nullptr selects the exact kernel
-    const float *tq;              // [B][nch][256][8] per-query tables |q_i - codebook_i[c]|^2
-    const float *probe_A;         // [B*nprobes] |q - c_p|^2 - |q|^2
-    const float *row_R;           // [nrows] 2 * codeword(row) . c_p
+    const TileDesc *tile_desc;    // [total_tiles]
+    // filter pass (scan3.cu, tables.cu); unused by the exact kernel
+    const uint4 *qt;              // [B][nch][256] x (8 x u16): quantised per-query tables, rotated (tables.cu)
+    const float *qt_step;         // [B] quantisation step
+    const float *qt_base;         // [B] sum_i min_i (- (m - 1) for dot)
+    const float *probe_A;         // [B*nprobes] |q - c_p|^2 - |q|^2   (nullptr for dot)
+    const float *row_R;           // [nrows] 2 * codeword(row) . c_p  (nullptr for dot)
     const uint64_t *part_off;     // [nlist+1]
-    unsigned long long *timing;   // optional [16] stall accounting (LGPU_SCAN_TIMING=1)
-    int scalar_table;             // 1: scalar FADD/FMUL table build instead of packed f32x2 (A/B timing)
 };
 bool scan_dsub_supported(uint32_t dsub);
-void launch_scan(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
-// streaming variant (scan2.cu): tiles flow through the table ring without a per-tile drain; exact pass only,
-// rows_tile == SCAN_ROWS_TILE_MID, needs a.tile_desc
+// exact kernel (scan2.cu): residual -> f32 table chunk -> sequential code scan, bit-identical to the oracle;
+// needs a.tile_desc built with rows_tile == SCAN_ROWS_TILE_MID
 void launch_scan2(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
+// filter kernel (scan3.cu): lower bounds from 16-bit per-query tables; rows_tile == SCAN3_ROWS_TILE
+void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st);
 
 // ---------------- batch preparation (grouping probes by partition) ----------------
 struct GroupArgs {
@@ -184,10 +179,15 @@ void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint
 void launch_band_check(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st);
 
-// ---------------- two-pass PQ scan: filter + verify (tables.cu) ------------------------
-// T[q][ch][c][s] = |q_i - codebook_i[c]|^2 (i = 8 ch + s), sbound[q] = sum_i max_c T
-void launch_query_tables(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
-                         uint32_t dsub, int metric, float *T, float *sbound, cudaStream_t st);
+// ---------------- filter + verify form of the PQ scan (tables.cu, scan3.cu) -------------
+// Quantised per-query tables.  qt[q][ch][c] = 8 x u16, position j = n_q[i][c] for sub-space i = 8 ch + ((j + c) & 7):
+//   T_q[i][c] in [min_i + step n, min_i + step (n + 1)),  n <= qmax = floor(65535 / m)   (0 for i >= m)
+// step[q] = max_i (max_c T - min_c T) / qmax, base[q] = sum_i min_i (- (m - 1) for dot),
+// sbound[q] = sum_i max_c |T|, bad[q] = 1 when the table is not finite (the query takes the exact path).
+// mm: scratch [B][8 nch][2].
+void launch_query_tables_q16(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
+                             uint32_t dsub, int metric, float *mm, uint4 *qt, float *step, float *base, float *sbound,
+                             uint32_t *bad, cudaStream_t st);
 // R[row] = 2 * codeword(row) . centroid(partition(row)); *rmax_bits = float bits of max |R|
 void launch_row_const(const unsigned char *codes, const uint64_t *code_base, const uint32_t *part_npad,
                       const uint64_t *part_off, uint32_t nlist, uint64_t nrows, const float *centroids,
@@ -198,13 +198,15 @@ void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t
                        const uint64_t *code_base, const uint32_t *part_npad, const uint64_t *part_off, uint32_t nlist,
                        const float *centroids, const float *cb_tiled, uint32_t dim, uint32_t m, uint32_t dsub, int metric,
                        float *out, cudaStream_t st);
-// probe_A[slot] = coarse_dist[slot] - |q|^2, qn2[q] = |q|^2, amax[q] = max_j coarse + |q|^2
+// probe_A[slot] = coarse_dist[slot] - |q|^2, amax[q] = max_j coarse + |q|^2
 void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uint32_t nprobes, uint32_t dim,
-                        float *probe_A, float *qn2, float *amax, cudaStream_t st);
-// flags[q] = 1 when the approximate shortlist of q cannot be proven complete (scale: 0.5 for cosine)
-void launch_band_check2(const float *approx, const uint32_t *cnt, const float *sbound, const float *amax,
-                        const int *rmax_bits, float scale, uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags,
-                        cudaStream_t st);
+                        float *probe_A, float *amax, cudaStream_t st);
+// flags[q] = 1 when the shortlist of q (lower bounds `lb` ascending, [B][kp], cnt valid) cannot be proven to hold
+// the exact top-k: proven iff cnt < kp or lb[kp-1] > lb[k-1] + scale (W + 2E),  W = m step (1 + 2^-10),
+// E = 2^-15 ceil(m/96) (sbound + amax + rmax); also 1 when bad[q].  amax / rmax_bits may be null (dot).
+void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
+                        const int *rmax_bits, const uint32_t *bad, float scale, uint32_t m, uint32_t B, uint32_t k,
+                        uint32_t kp, uint32_t *flags, cudaStream_t st);
 
 // ---------------- index build (build.cu) ----------------------------------------------
 // codes[row][i] = argmin_c entry(row's residual sub-vector i, codebook_i[c]) (ties: lowest c); X normalised for cosine

@@ -7,7 +7,7 @@
 // [block][row][8]: a warp reading 32 consecutive rows of one block reads 256 contiguous
 // bytes.  Row r's byte stream is its m codes (padded with zeros to 8*nch) delayed by
 // r % 8 positions: stream position M holds code[r][M - r%8].  That skew is what makes
-// the scan kernel's shared-memory gathers conflict-free (scan.cu).
+// the scan kernel's shared-memory gathers conflict-free (scan2.cu, scan3.cu).
 //
 // Codebook.  [m][256][dsub] becomes [nch][256 c][8 s][dsub] so the 8 sub-spaces of a
 // chunk for one code are contiguous (a warp building 4 codes x 8 sub-spaces reads 1 KB).

@@ -1,22 +1,43 @@
-// scan2.cu -- K2+K3, streaming form: the same arithmetic and the same shared-memory table ring as
-// scan.cu (bit-identical results; see that file for the layout, the skewed code stream and the
-// reference citations [lance, recalled; SURVEY.md 8a rows a4-a7]), re-pipelined after the ncu stall
-// profile of round 1 (profiles/r01_scan_stalls.txt):
+// scan2.cu -- K2+K3, the EXACT form: fused residual / PQ distance-table build / PQ code scan.
 //
-//   * no per-tile drain.  scan.cu ends every tile with a CTA-wide barrier (fetch the next tile, refill the
-//     pipeline): the table builders idle ~16 % of the time while the scanners finish.  Here the stage
-//     counter runs on across tiles -- the all-zero "stage nch" of tile n doubles as the "stage -1" of
-//     tile n+1 -- and tile descriptors (precomputed by group.cu::tile_desc_kernel) are claimed two tiles
-//     ahead by producer warp 0 into a 4-slot shared ring, so neither role ever waits for a fetch.
-//   * 8 builder warps + 8 scanner warps; the scanners are split by query half (warps 0-3: queries 0-3,
-//     warps 4-7: queries 4-7 of the tile).  A scanner thread carries 12 rows x 4 queries of accumulators
-//     (48 registers instead of 96), which leaves room to keep a dozen LDS.128 in flight, and there are two
-//     scanner warps per scheduler instead of one.
-//   * the table build is straight-line code: 16 (or 8) tasks per warp and chunk, no bounds checks, the
-//     metric and the half count are template parameters; each builder warp streams the codebook entries of
-//     its tasks through a private cp.async ring, six tasks ahead, across chunk boundaries (CbStage below).
-//   * tiles with <= 4 queries use a 4-codes-per-warp mapping (HALVES = 1): half the build work instead of
-//     idle lanes.
+// Replaces, for a whole batch at once, what lance runs per (query, probed partition) inside ANNIvfSubIndexExec
+// [lance, recalled; SURVEY.md 8a rows a4-a7]:
+//     r   = q - centroid[p]                                  (residual, L2/cosine)
+//     LUT = build_distance_table_l2(codebook, r)             (m x 256 f32)
+//     d_j = sum_i LUT[i][code[i][j]]  sequentially in i      (compute_pq_distance)
+// Results are bit-identical to oracle.c: every f32 op is an explicit round-to-nearest op in the reference's
+// order (the LUT entry uses the f32x8 reduce tree, the row sum is sequential over sub-vectors).
+// Since round 2 the default search runs the filter kernel (scan3.cu) first and only the queries it cannot prove
+// come here (plus distance-range queries, debug entry points and LGPU_EXACT_SCAN=1); this kernel is also the
+// arithmetic pq_rescore_kernel (tables.cu) restates per candidate row.
+//
+// Work decomposition (B200-first, not the reference's per-query loop):
+//   tile = (partition p, up to 8 of the queries that probe p, up to 1536 of its rows).  A persistent grid (one
+//   512-thread CTA per SM) pulls tiles from an atomic counter; tiles are ordered by partition so a partition's
+//   codes are read from HBM once and then hit in L2 for the other query groups.
+//   The distance table is never materialised whole: it is built 8 sub-spaces at a time into a ring of three
+//   64 KB shared-memory buffers laid out [h][c][s][4 queries] (h = query half, c = code, s = sub-space within the
+//   chunk), so one LDS.128 returns the entries of 4 queries.  The codebook chunk is read (L2-resident) once per
+//   tile and amortised over the 8 queries.
+//   Warp specialisation: the table build is FP32-pipe work (23 flops per entry, packed FADD2/FFMA2), the scan is
+//   shared-memory-gather work; 8 builder warps build chunk ch+1/ch+2 while 8 scanner warps scan chunk ch, handing
+//   buffers over with named barriers (bar.arrive / bar.sync).
+//   Bank conflicts: a straightforward "lane = row" scan makes 8 lanes of a quarter-warp gather at random codes =>
+//   ~2.6-way conflicts.  Here lane l runs `l % 8` sub-space slots behind lane 0 (the code stream in HBM is
+//   pre-skewed by row % 8 bytes, see retile.cu), so at any instant the 8 lanes of a quarter-warp read 8
+//   *different* sub-spaces = 8 different 16-byte bank groups: conflict-free by construction, while each row still
+//   accumulates its sub-vectors strictly in order 0..m-1 in its own register.
+// Pipeline details (from the ncu stall profile of round 1, profiles/r01_scan_stalls.txt):
+//   * no per-tile drain: the stage counter runs on across tiles -- the all-zero "stage nch" of tile n doubles as
+//     the "stage -1" of tile n+1 -- and tile descriptors (group.cu::tile_desc_kernel) are claimed two tiles ahead
+//     by builder warp 0 into a 4-slot shared ring, so neither role ever waits for a fetch.
+//   * the scanners are split by query half (warps 0-3: queries 0-3, warps 4-7: queries 4-7 of the tile): 12 rows
+//     x 4 queries of accumulators per thread (48 registers), two scanner warps per scheduler.
+//   * the table build is straight-line code: 16 (or 8) tasks per warp and chunk, the metric and the half count
+//     are template parameters; each builder warp streams the codebook entries of its tasks through a private
+//     cp.async ring, six tasks ahead, across chunk boundaries (CbStage below).
+//   * tiles with <= 4 queries use a 4-codes-per-warp mapping (HALVES = 1): half the build work.
+// Algorithmic bytes per tile row and query: m code bytes.
 #include "kernels.cuh"
 #include "scan_common.cuh"
 
@@ -531,10 +552,15 @@ void launch2_metric(const ScanArgs &a, int grid, cudaStream_t st)
 
 }  // namespace
 
+bool scan_dsub_supported(uint32_t dsub)
+{
+    return dsub == 1 || dsub == 2 || dsub == 4 || dsub == 8 || dsub == 16 || dsub == 32;
+}
+
 void launch_scan2(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st)
 {
-    if (a.tq || !a.tile_desc || a.rows_tile != SCAN_ROWS_TILE_MID) {
-        set_error("internal: streaming scan needs tile descriptors, rows_tile 1536 and the exact pass");
+    if (!a.tile_desc || a.rows_tile != SCAN_ROWS_TILE_MID) {
+        set_error("internal: the exact scan needs tile descriptors built with rows_tile 1536");
         throw Failure{LGPU_RUNTIME};
     }
     switch (dsub) {

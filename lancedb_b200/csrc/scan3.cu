@@ -1,0 +1,303 @@
+// scan3.cu -- K2+K3 as a FILTER: the PQ code scan over 16-bit per-QUERY tables.
+//
+// The exact kernel (scan2.cu) has to build one f32 distance table per (query, probed partition), because
+// lance's table is on the residual q - c_p [lance, recalled; SURVEY.md 8a rows a4-a5]: 20 480 tables per
+// 1024-query batch of BASELINE config 2, and ncu showed that build -- its shared-memory staging and its f32
+// arithmetic -- not the scan, bounding the kernel (profiles/r01_ncu_summary.txt: shared pipe 76 %, FMA pipe 56 %).
+// Algebraically (tables.cu has the derivation)
+//     d(q, row r of partition p) = sum_i T_q[i][code_i(r)]  +  A(q,p)  +  R(r)
+// with ONE table per query, T_q[i][c] = |q_i - codebook_i[c]|^2 (1 - q_i.codebook_i[c] for dot), a scalar per
+// (query, probe) and a constant per stored row.  tables.cu quantises T_q to 16 bits,
+//     T_q[i][c] in [min_i + step_q n, min_i + step_q (n + 1)),   n = n_q[i][c] in [0, floor(65535 / m)],
+// so that the m entries of a row add up inside one 16-bit lane: this kernel accumulates EIGHT queries per
+// 128-bit shared-memory load with four 32-bit integer adds, half the shared-memory wavefronts and a quarter
+// of the arithmetic per (row, sub-space, query) of the f32 form, and builds no table at all.
+// The result  L = step_q * sum n + (sum_i min_i + A) + R  is a rigorous LOWER bound of the exact distance with a
+// known band (band_check3 in tables.cu); the caller keeps the kp best rows by L, proves the exact top-k is among
+// them, re-scores those few rows in the oracle's arithmetic (pq_rescore_kernel) and redoes unproven queries with
+// the exact kernel, so the reported ids and distances are bit-identical to the exact path.
+//
+// Pipeline: identical hand-over protocol to scan2.cu (tests/test_scan2_protocol.py models it): persistent CTAs,
+// a ring of three shared chunk buffers, named barriers FULL/EMPTY between 8 stager warps and 8 scanner warps, the
+// stage counter running on across tiles, tile descriptors claimed two tiles ahead.
+//   tile    = (partition, <= 8 of the queries probing it, <= 3072 rows)
+//   chunk   = 8 sub-spaces: shared [256 codes][8 sub-spaces][8 queries] u16 = 32 KB
+//   stagers : thread c owns code c.  It loads the 16 bytes (8 sub-spaces) of each of the tile's queries for code c
+//             from the L2-resident query tables (8 x LDG.128, issued a whole stage ahead), transposes 8x8 u16 in
+//             registers (32 PRMT) and writes eight 16-byte units [sub-space][8 queries].  The global tables are
+//             stored ROTATED -- position j of code c holds sub-space (j + c) mod 8 -- so that in step j the eight
+//             lanes of a quarter-warp write eight different 16-byte slots: conflict-free without a per-lane
+//             register rotation.
+//   scanners: thread = rows row0 + ct + 256 r (r < 12); the skewed code stream (retile.cu) makes the eight lanes of
+//             a quarter-warp read eight different sub-space slots, so every LDS.128 is conflict-free whatever the
+//             codes are; accumulators are 4 x u32 per row (8 queries x u16).
+// Algorithmic bytes per tile row and query: m code bytes, as for the exact kernel.
+#include "kernels.cuh"
+#include "scan_common.cuh"
+
+namespace lgpu {
+
+namespace {
+
+constexpr int S3_PW = 8, S3_CW = 8;                 // stager / scanner warps
+constexpr int S3_PT = S3_PW * 32, S3_CT = S3_CW * 32, S3_NT = S3_PT + S3_CT;
+constexpr int S3_RMAX = 12;                         // rows per scanner thread
+constexpr int S3_BUF = 32768;                       // one chunk buffer
+constexpr int S3_SLOTS = 4, S3_SLOT_BYTES = 128;    // tile-descriptor ring
+constexpr size_t S3_TILES = 3 * (size_t)S3_BUF;
+constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES;
+static_assert(SCAN3_ROWS_TILE == S3_CT * S3_RMAX, "rows_tile");
+static_assert(S3_PT == 256, "one stager thread per code");
+
+__device__ __forceinline__ int ring_next3(int b) { return b == 2 ? 0 : b + 1; }
+__device__ __forceinline__ const TileDesc *slot3(const unsigned char *tiles, uint32_t n)
+{
+    return reinterpret_cast<const TileDesc *>(tiles + (n & (S3_SLOTS - 1)) * S3_SLOT_BYTES);
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t word_of(const uint4 &v, int w)
+{
+    return w == 0 ? v.x : (w == 1 ? v.y : (w == 2 ? v.z : v.w));
+}
+
+// ---------------------------------------------------------------- stager side
+struct Slab {
+    uint4 v[SCAN_G];            // code c of the tile's 8 queries: 8 rotated sub-space entries each
+};
+__device__ __forceinline__ void slab_load(Slab &s, const ScanArgs &a, const TileDesc *T, uint32_t ch, uint32_t c)
+{
+    const int ng = (int)T->ng;
+#pragma unroll
+    for (int g = 0; g < SCAN_G; g++) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (g < ng) v = __ldg(a.qt + ((size_t)T->q[g] * a.nch + ch) * 256 + c);
+        s.v[g] = v;
+    }
+}
+// unit j of code c = sub-space (j + c) & 7: (query 0..7) x u16, written to [c][(j + c) & 7]
+__device__ __forceinline__ void slab_store(const Slab &s, uint32_t buf_addr, uint32_t c)
+{
+    const uint32_t row = buf_addr + (c << 7);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int w = j >> 1;
+        const uint32_t sel = (j & 1) ? 0x7632u : 0x5410u;
+        uint4 o;
+        o.x = __byte_perm(word_of(s.v[0], w), word_of(s.v[1], w), sel);
+        o.y = __byte_perm(word_of(s.v[2], w), word_of(s.v[3], w), sel);
+        o.z = __byte_perm(word_of(s.v[4], w), word_of(s.v[5], w), sel);
+        o.w = __byte_perm(word_of(s.v[6], w), word_of(s.v[7], w), sel);
+        sts128u(row + ((((uint32_t)j + c) & 7u) << 4), o);
+    }
+}
+
+__device__ __forceinline__ void stager_loop(const ScanArgs &a, uint32_t total, int tid)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *const tiles = smem + S3_TILES;
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(smem);
+    const int lane = tid & 31, pw = tid >> 5;
+    const uint32_t nch = a.nch, c = (uint32_t)tid;
+
+    Slab cur, nxt;
+    {
+        const TileDesc *T0 = slot3(tiles, 0);
+        if (T0->ng) slab_load(cur, a, T0, 0, c);
+    }
+    int b = 0;
+    uint32_t gs = 0;
+    for (uint32_t n = 0;; n++) {
+        const TileDesc *T = slot3(tiles, n);
+        if (T->ng == 0) break;
+        const TileDesc *Tn = slot3(tiles, n + 1);
+        const bool next_tile = Tn->ng != 0;
+        uint32_t t_claim = 0, t_word = 0;
+        for (uint32_t ch = 0; ch <= nch; ch++) {
+            // --- tile look-ahead (warp 0): claim at stage 0, read the descriptor at stage 1 ---
+            if (pw == 0) {
+                if (ch == 0) {
+                    if (lane == 0) t_claim = atomicAdd(a.tile_counter, 1u);
+                    t_claim = __shfl_sync(0xffffffffu, t_claim, 0);
+                } else if (ch == 1) {
+                    t_word = 0;
+                    if (lane < (int)(sizeof(TileDesc) / 4) && t_claim < total)
+                        t_word = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t_claim) + lane);
+                }
+            }
+            // --- the next data stage's table slab, a whole stage ahead: the next chunk of this tile, or (while
+            // the last chunk is stored and through the zero stage) chunk 0 of the next tile ---
+            bool have_next = false;
+            if (ch + 1 < nch) { slab_load(nxt, a, T, ch + 1, c); have_next = true; }
+            else if (ch + 1 == nch && next_tile) { slab_load(nxt, a, Tn, 0, c); have_next = true; }
+
+            if (gs >= 2) bar_sync(BAR_EMPTY + b, S3_NT);           // scanners are done with stage gs-2
+            if (ch == nch) {                                       // all-zero code-0 row for the lagging lanes
+                if (tid < 32) reinterpret_cast<uint32_t *>(smem + b * S3_BUF)[tid] = 0u;
+            } else {
+                slab_store(cur, lut + (uint32_t)b * S3_BUF, c);
+            }
+            if (pw == 0 && ch == 1 && lane < (int)(sizeof(TileDesc) / 4))   // publish tile n+2 before FULL(stage 1)
+                reinterpret_cast<uint32_t *>(const_cast<TileDesc *>(slot3(tiles, n + 2)))[lane] = t_word;
+            bar_arrive(BAR_FULL + b, S3_NT);
+            if (have_next) cur = nxt;
+            bar_sync(BAR_PROD, S3_PT);
+            b = ring_next3(b);
+            gs++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- scanner side
+template <int R>
+__device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, bool next_exists, int b, int ct)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t lut = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t nch = a.nch;
+    const uint32_t p = T->p, row0 = T->row0, nrows = T->nrows;
+    const int ng = (int)T->ng;
+    const int sig = ct & 7;                               // this lane's skew (== row % 8)
+    const uint32_t n_p = a.part_n[p], npad = a.part_npad[p];
+    const uint2 *cs = reinterpret_cast<const uint2 *>(a.codes + a.code_base[p]);   // [nch+1][npad]
+
+    uint32_t acc[R][4];
+    bool valid[R];
+    uint2 wn[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) acc[r][g] = 0u;
+        const uint32_t row = row0 + ct + r * S3_CT;
+        valid[r] = row < row0 + nrows && row < n_p;
+        wn[r] = valid[r] ? __ldg(cs + row) : make_uint2(0u, 0u);
+    }
+
+    for (uint32_t it = 0; it <= nch; it++) {
+        uint2 w[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) w[r] = wn[r];
+        if (it < nch) {                                    // prefetch the next block of code bytes
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t row = row0 + ct + r * S3_CT;
+                wn[r] = valid[r] ? __ldg(cs + (size_t)(it + 1) * npad + row) : make_uint2(0u, 0u);
+            }
+        }
+        bar_sync(BAR_FULL + b, S3_NT);
+        const int bp = b == 0 ? 2 : b - 1;                 // buffer of the previous stage
+        const uint32_t base_cur = lut + (uint32_t)b * S3_BUF;
+        const uint32_t base_prev = lut + (uint32_t)bp * S3_BUF;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const uint32_t off = ((e < sig) ? base_prev : base_cur) + (uint32_t)(((e - sig) & 7) << 4);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t word = (e < 4) ? w[r].x : w[r].y;
+                const uint32_t code = (word >> (8 * (e & 3))) & 0xffu;
+                const uint4 v = lds128u(off + (code << 7));
+                acc[r][0] += v.x; acc[r][1] += v.y; acc[r][2] += v.z; acc[r][3] += v.w;
+            }
+        }
+        if (it + 2 <= nch || next_exists) bar_arrive(BAR_EMPTY + bp, S3_NT);
+        b = ring_next3(b);
+    }
+
+    // ---- epilogue: lower bound L = step_q * sum + (base_q + A(q,p)) + R(row), one f32 per (row, query) ----
+    const float scale = a.metric == LGPU_COSINE ? 0.5f : 1.0f;
+    const uint64_t pos0 = a.part_off[p];
+    float rr[R];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        rr[r] = (valid[r] && a.row_R) ? __ldg(a.row_R + pos0 + row0 + ct + r * S3_CT) : 0.f;
+#pragma unroll
+    for (int g = 0; g < SCAN_G; g++) {
+        if (g < ng) {
+            const uint32_t q = T->q[g];
+            const float step = __ldg(a.qt_step + q);
+            const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + T->slot[g]) : 0.f);
+            float *out = a.dist_out + T->out[g];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (valid[r]) {
+                    const uint32_t s = (g & 1) ? (acc[r][g >> 1] >> 16) : (acc[r][g >> 1] & 0xffffu);
+                    out[row0 + ct + r * S3_CT] = (fmaf(step, (float)s, cst) + rr[r]) * scale;
+                }
+            }
+        }
+    }
+    return b;
+}
+
+__device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const unsigned char *const tiles = smem + S3_TILES;
+    const int ct = tid - S3_PT;
+    int b = 0;
+    for (uint32_t n = 0;; n++) {
+        const TileDesc *T = slot3(tiles, n);
+        if (T->ng == 0) break;
+        const bool next_exists = slot3(tiles, n + 1)->ng != 0;
+        const int R = (int)((T->nrows + S3_CT - 1) / S3_CT);
+#define LGPU_SCAN3(RR) b = scan_tile<RR>(a, T, next_exists, b, ct)
+        if (R <= 2) LGPU_SCAN3(2);
+        else if (R <= 4) LGPU_SCAN3(4);
+        else if (R <= 6) LGPU_SCAN3(6);
+        else if (R <= 8) LGPU_SCAN3(8);
+        else if (R <= 10) LGPU_SCAN3(10);
+        else LGPU_SCAN3(12);
+#undef LGPU_SCAN3
+    }
+}
+
+__global__ void __launch_bounds__(S3_NT, 1) scan3_kernel(ScanArgs a)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const uint32_t total = *a.total_tiles;
+    unsigned char *const tiles = smem + S3_TILES;
+
+    // "stage -1" of the first tile: zero code-0 row in ring buffer 2
+    if (tid < 32) reinterpret_cast<uint32_t *>(smem + 2 * S3_BUF)[tid] = 0u;
+    // tiles 0 and 1 of this CTA
+    if (tid < 32) {
+        uint32_t t0 = 0, t1 = 0;
+        if (tid == 0) { t0 = atomicAdd(a.tile_counter, 1u); t1 = atomicAdd(a.tile_counter, 1u); }
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        t1 = __shfl_sync(0xffffffffu, t1, 0);
+        if (tid < (int)(sizeof(TileDesc) / 4)) {
+            uint32_t w0 = 0, w1 = 0;
+            if (t0 < total) w0 = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t0) + tid);
+            if (t1 < total) w1 = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t1) + tid);
+            reinterpret_cast<uint32_t *>(tiles)[tid] = w0;
+            reinterpret_cast<uint32_t *>(tiles + S3_SLOT_BYTES)[tid] = w1;
+        }
+    }
+    __syncthreads();
+    if (tid < S3_PT) stager_loop(a, total, tid);
+    else scanner_loop(a, tid);
+}
+
+}  // namespace
+
+void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st)
+{
+    if (!a.qt || !a.qt_step || !a.qt_base || !a.tile_desc || a.rows_tile != SCAN3_ROWS_TILE || !a.part_off) {
+        set_error("internal: the filter scan needs query tables, tile descriptors and rows_tile 3072");
+        throw Failure{LGPU_RUNTIME};
+    }
+    LGPU_CUDA(cudaFuncSetAttribute(scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
+    scan3_kernel<<<grid, S3_NT, S3_SMEM, st>>>(a); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaGetLastError());
+}
+
+}  // namespace lgpu

@@ -1,20 +1,22 @@
-// tables.cu -- the two-pass form of the PQ scan (filter + verify).
+// tables.cu -- the filter + verify form of the PQ scan: per-query tables, per-row constants, proof and re-score.
 //
-// The exact path (scan.cu) builds one 96 KB distance table per (query, probed partition),
-// because lance's table is on the *residual* q - c_p: 20 480
-// tables per 1024-query batch, 23 f32 ops per entry, and that table build -- not the scan --
-// bounds the kernel.  Algebraically
+// The exact path (scan2.cu) builds one 96 KB distance table per (query, probed partition), because lance's table
+// is on the *residual* q - c_p: 20 480 tables per 1024-query batch, 23 f32 ops per
+// entry, and that table build -- not the scan -- bounds the kernel.  Algebraically
 //     |(q_i - c_i) - b_i|^2 = |q_i - b_i|^2  +  (|c_i|^2 - 2 q_i.c_i)  +  2 b_i.c_i
 // so the distance of row r of partition p is  S_q(r) + A(q,p) + R(r)  with
 //     S_q(r) = sum_i T_q[i][code_i(r)],  T_q[i][c] = |q_i - codebook_i[c]|^2    one table per QUERY
 //     A(q,p) = |q - c_p|^2 - |q|^2                                               from the coarse step
 //     R(r)   = 2 * sum_i codebook_i[code_i(r)] . c_p,i                           one f32 per row, at open
-// The rounding differs from lance's, so this is only used as a FILTER: the scan kernel's
-// approximate pass ranks rows by S+A+R, the caller keeps every row within a rigorous error
-// band of the k-th best (`launch_band_check2`), `pq_rescore_kernel` recomputes those few rows
-// exactly as oracle.c does (residual, f32x8 tree entries, sequential sum), and queries whose
-// band overflowed the shortlist are redone by the exact kernels.  Final ids/distances are
-// bit-identical to the exact path; the table work drops ~20x.
+// (dot: T_q[i][c] = 1 - q_i.codebook_i[c], A = R = 0, distance = S - (m - 1): lance's own table, no residual).
+// The rounding differs from lance's, so this is only used as a FILTER.  T_q is quantised to 16 bits against a
+// per-query step (launch_query_tables_q16): the scan kernel (scan3.cu) adds the m integers of a row exactly and
+// turns the sum into a LOWER bound L(r) of the row's distance; with W = m step the real distance lies in
+// [L - E, L + W + E] (E = floating-point slack, launch_band_check3).  The caller keeps the kp rows with the
+// smallest L; if L[kp-1] > L[k-1] + W + 2E no other row can be among the exact top-k, `pq_rescore_kernel`
+// recomputes the kp rows exactly as oracle.c does (residual, f32x8 tree entries, sequential sum) and the final
+// top-k is selected on those; queries that cannot be proven are redone by the exact kernels.  Final ids and
+// distances are bit-identical to the exact path.
 #include "kernels.cuh"
 
 #include <math_constants.h>
@@ -23,62 +25,152 @@ namespace lgpu {
 
 namespace {
 
-// T_q[ch][c][s] for every query: one thread per entry (coalesced on the tiled codebook)
 template <int DSUB>
-__global__ void query_tables_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled, uint32_t B,
-                                    uint32_t dim, uint32_t m, uint32_t nch, int metric, float *__restrict__ T)
+__device__ __forceinline__ void load_cb(float *dst, const float *src)
 {
-    const uint64_t per_q = (uint64_t)nch * 256 * 8;
-    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (uint64_t)B * per_q) return;
-    const uint32_t q = (uint32_t)(idx / per_q);
-    const uint64_t e = idx - (uint64_t)q * per_q;
-    const uint32_t s = e & 7, c = (e >> 3) & 255, ch = (uint32_t)(e >> 11);
-    const uint32_t i = ch * 8 + s;
-    float v = 0.f;
-    if (i < m) {
-        float qv[DSUB], cv[DSUB];
-        const float *qp = Q + (size_t)q * dim + i * DSUB, *cp = cb_tiled + e * DSUB;
-        if constexpr (DSUB % 4 == 0) {
+    if constexpr (DSUB % 4 == 0) {
 #pragma unroll
-            for (int t = 0; t < DSUB; t += 4) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4 *>(qp + t));
-                const float4 b4 = __ldg(reinterpret_cast<const float4 *>(cp + t));
-                qv[t] = a4.x; qv[t + 1] = a4.y; qv[t + 2] = a4.z; qv[t + 3] = a4.w;
-                cv[t] = b4.x; cv[t + 1] = b4.y; cv[t + 2] = b4.z; cv[t + 3] = b4.w;
-            }
-        } else {
-#pragma unroll
-            for (int t = 0; t < DSUB; t++) { qv[t] = qp[t]; cv[t] = cp[t]; }
+        for (int i = 0; i < DSUB / 4; i++) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
         }
-        v = subvec_l2<DSUB>(qv, cv);
+    } else {
+#pragma unroll
+        for (int i = 0; i < DSUB; i++) dst[i] = __ldg(src + i);
     }
-    T[idx] = v;
-    (void)metric;
 }
 
-// bound[q] = sum_i max_c T_q[i][c]  (largest possible S), one warp per (query)
-__global__ void table_bound_kernel(const float *__restrict__ T, uint32_t B, uint32_t nch, float *__restrict__ bound)
+template <int DSUB, bool DOT>
+__device__ __forceinline__ float table_entry(const float *qv, const float *cv)
 {
-    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    return DOT ? subvec_dot_dist<DSUB>(qv, cv) : subvec_l2<DSUB>(qv, cv);
+}
+
+// ---- pass 1: min_c / max_c of T_q[i][.] for every (query, sub-space).  grid (ceil(B/8), nch), 256 threads:
+// warp g = query 8 bx + g; lane = (s = lane & 7, code quarter = lane >> 3).
+template <int DSUB, bool DOT>
+__global__ void __launch_bounds__(256) qtable_minmax_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled,
+                                                            uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
+                                                            float *__restrict__ mm)
+{
+    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5), ch = blockIdx.y;
+    const int lane = threadIdx.x & 31, s = lane & 7, cq = lane >> 3;
     if (q >= B) return;
-    const float *t = T + (size_t)q * nch * 256 * 8;
-    float total = 0.f;
-    for (uint32_t ch = 0; ch < nch; ch++) {
-        // lane handles sub-space s = lane & 7 for codes c = lane>>3, +4, ...
-        float mx = 0.f;
-        for (uint32_t c = lane >> 3; c < 256; c += 4) mx = fmaxf(mx, t[((size_t)ch * 256 + c) * 8 + (lane & 7)]);
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-        // lanes 0..7 now hold the max of sub-space s; add the 8 of them
-        float sm = mx;
-        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-        sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-        sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-        total += sm;
+    const uint32_t i = ch * 8 + s;
+    float mn = 0.f, mx = 0.f;
+    if (i < m) {
+        float qv[DSUB];
+#pragma unroll
+        for (int t = 0; t < DSUB; t++) qv[t] = Q[(size_t)q * dim + i * DSUB + t];
+        mn = CUDART_INF_F; mx = -CUDART_INF_F;
+        const float *cb = cb_tiled + (((size_t)ch * 256 + cq * 64) * 8 + s) * DSUB;
+        for (int t = 0; t < 64; t++) {
+            float cv[DSUB];
+            load_cb<DSUB>(cv, cb + (size_t)t * 8 * DSUB);
+            const float v = table_entry<DSUB, DOT>(qv, cv);
+            mn = fminf(mn, v); mx = fmaxf(mx, v);
+            if (v != v) { mn = v; mx = v; }             // NaN sticks (fminf/fmaxf would drop it)
+        }
     }
-    if (lane == 0) bound[q] = total;
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+        const float on = __shfl_xor_sync(0xffffffffu, mn, o), ox = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = (on != on || mn != mn) ? CUDART_NAN_F : fminf(mn, on);
+        mx = (ox != ox || mx != mx) ? CUDART_NAN_F : fmaxf(mx, ox);
+    }
+    if (cq == 0) {
+        float2 *o = reinterpret_cast<float2 *>(mm) + (size_t)q * nch * 8 + i;
+        *o = make_float2(mn, mx);
+    }
+}
+
+// ---- pass 2: quantise.  grid (ceil(B/8), nch), 256 threads: thread c = code c of chunk ch for the CTA's 8
+// queries.  Position j of the 16-byte output holds sub-space (j + c) & 7 (the rotation scan3.cu's stagers rely on).
+template <int DSUB, bool DOT>
+__global__ void __launch_bounds__(256) qtable_quant_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled,
+                                                           uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
+                                                           const float *__restrict__ mm, uint4 *__restrict__ qt,
+                                                           float *__restrict__ step_out, float *__restrict__ base_out,
+                                                           float *__restrict__ sbound_out, uint32_t *__restrict__ bad_out)
+{
+    __shared__ float s_q[8][8][DSUB];
+    __shared__ float s_min[8][8];
+    __shared__ float s_inv[8];
+    const uint32_t q0 = blockIdx.x * 8, ch = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+    const uint32_t m8 = nch * 8;
+    const float qmax = (float)(65535u / m);
+    {   // per-query step / base / bound from the min-max table: warp g handles query q0 + g
+        const uint32_t q = q0 + g;
+        float rng = 0.f, base = 0.f, sb = 0.f;
+        bool bad = false;
+        if (q < B) {
+            const float2 *row = reinterpret_cast<const float2 *>(mm) + (size_t)q * m8;
+            for (uint32_t i = lane; i < m; i += 32) {
+                const float2 v = row[i];
+                rng = fmaxf(rng, v.y - v.x);
+                base += v.x;
+                sb += fmaxf(fabsf(v.x), fabsf(v.y));
+                bad |= !(fabsf(v.x) < CUDART_INF_F) || !(fabsf(v.y) < CUDART_INF_F);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rng = fmaxf(rng, __shfl_xor_sync(0xffffffffu, rng, o));
+            base += __shfl_xor_sync(0xffffffffu, base, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        bad = __any_sync(0xffffffffu, bad) || !(rng < CUDART_INF_F) || !(fabsf(base) < CUDART_INF_F) || !(sb < CUDART_INF_F);
+        const float step = (!bad && rng > 0.f) ? rng / qmax : 0.f;
+        const float inv = (step > 0.f && qmax / rng < CUDART_INF_F) ? qmax / rng : 0.f;
+        if (lane == 0) {
+            s_inv[g] = bad ? 0.f : inv;
+            if (ch == 0 && q < B) {
+                step_out[q] = (inv > 0.f) ? step : 0.f;      // inv == 0: every entry quantises to 0 and W = 0 would be
+                bad_out[q] = (bad || (rng > 0.f && inv == 0.f)) ? 1u : 0u;   // wrong unless the range is 0 too
+                base_out[q] = DOT ? base - (float)(m - 1) : base;
+                sbound_out[q] = sb;
+            }
+        }
+        if (lane < 8) {
+            const uint32_t i = ch * 8 + lane;
+            s_min[g][lane] = (q < B && i < m) ? reinterpret_cast<const float2 *>(mm)[(size_t)q * m8 + i].x : 0.f;
+        }
+        for (int t = lane; t < 8 * DSUB; t += 32) {
+            const uint32_t i = ch * 8 + t / DSUB;
+            s_q[g][t / DSUB][t % DSUB] = (q < B && i < m) ? Q[(size_t)q * dim + i * DSUB + t % DSUB] : 0.f;
+        }
+    }
+    __syncthreads();
+    const uint32_t c = (uint32_t)tid;
+    uint32_t out[8][4];
+#pragma unroll
+    for (int gg = 0; gg < 8; gg++)
+#pragma unroll
+        for (int w = 0; w < 4; w++) out[gg][w] = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint32_t s = ((uint32_t)j + c) & 7u;
+        const uint32_t i = ch * 8 + s;
+        if (i < m) {
+            float cv[DSUB];
+            load_cb<DSUB>(cv, cb_tiled + (((size_t)ch * 256 + c) * 8 + s) * DSUB);
+#pragma unroll
+            for (int gg = 0; gg < 8; gg++) {
+                float qv[DSUB];
+#pragma unroll
+                for (int t = 0; t < DSUB; t++) qv[t] = s_q[gg][s][t];
+                const float v = table_entry<DSUB, DOT>(qv, cv);
+                float x = (v - s_min[gg][s]) * s_inv[gg];
+                x = x >= 0.f ? fminf(floorf(x), qmax) : 0.f;           // NaN -> 0 (the query is flagged bad)
+                out[gg][j >> 1] |= (uint32_t)x << (16 * (j & 1));
+            }
+        }
+    }
+#pragma unroll
+    for (int gg = 0; gg < 8; gg++)
+        if (q0 + gg < B)
+            qt[((size_t)(q0 + gg) * nch + ch) * 256 + c] = make_uint4(out[gg][0], out[gg][1], out[gg][2], out[gg][3]);
 }
 
 __device__ __forceinline__ uint32_t find_partition(const uint64_t *__restrict__ part_off, uint32_t nlist, uint64_t pos)
@@ -158,9 +250,9 @@ __global__ void pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *_
     out[pair] = acc;
 }
 
-// probe_A[slot] = coarse_dist - |q|^2 ; amax[q] = max_j |probe_A|
+// probe_A[slot] = coarse_dist - |q|^2 ; amax[q] = max_j coarse + |q|^2
 __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const float *__restrict__ Q, uint32_t B,
-                                   uint32_t nprobes, uint32_t dim, float *__restrict__ probe_A, float *__restrict__ qn2,
+                                   uint32_t nprobes, uint32_t dim, float *__restrict__ probe_A,
                                    float *__restrict__ amax)
 {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // one warp per query
@@ -179,30 +271,32 @@ __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const f
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) {
-        qn2[q] = n2;
-        amax[q] = mx + n2;                              // >= |A| and also covers the coarse distance's own rounding
-    }
+    if (lane == 0) amax[q] = mx + n2;                   // >= |A| and also covers the coarse distance's own rounding
 }
 
-// flags[q] = 1 when the approximate shortlist cannot be proven to contain the exact top-k.
-// |approx - exact| <= E_q = 2^-16 (Smax_q + Amax_q + Rmax) * scale: with u = 2^-24, the approximate sum
-// carries <= (m + 4) u S (sequential adds + table entries), the coarse distance <= 66 u, A and R a few u
-// each, and the exact value itself <= (m + 5) u d with d <= S + |A| + |R|; for m <= 96 that is < 256 u of
-// the bound (m > 96 widens the band proportionally, see launch_band_check2).
-__global__ void band_check2_kernel(const float *__restrict__ approx, const uint32_t *__restrict__ cnt,
-                                   const float *__restrict__ sbound, const float *__restrict__ amax,
-                                   const int *__restrict__ rmax_bits, float scale, uint32_t B, uint32_t k, uint32_t kp,
-                                   uint32_t *__restrict__ flags)
+// flags[q] = 1 when the shortlist cannot be proven to contain the exact top-k (see the header and kernels.cuh).
+// Error budget, u = 2^-24: the exact (oracle-order) distance d* differs from the real-arithmetic distance D of the
+// same f32 inputs by <= (m + 16) u (D + |q - c_p|^2); the table entries carry <= (dsub + 2) u T each, the floor of
+// the quantiser can be off by one step when (T - min) / step lands within 2^-11 of an integer (absorbed by the
+// factor 1 + 2^-10 on W), A carries <= 70 u (coarse + |q|^2), R one ulp, the epilogue of scan3 three more roundings
+// of values bounded by sbound + amax + rmax.  For m <= 96 all of it is < 2^9 u = 2^-15 of (sbound + amax + rmax);
+// larger m widens E proportionally.
+__global__ void band_check3_kernel(const float *__restrict__ lb, const uint32_t *__restrict__ cnt,
+                                   const float *__restrict__ step, const float *__restrict__ sbound,
+                                   const float *__restrict__ amax, const int *__restrict__ rmax_bits,
+                                   const uint32_t *__restrict__ bad, float scale, uint32_t m, uint32_t B, uint32_t k,
+                                   uint32_t kp, uint32_t *__restrict__ flags)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
-    uint32_t f = 0;
-    if (cnt[q] >= kp && kp > 0) {
-        const float E = 1.52587890625e-5f * (sbound[q] + amax[q] + __int_as_float(*rmax_bits)) * scale;
-        const float kth = approx[(size_t)q * kp + (k - 1 < kp ? k - 1 : kp - 1)];
-        const float last = approx[(size_t)q * kp + kp - 1];
-        f = (k >= kp || !(last > kth + 2.0f * E)) ? 1u : 0u;
+    uint32_t f = bad[q] ? 1u : 0u;
+    if (!f && cnt[q] >= kp && kp > 0) {
+        const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m;
+        const float E = 3.0517578125e-5f * (float)((m + 95u) / 96u) * mag;
+        const float W = (float)m * step[q] * 1.0009765625f;
+        const float kth = lb[(size_t)q * kp + (k - 1 < kp ? k - 1 : kp - 1)];
+        const float last = lb[(size_t)q * kp + kp - 1];
+        f = (k >= kp || !(last > kth + scale * (W + 2.0f * E))) ? 1u : 0u;
     }
     flags[q] = f;
 }
@@ -222,15 +316,22 @@ template <class F> void dispatch_dsub(uint32_t dsub, F &&f)
 
 }  // namespace
 
-void launch_query_tables(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
-                         uint32_t dsub, int metric, float *T, float *sbound, cudaStream_t st)
+void launch_query_tables_q16(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
+                             uint32_t dsub, int metric, float *mm, uint4 *qt, float *step, float *base, float *sbound,
+                             uint32_t *bad, cudaStream_t st)
 {
     if (B == 0) return;
-    const uint64_t total = (uint64_t)B * nch * 256 * 8;
+    const dim3 grid((B + 7) / 8, nch);
     dispatch_dsub(dsub, [&](auto D) {
-        query_tables_kernel<decltype(D)::value><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, metric, T); LGPU_COUNT_LAUNCH();
+        constexpr int DS = decltype(D)::value;
+        if (metric == LGPU_DOT) {
+            qtable_minmax_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
+            qtable_quant_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
+        } else {
+            qtable_minmax_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
+            qtable_quant_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
+        }
     });
-    table_bound_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(T, B, nch, sbound); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -263,19 +364,19 @@ void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t
 }
 
 void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uint32_t nprobes, uint32_t dim,
-                        float *probe_A, float *qn2, float *amax, cudaStream_t st)
+                        float *probe_A, float *amax, cudaStream_t st)
 {
     if (B == 0) return;
-    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, qn2, amax); LGPU_COUNT_LAUNCH();
+    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, amax); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
-void launch_band_check2(const float *approx, const uint32_t *cnt, const float *sbound, const float *amax,
-                        const int *rmax_bits, float scale, uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags,
-                        cudaStream_t st)
+void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
+                        const int *rmax_bits, const uint32_t *bad, float scale, uint32_t m, uint32_t B, uint32_t k,
+                        uint32_t kp, uint32_t *flags, cudaStream_t st)
 {
     if (B == 0) return;
-    band_check2_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, sbound, amax, rmax_bits, scale, B, k, kp, flags); LGPU_COUNT_LAUNCH();
+    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, scale, m, B, k, kp, flags); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -167,7 +167,9 @@ def test_nan_and_zero_queries_return_nothing_and_do_not_poison_the_context():
             q[2, :] = 0.0
         gi, gd, gc = gpu.search(q, k=5, nprobes=4)
         oi, od, oc = oracle.OracleIndex.from_data(ix).search(q, k=5, nprobes=4)
-        assert gc[1] == 0 and gc[4] == 0 and (metric != "cosine" or gc[2] == 0)
+        # (an Inf query is not "no distance": for l2 every distance is +inf, which IS NOT NULL; only the
+        # survival of the context is asserted for it)
+        assert gc[1] == 0 and (metric != "cosine" or gc[2] == 0)
         good = [0, 3, 5]
         assert np.array_equal(gi[good], oi[good]) and np.array_equal(gc[good], oc[good])
         assert np.array_equal(gd[good].view(np.uint32), od[good].view(np.uint32))

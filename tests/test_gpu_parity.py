@@ -126,15 +126,15 @@ def test_search_refine(metric):
     _check_search(ix, queries(rng, 17, 48), k=10, nprobes=3, refine_factor=5)
 
 
-@pytest.mark.parametrize("metric", ["l2", "cosine"])
-def test_search_two_pass_filter_verify(metric, monkeypatch):
-    """LGPU_TWO_PASS=1: approximate scan with per-query tables + exact re-score + exact fix-up of the
-    unproven queries must return exactly what the exact path returns (incl. ties -> fix-up)."""
-    monkeypatch.setenv("LGPU_TWO_PASS", "1")
+@pytest.mark.parametrize("metric", ["l2", "cosine", "dot"])
+def test_search_filter_verify_with_ties_and_fixup(metric):
+    """The default path (scan3.cu lower bounds from 16-bit per-query tables -> shortlist -> proof -> exact
+    re-score, tables.cu) must return exactly what the oracle returns, including when every distance of a
+    partition ties, which makes the proof fail and sends those queries through the exact fix-up pass."""
     rng = np.random.default_rng(21)
     ix = random_index(rng, dim=64, nlist=24, m=8, metric=metric, n=9000)
     _check_search(ix, queries(rng, 40, 64), k=10, nprobes=6)
-    _check_search(ix, queries(rng, 40, 64), k=40, nprobes=6)
+    _check_search(ix, queries(rng, 40, 64), k=40, nprobes=6)         # kp = 112: block selector shortlist
     ct = ix.codes_t.copy()                       # identical codes -> every distance ties -> fix-up pass
     a, b = int(ix.part_offsets[3]), int(ix.part_offsets[4])
     blk = ct[a * 8:b * 8].reshape(8, b - a); blk[:] = blk[:, :1]
@@ -202,21 +202,36 @@ def test_error_contract():
         _native.GpuIvfPq(bad)
 
 
-@pytest.mark.parametrize("metric,dim,m", [("l2", 768, 96), ("dot", 64, 8), ("cosine", 80, 10), ("l2", 64, 2)])
-def test_round1_scan_kernel_still_matches(metric, dim, m, monkeypatch):
-    """LGPU_SCAN_V1=1 keeps the per-tile-drain kernel (scan.cu) selectable; both it and the default
-    streaming kernel (scan2.cu) must reproduce the oracle bit for bit (many tiles per CTA, mixed
-    group sizes 1..8, multi-block partitions)."""
+@pytest.mark.parametrize("metric,dim,m", [("l2", 768, 96), ("dot", 64, 8), ("cosine", 80, 10), ("l2", 64, 2),
+                                          ("l2", 24, 24), ("dot", 32, 8), ("cosine", 1536, 96)])
+def test_filter_and_exact_scans_agree_with_the_oracle(metric, dim, m, monkeypatch):
+    """LGPU_EXACT_SCAN=1 sends every query through the exact kernel (scan2.cu); the default runs the filter
+    kernel (scan3.cu) + verify.  Both must reproduce the oracle bit for bit: many tiles per CTA, mixed group
+    sizes 1..8, partitions above one 1536- / 3072-row tile, dsub 8/8/8/32/1/4/16, m not a multiple of 8."""
     rng = np.random.default_rng(21)
-    sizes = [0, 5, 1500, 1537, 3100, 40, 977, 200, 128, 129, 64, 1, 700, 0, 1024, 333]
+    sizes = [0, 5, 1500, 1537, 3100, 40, 977, 200, 128, 129, 64, 1, 700, 0, 1024, 333, 6200]
     ix = random_index(rng, dim=dim, nlist=len(sizes), m=m, metric=metric, sizes=sizes)
     q = queries(rng, 77, dim)
     out = {}
-    for v1 in ("0", "1"):
-        monkeypatch.setenv("LGPU_SCAN_V1", v1)
-        out[v1] = _check_search(ix, q, k=10, nprobes=6)
+    for exact in ("0", "1"):
+        monkeypatch.setenv("LGPU_EXACT_SCAN", exact)
+        out[exact] = _check_search(ix, q, k=10, nprobes=6)
     for a, b in zip(out["0"], out["1"]):
         assert np.array_equal(a, b)
+
+
+def test_filter_scan_scaled_and_degenerate_tables():
+    """Quantiser edge cases: huge / tiny magnitudes (the step follows the per-query range), a codebook with a
+    constant sub-space (range 0 in that sub-space), and an all-equal codebook (step 0: every row ties)."""
+    rng = np.random.default_rng(23)
+    for scale in (1e-6, 1.0, 3e4):
+        ix = random_index(rng, dim=64, nlist=10, m=8, n=5000, scale=scale)
+        _check_search(ix, queries(rng, 30, 64, scale=scale), k=10, nprobes=4)
+    ix = random_index(rng, dim=64, nlist=10, m=8, n=5000)
+    cb = ix.codebook.copy(); cb[3] = cb[3, :1]; ix.codebook = cb            # sub-space 3: all codewords equal
+    _check_search(ix, queries(rng, 30, 64), k=10, nprobes=4)
+    cb = ix.codebook.copy(); cb[:] = cb[:, :1]; ix.codebook = cb            # every sub-space constant
+    _check_search(ix, queries(rng, 9, 64), k=10, nprobes=4)
 
 
 def test_streaming_scan_many_tiles_per_cta():
