@@ -94,6 +94,7 @@ struct Workspace {
     DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars, tile_desc, allow;
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
+    DevBuf widen;                       // maximum_nprobes widening: queries that found fewer than k rows
     DevBuf qb, qn2, flags;              // tensor-core shortlist: bf16 queries, |q|^2, unproven-query flags
     // CUDA graph of one host-buffer search (lgpu_search): the ~15 launches of a batch replayed as one
     cudaGraphExec_t graph = nullptr;
@@ -469,8 +470,11 @@ void check_params(const lgpu_search_params *p)
 // one sub-batch of an IVF_PQ search, everything device-side on `st`
 void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *d_q, uint32_t B,
                    const lgpu_search_params &sp, uint32_t nprobes, uint64_t *d_ids, float *d_dist,
-                   uint32_t *d_cnt, bool prof, const uint64_t *forced_probes = nullptr, RowFilter rf = RowFilter())
+                   uint32_t *d_cnt, bool prof, const uint64_t *forced_probes = nullptr, RowFilter rf = RowFilter(),
+                   const uint32_t *only = nullptr)
 {
+    // `only` (device, [B]): redo just the flagged queries (maximum_nprobes widening) -- exact kernels, outputs of
+    // the other queries are left untouched
     const uint32_t dim = ix->dim, nlist = ix->nlist;
     const uint32_t slots = B * nprobes;
     int evi = 0;
@@ -557,7 +561,8 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     // ---- which scan: filter + verify (scan3.cu) unless the request needs every exact distance ----
     const uint32_t kp = kk <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * kk + 32);
     const bool filter_scan = ix->has_tables && !exact_scan_forced() && !sp.has_lower && !sp.has_upper && !forced_probes &&
-                             d_ids && kp > kk && ix->m <= 512;
+                             d_ids && kp > kk && ix->m <= 512 && !only;
+    ga.only = only;
     ga.rows_tile = filter_scan ? SCAN3_ROWS_TILE : SCAN_ROWS_TILE_MID;
     launch_group(ga, st);
     mark();
@@ -583,6 +588,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sa.nprobes = nprobes; sa.nlist = nlist; sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
     sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B;
     sa.allow = rf.bits; sa.allow_bits = rf.nbits;
+    sa.only = only;
     // where the PQ top-kk goes: straight to the caller, or to the refine stage's candidate lists
     uint64_t *pq_ids = d_ids; float *pq_dist = d_dist; uint32_t *pq_cnt = d_cnt; uint64_t *pq_pos = nullptr;
     if (sp.refine_factor) {
@@ -662,6 +668,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     sr.mode = 2; sr.dense = ws->t_exact.as<float>(); sr.cand_ids = ws->t_ids.as<uint64_t>();
     sr.ncols = kk; sr.inner = kk; sr.row_stride = kk; sr.outer_stride = 0;
     sr.B = B; sr.k = sp.k; sr.out_ids = d_ids; sr.out_dist = d_dist; sr.out_count = d_cnt;
+    sr.only = only;
     launch_select(sr, st);
     mark();
 }
@@ -682,13 +689,24 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
                        RowFilter rf = RowFilter(), const Deadline *deadline = nullptr)
 {
     const uint32_t nprobes = std::min<uint32_t>(std::max<uint32_t>(sp.nprobes, 1), ix->nlist);
-    const uint32_t bs = ivf_sub_batch_size(ix, B, nprobes);
+    const uint32_t np_widest = rf.bits ? std::max(nprobes, std::min<uint32_t>(sp.max_nprobes, ix->nlist)) : nprobes;
+    const uint32_t bs = ivf_sub_batch_size(ix, B, np_widest);
     const bool prof = profiling_enabled();
     for (uint32_t q0 = 0; q0 < B; q0 += bs) {
         uint32_t b = std::min(bs, B - q0);
         if (deadline && q0 > 0) deadline->wait(st, ws->ev[7]);      // the previous sub-batch, or LGPU_TIMEOUT
         ivf_sub_batch(ix, ws, st, d_q + (size_t)q0 * ix->dim, b, sp, nprobes, d_ids + (size_t)q0 * sp.k,
                       d_dist + (size_t)q0 * sp.k, d_cnt + q0, prof && q0 == 0, nullptr, rf);
+        // maximum_nprobes (query.rs:1250-1275): under a prefilter, the queries that found fewer than k rows in their
+        // minimum_nprobes partitions are searched again over their maximum_nprobes nearest (no work if none is)
+        const uint32_t np_max = std::min<uint32_t>(sp.max_nprobes, ix->nlist);
+        if (rf.bits && np_max > nprobes) {
+            LGPU_REQUIRE(np_max <= SELECT_KMAX || np_max >= ix->nlist, "maximum_nprobes above 2048 is not supported");
+            ws->widen.ensure((size_t)b * 4);
+            launch_count_below(d_cnt + q0, b, sp.k, ws->widen.as<uint32_t>(), st);
+            ivf_sub_batch(ix, ws, st, d_q + (size_t)q0 * ix->dim, b, sp, np_max, d_ids + (size_t)q0 * sp.k,
+                          d_dist + (size_t)q0 * sp.k, d_cnt + q0, false, nullptr, rf, ws->widen.as<uint32_t>());
+        }
     }
     if (prof) {
         LGPU_CUDA(cudaStreamSynchronize(st));

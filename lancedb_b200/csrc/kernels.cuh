@@ -148,6 +148,8 @@ struct SelectArgs {
     uint64_t allow_bits;
 };
 void launch_select(const SelectArgs &a, cudaStream_t st);
+// flags[q] = cnt[q] < k (maximum_nprobes widening: the queries that did not find k rows)
+void launch_count_below(const uint32_t *cnt, uint32_t B, uint32_t k, uint32_t *flags, cudaStream_t st);
 // rec[i] = (ids[i], dist[i]) for i < n
 void launch_pack_records(const uint64_t *ids, const float *dist, uint64_t n, TopkRecord *out, cudaStream_t st);
 

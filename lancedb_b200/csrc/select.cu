@@ -434,6 +434,19 @@ __global__ void pack_records_kernel(const uint64_t *__restrict__ ids, const floa
 
 }  // namespace
 
+__global__ void count_below_kernel(const uint32_t *__restrict__ cnt, uint32_t B, uint32_t k, uint32_t *__restrict__ flags)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < B) flags[q] = cnt[q] < k ? 1u : 0u;
+}
+
+void launch_count_below(const uint32_t *cnt, uint32_t B, uint32_t k, uint32_t *flags, cudaStream_t st)
+{
+    if (B == 0) return;
+    count_below_kernel<<<(B + 255) / 256, 256, 0, st>>>(cnt, B, k, flags); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaGetLastError());
+}
+
 void launch_pack_records(const uint64_t *ids, const float *dist, uint64_t n, TopkRecord *out, cudaStream_t st)
 {
     if (n == 0) return;

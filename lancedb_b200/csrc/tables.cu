@@ -215,39 +215,59 @@ __global__ void row_const_kernel(const unsigned char *__restrict__ codes, const 
 }
 
 // exact PQ distance of (query, stored row) pairs, exactly as oracle.c::partition_distances:
-// residual -> sub-vector table entry (l2_once tree for dsub 8/16) -> sequential f32 sum -> metric scale
+// residual -> sub-vector table entry (l2_once tree for dsub 8/16) -> sequential f32 sum -> metric scale.
+// One WARP per pair: lane l evaluates the entries of sub-spaces l, l + 32, ... (independent loads of the code
+// byte, the codeword and the query / centroid sub-vectors), then the entries are summed in order i = 0..m-1
+// (the oracle's order) by walking them through a shuffle.  m <= 512.
 template <int DSUB>
-__global__ void pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *__restrict__ pos, uint32_t B, uint32_t nc,
-                                  const unsigned char *__restrict__ codes, const uint64_t *__restrict__ code_base,
-                                  const uint32_t *__restrict__ part_npad, const uint64_t *__restrict__ part_off,
-                                  uint32_t nlist, const float *__restrict__ centroids,
-                                  const float *__restrict__ cb_tiled, uint32_t dim, uint32_t m, int metric,
-                                  float *__restrict__ out)
+__global__ void __launch_bounds__(256) pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *__restrict__ pos,
+                                                         uint32_t B, uint32_t nc, const unsigned char *__restrict__ codes,
+                                                         const uint64_t *__restrict__ code_base,
+                                                         const uint32_t *__restrict__ part_npad,
+                                                         const uint64_t *__restrict__ part_off, uint32_t nlist,
+                                                         const float *__restrict__ centroids,
+                                                         const float *__restrict__ cb_tiled, uint32_t dim, uint32_t m,
+                                                         int metric, float *__restrict__ out)
 {
-    const uint64_t pair = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (pair >= (uint64_t)B * nc) return;
     const uint64_t ps = pos[pair];
-    if (ps == UINT64_MAX) { out[pair] = CUDART_INF_F; return; }
+    if (ps == UINT64_MAX) { if (lane == 0) out[pair] = CUDART_INF_F; return; }
     const uint32_t q = (uint32_t)(pair / nc);
     const uint32_t p = find_partition(part_off, nlist, ps);
     const uint32_t row = (uint32_t)(ps - part_off[p]);
     const float *qv = Q + (size_t)q * dim, *cen = centroids + (size_t)p * dim;
-    float acc = 0.f;
-    for (uint32_t i = 0; i < m; i++) {
-        const uint32_t c = stream_code(codes, code_base[p], part_npad[p], row, i);
-        const float *cb = cb_tiled + (((size_t)(i >> 3) * 256 + c) * 8 + (i & 7)) * DSUB;
-        float r[DSUB], cv[DSUB];
+    const uint64_t cbase = code_base[p];
+    const uint32_t npad = part_npad[p];
+    float tv[16];
 #pragma unroll
-        for (int t = 0; t < DSUB; t++) {
-            cv[t] = cb[t];
-            r[t] = (metric == LGPU_DOT) ? qv[i * DSUB + t] : __fsub_rn(qv[i * DSUB + t], cen[i * DSUB + t]);
+    for (int it = 0; it < 16; it++) {
+        tv[it] = 0.f;
+        const uint32_t i = (uint32_t)it * 32 + lane;
+        if ((uint32_t)it * 32 < m && i < m) {
+            const uint32_t c = stream_code(codes, cbase, npad, row, i);
+            const float *cb = cb_tiled + (((size_t)(i >> 3) * 256 + c) * 8 + (i & 7)) * DSUB;
+            float r[DSUB], cv[DSUB];
+#pragma unroll
+            for (int t = 0; t < DSUB; t++) {
+                cv[t] = cb[t];
+                r[t] = (metric == LGPU_DOT) ? qv[i * DSUB + t] : __fsub_rn(qv[i * DSUB + t], cen[i * DSUB + t]);
+            }
+            tv[it] = (metric == LGPU_DOT) ? subvec_dot_dist<DSUB>(r, cv) : subvec_l2<DSUB>(r, cv);
         }
-        const float e = (metric == LGPU_DOT) ? subvec_dot_dist<DSUB>(r, cv) : subvec_l2<DSUB>(r, cv);
-        acc = __fadd_rn(acc, e);
+    }
+    float acc = 0.f;
+#pragma unroll
+    for (int it = 0; it < 16; it++) {
+        if ((uint32_t)it * 32 < m) {
+            const uint32_t lim = min(32u, m - (uint32_t)it * 32);
+            for (uint32_t l = 0; l < lim; l++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, tv[it], (int)l));
+        }
     }
     if (metric == LGPU_COSINE) acc = __fmul_rn(acc, 0.5f);
     else if (metric == LGPU_DOT) acc = __fsub_rn(acc, (float)(m - 1));
-    out[pair] = acc;
+    if (lane == 0) out[pair] = acc;
 }
 
 // probe_A[slot] = coarse_dist - |q|^2 ; amax[q] = max_j coarse + |q|^2
@@ -355,9 +375,10 @@ void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t
                        float *out, cudaStream_t st)
 {
     if (B == 0 || nc == 0) return;
-    const uint64_t total = (uint64_t)B * nc;
+    if (m > 512) { set_error("internal: pq_rescore supports m <= 512"); throw Failure{LGPU_RUNTIME}; }
+    const uint64_t total = (uint64_t)B * nc * 32;              // one warp per pair
     dispatch_dsub(dsub, [&](auto D) {
-        pq_rescore_kernel<decltype(D)::value><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+        pq_rescore_kernel<decltype(D)::value><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
             Q, pos, B, nc, codes, code_base, part_npad, part_off, nlist, centroids, cb_tiled, dim, m, metric, out); LGPU_COUNT_LAUNCH();
     });
     LGPU_CUDA(cudaGetLastError());

@@ -33,7 +33,7 @@ class _Params(C.Structure):
     _fields_ = [
         ("k", C.c_uint32), ("nprobes", C.c_uint32), ("refine_factor", C.c_uint32),
         ("has_lower", C.c_int), ("has_upper", C.c_int), ("lower", C.c_float), ("upper", C.c_float),
-        ("allow", C.c_void_p), ("allow_bits", C.c_uint64),
+        ("allow", C.c_void_p), ("allow_bits", C.c_uint64), ("max_nprobes", C.c_uint32),
     ]
 
 
@@ -46,9 +46,9 @@ def allow_bitmap(row_ids, nbits: int) -> np.ndarray:
     return bm
 
 
-def _params(k, nprobes, refine_factor, lower, upper, allow=None, allow_bits=0):
+def _params(k, nprobes, refine_factor, lower, upper, allow=None, allow_bits=0, max_nprobes=0):
     p = _Params(k, nprobes, refine_factor, lower is not None, upper is not None,
-                0.0 if lower is None else lower, 0.0 if upper is None else upper, None, 0)
+                0.0 if lower is None else lower, 0.0 if upper is None else upper, None, 0, int(max_nprobes or 0))
     if allow is not None:
         p.allow = allow.ctypes.data
         p.allow_bits = int(allow_bits)
@@ -200,11 +200,11 @@ class OracleIndex:
         return out
 
     def search(self, queries, k=10, nprobes=20, refine_factor=0, lower=None, upper=None, nthreads=1,
-               allow=None, allow_bits=0):
+               allow=None, allow_bits=0, max_nprobes=0):
         q = _f32(queries).reshape(-1, self.dim)
         B = q.shape[0]
         allow = None if allow is None else np.ascontiguousarray(allow, np.uint32)
-        p = _params(k, nprobes, refine_factor, lower, upper, allow, allow_bits)
+        p = _params(k, nprobes, refine_factor, lower, upper, allow, allow_bits, max_nprobes)
         ids = np.empty((B, k), np.uint64)
         dist = np.empty((B, k), np.float32)
         cnt = np.empty(B, np.uint32)

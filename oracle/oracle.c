@@ -327,28 +327,38 @@ static void *ivf_worker(void *arg)
     const orc_index *ix = job->ix;
     const orc_params *p = job->p;
     uint32_t dim = ix->dim, nprobes = p->nprobes < ix->nlist ? p->nprobes : ix->nlist;
+    /* maximum_nprobes (rust/lancedb/src/query.rs:1250-1275): "the excess partitions will only be searched if
+     * the initial search does not return enough results ... useful when there is a narrow filter".  Restated as:
+     * under a prefilter, a query whose minimum_nprobes partitions yield fewer than k rows is searched again
+     * over its maximum_nprobes nearest partitions. */
+    uint32_t nprobes_max = nprobes;
+    if (p->allow && p->max_nprobes > nprobes) nprobes_max = p->max_nprobes < ix->nlist ? p->max_nprobes : ix->nlist;
     uint32_t kk = p->refine_factor ? p->k * p->refine_factor : p->k;
     float *qn = (float *)malloc(sizeof(float) * dim * 2);
     float *resid = qn + dim;
     float *lut = (float *)malloc(sizeof(float) * ix->m * 256);
     float *dists = (float *)malloc(sizeof(float) * (job->max_part ? job->max_part : 1));
-    uint32_t *parts = (uint32_t *)malloc(sizeof(uint32_t) * (nprobes ? nprobes : 1));
+    uint32_t *parts = (uint32_t *)malloc(sizeof(uint32_t) * (nprobes_max ? nprobes_max : 1));
     heap_t h; h.a = (cand_t *)malloc(sizeof(cand_t) * (kk ? kk : 1)); h.cap = kk;
 
     for (uint32_t qi = job->q0; qi < job->q1; qi++) {
         const float *q = job->queries + (size_t)qi * dim;
         if (ix->metric == ORC_COSINE) orc_normalize_f32(q, dim, qn);
         else memcpy(qn, q, sizeof(float) * dim);
-        orc_find_partitions(ix, qn, nprobes, parts, NULL, NULL);
-        h.n = 0;
-        for (uint32_t j = 0; j < nprobes; j++) {
-            uint32_t part = parts[j];
-            size_t off = ix->part_offsets[part], n = ix->part_offsets[part + 1] - off;
-            if (n == 0) continue;
-            partition_distances(ix, qn, part, resid, lut, dists);
-            for (size_t r = 0; r < n; r++)
-                if (in_range(p, dists[r]) && allowed(p, ix->row_ids[off + r]))
-                    heap_offer(&h, dists[r], ix->row_ids[off + r], off + r);
+        for (uint32_t np_use = nprobes;;) {
+            orc_find_partitions(ix, qn, np_use, parts, NULL, NULL);
+            h.n = 0;
+            for (uint32_t j = 0; j < np_use; j++) {
+                uint32_t part = parts[j];
+                size_t off = ix->part_offsets[part], n = ix->part_offsets[part + 1] - off;
+                if (n == 0) continue;
+                partition_distances(ix, qn, part, resid, lut, dists);
+                for (size_t r = 0; r < n; r++)
+                    if (in_range(p, dists[r]) && allowed(p, ix->row_ids[off + r]))
+                        heap_offer(&h, dists[r], ix->row_ids[off + r], off + r);
+            }
+            if (np_use >= nprobes_max || h.n >= p->k) break;
+            np_use = nprobes_max;
         }
         if (p->refine_factor && ix->vectors) {
             /* refine (rust/lancedb/src/query.rs:1302-1332): exact distance of the

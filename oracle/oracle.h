@@ -73,6 +73,9 @@ typedef struct {
      * partitions hold that many. */
     const uint32_t *allow;
     uint64_t allow_bits;
+    /* maximum_nprobes (rust/lancedb/src/query.rs:1250-1275); 0 or <= nprobes = no widening.  Only consulted
+     * under a prefilter. */
+    uint32_t max_nprobes;
 } orc_params;
 
 /* IvfModel::find_partitions [lance, recalled]: all-centroid distances, then the

@@ -304,3 +304,37 @@ def test_streaming_scan_many_tiles_dsub8(metric):
     sizes = rng.integers(1, 260, size=nlist)
     ix = random_index(rng, dim=160, nlist=nlist, m=20, metric=metric, sizes=sizes)
     _check_search(ix, queries(rng, 500, 160), k=10, nprobes=12)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_maximum_nprobes_widening_under_a_selective_prefilter(metric):
+    """rust/lancedb/src/query.rs:1250-1275: "the excess partitions will only be searched if the initial search
+    does not return enough results ... useful when there is a narrow filter".  With a 1 % allow-list and
+    minimum_nprobes = 2 most queries find fewer than k rows; those (and only those) must be answered from their
+    maximum_nprobes nearest partitions, exactly as the oracle's restatement does."""
+    rng = np.random.default_rng(41)
+    n = 20000
+    ix = random_index(rng, dim=64, nlist=32, m=8, metric=metric, n=n, shuffle_ids=False)
+    q = queries(rng, 60, 64)
+    keep = rng.random(n) < 0.01
+    bm = oracle.allow_bitmap(np.nonzero(keep)[0], n)
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    narrow = gpu.search(q, k=10, nprobes=2, allow=bm, allow_bits=n)
+    wide = gpu.search(q, k=10, nprobes=2, max_nprobes=24, allow=bm, allow_bits=n)
+    o_narrow = orc.search(q, k=10, nprobes=2, allow=bm, allow_bits=n)
+    o_wide = orc.search(q, k=10, nprobes=2, max_nprobes=24, allow=bm, allow_bits=n)
+    o_24 = orc.search(q, k=10, nprobes=24, allow=bm, allow_bits=n)
+    gpu.close()
+    for got, want in ((narrow, o_narrow), (wide, o_wide)):
+        assert np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0])
+        assert np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    short = o_narrow[2] < 10
+    assert short.any() and (~short).any()                       # the case has both kinds of queries
+    assert np.array_equal(o_wide[0][short], o_24[0][short])      # widened queries = a 24-probe search
+    assert np.array_equal(o_wide[0][~short], o_narrow[0][~short])  # the others are untouched
+    # without a filter maximum_nprobes changes nothing
+    gpu = _native.GpuIvfPq(ix)
+    a = gpu.search(q, k=10, nprobes=2); b = gpu.search(q, k=10, nprobes=2, max_nprobes=24)
+    gpu.close()
+    assert np.array_equal(a[0], b[0])
