@@ -104,7 +104,8 @@ struct Workspace {
     int graph_state = 0;                // 0: next call runs eagerly (warm-up), 1: capture, 2: replay, -1: disabled
     DevBuf sbound, probe_A, amax;       // tensor-core shortlists: thresholds / counters; filter scan: bounds, per-probe scalars
     DevBuf qt, qt_mm, qt_step, qt_base, qt_bad;   // filter scan (scan3.cu): quantised per-query tables
-    DevBuf s_ids, s_lb, s_pos, s_cnt, s_exact;    // filter scan: shortlist by lower bound, exact re-score
+    DevBuf s_ids, s_lb, s_pos, s_cnt, s_exact;    // filter scan (dense mode): shortlist by lower bound, exact re-score
+    DevBuf c_thr, c_slack, c_cnt, c_rec;          // filter scan (candidate mode): thresholds, bands, candidate lists
     Workspace()
     {
         LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -203,6 +204,8 @@ struct lgpu_index {
     uint64_t nrows = 0, device_bytes = 0;
     DevBuf centroids, cb_tiled, codes, code_base, part_n, part_npad, part_off, row_ids, vectors;
     DevBuf row_R, rmax_bits;            // filter scan: per-row constant 2 b.c and max |R| (tables.cu)
+    DevBuf cb_n2;                       // filter scan: |b|^2 of every tiled codebook entry
+    float cb2 = 0.f;                    // sum_i max_c |codebook_i[c]|^2 (error budget of the filter's table entries)
     bool has_tables = false;
     DevBuf cent_b, cent_n2;             // bf16 centroids + |c|^2 for the tensor-core coarse step
     float cent_max = 0.f;
@@ -607,16 +610,48 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         ws->sbound.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
         ws->s_ids.ensure((size_t)B * kp * 8); ws->s_lb.ensure((size_t)B * kp * 4); ws->s_pos.ensure((size_t)B * kp * 8);
         ws->s_cnt.ensure((size_t)B * 4); ws->s_exact.ensure((size_t)B * kp * 4);
-        launch_query_tables_q16(qsearch, ix->cb_tiled.as<float>(), B, dim, ix->m, ix->nch, ix->dsub, ix->metric,
+        launch_query_tables_q16(qsearch, ix->cb_tiled.as<float>(), ix->cb_n2.as<float>(), B, dim, ix->m, ix->nch, ix->dsub, ix->metric,
                                 ws->qt_mm.as<float>(), ws->qt.as<uint4>(), ws->qt_step.as<float>(), ws->qt_base.as<float>(),
                                 ws->sbound.as<float>(), ws->qt_bad.as<uint32_t>(), st);
+        ws->qn2.ensure((size_t)B * 4);
         if (!dot) {
             ws->probe_A.ensure((size_t)slots * 4); ws->amax.ensure((size_t)B * 4);
-            launch_probe_terms(ws->probe_dist.as<float>(), qsearch, B, nprobes, dim, ws->probe_A.as<float>(),
-                               ws->amax.as<float>(), st);
             sc.probe_A = ws->probe_A.as<float>(); sc.row_R = ix->row_R.as<float>();
         }
+        launch_probe_terms(ws->probe_dist.as<float>(), qsearch, B, nprobes, dim, dot ? nullptr : ws->probe_A.as<float>(),
+                           dot ? nullptr : ws->amax.as<float>(), ws->qn2.as<float>(), st);
         sc.qt = ws->qt.as<uint4>(); sc.qt_step = ws->qt_step.as<float>(); sc.qt_base = ws->qt_base.as<float>();
+        const float mscale = ix->metric == LGPU_COSINE ? 0.5f : 1.0f;
+        // candidate mode (no prefilter, k <= 32): the scanners threshold the rows themselves, nothing dense is written
+        static const bool dense_forced = getenv("LGPU_DENSE_FILTER") != nullptr;
+        const bool cand_mode = !rf.bits && kk <= CAND_TOPK_MAX && !dense_forced;
+        if (cand_mode) {
+            // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
+            static const uint32_t cap_env = getenv("LGPU_CAND_CAP") ? (uint32_t)atoi(getenv("LGPU_CAND_CAP")) : 0u;
+            uint32_t cap = 512;
+            if (cap_env >= 32 && cap_env <= 4096 && !(cap_env & (cap_env - 1))) cap = cap_env;
+            ws->c_thr.ensure((size_t)B * 4); ws->c_slack.ensure((size_t)B * 4); ws->c_cnt.ensure((size_t)B * 4);
+            ws->c_rec.ensure((size_t)B * cap * sizeof(CandRec));
+            launch_cand_prepare(ws->qt_step.as<float>(), ws->sbound.as<float>(), dot ? nullptr : ws->amax.as<float>(),
+                                dot ? nullptr : ix->rmax_bits.as<int>(), ws->qn2.as<float>(), ix->cb2, mscale, ix->m, B,
+                                ws->c_slack.as<float>(), ws->c_thr.as<uint32_t>(), ws->c_cnt.as<uint32_t>(), st);
+            sc.nprobes = nprobes; sc.topk = kk; sc.thr = ws->c_thr.as<uint32_t>(); sc.slack = ws->c_slack.as<float>();
+            sc.cand_cnt = ws->c_cnt.as<uint32_t>(); sc.cand = ws->c_rec.as<CandRec>(); sc.cand_cap = cap;
+            launch_scan3(sc, ix->num_sms, st);
+            mark();
+            FinalizeArgs fa{};
+            fa.Q = qsearch; fa.cand = sc.cand; fa.cand_cnt = sc.cand_cnt; fa.cand_cap = cap; fa.thr = sc.thr;
+            fa.slack = sc.slack; fa.bad = ws->qt_bad.as<uint32_t>();
+            fa.codes = ix->codes.as<unsigned char>(); fa.code_base = ix->code_base.as<uint64_t>();
+            fa.part_npad = ix->part_npad.as<uint32_t>(); fa.part_off = ix->part_off.as<uint64_t>();
+            fa.row_ids = ix->row_ids.as<uint64_t>(); fa.centroids = ix->centroids.as<float>();
+            fa.cb_tiled = ix->cb_tiled.as<float>();
+            fa.B = B; fa.dim = dim; fa.m = ix->m; fa.dsub = ix->dsub; fa.k = kk; fa.metric = ix->metric;
+            fa.out_ids = pq_ids; fa.out_dist = pq_dist; fa.out_count = pq_cnt; fa.out_pos = pq_pos;
+            fa.flags = ws->flags.as<uint32_t>();
+            launch_cand_finalize(fa, st);
+            sc.cand = nullptr;                      // (the fix-up pass below is the exact kernel)
+        } else {
         launch_scan3(sc, ix->num_sms, st);
         mark();
         // shortlist: the kp smallest lower bounds (with their storage positions)
@@ -626,7 +661,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         launch_select(ss, st);
         launch_band_check3(ws->s_lb.as<float>(), ws->s_cnt.as<uint32_t>(), ws->qt_step.as<float>(), ws->sbound.as<float>(),
                            dot ? nullptr : ws->amax.as<float>(), dot ? nullptr : ix->rmax_bits.as<int>(),
-                           ws->qt_bad.as<uint32_t>(), ix->metric == LGPU_COSINE ? 0.5f : 1.0f, ix->m, B, kk, kp,
+                           ws->qt_bad.as<uint32_t>(), ws->qn2.as<float>(), ix->cb2, mscale, ix->m, B, kk, kp,
                            ws->flags.as<uint32_t>(), st);
         // exact PQ distances of the shortlist (oracle arithmetic), then the kk best of those
         launch_pq_rescore(qsearch, ws->s_pos.as<uint64_t>(), B, kp, ix->codes.as<unsigned char>(),
@@ -639,6 +674,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         sb.ncols = kp; sb.inner = kp; sb.row_stride = kp; sb.outer_stride = 0;
         sb.B = B; sb.k = kk; sb.out_ids = pq_ids; sb.out_dist = pq_dist; sb.out_count = pq_cnt; sb.out_pos = pq_pos;
         launch_select(sb, st);
+        }
         // fix-up of the queries whose shortlist could not be proven (no tiles, hence no work, unless one is
         // flagged): regroup them alone, exact scan, exact top-kk over their segments
         ga.only = ws->flags.as<uint32_t>();
@@ -1022,6 +1058,24 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
                                     ix->part_npad.as<uint32_t>(), ix->codes.as<unsigned char>(), st);
             }
             LGPU_CUDA(cudaStreamSynchronize(st));
+        }
+        {   // |b|^2 of the tiled codebook entries and CB2 = sum_i max_c |b|^2 (filter scan, tables.cu)
+            const size_t ne = (size_t)ix->nch * 256 * 8;
+            ix->cb_n2.ensure(ne * 4);
+            ix->device_bytes += ix->cb_n2.bytes;
+            launch_cb_norms(ix->cb_tiled.as<float>(), ix->nch, ix->dsub, ix->cb_n2.as<float>(), st);
+            double cb2 = 0.0;
+            for (uint32_t i = 0; i < d->m; i++) {
+                double mx = 0.0;
+                for (uint32_t c = 0; c < 256; c++) {
+                    double n2 = 0.0;
+                    const float *e = d->codebook + ((size_t)i * 256 + c) * ix->dsub;
+                    for (uint32_t t = 0; t < ix->dsub; t++) n2 += (double)e[t] * e[t];
+                    mx = std::max(mx, n2);
+                }
+                cb2 += mx;
+            }
+            ix->cb2 = (float)(cb2 * 1.000001);
         }
         if (d->metric != LGPU_DOT) {   // per-row constants of the filter scan (tables.cu)
             ix->row_R.ensure(std::max<size_t>((size_t)d->nrows * 4, 16));

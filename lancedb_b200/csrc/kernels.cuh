@@ -8,7 +8,7 @@ namespace lgpu {
 // ---------------- scan (K2+K3) geometry ------------------------------------------
 constexpr int SCAN_G = 8;                         // queries per tile
 constexpr uint32_t SCAN_ROWS_TILE_MID = 4 * 32 * 12;   // exact kernel (scan2.cu): 2 x 128 scanner threads x 12 rows
-constexpr uint32_t SCAN3_ROWS_TILE = 8 * 32 * 12;      // filter kernel (scan3.cu): 256 scanner threads x 12 rows
+constexpr uint32_t SCAN3_ROWS_TILE = 8 * 32 * 6;       // filter kernel (scan3.cu): 256 scanner threads x 6 rows
 constexpr int SCAN_LUT_HALF = 32768;              // exact kernel: [256 c][8 s][4 g] f32
 constexpr int SCAN_LUT_BYTES = 2 * SCAN_LUT_HALF; // [2 h] halves
 
@@ -31,6 +31,15 @@ struct alignas(16) TileDesc {
     uint32_t out[SCAN_G];         // offset (floats) of the slot's distance segment; sub-batches keep it < 2^32
 };
 static_assert(sizeof(TileDesc) == 112, "TileDesc layout");
+
+// one surviving row of the filter scan's candidate mode
+struct alignas(16) CandRec {
+    float lb;                     // lower bound L of the row's distance
+    uint32_t p, row;              // partition and row inside it
+    uint32_t pad;
+};
+constexpr uint32_t CAND_NO_THR = 0xffffffffu;
+constexpr uint32_t CAND_TOPK_MAX = 32;
 
 struct ScanArgs {
     // index (device)
@@ -56,6 +65,14 @@ struct ScanArgs {
     const float *probe_A;         // [B*nprobes] |q - c_p|^2 - |q|^2   (nullptr for dot)
     const float *row_R;           // [nrows] 2 * codeword(row) . c_p  (nullptr for dot)
     const uint64_t *part_off;     // [nlist+1]
+    // filter pass, candidate mode (cand != nullptr): instead of one f32 per (row, query) in dist_out, the scanners
+    // keep a running per-query threshold and append only the rows that can still be among the exact top-k
+    uint32_t nprobes, topk;       // probe slots per query; k (the number of neighbours the threshold is for, <= 32)
+    uint32_t *thr;                // [B] ordered-uint key (f32_key) of tau_q, CAND_NO_THR = none yet; atomicMin
+    const float *slack;           // [B] scale (W + 2E): a row survives iff L <= tau_q + slack_q
+    uint32_t *cand_cnt;           // [B] appended candidates (may exceed cand_cap: the overflow is dropped and flagged)
+    CandRec *cand;                // [B][cand_cap]
+    uint32_t cand_cap;
 };
 bool scan_dsub_supported(uint32_t dsub);
 // exact kernel (scan2.cu): residual -> f32 table chunk -> sequential code scan, bit-identical to the oracle;
@@ -187,9 +204,11 @@ void launch_band_check(const float *approx, const uint32_t *cnt, const float *qn
 // step[q] = max_i (max_c T - min_c T) / qmax, base[q] = sum_i min_i (- (m - 1) for dot),
 // sbound[q] = sum_i max_c |T|, bad[q] = 1 when the table is not finite (the query takes the exact path).
 // mm: scratch [B][8 nch][2].
-void launch_query_tables_q16(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
-                             uint32_t dsub, int metric, float *mm, uint4 *qt, float *step, float *base, float *sbound,
-                             uint32_t *bad, cudaStream_t st);
+void launch_query_tables_q16(const float *Q, const float *cb_tiled, const float *cb_n2, uint32_t B, uint32_t dim,
+                             uint32_t m, uint32_t nch, uint32_t dsub, int metric, float *mm, uint4 *qt, float *step,
+                             float *base, float *sbound, uint32_t *bad, cudaStream_t st);
+// out[e] = |cb_tiled entry e|^2 for the nch * 256 * 8 tiled codebook entries (open time)
+void launch_cb_norms(const float *cb_tiled, uint32_t nch, uint32_t dsub, float *out, cudaStream_t st);
 // R[row] = 2 * codeword(row) . centroid(partition(row)); *rmax_bits = float bits of max |R|
 void launch_row_const(const unsigned char *codes, const uint64_t *code_base, const uint32_t *part_npad,
                       const uint64_t *part_off, uint32_t nlist, uint64_t nrows, const float *centroids,
@@ -200,15 +219,36 @@ void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t
                        const uint64_t *code_base, const uint32_t *part_npad, const uint64_t *part_off, uint32_t nlist,
                        const float *centroids, const float *cb_tiled, uint32_t dim, uint32_t m, uint32_t dsub, int metric,
                        float *out, cudaStream_t st);
-// probe_A[slot] = coarse_dist[slot] - |q|^2, amax[q] = max_j coarse + |q|^2
+// probe_A[slot] = coarse_dist[slot] - |q|^2, amax[q] = max_j coarse + |q|^2, qn2[q] = |q|^2
+// (probe_A / amax may be null: dot has no residual)
 void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uint32_t nprobes, uint32_t dim,
-                        float *probe_A, float *amax, cudaStream_t st);
+                        float *probe_A, float *amax, float *qn2, cudaStream_t st);
+// the band of every query, for the candidate mode: slack[q] = scale (W + 2E) (same W, E as launch_band_check3);
+// also resets thr[q] = CAND_NO_THR and cand_cnt[q] = 0
+void launch_cand_prepare(const float *step, const float *sbound, const float *amax, const int *rmax_bits, const float *qn2,
+                         float cb2, float scale, uint32_t m, uint32_t B, float *slack, uint32_t *thr, uint32_t *cand_cnt,
+                         cudaStream_t st);
+// candidate mode, after the scan: per query, drop the candidates above the final threshold, re-score the survivors
+// exactly (oracle arithmetic, as launch_pq_rescore), and write the k best by (_distance, _rowid) -- ids, distances,
+// count and (optional) storage positions.  flags[q] = 1 when the query must be redone by the exact kernels (list
+// overflow, or bad[q]); such a query's outputs are overwritten by the fix-up pass.
+struct FinalizeArgs {
+    const float *Q;               // [B][dim] (normalised for cosine)
+    const CandRec *cand; const uint32_t *cand_cnt; uint32_t cand_cap;
+    const uint32_t *thr; const float *slack; const uint32_t *bad;
+    const unsigned char *codes; const uint64_t *code_base; const uint32_t *part_npad; const uint64_t *part_off;
+    const uint64_t *row_ids; const float *centroids; const float *cb_tiled;
+    uint32_t B, dim, m, dsub, k; int metric;
+    uint64_t *out_ids; float *out_dist; uint32_t *out_count; uint64_t *out_pos; uint32_t *flags;
+};
+void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st);
 // flags[q] = 1 when the shortlist of q (lower bounds `lb` ascending, [B][kp], cnt valid) cannot be proven to hold
 // the exact top-k: proven iff cnt < kp or lb[kp-1] > lb[k-1] + scale (W + 2E),  W = m step (1 + 2^-10),
-// E = 2^-15 ceil(m/96) (sbound + amax + rmax); also 1 when bad[q].  amax / rmax_bits may be null (dot).
+// E = 2^-15 ceil(m/96) (sbound + amax + rmax + m + 2 (qn2 + cb2)); also 1 when bad[q].  amax / rmax_bits may be null
+// (dot).  cb2 = sum_i max_c |codebook_i[c]|^2.
 void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
-                        const int *rmax_bits, const uint32_t *bad, float scale, uint32_t m, uint32_t B, uint32_t k,
-                        uint32_t kp, uint32_t *flags, cudaStream_t st);
+                        const int *rmax_bits, const uint32_t *bad, const float *qn2, float cb2, float scale, uint32_t m,
+                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st);
 
 // ---------------- index build (build.cu) ----------------------------------------------
 // codes[row][i] = argmin_c entry(row's residual sub-vector i, codebook_i[c]) (ties: lowest c); X normalised for cosine

@@ -20,7 +20,7 @@
 // Pipeline: identical hand-over protocol to scan2.cu (tests/test_scan2_protocol.py models it): persistent CTAs,
 // a ring of three shared chunk buffers, named barriers FULL/EMPTY between 8 stager warps and 8 scanner warps, the
 // stage counter running on across tiles, tile descriptors claimed two tiles ahead.
-//   tile    = (partition, <= 8 of the queries probing it, <= 3072 rows)
+//   tile    = (partition, <= 8 of the queries probing it, <= 1536 rows); two CTAs per SM
 //   chunk   = 8 sub-spaces: shared [256 codes][8 sub-spaces][8 queries] u16 = 32 KB
 //   stagers : thread c owns code c.  It loads the 16 bytes (8 sub-spaces) of each of the tile's queries for code c
 //             from the L2-resident query tables (8 x LDG.128, issued a whole stage ahead), transposes 8x8 u16 in
@@ -28,12 +28,14 @@
 //             stored ROTATED -- position j of code c holds sub-space (j + c) mod 8 -- so that in step j the eight
 //             lanes of a quarter-warp write eight different 16-byte slots: conflict-free without a per-lane
 //             register rotation.
-//   scanners: thread = rows row0 + ct + 256 r (r < 12); the skewed code stream (retile.cu) makes the eight lanes of
+//   scanners: thread = rows row0 + ct + 256 r (r < 6); the skewed code stream (retile.cu) makes the eight lanes of
 //             a quarter-warp read eight different sub-space slots, so every LDS.128 is conflict-free whatever the
 //             codes are; accumulators are 4 x u32 per row (8 queries x u16).
 // Algorithmic bytes per tile row and query: m code bytes, as for the exact kernel.
 #include "kernels.cuh"
 #include "scan_common.cuh"
+
+#include <math_constants.h>
 
 namespace lgpu {
 
@@ -41,7 +43,12 @@ namespace {
 
 constexpr int S3_PW = 8, S3_CW = 8;                 // stager / scanner warps
 constexpr int S3_PT = S3_PW * 32, S3_CT = S3_CW * 32, S3_NT = S3_PT + S3_CT;
-constexpr int S3_RMAX = 12;                         // rows per scanner thread
+constexpr int S3_RMAX = 6;                          // rows per scanner thread
+// two CTAs per SM (2 x 512 threads, 2 x 97 KB of shared memory): while one CTA sits in a tile's prologue /
+// epilogue or at a barrier, the other keeps the shared-memory pipe busy.  64 registers per thread at launch,
+// re-split by role: the stagers hold one 32-register slab, the scanners 6 rows x (4 accumulators + 2 + 2 code words)
+constexpr int S3_PREG = 48, S3_CREG = 80;
+static_assert(S3_PT * S3_PREG + S3_CT * S3_CREG <= 32768, "register budget of half an SM");
 constexpr int S3_BUF = 32768;                       // one chunk buffer
 constexpr int S3_SLOTS = 4, S3_SLOT_BYTES = 128;    // tile-descriptor ring
 constexpr size_t S3_TILES = 3 * (size_t)S3_BUF;
@@ -73,14 +80,16 @@ __device__ __forceinline__ uint32_t word_of(const uint4 &v, int w)
 struct Slab {
     uint4 v[SCAN_G];            // code c of the tile's 8 queries: 8 rotated sub-space entries each
 };
+// Unused query slots of a tile (g >= ng) load query slot 0's entries again: an L1 hit, no branch, and sums that
+// nobody reads but that still fit their 16-bit lane.
 __device__ __forceinline__ void slab_load(Slab &s, const ScanArgs &a, const TileDesc *T, uint32_t ch, uint32_t c)
 {
     const int ng = (int)T->ng;
+    const uint32_t q0 = T->q[0];
 #pragma unroll
     for (int g = 0; g < SCAN_G; g++) {
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (g < ng) v = __ldg(a.qt + ((size_t)T->q[g] * a.nch + ch) * 256 + c);
-        s.v[g] = v;
+        const uint32_t q = g < ng ? T->q[g] : q0;
+        s.v[g] = __ldg(a.qt + ((size_t)q * a.nch + ch) * 256 + c);
     }
 }
 // unit j of code c = sub-space (j + c) & 7: (query 0..7) x u16, written to [c][(j + c) & 7]
@@ -108,7 +117,10 @@ __device__ __forceinline__ void stager_loop(const ScanArgs &a, uint32_t total, i
     const int lane = tid & 31, pw = tid >> 5;
     const uint32_t nch = a.nch, c = (uint32_t)tid;
 
-    Slab cur, nxt;
+    // One slab in registers.  The loads of the next data stage are issued right after this stage's slab has been
+    // written to shared memory, i.e. a whole scanner stage before they are needed: they land while the stagers
+    // wait for the ring buffer to come free.
+    Slab cur;
     {
         const TileDesc *T0 = slot3(tiles, 0);
         if (T0->ng) slab_load(cur, a, T0, 0, c);
@@ -133,22 +145,19 @@ __device__ __forceinline__ void stager_loop(const ScanArgs &a, uint32_t total, i
                         t_word = __ldg(reinterpret_cast<const uint32_t *>(a.tile_desc + t_claim) + lane);
                 }
             }
-            // --- the next data stage's table slab, a whole stage ahead: the next chunk of this tile, or (while
-            // the last chunk is stored and through the zero stage) chunk 0 of the next tile ---
-            bool have_next = false;
-            if (ch + 1 < nch) { slab_load(nxt, a, T, ch + 1, c); have_next = true; }
-            else if (ch + 1 == nch && next_tile) { slab_load(nxt, a, Tn, 0, c); have_next = true; }
-
             if (gs >= 2) bar_sync(BAR_EMPTY + b, S3_NT);           // scanners are done with stage gs-2
             if (ch == nch) {                                       // all-zero code-0 row for the lagging lanes
                 if (tid < 32) reinterpret_cast<uint32_t *>(smem + b * S3_BUF)[tid] = 0u;
             } else {
                 slab_store(cur, lut + (uint32_t)b * S3_BUF, c);
+                // the next data stage: the next chunk of this tile, or chunk 0 of the next tile (which then
+                // rides through the zero stage)
+                if (ch + 1 < nch) slab_load(cur, a, T, ch + 1, c);
+                else if (next_tile) slab_load(cur, a, Tn, 0, c);
             }
             if (pw == 0 && ch == 1 && lane < (int)(sizeof(TileDesc) / 4))   // publish tile n+2 before FULL(stage 1)
                 reinterpret_cast<uint32_t *>(const_cast<TileDesc *>(slot3(tiles, n + 2)))[lane] = t_word;
             bar_arrive(BAR_FULL + b, S3_NT);
-            if (have_next) cur = nxt;
             bar_sync(BAR_PROD, S3_PT);
             b = ring_next3(b);
             gs++;
@@ -211,25 +220,106 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
         b = ring_next3(b);
     }
 
-    // ---- epilogue: lower bound L = step_q * sum + (base_q + A(q,p)) + R(row), one f32 per (row, query) ----
+    // ---- epilogue: lower bound L = step_q * sum + (base_q + A(q,p)) + R(row) per (row, query) ----
     const float scale = a.metric == LGPU_COSINE ? 0.5f : 1.0f;
     const uint64_t pos0 = a.part_off[p];
     float rr[R];
 #pragma unroll
     for (int r = 0; r < R; r++)
         rr[r] = (valid[r] && a.row_R) ? __ldg(a.row_R + pos0 + row0 + ct + r * S3_CT) : 0.f;
+    if (a.cand == nullptr) {
+        // dense mode: one f32 per (row, query) to HBM; the caller selects a shortlist from them
 #pragma unroll
-    for (int g = 0; g < SCAN_G; g++) {
-        if (g < ng) {
-            const uint32_t q = T->q[g];
-            const float step = __ldg(a.qt_step + q);
-            const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + T->slot[g]) : 0.f);
-            float *out = a.dist_out + T->out[g];
+        for (int g = 0; g < SCAN_G; g++) {
+            if (g < ng) {
+                const uint32_t q = T->q[g];
+                const float step = __ldg(a.qt_step + q);
+                const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + T->slot[g]) : 0.f);
+                float *out = a.dist_out + T->out[g];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (valid[r]) {
+                        const uint32_t s = (g & 1) ? (acc[r][g >> 1] >> 16) : (acc[r][g >> 1] & 0xffffu);
+                        out[row0 + ct + r * S3_CT] = (fmaf(step, (float)s, cst) + rr[r]) * scale;
+                    }
+                }
+            }
+        }
+        return b;
+    }
+    // candidate mode.  tau_q (global, atomicMin) is any value such that at least k rows of the query have L <= tau_q:
+    // then the k-th smallest exact distance is <= tau_q + W + E and every row of the exact top-k has
+    // L <= tau_q + W + 2E = tau_q + slack_q.  A warp tightens tau_q from its own rows (k-th smallest of its <= 32 R
+    // lower bounds, by bisection) when the query has no threshold yet or when this is one of its three nearest
+    // partitions -- that is where the small distances are; every warp then appends the rows under the threshold.
+    const int lane = ct & 31;
+    const uint32_t k = a.topk;
+#pragma unroll 1
+    for (int g = 0; g < ng; g++) {
+        const uint32_t q = T->q[g], slot = T->slot[g];
+        const float step = __ldg(a.qt_step + q);
+        const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + slot) : 0.f);
+        const float slack = __ldg(a.slack + q);
+        float L[R];
+        uint32_t nvalid = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t w = (g & 2) ? ((g & 4) ? acc[r][3] : acc[r][1]) : ((g & 4) ? acc[r][2] : acc[r][0]);
+            const uint32_t s = (g & 1) ? (w >> 16) : (w & 0xffffu);
+            L[r] = valid[r] ? (fmaf(step, (float)s, cst) + rr[r]) * scale : CUDART_INF_F;
+            nvalid += valid[r] ? 1u : 0u;
+        }
+        uint32_t tkey = __ldcg(a.thr + q);
+        const uint32_t rank = slot - q * a.nprobes;
+        if (tkey == CAND_NO_THR || rank < 3u) {
+            const uint32_t wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+            if (wvalid >= k) {
+                uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+                for (int r = 0; r < R; r++)
+                    if (valid[r]) { const uint32_t kk = f32_key(L[r]); kmin = min(kmin, kk); kmax = max(kmax, kk); }
+                float lo = key_f32(__reduce_min_sync(0xffffffffu, kmin));
+                float hi = key_f32(__reduce_max_sync(0xffffffffu, kmax));
+                if (hi < CUDART_INF_F && lo == lo && hi == hi) {       // invariant: count(L <= hi) >= k
+#pragma unroll 1
+                    for (int it = 0; it < 10; it++) {
+                        const float mid = 0.5f * lo + 0.5f * hi;
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int r = 0; r < R; r++) c += L[r] <= mid ? 1u : 0u;
+                        c = __reduce_add_sync(0xffffffffu, c);
+                        if (c >= k) hi = mid; else lo = mid;
+                    }
+                    const uint32_t nk = f32_key(hi);
+                    if (nk < tkey) {
+                        if (lane == 0) atomicMin(a.thr + q, nk);
+                        tkey = nk;
+                    }
+                }
+            }
+        }
+        const float lim = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey) + slack;
+        uint32_t npass = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) npass += (valid[r] && L[r] <= lim) ? 1u : 0u;
+        const uint32_t wpass = __reduce_add_sync(0xffffffffu, npass);
+        if (wpass) {
+            uint32_t pre = npass;                          // inclusive scan over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += t;
+            }
+            uint32_t base = 0;
+            if (lane == 31) base = atomicAdd(a.cand_cnt + q, wpass);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            uint32_t at = base + pre - npass;
+            CandRec *dst = a.cand + (size_t)q * a.cand_cap;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                if (valid[r]) {
-                    const uint32_t s = (g & 1) ? (acc[r][g >> 1] >> 16) : (acc[r][g >> 1] & 0xffffu);
-                    out[row0 + ct + r * S3_CT] = (fmaf(step, (float)s, cst) + rr[r]) * scale;
+                if (valid[r] && L[r] <= lim) {
+                    if (at < a.cand_cap) { CandRec rec; rec.lb = L[r]; rec.p = p; rec.row = row0 + ct + r * S3_CT; rec.pad = 0u; dst[at] = rec; }
+                    at++;
                 }
             }
         }
@@ -251,15 +341,12 @@ __device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
 #define LGPU_SCAN3(RR) b = scan_tile<RR>(a, T, next_exists, b, ct)
         if (R <= 2) LGPU_SCAN3(2);
         else if (R <= 4) LGPU_SCAN3(4);
-        else if (R <= 6) LGPU_SCAN3(6);
-        else if (R <= 8) LGPU_SCAN3(8);
-        else if (R <= 10) LGPU_SCAN3(10);
-        else LGPU_SCAN3(12);
+        else LGPU_SCAN3(6);
 #undef LGPU_SCAN3
     }
 }
 
-__global__ void __launch_bounds__(S3_NT, 1) scan3_kernel(ScanArgs a)
+__global__ void __launch_bounds__(S3_NT, 2) scan3_kernel(ScanArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -283,20 +370,26 @@ __global__ void __launch_bounds__(S3_NT, 1) scan3_kernel(ScanArgs a)
         }
     }
     __syncthreads();
-    if (tid < S3_PT) stager_loop(a, total, tid);
-    else scanner_loop(a, tid);
+    if (tid < S3_PT) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(S3_PREG));
+        stager_loop(a, total, tid);
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S3_CREG));
+        scanner_loop(a, tid);
+    }
 }
 
 }  // namespace
 
 void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st)
 {
-    if (!a.qt || !a.qt_step || !a.qt_base || !a.tile_desc || a.rows_tile != SCAN3_ROWS_TILE || !a.part_off) {
-        set_error("internal: the filter scan needs query tables, tile descriptors and rows_tile 3072");
+    if (!a.qt || !a.qt_step || !a.qt_base || !a.tile_desc || a.rows_tile != SCAN3_ROWS_TILE || !a.part_off ||
+        (a.cand && (!a.thr || !a.slack || !a.cand_cnt || a.topk < 1 || a.topk > CAND_TOPK_MAX || a.nprobes < 1))) {
+        set_error("internal: the filter scan needs query tables and tile descriptors built with rows_tile 1536");
         throw Failure{LGPU_RUNTIME};
     }
     LGPU_CUDA(cudaFuncSetAttribute(scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
-    scan3_kernel<<<grid, S3_NT, S3_SMEM, st>>>(a); LGPU_COUNT_LAUNCH();
+    scan3_kernel<<<2 * grid, S3_NT, S3_SMEM, st>>>(a); LGPU_COUNT_LAUNCH();   // two CTAs per SM
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -25,33 +25,72 @@ namespace lgpu {
 
 namespace {
 
+// ---- table entries for the FILTER.  Not lance's arithmetic (that is pq_rescore_kernel's job): the expansion
+//     |q_i - b|^2 = |q_i|^2 + |b|^2 - 2 q_i.b      (1 - q_i.b for dot)
+// with |b|^2 precomputed at open and the dot product as packed FFMA2 over (even, odd) dimension pairs: ~10
+// instructions per entry instead of ~25.  Its rounding error, <= ~12 u (|q_i| + |b|)^2 per entry, is part of the band
+// (band_check3: the 2 (|q|^2 + CB2) term).  Both table passes call this one function, so they see identical values.
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+{
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t pack2(float a, float b)
+{
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float sum2(uint64_t v)
+{
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a + b;
+}
 template <int DSUB>
-__device__ __forceinline__ void load_cb(float *dst, const float *src)
-{
-    if constexpr (DSUB % 4 == 0) {
+struct SubVec {
+    static constexpr int NP = (DSUB + 1) / 2;
+    uint64_t p[NP];             // (even, odd) dimension pairs; an odd DSUB pads with 0
+    __device__ __forceinline__ void load(const float *src)
+    {
+        if constexpr (DSUB % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < DSUB / 4; i++) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
-            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+            for (int i = 0; i < DSUB / 4; i++) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                p[2 * i] = pack2(v.x, v.y); p[2 * i + 1] = pack2(v.z, v.w);
+            }
+        } else if constexpr (DSUB == 2) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(src));
+            p[0] = pack2(v.x, v.y);
+        } else {
+            p[0] = pack2(__ldg(src), 0.f);
         }
-    } else {
-#pragma unroll
-        for (int i = 0; i < DSUB; i++) dst[i] = __ldg(src + i);
     }
-}
-
+    __device__ __forceinline__ float dot(const SubVec &o) const
+    {
+        uint64_t acc = 0ull;
+#pragma unroll
+        for (int i = 0; i < NP; i++) acc = fma2(p[i], o.p[i], acc);
+        return sum2(acc);
+    }
+};
 template <int DSUB, bool DOT>
-__device__ __forceinline__ float table_entry(const float *qv, const float *cv)
+__device__ __forceinline__ float filter_entry(const SubVec<DSUB> &q, float qi2, const SubVec<DSUB> &cb, float cbn2)
 {
-    return DOT ? subvec_dot_dist<DSUB>(qv, cv) : subvec_l2<DSUB>(qv, cv);
+    const float d = q.dot(cb);
+    return DOT ? 1.0f - d : fmaf(-2.0f, d, qi2 + cbn2);
 }
 
-// ---- pass 1: min_c / max_c of T_q[i][.] for every (query, sub-space).  grid (ceil(B/8), nch), 256 threads:
-// warp g = query 8 bx + g; lane = (s = lane & 7, code quarter = lane >> 3).
+// thread mapping of both table passes: grid (ceil(B/8), nch), 256 threads; warp g = query 8 bx + g; lane =
+// (s = lane & 7, cq = lane >> 3); step t handles code c = 4 t + cq, so a warp reads 4 codes x 8 sub-spaces of the
+// tiled codebook (1 KB contiguous) and writes 4 codes x 16 bytes of the output (64 bytes contiguous).
+
+// ---- pass 1: min_c / max_c of T_q[i][.] for every (query, sub-space)
 template <int DSUB, bool DOT>
 __global__ void __launch_bounds__(256) qtable_minmax_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled,
-                                                            uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
-                                                            float *__restrict__ mm)
+                                                            const float *__restrict__ cb_n2, uint32_t B, uint32_t dim,
+                                                            uint32_t m, uint32_t nch, float *__restrict__ mm)
 {
     const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5), ch = blockIdx.y;
     const int lane = threadIdx.x & 31, s = lane & 7, cq = lane >> 3;
@@ -59,18 +98,22 @@ __global__ void __launch_bounds__(256) qtable_minmax_kernel(const float *__restr
     const uint32_t i = ch * 8 + s;
     float mn = 0.f, mx = 0.f;
     if (i < m) {
-        float qv[DSUB];
-#pragma unroll
-        for (int t = 0; t < DSUB; t++) qv[t] = Q[(size_t)q * dim + i * DSUB + t];
+        SubVec<DSUB> qv;
+        qv.load(Q + (size_t)q * dim + i * DSUB);
+        const float qi2 = qv.dot(qv);
         mn = CUDART_INF_F; mx = -CUDART_INF_F;
-        const float *cb = cb_tiled + (((size_t)ch * 256 + cq * 64) * 8 + s) * DSUB;
+        bool nan = false;
+        const float *cb = cb_tiled + (((size_t)ch * 256 + cq) * 8 + s) * DSUB;
+        const float *n2 = cb_n2 + ((size_t)ch * 256 + cq) * 8 + s;
+#pragma unroll 4
         for (int t = 0; t < 64; t++) {
-            float cv[DSUB];
-            load_cb<DSUB>(cv, cb + (size_t)t * 8 * DSUB);
-            const float v = table_entry<DSUB, DOT>(qv, cv);
+            SubVec<DSUB> cv;
+            cv.load(cb + (size_t)t * 32 * DSUB);
+            const float v = filter_entry<DSUB, DOT>(qv, qi2, cv, __ldg(n2 + t * 32));
             mn = fminf(mn, v); mx = fmaxf(mx, v);
-            if (v != v) { mn = v; mx = v; }             // NaN sticks (fminf/fmaxf would drop it)
+            nan |= v != v;                              // fminf / fmaxf drop NaN
         }
+        if (nan) { mn = CUDART_NAN_F; mx = CUDART_NAN_F; }
     }
 #pragma unroll
     for (int o = 8; o <= 16; o <<= 1) {
@@ -78,99 +121,85 @@ __global__ void __launch_bounds__(256) qtable_minmax_kernel(const float *__restr
         mn = (on != on || mn != mn) ? CUDART_NAN_F : fminf(mn, on);
         mx = (ox != ox || mx != mx) ? CUDART_NAN_F : fmaxf(mx, ox);
     }
-    if (cq == 0) {
-        float2 *o = reinterpret_cast<float2 *>(mm) + (size_t)q * nch * 8 + i;
-        *o = make_float2(mn, mx);
+    if (cq == 0) reinterpret_cast<float2 *>(mm)[(size_t)q * nch * 8 + i] = make_float2(mn, mx);
+}
+
+// ---- pass 2: quantise.  Position j of code c's 16-byte output holds sub-space (j + c) & 7 (the rotation scan3.cu's
+// stagers rely on), i.e. sub-space s goes to position (s - c) & 7.
+template <int DSUB, bool DOT>
+__global__ void __launch_bounds__(256) qtable_quant_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled,
+                                                           const float *__restrict__ cb_n2, uint32_t B, uint32_t dim,
+                                                           uint32_t m, uint32_t nch, const float *__restrict__ mm,
+                                                           unsigned short *__restrict__ qt, float *__restrict__ step_out,
+                                                           float *__restrict__ base_out, float *__restrict__ sbound_out,
+                                                           uint32_t *__restrict__ bad_out)
+{
+    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5), ch = blockIdx.y;
+    const int lane = threadIdx.x & 31, s = lane & 7, cq = lane >> 3;
+    if (q >= B) return;
+    const uint32_t m8 = nch * 8;
+    const float qmax = (float)(65535u / m);
+    const float2 *row = reinterpret_cast<const float2 *>(mm) + (size_t)q * m8;
+    // per-query step / base / bound from the min-max table (every warp of the query's 12 CTAs recomputes it)
+    float rng = 0.f, base = 0.f, sb = 0.f;
+    bool bad = false;
+    for (uint32_t i = lane; i < m; i += 32) {
+        const float2 v = row[i];
+        rng = fmaxf(rng, v.y - v.x);
+        base += v.x;
+        sb += fmaxf(fabsf(v.x), fabsf(v.y));
+        bad |= !(fabsf(v.x) < CUDART_INF_F) || !(fabsf(v.y) < CUDART_INF_F);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rng = fmaxf(rng, __shfl_xor_sync(0xffffffffu, rng, o));
+        base += __shfl_xor_sync(0xffffffffu, base, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    bad = __any_sync(0xffffffffu, bad) || !(rng < CUDART_INF_F) || !(fabsf(base) < CUDART_INF_F) || !(sb < CUDART_INF_F);
+    float step = (!bad && rng > 0.f) ? rng / qmax : 0.f;
+    float inv = (step > 0.f && qmax / rng < CUDART_INF_F) ? qmax / rng : 0.f;
+    if (rng > 0.f && inv == 0.f) bad = true;            // a range too small to invert: take the exact path
+    if (bad) { step = 0.f; inv = 0.f; }
+    if (ch == 0 && lane == 0) {
+        step_out[q] = step;
+        bad_out[q] = bad ? 1u : 0u;
+        base_out[q] = DOT ? base - (float)(m - 1) : base;
+        sbound_out[q] = sb;
+    }
+    const uint32_t i = ch * 8 + s;
+    unsigned short *out = qt + ((size_t)q * nch + ch) * 2048;          // [256 codes][8 positions]
+    if (i >= m) {                                                       // padding sub-space: every entry is 0
+        for (int t = 0; t < 64; t++) { const uint32_t c = 4 * t + cq; out[c * 8 + ((s - c) & 7)] = 0; }
+        return;
+    }
+    SubVec<DSUB> qv;
+    qv.load(Q + (size_t)q * dim + i * DSUB);
+    const float qi2 = qv.dot(qv);
+    const float mn = row[i].x;
+    const float *cb = cb_tiled + (((size_t)ch * 256 + cq) * 8 + s) * DSUB;
+    const float *n2 = cb_n2 + ((size_t)ch * 256 + cq) * 8 + s;
+#pragma unroll 4
+    for (int t = 0; t < 64; t++) {
+        SubVec<DSUB> cv;
+        cv.load(cb + (size_t)t * 32 * DSUB);
+        const float v = filter_entry<DSUB, DOT>(qv, qi2, cv, __ldg(n2 + t * 32));
+        float x = (v - mn) * inv;
+        x = x >= 0.f ? fminf(floorf(x), qmax) : 0.f;                    // NaN -> 0 (the query is flagged bad)
+        const uint32_t c = 4 * t + cq;
+        out[c * 8 + ((s - c) & 7)] = (unsigned short)x;
     }
 }
 
-// ---- pass 2: quantise.  grid (ceil(B/8), nch), 256 threads: thread c = code c of chunk ch for the CTA's 8
-// queries.  Position j of the 16-byte output holds sub-space (j + c) & 7 (the rotation scan3.cu's stagers rely on).
-template <int DSUB, bool DOT>
-__global__ void __launch_bounds__(256) qtable_quant_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled,
-                                                           uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
-                                                           const float *__restrict__ mm, uint4 *__restrict__ qt,
-                                                           float *__restrict__ step_out, float *__restrict__ base_out,
-                                                           float *__restrict__ sbound_out, uint32_t *__restrict__ bad_out)
+// |b|^2 of every tiled codebook entry (open time), same pairing as SubVec::dot
+template <int DSUB>
+__global__ void cb_norms_kernel(const float *__restrict__ cb_tiled, uint64_t n, float *__restrict__ out)
 {
-    __shared__ float s_q[8][8][DSUB];
-    __shared__ float s_min[8][8];
-    __shared__ float s_inv[8];
-    const uint32_t q0 = blockIdx.x * 8, ch = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
-    const uint32_t m8 = nch * 8;
-    const float qmax = (float)(65535u / m);
-    {   // per-query step / base / bound from the min-max table: warp g handles query q0 + g
-        const uint32_t q = q0 + g;
-        float rng = 0.f, base = 0.f, sb = 0.f;
-        bool bad = false;
-        if (q < B) {
-            const float2 *row = reinterpret_cast<const float2 *>(mm) + (size_t)q * m8;
-            for (uint32_t i = lane; i < m; i += 32) {
-                const float2 v = row[i];
-                rng = fmaxf(rng, v.y - v.x);
-                base += v.x;
-                sb += fmaxf(fabsf(v.x), fabsf(v.y));
-                bad |= !(fabsf(v.x) < CUDART_INF_F) || !(fabsf(v.y) < CUDART_INF_F);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            rng = fmaxf(rng, __shfl_xor_sync(0xffffffffu, rng, o));
-            base += __shfl_xor_sync(0xffffffffu, base, o);
-            sb += __shfl_xor_sync(0xffffffffu, sb, o);
-        }
-        bad = __any_sync(0xffffffffu, bad) || !(rng < CUDART_INF_F) || !(fabsf(base) < CUDART_INF_F) || !(sb < CUDART_INF_F);
-        const float step = (!bad && rng > 0.f) ? rng / qmax : 0.f;
-        const float inv = (step > 0.f && qmax / rng < CUDART_INF_F) ? qmax / rng : 0.f;
-        if (lane == 0) {
-            s_inv[g] = bad ? 0.f : inv;
-            if (ch == 0 && q < B) {
-                step_out[q] = (inv > 0.f) ? step : 0.f;      // inv == 0: every entry quantises to 0 and W = 0 would be
-                bad_out[q] = (bad || (rng > 0.f && inv == 0.f)) ? 1u : 0u;   // wrong unless the range is 0 too
-                base_out[q] = DOT ? base - (float)(m - 1) : base;
-                sbound_out[q] = sb;
-            }
-        }
-        if (lane < 8) {
-            const uint32_t i = ch * 8 + lane;
-            s_min[g][lane] = (q < B && i < m) ? reinterpret_cast<const float2 *>(mm)[(size_t)q * m8 + i].x : 0.f;
-        }
-        for (int t = lane; t < 8 * DSUB; t += 32) {
-            const uint32_t i = ch * 8 + t / DSUB;
-            s_q[g][t / DSUB][t % DSUB] = (q < B && i < m) ? Q[(size_t)q * dim + i * DSUB + t % DSUB] : 0.f;
-        }
-    }
-    __syncthreads();
-    const uint32_t c = (uint32_t)tid;
-    uint32_t out[8][4];
-#pragma unroll
-    for (int gg = 0; gg < 8; gg++)
-#pragma unroll
-        for (int w = 0; w < 4; w++) out[gg][w] = 0u;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint32_t s = ((uint32_t)j + c) & 7u;
-        const uint32_t i = ch * 8 + s;
-        if (i < m) {
-            float cv[DSUB];
-            load_cb<DSUB>(cv, cb_tiled + (((size_t)ch * 256 + c) * 8 + s) * DSUB);
-#pragma unroll
-            for (int gg = 0; gg < 8; gg++) {
-                float qv[DSUB];
-#pragma unroll
-                for (int t = 0; t < DSUB; t++) qv[t] = s_q[gg][s][t];
-                const float v = table_entry<DSUB, DOT>(qv, cv);
-                float x = (v - s_min[gg][s]) * s_inv[gg];
-                x = x >= 0.f ? fminf(floorf(x), qmax) : 0.f;           // NaN -> 0 (the query is flagged bad)
-                out[gg][j >> 1] |= (uint32_t)x << (16 * (j & 1));
-            }
-        }
-    }
-#pragma unroll
-    for (int gg = 0; gg < 8; gg++)
-        if (q0 + gg < B)
-            qt[((size_t)(q0 + gg) * nch + ch) * 256 + c] = make_uint4(out[gg][0], out[gg][1], out[gg][2], out[gg][3]);
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    SubVec<DSUB> v;
+    v.load(cb_tiled + e * DSUB);
+    out[e] = v.dot(v);
 }
 
 __device__ __forceinline__ uint32_t find_partition(const uint64_t *__restrict__ part_off, uint32_t nlist, uint64_t pos)
@@ -214,32 +243,17 @@ __global__ void row_const_kernel(const unsigned char *__restrict__ codes, const 
     atomicMax(rmax_bits, __float_as_int(fabsf(r)));
 }
 
-// exact PQ distance of (query, stored row) pairs, exactly as oracle.c::partition_distances:
+// exact PQ distance of one (query, stored row) pair, exactly as oracle.c::partition_distances:
 // residual -> sub-vector table entry (l2_once tree for dsub 8/16) -> sequential f32 sum -> metric scale.
-// One WARP per pair: lane l evaluates the entries of sub-spaces l, l + 32, ... (independent loads of the code
-// byte, the codeword and the query / centroid sub-vectors), then the entries are summed in order i = 0..m-1
-// (the oracle's order) by walking them through a shuffle.  m <= 512.
+// Warp-cooperative: lane l evaluates the entries of sub-spaces l, l + 32, ... (independent loads of the code byte,
+// the codeword and the query / centroid sub-vectors), then the entries are summed in order i = 0..m-1 (the oracle's
+// order) by walking them through a shuffle.  m <= 512.  Every lane returns the distance.
 template <int DSUB>
-__global__ void __launch_bounds__(256) pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *__restrict__ pos,
-                                                         uint32_t B, uint32_t nc, const unsigned char *__restrict__ codes,
-                                                         const uint64_t *__restrict__ code_base,
-                                                         const uint32_t *__restrict__ part_npad,
-                                                         const uint64_t *__restrict__ part_off, uint32_t nlist,
-                                                         const float *__restrict__ centroids,
-                                                         const float *__restrict__ cb_tiled, uint32_t dim, uint32_t m,
-                                                         int metric, float *__restrict__ out)
+__device__ __forceinline__ float exact_pq_distance_warp(const float *__restrict__ qv, const float *__restrict__ cen,
+                                                        const unsigned char *__restrict__ codes, uint64_t cbase,
+                                                        uint32_t npad, uint32_t row, const float *__restrict__ cb_tiled,
+                                                        uint32_t m, int metric, int lane)
 {
-    const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (pair >= (uint64_t)B * nc) return;
-    const uint64_t ps = pos[pair];
-    if (ps == UINT64_MAX) { if (lane == 0) out[pair] = CUDART_INF_F; return; }
-    const uint32_t q = (uint32_t)(pair / nc);
-    const uint32_t p = find_partition(part_off, nlist, ps);
-    const uint32_t row = (uint32_t)(ps - part_off[p]);
-    const float *qv = Q + (size_t)q * dim, *cen = centroids + (size_t)p * dim;
-    const uint64_t cbase = code_base[p];
-    const uint32_t npad = part_npad[p];
     float tv[16];
 #pragma unroll
     for (int it = 0; it < 16; it++) {
@@ -267,13 +281,120 @@ __global__ void __launch_bounds__(256) pq_rescore_kernel(const float *__restrict
     }
     if (metric == LGPU_COSINE) acc = __fmul_rn(acc, 0.5f);
     else if (metric == LGPU_DOT) acc = __fsub_rn(acc, (float)(m - 1));
-    if (lane == 0) out[pair] = acc;
+    return acc;
+}
+
+// one warp per (query, candidate position) pair
+template <int DSUB>
+__global__ void __launch_bounds__(256) pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *__restrict__ pos,
+                                                         uint32_t B, uint32_t nc, const unsigned char *__restrict__ codes,
+                                                         const uint64_t *__restrict__ code_base,
+                                                         const uint32_t *__restrict__ part_npad,
+                                                         const uint64_t *__restrict__ part_off, uint32_t nlist,
+                                                         const float *__restrict__ centroids,
+                                                         const float *__restrict__ cb_tiled, uint32_t dim, uint32_t m,
+                                                         int metric, float *__restrict__ out)
+{
+    const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pair >= (uint64_t)B * nc) return;
+    const uint64_t ps = pos[pair];
+    if (ps == UINT64_MAX) { if (lane == 0) out[pair] = CUDART_INF_F; return; }
+    const uint32_t q = (uint32_t)(pair / nc);
+    const uint32_t p = find_partition(part_off, nlist, ps);
+    const uint32_t row = (uint32_t)(ps - part_off[p]);
+    const float d = exact_pq_distance_warp<DSUB>(Q + (size_t)q * dim, centroids + (size_t)p * dim, codes, code_base[p],
+                                                 part_npad[p], row, cb_tiled, m, metric, lane);
+    if (lane == 0) out[pair] = d;
+}
+
+// ---- candidate mode of the filter scan: per-query band, then the final exact top-k over the survivors ----
+__global__ void cand_prepare_kernel(const float *__restrict__ step, const float *__restrict__ sbound,
+                                    const float *__restrict__ amax, const int *__restrict__ rmax_bits,
+                                    const float *__restrict__ qn2, float cb2, float scale, uint32_t m, uint32_t B,
+                                    float *__restrict__ slack, uint32_t *__restrict__ thr, uint32_t *__restrict__ cand_cnt)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= B) return;
+    const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m +
+                      2.0f * (qn2[q] + cb2);
+    const float E = 3.0517578125e-5f * (float)((m + 95u) / 96u) * mag;       // same band as band_check3_kernel
+    const float W = (float)m * step[q] * 1.0009765625f;
+    slack[q] = scale * (W + 2.0f * E);
+    thr[q] = CAND_NO_THR;
+    cand_cnt[q] = 0u;
+}
+
+constexpr int FIN_THREADS = 256;
+template <int DSUB>
+__global__ void __launch_bounds__(FIN_THREADS) cand_finalize_kernel(FinalizeArgs a)
+{
+    extern __shared__ __align__(16) unsigned char fsm[];
+    uint64_t *s_id = reinterpret_cast<uint64_t *>(fsm);
+    uint64_t *s_pos = s_id + a.cand_cap;
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pos + a.cand_cap);
+    __shared__ uint32_t s_n;
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const uint32_t total = a.cand_cnt[q];
+    const uint32_t n = min(total, a.cand_cap);
+    if (tid == 0) {
+        s_n = 0;
+        a.flags[q] = (total > a.cand_cap || a.bad[q]) ? 1u : 0u;
+    }
+    __syncthreads();
+    const uint32_t tkey = a.thr[q];
+    const float lim = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey) + a.slack[q];
+    const CandRec *cand = a.cand + (size_t)q * a.cand_cap;
+    const float *qv = a.Q + (size_t)q * a.dim;
+    for (uint32_t c = w; c < n; c += FIN_THREADS / 32) {
+        const CandRec rec = cand[c];
+        if (!(rec.lb <= lim)) continue;                     // the threshold tightened after this row was appended
+        float d = exact_pq_distance_warp<DSUB>(qv, a.centroids + (size_t)rec.p * a.dim, a.codes, a.code_base[rec.p],
+                                               a.part_npad[rec.p], rec.row, a.cb_tiled, a.m, a.metric, lane);
+        if (d != d) continue;                               // FilterExec: _distance IS NOT NULL
+        if (d == 0.f) d = 0.f;                              // -0 and +0 tie
+        if (lane == 0) {
+            const uint32_t at = atomicAdd(&s_n, 1u);
+            const uint64_t ps = a.part_off[rec.p] + rec.row;
+            s_key[at] = f32_key(d); s_id[at] = a.row_ids[ps]; s_pos[at] = ps;
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = s_n;
+    uint32_t n2 = 2;
+    while (n2 < cnt) n2 <<= 1;
+    for (uint32_t i = cnt + tid; i < n2; i += FIN_THREADS) { s_key[i] = 0xffffffffu; s_id[i] = UINT64_MAX; s_pos[i] = UINT64_MAX; }
+    __syncthreads();
+    for (uint32_t size = 2; size <= n2; size <<= 1) {       // bitonic sort by (distance key, row id), ascending
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (n2 >> 1); i += FIN_THREADS) {
+                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool asc = (lo & size) == 0;
+                const uint32_t ka = s_key[lo], kb = s_key[hi];
+                const uint64_t ia = s_id[lo], ib = s_id[hi];
+                const bool gt = kb < ka || (kb == ka && ib < ia);
+                if (gt == asc) {
+                    s_key[lo] = kb; s_key[hi] = ka; s_id[lo] = ib; s_id[hi] = ia;
+                    const uint64_t pa = s_pos[lo]; s_pos[lo] = s_pos[hi]; s_pos[hi] = pa;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (uint32_t i = tid; i < a.k; i += FIN_THREADS) {
+        const bool have = i < cnt;
+        a.out_ids[(size_t)q * a.k + i] = have ? s_id[i] : UINT64_MAX;
+        a.out_dist[(size_t)q * a.k + i] = have ? key_f32(s_key[i]) : CUDART_INF_F;
+        if (a.out_pos) a.out_pos[(size_t)q * a.k + i] = have ? s_pos[i] : UINT64_MAX;
+    }
+    if (tid == 0) a.out_count[q] = min(cnt, a.k);
 }
 
 // probe_A[slot] = coarse_dist - |q|^2 ; amax[q] = max_j coarse + |q|^2
 __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const float *__restrict__ Q, uint32_t B,
                                    uint32_t nprobes, uint32_t dim, float *__restrict__ probe_A,
-                                   float *__restrict__ amax)
+                                   float *__restrict__ amax, float *__restrict__ qn2)
 {
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // one warp per query
     const int lane = threadIdx.x & 31;
@@ -284,14 +405,19 @@ __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const f
     for (int o = 16; o > 0; o >>= 1) n2d += __shfl_xor_sync(0xffffffffu, n2d, o);
     const float n2 = (float)n2d;
     float mx = 0.f;
-    for (uint32_t j = lane; j < nprobes; j += 32) {
-        const float cd = probe_dist[(size_t)q * nprobes + j];
-        probe_A[(size_t)q * nprobes + j] = cd - n2;
-        mx = fmaxf(mx, fabsf(cd));
+    if (probe_A) {                                       // (dot: no residual, A = 0)
+        for (uint32_t j = lane; j < nprobes; j += 32) {
+            const float cd = probe_dist[(size_t)q * nprobes + j];
+            probe_A[(size_t)q * nprobes + j] = cd - n2;
+            mx = fmaxf(mx, fabsf(cd));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) amax[q] = mx + n2;                   // >= |A| and also covers the coarse distance's own rounding
+    if (lane == 0) {
+        qn2[q] = n2;
+        if (amax) amax[q] = mx + n2;                    // >= |A| and also covers the coarse distance's own rounding
+    }
 }
 
 // flags[q] = 1 when the shortlist cannot be proven to contain the exact top-k (see the header and kernels.cuh).
@@ -299,19 +425,21 @@ __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const f
 // same f32 inputs by <= (m + 16) u (D + |q - c_p|^2); the table entries carry <= (dsub + 2) u T each, the floor of
 // the quantiser can be off by one step when (T - min) / step lands within 2^-11 of an integer (absorbed by the
 // factor 1 + 2^-10 on W), A carries <= 70 u (coarse + |q|^2), R one ulp, the epilogue of scan3 three more roundings
-// of values bounded by sbound + amax + rmax.  For m <= 96 all of it is < 2^9 u = 2^-15 of (sbound + amax + rmax);
-// larger m widens E proportionally.
+// of values bounded by sbound + amax + rmax, and the expansion form of the entries (filter_entry) <= 12 u (|q_i| + |b|)^2
+// <= 24 u (|q_i|^2 + max_c |b|^2) each.  For m <= 96 all of it is < 2^9 u = 2^-15 of
+// (sbound + amax + rmax + m + 2 (|q|^2 + CB2)), CB2 = sum_i max_c |codebook_i[c]|^2; larger m widens E proportionally.
 __global__ void band_check3_kernel(const float *__restrict__ lb, const uint32_t *__restrict__ cnt,
                                    const float *__restrict__ step, const float *__restrict__ sbound,
                                    const float *__restrict__ amax, const int *__restrict__ rmax_bits,
-                                   const uint32_t *__restrict__ bad, float scale, uint32_t m, uint32_t B, uint32_t k,
-                                   uint32_t kp, uint32_t *__restrict__ flags)
+                                   const uint32_t *__restrict__ bad, const float *__restrict__ qn2, float cb2, float scale,
+                                   uint32_t m, uint32_t B, uint32_t k, uint32_t kp, uint32_t *__restrict__ flags)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
     uint32_t f = bad[q] ? 1u : 0u;
     if (!f && cnt[q] >= kp && kp > 0) {
-        const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m;
+        const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m +
+                          2.0f * (qn2[q] + cb2);
         const float E = 3.0517578125e-5f * (float)((m + 95u) / 96u) * mag;
         const float W = (float)m * step[q] * 1.0009765625f;
         const float kth = lb[(size_t)q * kp + (k - 1 < kp ? k - 1 : kp - 1)];
@@ -336,21 +464,31 @@ template <class F> void dispatch_dsub(uint32_t dsub, F &&f)
 
 }  // namespace
 
-void launch_query_tables_q16(const float *Q, const float *cb_tiled, uint32_t B, uint32_t dim, uint32_t m, uint32_t nch,
-                             uint32_t dsub, int metric, float *mm, uint4 *qt, float *step, float *base, float *sbound,
-                             uint32_t *bad, cudaStream_t st)
+void launch_query_tables_q16(const float *Q, const float *cb_tiled, const float *cb_n2, uint32_t B, uint32_t dim,
+                             uint32_t m, uint32_t nch, uint32_t dsub, int metric, float *mm, uint4 *qt, float *step,
+                             float *base, float *sbound, uint32_t *bad, cudaStream_t st)
 {
     if (B == 0) return;
     const dim3 grid((B + 7) / 8, nch);
+    unsigned short *qt16 = reinterpret_cast<unsigned short *>(qt);
     dispatch_dsub(dsub, [&](auto D) {
         constexpr int DS = decltype(D)::value;
         if (metric == LGPU_DOT) {
-            qtable_minmax_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
-            qtable_quant_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
+            qtable_minmax_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
+            qtable_quant_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt16, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
         } else {
-            qtable_minmax_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
-            qtable_quant_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
+            qtable_minmax_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
+            qtable_quant_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt16, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
         }
+    });
+    LGPU_CUDA(cudaGetLastError());
+}
+
+void launch_cb_norms(const float *cb_tiled, uint32_t nch, uint32_t dsub, float *out, cudaStream_t st)
+{
+    const uint64_t n = (uint64_t)nch * 256 * 8;
+    dispatch_dsub(dsub, [&](auto D) {
+        cb_norms_kernel<decltype(D)::value><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cb_tiled, n, out); LGPU_COUNT_LAUNCH();
     });
     LGPU_CUDA(cudaGetLastError());
 }
@@ -385,19 +523,44 @@ void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t
 }
 
 void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uint32_t nprobes, uint32_t dim,
-                        float *probe_A, float *amax, cudaStream_t st)
+                        float *probe_A, float *amax, float *qn2, cudaStream_t st)
 {
     if (B == 0) return;
-    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, amax); LGPU_COUNT_LAUNCH();
+    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, amax, qn2); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaGetLastError());
+}
+
+void launch_cand_prepare(const float *step, const float *sbound, const float *amax, const int *rmax_bits, const float *qn2,
+                         float cb2, float scale, uint32_t m, uint32_t B, float *slack, uint32_t *thr, uint32_t *cand_cnt,
+                         cudaStream_t st)
+{
+    if (B == 0) return;
+    cand_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(step, sbound, amax, rmax_bits, qn2, cb2, scale, m, B, slack, thr, cand_cnt); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaGetLastError());
+}
+
+void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
+{
+    if (a.B == 0) return;
+    if (a.m > 512 || a.cand_cap < 2 || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
+        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity >= k");
+        throw Failure{LGPU_RUNTIME};
+    }
+    const size_t smem = (size_t)a.cand_cap * 20;
+    dispatch_dsub(a.dsub, [&](auto D) {
+        auto kern = cand_finalize_kernel<decltype(D)::value>;
+        LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<a.B, FIN_THREADS, smem, st>>>(a); LGPU_COUNT_LAUNCH();
+    });
     LGPU_CUDA(cudaGetLastError());
 }
 
 void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
-                        const int *rmax_bits, const uint32_t *bad, float scale, uint32_t m, uint32_t B, uint32_t k,
-                        uint32_t kp, uint32_t *flags, cudaStream_t st)
+                        const int *rmax_bits, const uint32_t *bad, const float *qn2, float cb2, float scale, uint32_t m,
+                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st)
 {
     if (B == 0) return;
-    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, scale, m, B, k, kp, flags); LGPU_COUNT_LAUNCH();
+    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, qn2, cb2, scale, m, B, k, kp, flags); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

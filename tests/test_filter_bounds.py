@@ -1,7 +1,8 @@
 """Host restatement of the filter scan's arithmetic (lancedb_b200/csrc/tables.cu + scan3.cu) checked against the
 oracle on the CPU: the lower bound L built from the 16-bit per-query tables, the per-probe scalar A and the
 per-row constant R must bracket the oracle's exact PQ distance d*:   L - E <= d* <= L + W + E,
-with W = m * step * (1 + 2^-10) and E = 2^-15 * ceil(m/96) * (sbound + amax + rmax + m) (times 0.5 for cosine) --
+with W = m * step * (1 + 2^-10) and E = 2^-15 * ceil(m/96) * (sbound + amax + rmax + m + 2 (|q|^2 + CB2)) (times 0.5
+for cosine) --
 exactly the band `band_check3_kernel` uses to prove that a shortlist contains the exact top-k.  This pins the
 algebra (|r - b|^2 = |q - b|^2 + (|c|^2 - 2 q.c) + 2 b.c), the quantiser and the error budget without a GPU;
 the GPU parity tests then check the kernels themselves."""
@@ -19,7 +20,19 @@ def _bounds(ix, orc, q, p):
     m, dsub = ix.m, ix.dim // ix.m
     dot, cos = ix.metric == "dot", ix.metric == "cosine"
     qn = oracle.normalize(q) if cos else q.astype(F)
-    T = orc.build_lut(qn)                                   # [m,256] = |q_i - cb|^2, or 1 - q_i.cb for dot
+    # the filter's table entries (tables.cu filter_entry): the expansion |q_i|^2 + |b|^2 - 2 q_i.b in f32
+    # (1 - q_i.b for dot) -- NOT lance's (q_i - b)^2 tree; its rounding error is part of E below
+    qs = qn.reshape(m, 1, dsub).astype(F)
+    cbf = ix.codebook.astype(F)                              # [m,256,dsub]
+    dotp = np.zeros((m, 256), F)
+    for t in range(dsub):
+        dotp = (dotp + qs[:, :, t] * cbf[:, :, t]).astype(F)
+    if dot:
+        T = (F(1) - dotp).astype(F)
+    else:
+        qi2 = (qs * qs).sum(2, dtype=F)
+        cbn2 = (cbf * cbf).sum(2, dtype=F)
+        T = ((qi2 + cbn2).astype(F) - F(2) * dotp).astype(F)
     mn, mx = T.min(1), T.max(1)
     qmax = F(65535 // m)
     rng = F((mx - mn).max())
@@ -46,7 +59,9 @@ def _bounds(ix, orc, q, p):
     scale = F(0.5) if cos else F(1)
     L = ((step * S.astype(F) + F(base + A)).astype(F) + R).astype(F) * scale
     W = F(m) * step * F(1.0009765625) * scale
-    E = F(3.0517578125e-5) * F((m + 95) // 96) * F(sbound + amax + rmax + F(m)) * scale
+    qn2 = F(np.dot(qn.astype(np.float64), qn.astype(np.float64)))
+    cb2 = F((ix.codebook.astype(np.float64) ** 2).sum(2).max(1).sum() * 1.000001)
+    E = F(3.0517578125e-5) * F((m + 95) // 96) * F(sbound + amax + rmax + F(m) + F(2) * (qn2 + cb2)) * scale
     return L, W, E, orc.partition_distances(q, p)
 
 

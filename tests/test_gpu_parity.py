@@ -338,3 +338,20 @@ def test_maximum_nprobes_widening_under_a_selective_prefilter(metric):
     a = gpu.search(q, k=10, nprobes=2); b = gpu.search(q, k=10, nprobes=2, max_nprobes=24)
     gpu.close()
     assert np.array_equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("mode", ["cand_overflow", "dense"])
+def test_filter_scan_modes_and_candidate_overflow(mode, monkeypatch):
+    """The filter scan's candidate mode (thresholds inside the scanners, per-query candidate lists) against its
+    dense mode (LGPU_DENSE_FILTER=1: one lower bound per row + shortlist select) and against a candidate capacity
+    of 32 (LGPU_CAND_CAP), which overflows for most queries and sends them through the exact fix-up pass."""
+    if mode == "dense":
+        monkeypatch.setenv("LGPU_DENSE_FILTER", "1")
+    else:
+        monkeypatch.setenv("LGPU_CAND_CAP", "32")
+    rng = np.random.default_rng(51)
+    ix = random_index(rng, dim=64, nlist=40, m=8, n=60000)
+    _check_search(ix, queries(rng, 90, 64), k=10, nprobes=12)
+    _check_search(ix, queries(rng, 90, 64), k=32, nprobes=12)
+    ixv = random_index(rng, dim=48, nlist=6, m=6, metric="cosine", n=4000, with_vectors=True)
+    _check_search(ixv, queries(rng, 17, 48), k=5, nprobes=3, refine_factor=4)
