@@ -741,6 +741,7 @@ def main():
             stage[kk] = stage.get(kk, 0.0) + v / prof_steps
         scan_ms.append(s["scan"])
         code_bytes = _native.last_scanned_code_bytes()
+    filter_stats = _native.last_filter_stats()
     _native.set_profiling(False)
     scan_avg = float(np.mean(scan_ms))
     achieved = code_bytes / (scan_avg / 1e3) / 1e9
@@ -760,6 +761,7 @@ def main():
             "gate": gate,
             "index_build_s": build_s,
             "stage_ms": stage,
+            "filter_stats": filter_stats,        # last profiled batch: candidates appended / re-scored, exact fix-ups
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                          "traffic": traffic, "traffic_kernel": traffic_kernel,
                          "kernel": "PQ code scan (dominant kernel of the step; name in profiles/)",

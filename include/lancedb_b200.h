@@ -240,6 +240,9 @@ int lgpu_debug_gemm(const float *queries, const float *vectors, uint32_t B, uint
  * LGPU_PROFILE=1 in the environment: coarse, select-probes, group, scan, top-k,
  * refine, total.  times: [7] */
 int lgpu_last_stage_ms(float *times);
+/* filter-scan counters of the most recent profiled lgpu_search* call on this thread (first sub-batch): candidates the
+ * scanners appended, survivors re-scored exactly, queries sent to the exact fix-up pass, queries.  stats: [4] */
+int lgpu_last_filter_stats(uint64_t *stats);
 /* kernels this process has launched through the library so far (eager launches and graph replays alike) */
 int lgpu_kernel_launch_count(uint64_t *count);
 /* switch per-stage CUDA-event timing (and the scanned-bytes counter) on/off for the

@@ -31,7 +31,7 @@ EXPORTS = [
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
     "lgpu_ivf_assign", "lgpu_pq_encode",
     "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
-    "lgpu_kernel_launch_count",
+    "lgpu_kernel_launch_count", "lgpu_last_filter_stats",
 ]
 
 
@@ -392,6 +392,12 @@ def kernel_launch_count() -> int:
     n = C.c_uint64(0)
     check(load().lgpu_kernel_launch_count(C.byref(n)))
     return n.value
+
+
+def last_filter_stats():
+    t = (C.c_uint64 * 4)()
+    check(load().lgpu_last_filter_stats(t))
+    return dict(zip(["candidates", "rescored", "flagged_queries", "queries"], [int(x) for x in t]))
 
 
 def set_profiling(enabled: bool) -> None:

@@ -30,6 +30,7 @@ namespace lgpu {
 static thread_local std::string g_err;
 static thread_local float g_stage_ms[7] = {0, 0, 0, 0, 0, 0, 0};
 static thread_local uint64_t g_scanned_bytes = 0;
+static thread_local uint64_t g_filter_stats[4] = {0, 0, 0, 0};
 void set_error(const std::string &msg) { g_err = msg; }
 
 // every kernel the library launches (eagerly, into a stream capture, or through a graph replay) is counted
@@ -105,6 +106,7 @@ struct Workspace {
     DevBuf sbound, probe_A, amax;       // tensor-core shortlists: thresholds / counters; filter scan: bounds, per-probe scalars
     DevBuf qt, qt_mm, qt_step, qt_base, qt_bad;   // filter scan (scan3.cu): quantised per-query tables
     DevBuf s_ids, s_lb, s_pos, s_cnt, s_exact;    // filter scan (dense mode): shortlist by lower bound, exact re-score
+    DevBuf c_stats;                               // candidate-mode counters (profiling only)
     DevBuf c_thr, c_slack, c_cnt, c_rec;          // filter scan (candidate mode): thresholds, bands, candidate lists
     Workspace()
     {
@@ -649,6 +651,11 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
             fa.B = B; fa.dim = dim; fa.m = ix->m; fa.dsub = ix->dsub; fa.k = kk; fa.metric = ix->metric;
             fa.out_ids = pq_ids; fa.out_dist = pq_dist; fa.out_count = pq_cnt; fa.out_pos = pq_pos;
             fa.flags = ws->flags.as<uint32_t>();
+            if (prof) {
+                ws->c_stats.ensure(32);
+                LGPU_CUDA(cudaMemsetAsync(ws->c_stats.p, 0, 32, st));
+                fa.stats = ws->c_stats.as<unsigned long long>();
+            }
             launch_cand_finalize(fa, st);
             sc.cand = nullptr;                      // (the fix-up pass below is the exact kernel)
         } else {
@@ -751,6 +758,8 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
         unsigned long long rows = 0;
         LGPU_CUDA(cudaMemcpy(&rows, ws->scalars.as<char>() + 16, 8, cudaMemcpyDeviceToHost));
         g_scanned_bytes = (uint64_t)rows * ix->m;
+        memset(g_filter_stats, 0, sizeof(g_filter_stats));
+        if (ws->c_stats.p) LGPU_CUDA(cudaMemcpy(g_filter_stats, ws->c_stats.p, 32, cudaMemcpyDeviceToHost));
     }
 }
 
@@ -1120,6 +1129,11 @@ int lgpu_last_scanned_code_bytes(uint64_t *bytes)
 int lgpu_kernel_launch_count(uint64_t *count)
 {
     return guarded([&] { LGPU_REQUIRE(count, "null argument"); *count = g_kernel_launches.load(); });
+}
+
+int lgpu_last_filter_stats(uint64_t *stats)
+{
+    return guarded([&] { LGPU_REQUIRE(stats, "null argument"); memcpy(stats, g_filter_stats, sizeof(g_filter_stats)); });
 }
 
 int lgpu_set_profiling(int enabled)

@@ -240,6 +240,7 @@ struct FinalizeArgs {
     const uint64_t *row_ids; const float *centroids; const float *cb_tiled;
     uint32_t B, dim, m, dsub, k; int metric;
     uint64_t *out_ids; float *out_dist; uint32_t *out_count; uint64_t *out_pos; uint32_t *flags;
+    unsigned long long *stats;    // optional [4]: candidates appended, survivors re-scored, queries flagged, queries
 };
 void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st);
 // flags[q] = 1 when the shortlist of q (lower bounds `lb` ascending, [B][kp], cnt valid) cannot be proven to hold

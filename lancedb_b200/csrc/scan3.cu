@@ -52,7 +52,8 @@ static_assert(S3_PT * S3_PREG + S3_CT * S3_CREG <= 32768, "register budget of ha
 constexpr int S3_BUF = 32768;                       // one chunk buffer
 constexpr int S3_SLOTS = 4, S3_SLOT_BYTES = 128;    // tile-descriptor ring
 constexpr size_t S3_TILES = 3 * (size_t)S3_BUF;
-constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES;
+constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES + 128;   // + 2 x 16 words of threshold scratch
+constexpr int BAR_SCAN = 8;                         // named barrier of the 256 scanner threads (candidate mode)
 static_assert(SCAN3_ROWS_TILE == S3_CT * S3_RMAX, "rows_tile");
 static_assert(S3_PT == 256, "one stager thread per code");
 
@@ -249,50 +250,78 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
     }
     // candidate mode.  tau_q (global, atomicMin) is any value such that at least k rows of the query have L <= tau_q:
     // then the k-th smallest exact distance is <= tau_q + W + E and every row of the exact top-k has
-    // L <= tau_q + W + 2E = tau_q + slack_q.  A warp tightens tau_q from its own rows (k-th smallest of its <= 32 R
-    // lower bounds, by bisection) when the query has no threshold yet or when this is one of its three nearest
-    // partitions -- that is where the small distances are; every warp then appends the rows under the threshold.
+    // L <= tau_q + W + 2E = tau_q + slack_q.  The CTA's 256 scanner threads tighten tau_q from the tile's own rows (an
+    // upper bound of their k-th smallest L, by 8 counting bisections through shared counters) when the query has no
+    // threshold yet or when this is one of its three nearest partitions -- that is where the small distances are;
+    // every warp then appends the rows under the threshold.
     const int lane = ct & 31;
     const uint32_t k = a.topk;
+    // scratch, two banks alternating by query so that the reset for query g+1 cannot overtake a slow warp still
+    // reading query g's counters: [0] threshold key, [1] min key, [2] max key, [3] valid rows, [4..12] counters
 #pragma unroll 1
     for (int g = 0; g < ng; g++) {
+        volatile uint32_t *const sh =
+            reinterpret_cast<volatile uint32_t *>(smem + S3_TILES + S3_SLOTS * S3_SLOT_BYTES) + (g & 1) * 16;
         const uint32_t q = T->q[g], slot = T->slot[g];
         const float step = __ldg(a.qt_step + q);
         const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + slot) : 0.f);
         const float slack = __ldg(a.slack + q);
         float L[R];
-        uint32_t nvalid = 0;
+        uint32_t nvalid = 0, kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const uint32_t w = (g & 2) ? ((g & 4) ? acc[r][3] : acc[r][1]) : ((g & 4) ? acc[r][2] : acc[r][0]);
             const uint32_t s = (g & 1) ? (w >> 16) : (w & 0xffffu);
             L[r] = valid[r] ? (fmaf(step, (float)s, cst) + rr[r]) * scale : CUDART_INF_F;
-            nvalid += valid[r] ? 1u : 0u;
+            if (valid[r]) { const uint32_t kk = f32_key(L[r]); kmin = min(kmin, kk); kmax = max(kmax, kk); nvalid++; }
         }
-        uint32_t tkey = __ldcg(a.thr + q);
-        const uint32_t rank = slot - q * a.nprobes;
-        if (tkey == CAND_NO_THR || rank < 3u) {
-            const uint32_t wvalid = __reduce_add_sync(0xffffffffu, nvalid);
-            if (wvalid >= k) {
-                uint32_t kmin = 0xffffffffu, kmax = 0u;
+        if (ct == 0) {
+            sh[0] = __ldcg(a.thr + q); sh[1] = 0xffffffffu; sh[2] = 0u; sh[3] = 0u;
 #pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (valid[r]) { const uint32_t kk = f32_key(L[r]); kmin = min(kmin, kk); kmax = max(kmax, kk); }
-                float lo = key_f32(__reduce_min_sync(0xffffffffu, kmin));
-                float hi = key_f32(__reduce_max_sync(0xffffffffu, kmax));
-                if (hi < CUDART_INF_F && lo == lo && hi == hi) {       // invariant: count(L <= hi) >= k
+            for (int i = 0; i < 9; i++) sh[4 + i] = 0u;
+        }
+        bar_sync(BAR_SCAN, S3_CT);
+        uint32_t tkey = sh[0];
+        const uint32_t rank = slot - q * a.nprobes;
+        if (tkey == CAND_NO_THR || rank < 3u) {              // uniform over the CTA's scanners
+            kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+            nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+            if (lane == 0) {
+                atomicMin(const_cast<uint32_t *>(sh + 1), kmin); atomicMax(const_cast<uint32_t *>(sh + 2), kmax);
+                atomicAdd(const_cast<uint32_t *>(sh + 3), nvalid);
+            }
+            bar_sync(BAR_SCAN, S3_CT);
+            float lo = key_f32(sh[1]), hi = key_f32(sh[2]);
+            if (sh[3] >= k && hi < CUDART_INF_F && lo == lo && hi == hi) {
+                // only values below the current threshold can improve it: start from hi = min(hi, tau) if that
+                // still has k rows under it (first counter), else this tile cannot tighten tau
+                bool ok = true;
+                if (tkey != CAND_NO_THR && key_f32(tkey) < hi) {
+                    const float cur = key_f32(tkey);
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int r = 0; r < R; r++) c += L[r] <= cur ? 1u : 0u;
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 4), c);
+                    bar_sync(BAR_SCAN, S3_CT);
+                    ok = sh[4] >= k;
+                    hi = cur;
+                }
+                if (ok) {                                   // invariant: count(L <= hi) >= k
 #pragma unroll 1
-                    for (int it = 0; it < 10; it++) {
+                    for (int it = 0; it < 8; it++) {
                         const float mid = 0.5f * lo + 0.5f * hi;
                         uint32_t c = 0;
 #pragma unroll
                         for (int r = 0; r < R; r++) c += L[r] <= mid ? 1u : 0u;
                         c = __reduce_add_sync(0xffffffffu, c);
-                        if (c >= k) hi = mid; else lo = mid;
+                        if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 5 + it), c);
+                        bar_sync(BAR_SCAN, S3_CT);
+                        if (sh[5 + it] >= k) hi = mid; else lo = mid;
                     }
                     const uint32_t nk = f32_key(hi);
                     if (nk < tkey) {
-                        if (lane == 0) atomicMin(a.thr + q, nk);
+                        if (ct == 0) atomicMin(a.thr + q, nk);
                         tkey = nk;
                     }
                 }

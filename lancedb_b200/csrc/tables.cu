@@ -55,10 +55,15 @@ struct SubVec {
     __device__ __forceinline__ void load(const float *src)
     {
         if constexpr (DSUB % 4 == 0) {
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
 #pragma unroll
-            for (int i = 0; i < DSUB / 4; i++) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
-                p[2 * i] = pack2(v.x, v.y); p[2 * i + 1] = pack2(v.z, v.w);
+                for (int i = 0; i < DSUB / 4; i++) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                    p[2 * i] = pack2(v.x, v.y); p[2 * i + 1] = pack2(v.z, v.w);
+                }
+            } else {                                    // caller-owned query buffer that is not 16-byte aligned
+#pragma unroll
+                for (int i = 0; i < DSUB / 2; i++) p[i] = pack2(__ldg(src + 2 * i), __ldg(src + 2 * i + 1));
             }
         } else if constexpr (DSUB == 2) {
             const float2 v = __ldg(reinterpret_cast<const float2 *>(src));
@@ -82,9 +87,57 @@ __device__ __forceinline__ float filter_entry(const SubVec<DSUB> &q, float qi2, 
     return DOT ? 1.0f - d : fmaf(-2.0f, d, qi2 + cbn2);
 }
 
-// thread mapping of both table passes: grid (ceil(B/8), nch), 256 threads; warp g = query 8 bx + g; lane =
-// (s = lane & 7, cq = lane >> 3); step t handles code c = 4 t + cq, so a warp reads 4 codes x 8 sub-spaces of the
-// tiled codebook (1 KB contiguous) and writes 4 codes x 16 bytes of the output (64 bytes contiguous).
+// thread mapping of both table passes: grid (ceil(B/32), nch), 256 threads; warp g = the 4 queries 32 bx + 4 g + j;
+// lane = (s = lane & 7, cq = lane >> 3); step t handles code c = 4 t + cq.  The CTA first stages its codebook chunk
+// (256 codes x 8 sub-spaces x DSUB floats, 64 KB at DSUB = 8) and the |b|^2 in shared memory -- read once from L2
+// instead of once per warp, which was the kernels' bound (L1 sector throughput) -- and the quantiser collects 32 codes
+// per query in a per-warp scratch so that its output leaves as full 16-byte stores.
+constexpr int QT_NQ = 4;
+template <int DSUB> struct QtSmem {
+    static constexpr bool STAGE = DSUB <= 16;                       // DSUB = 32 would need 256 KB: read from L2 instead
+    static constexpr size_t CB = STAGE ? (size_t)2048 * DSUB * 4 : 0;
+    static constexpr size_t N2 = CB, SCRATCH = N2 + (STAGE ? 2048 * 4 : 0);
+    static constexpr size_t TOTAL_MINMAX = SCRATCH, TOTAL_QUANT = SCRATCH + 8 * QT_NQ * 32 * 16;
+};
+template <int DSUB>
+__device__ __forceinline__ void stage_chunk(const float *__restrict__ cb_tiled, const float *__restrict__ cb_n2, uint32_t ch,
+                                            unsigned char *sm)
+{
+    if constexpr (QtSmem<DSUB>::STAGE) {
+        const float4 *src = reinterpret_cast<const float4 *>(cb_tiled + (size_t)ch * 2048 * DSUB);
+        float4 *dst = reinterpret_cast<float4 *>(sm);
+        for (int i = threadIdx.x; i < 2048 * DSUB / 4; i += 256) dst[i] = __ldg(src + i);
+        const float4 *s2 = reinterpret_cast<const float4 *>(cb_n2 + (size_t)ch * 2048);
+        float4 *d2 = reinterpret_cast<float4 *>(sm + QtSmem<DSUB>::N2);
+        for (int i = threadIdx.x; i < 512; i += 256) d2[i] = __ldg(s2 + i);
+        __syncthreads();
+    }
+}
+template <int DSUB>
+__device__ __forceinline__ void load_entry(SubVec<DSUB> &cv, float &cn, const float *__restrict__ cb_tiled,
+                                           const float *__restrict__ cb_n2, uint32_t ch, uint32_t c, int s,
+                                           const unsigned char *sm)
+{
+    if constexpr (QtSmem<DSUB>::STAGE) {
+        const float *e = reinterpret_cast<const float *>(sm) + ((size_t)c * 8 + s) * DSUB;
+        if constexpr (DSUB % 4 == 0) {
+#pragma unroll
+            for (int i = 0; i < DSUB / 4; i++) {
+                const float4 v = reinterpret_cast<const float4 *>(e)[i];
+                cv.p[2 * i] = pack2(v.x, v.y); cv.p[2 * i + 1] = pack2(v.z, v.w);
+            }
+        } else if constexpr (DSUB == 2) {
+            const float2 v = *reinterpret_cast<const float2 *>(e);
+            cv.p[0] = pack2(v.x, v.y);
+        } else {
+            cv.p[0] = pack2(e[0], 0.f);
+        }
+        cn = reinterpret_cast<const float *>(sm + QtSmem<DSUB>::N2)[c * 8 + s];
+    } else {
+        cv.load(cb_tiled + (((size_t)ch * 256 + c) * 8 + s) * DSUB);
+        cn = __ldg(cb_n2 + ((size_t)ch * 256 + c) * 8 + s);
+    }
+}
 
 // ---- pass 1: min_c / max_c of T_q[i][.] for every (query, sub-space)
 template <int DSUB, bool DOT>
@@ -92,36 +145,49 @@ __global__ void __launch_bounds__(256) qtable_minmax_kernel(const float *__restr
                                                             const float *__restrict__ cb_n2, uint32_t B, uint32_t dim,
                                                             uint32_t m, uint32_t nch, float *__restrict__ mm)
 {
-    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5), ch = blockIdx.y;
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const uint32_t q0 = blockIdx.x * 32 + (threadIdx.x >> 5) * QT_NQ, ch = blockIdx.y;
     const int lane = threadIdx.x & 31, s = lane & 7, cq = lane >> 3;
-    if (q >= B) return;
+    stage_chunk<DSUB>(cb_tiled, cb_n2, ch, qsm);
+    if (q0 >= B) return;
     const uint32_t i = ch * 8 + s;
-    float mn = 0.f, mx = 0.f;
+    float mn[QT_NQ], mx[QT_NQ];
+    bool nan[QT_NQ];
+#pragma unroll
+    for (int j = 0; j < QT_NQ; j++) { mn[j] = 0.f; mx[j] = 0.f; nan[j] = false; }
     if (i < m) {
-        SubVec<DSUB> qv;
-        qv.load(Q + (size_t)q * dim + i * DSUB);
-        const float qi2 = qv.dot(qv);
-        mn = CUDART_INF_F; mx = -CUDART_INF_F;
-        bool nan = false;
-        const float *cb = cb_tiled + (((size_t)ch * 256 + cq) * 8 + s) * DSUB;
-        const float *n2 = cb_n2 + ((size_t)ch * 256 + cq) * 8 + s;
-#pragma unroll 4
+        SubVec<DSUB> qv[QT_NQ];
+        float qi2[QT_NQ];
+#pragma unroll
+        for (int j = 0; j < QT_NQ; j++) {
+            qv[j].load(Q + (size_t)min(q0 + j, B - 1) * dim + i * DSUB);
+            qi2[j] = qv[j].dot(qv[j]);
+            mn[j] = CUDART_INF_F; mx[j] = -CUDART_INF_F;
+        }
+#pragma unroll 2
         for (int t = 0; t < 64; t++) {
             SubVec<DSUB> cv;
-            cv.load(cb + (size_t)t * 32 * DSUB);
-            const float v = filter_entry<DSUB, DOT>(qv, qi2, cv, __ldg(n2 + t * 32));
-            mn = fminf(mn, v); mx = fmaxf(mx, v);
-            nan |= v != v;                              // fminf / fmaxf drop NaN
+            float cn;
+            load_entry<DSUB>(cv, cn, cb_tiled, cb_n2, ch, 4 * t + cq, s, qsm);
+#pragma unroll
+            for (int j = 0; j < QT_NQ; j++) {
+                const float v = filter_entry<DSUB, DOT>(qv[j], qi2[j], cv, cn);
+                mn[j] = fminf(mn[j], v); mx[j] = fmaxf(mx[j], v);
+                nan[j] |= v != v;                          // fminf / fmaxf drop NaN
+            }
         }
-        if (nan) { mn = CUDART_NAN_F; mx = CUDART_NAN_F; }
     }
 #pragma unroll
-    for (int o = 8; o <= 16; o <<= 1) {
-        const float on = __shfl_xor_sync(0xffffffffu, mn, o), ox = __shfl_xor_sync(0xffffffffu, mx, o);
-        mn = (on != on || mn != mn) ? CUDART_NAN_F : fminf(mn, on);
-        mx = (ox != ox || mx != mx) ? CUDART_NAN_F : fmaxf(mx, ox);
+    for (int j = 0; j < QT_NQ; j++) {
+        float a = nan[j] ? CUDART_NAN_F : mn[j], b = nan[j] ? CUDART_NAN_F : mx[j];
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            const float on = __shfl_xor_sync(0xffffffffu, a, o), ox = __shfl_xor_sync(0xffffffffu, b, o);
+            a = (on != on || a != a) ? CUDART_NAN_F : fminf(a, on);
+            b = (ox != ox || b != b) ? CUDART_NAN_F : fmaxf(b, ox);
+        }
+        if (cq == 0 && q0 + j < B) reinterpret_cast<float2 *>(mm)[(size_t)(q0 + j) * nch * 8 + i] = make_float2(a, b);
     }
-    if (cq == 0) reinterpret_cast<float2 *>(mm)[(size_t)q * nch * 8 + i] = make_float2(mn, mx);
 }
 
 // ---- pass 2: quantise.  Position j of code c's 16-byte output holds sub-space (j + c) & 7 (the rotation scan3.cu's
@@ -130,64 +196,88 @@ template <int DSUB, bool DOT>
 __global__ void __launch_bounds__(256) qtable_quant_kernel(const float *__restrict__ Q, const float *__restrict__ cb_tiled,
                                                            const float *__restrict__ cb_n2, uint32_t B, uint32_t dim,
                                                            uint32_t m, uint32_t nch, const float *__restrict__ mm,
-                                                           unsigned short *__restrict__ qt, float *__restrict__ step_out,
+                                                           uint4 *__restrict__ qt, float *__restrict__ step_out,
                                                            float *__restrict__ base_out, float *__restrict__ sbound_out,
                                                            uint32_t *__restrict__ bad_out)
 {
-    const uint32_t q = blockIdx.x * 8 + (threadIdx.x >> 5), ch = blockIdx.y;
+    extern __shared__ __align__(16) unsigned char qsm[];
+    const int wid = threadIdx.x >> 5;
+    const uint32_t q0 = blockIdx.x * 32 + wid * QT_NQ, ch = blockIdx.y;
     const int lane = threadIdx.x & 31, s = lane & 7, cq = lane >> 3;
-    if (q >= B) return;
+    stage_chunk<DSUB>(cb_tiled, cb_n2, ch, qsm);
+    if (q0 >= B) return;
+    unsigned short *scratch = reinterpret_cast<unsigned short *>(qsm + QtSmem<DSUB>::SCRATCH) + wid * (QT_NQ * 32 * 8);
     const uint32_t m8 = nch * 8;
     const float qmax = (float)(65535u / m);
-    const float2 *row = reinterpret_cast<const float2 *>(mm) + (size_t)q * m8;
-    // per-query step / base / bound from the min-max table (every warp of the query's 12 CTAs recomputes it)
-    float rng = 0.f, base = 0.f, sb = 0.f;
-    bool bad = false;
-    for (uint32_t i = lane; i < m; i += 32) {
-        const float2 v = row[i];
-        rng = fmaxf(rng, v.y - v.x);
-        base += v.x;
-        sb += fmaxf(fabsf(v.x), fabsf(v.y));
-        bad |= !(fabsf(v.x) < CUDART_INF_F) || !(fabsf(v.y) < CUDART_INF_F);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        rng = fmaxf(rng, __shfl_xor_sync(0xffffffffu, rng, o));
-        base += __shfl_xor_sync(0xffffffffu, base, o);
-        sb += __shfl_xor_sync(0xffffffffu, sb, o);
-    }
-    bad = __any_sync(0xffffffffu, bad) || !(rng < CUDART_INF_F) || !(fabsf(base) < CUDART_INF_F) || !(sb < CUDART_INF_F);
-    float step = (!bad && rng > 0.f) ? rng / qmax : 0.f;
-    float inv = (step > 0.f && qmax / rng < CUDART_INF_F) ? qmax / rng : 0.f;
-    if (rng > 0.f && inv == 0.f) bad = true;            // a range too small to invert: take the exact path
-    if (bad) { step = 0.f; inv = 0.f; }
-    if (ch == 0 && lane == 0) {
-        step_out[q] = step;
-        bad_out[q] = bad ? 1u : 0u;
-        base_out[q] = DOT ? base - (float)(m - 1) : base;
-        sbound_out[q] = sb;
-    }
     const uint32_t i = ch * 8 + s;
-    unsigned short *out = qt + ((size_t)q * nch + ch) * 2048;          // [256 codes][8 positions]
-    if (i >= m) {                                                       // padding sub-space: every entry is 0
-        for (int t = 0; t < 64; t++) { const uint32_t c = 4 * t + cq; out[c * 8 + ((s - c) & 7)] = 0; }
-        return;
+    float inv[QT_NQ], mn[QT_NQ];
+    // per-query step / base / bound from the min-max table (every warp of the query's nch CTAs recomputes it)
+#pragma unroll
+    for (int j = 0; j < QT_NQ; j++) {
+        const uint32_t q = min(q0 + j, B - 1);
+        const float2 *row = reinterpret_cast<const float2 *>(mm) + (size_t)q * m8;
+        float rng = 0.f, base = 0.f, sb = 0.f;
+        bool bad = false;
+        for (uint32_t ii = lane; ii < m; ii += 32) {
+            const float2 v = row[ii];
+            rng = fmaxf(rng, v.y - v.x);
+            base += v.x;
+            sb += fmaxf(fabsf(v.x), fabsf(v.y));
+            bad |= !(fabsf(v.x) < CUDART_INF_F) || !(fabsf(v.y) < CUDART_INF_F);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rng = fmaxf(rng, __shfl_xor_sync(0xffffffffu, rng, o));
+            base += __shfl_xor_sync(0xffffffffu, base, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        bad = __any_sync(0xffffffffu, bad) || !(rng < CUDART_INF_F) || !(fabsf(base) < CUDART_INF_F) || !(sb < CUDART_INF_F);
+        float step = (!bad && rng > 0.f) ? rng / qmax : 0.f;
+        float iv = (step > 0.f && qmax / rng < CUDART_INF_F) ? qmax / rng : 0.f;
+        if (rng > 0.f && iv == 0.f) bad = true;         // a range too small to invert: take the exact path
+        if (bad) { step = 0.f; iv = 0.f; }
+        if (ch == 0 && lane == 0 && q0 + j < B) {
+            step_out[q] = step;
+            bad_out[q] = bad ? 1u : 0u;
+            base_out[q] = DOT ? base - (float)(m - 1) : base;
+            sbound_out[q] = sb;
+        }
+        inv[j] = iv;
+        mn[j] = i < m ? row[i].x : 0.f;
     }
-    SubVec<DSUB> qv;
-    qv.load(Q + (size_t)q * dim + i * DSUB);
-    const float qi2 = qv.dot(qv);
-    const float mn = row[i].x;
-    const float *cb = cb_tiled + (((size_t)ch * 256 + cq) * 8 + s) * DSUB;
-    const float *n2 = cb_n2 + ((size_t)ch * 256 + cq) * 8 + s;
-#pragma unroll 4
-    for (int t = 0; t < 64; t++) {
-        SubVec<DSUB> cv;
-        cv.load(cb + (size_t)t * 32 * DSUB);
-        const float v = filter_entry<DSUB, DOT>(qv, qi2, cv, __ldg(n2 + t * 32));
-        float x = (v - mn) * inv;
-        x = x >= 0.f ? fminf(floorf(x), qmax) : 0.f;                    // NaN -> 0 (the query is flagged bad)
-        const uint32_t c = 4 * t + cq;
-        out[c * 8 + ((s - c) & 7)] = (unsigned short)x;
+    SubVec<DSUB> qv[QT_NQ];
+    float qi2[QT_NQ];
+#pragma unroll
+    for (int j = 0; j < QT_NQ; j++) {
+        if (i < m) qv[j].load(Q + (size_t)min(q0 + j, B - 1) * dim + i * DSUB);
+        else { for (int e = 0; e < SubVec<DSUB>::NP; e++) qv[j].p[e] = 0ull; }
+        qi2[j] = qv[j].dot(qv[j]);
+    }
+    const size_t qstride = (size_t)nch * 256;                           // uint4 per query
+    uint4 *out0 = qt + ((size_t)q0 * nch + ch) * 256;
+    for (int t8 = 0; t8 < 8; t8++) {                                    // 32 codes at a time
+#pragma unroll 2
+        for (int tt = 0; tt < 8; tt++) {
+            const int t = t8 * 8 + tt;
+            const uint32_t c = 4 * t + cq;
+            SubVec<DSUB> cv;
+            float cn;
+            load_entry<DSUB>(cv, cn, cb_tiled, cb_n2, ch, c, s, qsm);
+            const uint32_t at = (4 * tt + cq) * 8 + ((s - c) & 7);
+#pragma unroll
+            for (int j = 0; j < QT_NQ; j++) {
+                const float v = filter_entry<DSUB, DOT>(qv[j], qi2[j], cv, cn);
+                float x = (v - mn[j]) * inv[j];
+                x = (x >= 0.f && i < m) ? fminf(floorf(x), qmax) : 0.f;  // NaN -> 0 (flagged bad); padding sub-space -> 0
+                scratch[j * 256 + at] = (unsigned short)x;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < QT_NQ; j++)
+            if (q0 + j < B)
+                out0[j * qstride + t8 * 32 + lane] = reinterpret_cast<const uint4 *>(scratch + j * 256)[lane];
+        __syncwarp();
     }
 }
 
@@ -200,6 +290,42 @@ __global__ void cb_norms_kernel(const float *__restrict__ cb_tiled, uint64_t n, 
     SubVec<DSUB> v;
     v.load(cb_tiled + e * DSUB);
     out[e] = v.dot(v);
+}
+
+// DSUB floats from global memory; 16-byte loads when DSUB is a multiple of 4 and the address allows it
+template <int DSUB>
+__device__ __forceinline__ void load_cb(float *dst, const float *src)
+{
+    if constexpr (DSUB % 4 == 0) {
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < DSUB / 4; i++) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < DSUB; i++) dst[i] = __ldg(src + i);
+}
+
+// same with generic (global or shared) loads: the finalize kernel keeps the query in shared memory
+template <int DSUB>
+__device__ __forceinline__ void load_any(float *dst, const float *src)
+{
+    if constexpr (DSUB % 4 == 0) {
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < DSUB / 4; i++) {
+                const float4 v = reinterpret_cast<const float4 *>(src)[i];
+                dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < DSUB; i++) dst[i] = src[i];
 }
 
 __device__ __forceinline__ uint32_t find_partition(const uint64_t *__restrict__ part_off, uint32_t nlist, uint64_t pos)
@@ -249,7 +375,7 @@ __global__ void row_const_kernel(const unsigned char *__restrict__ codes, const 
 // the codeword and the query / centroid sub-vectors), then the entries are summed in order i = 0..m-1 (the oracle's
 // order) by walking them through a shuffle.  m <= 512.  Every lane returns the distance.
 template <int DSUB>
-__device__ __forceinline__ float exact_pq_distance_warp(const float *__restrict__ qv, const float *__restrict__ cen,
+__device__ __forceinline__ float exact_pq_distance_warp(const float *qv, const float *__restrict__ cen,
                                                         const unsigned char *__restrict__ codes, uint64_t cbase,
                                                         uint32_t npad, uint32_t row, const float *__restrict__ cb_tiled,
                                                         uint32_t m, int metric, int lane)
@@ -262,12 +388,14 @@ __device__ __forceinline__ float exact_pq_distance_warp(const float *__restrict_
         if ((uint32_t)it * 32 < m && i < m) {
             const uint32_t c = stream_code(codes, cbase, npad, row, i);
             const float *cb = cb_tiled + (((size_t)(i >> 3) * 256 + c) * 8 + (i & 7)) * DSUB;
-            float r[DSUB], cv[DSUB];
+            // 16-byte loads: with 4-byte loads a warp re-touches the same 32 sectors DSUB times per array and the
+            // L1 sector throughput, not latency, bounds the kernel
+            float r[DSUB], cv[DSUB], qq[DSUB], cc[DSUB];
+            load_cb<DSUB>(cv, cb);
+            load_any<DSUB>(qq, qv + i * DSUB);
+            if (metric != LGPU_DOT) load_cb<DSUB>(cc, cen + i * DSUB);
 #pragma unroll
-            for (int t = 0; t < DSUB; t++) {
-                cv[t] = cb[t];
-                r[t] = (metric == LGPU_DOT) ? qv[i * DSUB + t] : __fsub_rn(qv[i * DSUB + t], cen[i * DSUB + t]);
-            }
+            for (int t = 0; t < DSUB; t++) r[t] = (metric == LGPU_DOT) ? qq[t] : __fsub_rn(qq[t], cc[t]);
             tv[it] = (metric == LGPU_DOT) ? subvec_dot_dist<DSUB>(r, cv) : subvec_l2<DSUB>(r, cv);
         }
     }
@@ -326,6 +454,25 @@ __global__ void cand_prepare_kernel(const float *__restrict__ step, const float 
 }
 
 constexpr int FIN_THREADS = 256;
+// bitonic sort of n2 (power of two) shared-memory entries by (key, tie), ascending; `payload` follows
+template <class Swap>
+__device__ __forceinline__ void bitonic_smem(uint32_t n2, int tid, Swap &&cmp_swap)
+{
+    for (uint32_t size = 2; size <= n2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (n2 >> 1); i += FIN_THREADS) {
+                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                cmp_swap(lo, hi, (lo & size) == 0);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per query.  (1) sort the query's candidates by lower bound; their k-th smallest L is the tightest
+// threshold this family of bounds allows (every row with L <= tau is in the list, and the list holds k of them), so
+// only candidates with L <= L_(k) + slack are (2) re-scored exactly, one warp per candidate, the query staged in
+// shared memory; (3) the survivors are sorted by (distance, row id) and the best k written out.
 template <int DSUB>
 __global__ void __launch_bounds__(FIN_THREADS) cand_finalize_kernel(FinalizeArgs a)
 {
@@ -333,6 +480,9 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finalize_kernel(FinalizeArgs
     uint64_t *s_id = reinterpret_cast<uint64_t *>(fsm);
     uint64_t *s_pos = s_id + a.cand_cap;
     uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pos + a.cand_cap);
+    uint32_t *s_lkey = s_key + a.cand_cap;                  // lower-bound keys, then candidate order
+    uint32_t *s_lidx = s_lkey + a.cand_cap;
+    float *s_q = reinterpret_cast<float *>(s_lidx + a.cand_cap);
     __shared__ uint32_t s_n;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -342,15 +492,28 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finalize_kernel(FinalizeArgs
         s_n = 0;
         a.flags[q] = (total > a.cand_cap || a.bad[q]) ? 1u : 0u;
     }
-    __syncthreads();
-    const uint32_t tkey = a.thr[q];
-    const float lim = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey) + a.slack[q];
     const CandRec *cand = a.cand + (size_t)q * a.cand_cap;
-    const float *qv = a.Q + (size_t)q * a.dim;
+    for (uint32_t t = tid; t < a.dim; t += FIN_THREADS) s_q[t] = a.Q[(size_t)q * a.dim + t];
+    uint32_t n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = tid; i < n2; i += FIN_THREADS) {
+        s_lkey[i] = i < n ? f32_key(cand[i].lb) : 0xffffffffu;
+        s_lidx[i] = i;
+    }
+    __syncthreads();
+    bitonic_smem(n2, tid, [&](uint32_t lo, uint32_t hi, bool asc) {
+        const uint32_t ka = s_lkey[lo], kb = s_lkey[hi], ia = s_lidx[lo], ib = s_lidx[hi];
+        if ((kb < ka || (kb == ka && ib < ia)) == asc) { s_lkey[lo] = kb; s_lkey[hi] = ka; s_lidx[lo] = ib; s_lidx[hi] = ia; }
+    });
+    // threshold: the scanners' tau_q, tightened to the k-th smallest lower bound when the list has k rows
+    const uint32_t tkey = a.thr[q];
+    float tau = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey);
+    if (n >= a.k && total <= a.cand_cap) tau = fminf(tau, key_f32(s_lkey[a.k - 1]));
+    const float lim = tau + a.slack[q];
     for (uint32_t c = w; c < n; c += FIN_THREADS / 32) {
-        const CandRec rec = cand[c];
-        if (!(rec.lb <= lim)) continue;                     // the threshold tightened after this row was appended
-        float d = exact_pq_distance_warp<DSUB>(qv, a.centroids + (size_t)rec.p * a.dim, a.codes, a.code_base[rec.p],
+        if (!(key_f32(s_lkey[c]) <= lim)) break;            // sorted: nothing further can pass
+        const CandRec rec = cand[s_lidx[c]];
+        float d = exact_pq_distance_warp<DSUB>(s_q, a.centroids + (size_t)rec.p * a.dim, a.codes, a.code_base[rec.p],
                                                a.part_npad[rec.p], rec.row, a.cb_tiled, a.m, a.metric, lane);
         if (d != d) continue;                               // FilterExec: _distance IS NOT NULL
         if (d == 0.f) d = 0.f;                              // -0 and +0 tie
@@ -362,26 +525,22 @@ __global__ void __launch_bounds__(FIN_THREADS) cand_finalize_kernel(FinalizeArgs
     }
     __syncthreads();
     const uint32_t cnt = s_n;
-    uint32_t n2 = 2;
-    while (n2 < cnt) n2 <<= 1;
-    for (uint32_t i = cnt + tid; i < n2; i += FIN_THREADS) { s_key[i] = 0xffffffffu; s_id[i] = UINT64_MAX; s_pos[i] = UINT64_MAX; }
-    __syncthreads();
-    for (uint32_t size = 2; size <= n2; size <<= 1) {       // bitonic sort by (distance key, row id), ascending
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t i = tid; i < (n2 >> 1); i += FIN_THREADS) {
-                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                const bool asc = (lo & size) == 0;
-                const uint32_t ka = s_key[lo], kb = s_key[hi];
-                const uint64_t ia = s_id[lo], ib = s_id[hi];
-                const bool gt = kb < ka || (kb == ka && ib < ia);
-                if (gt == asc) {
-                    s_key[lo] = kb; s_key[hi] = ka; s_id[lo] = ib; s_id[hi] = ia;
-                    const uint64_t pa = s_pos[lo]; s_pos[lo] = s_pos[hi]; s_pos[hi] = pa;
-                }
-            }
-            __syncthreads();
-        }
+    if (a.stats && tid == 0) {
+        atomicAdd(a.stats + 0, (unsigned long long)total); atomicAdd(a.stats + 1, (unsigned long long)cnt);
+        atomicAdd(a.stats + 2, (unsigned long long)((total > a.cand_cap || a.bad[q]) ? 1 : 0)); atomicAdd(a.stats + 3, 1ull);
     }
+    uint32_t m2 = 2;
+    while (m2 < cnt) m2 <<= 1;
+    for (uint32_t i = cnt + tid; i < m2; i += FIN_THREADS) { s_key[i] = 0xffffffffu; s_id[i] = UINT64_MAX; s_pos[i] = UINT64_MAX; }
+    __syncthreads();
+    bitonic_smem(m2, tid, [&](uint32_t lo, uint32_t hi, bool asc) {
+        const uint32_t ka = s_key[lo], kb = s_key[hi];
+        const uint64_t ia = s_id[lo], ib = s_id[hi];
+        if ((kb < ka || (kb == ka && ib < ia)) == asc) {
+            s_key[lo] = kb; s_key[hi] = ka; s_id[lo] = ib; s_id[hi] = ia;
+            const uint64_t pa = s_pos[lo]; s_pos[lo] = s_pos[hi]; s_pos[hi] = pa;
+        }
+    });
     for (uint32_t i = tid; i < a.k; i += FIN_THREADS) {
         const bool have = i < cnt;
         a.out_ids[(size_t)q * a.k + i] = have ? s_id[i] : UINT64_MAX;
@@ -469,17 +628,18 @@ void launch_query_tables_q16(const float *Q, const float *cb_tiled, const float 
                              float *base, float *sbound, uint32_t *bad, cudaStream_t st)
 {
     if (B == 0) return;
-    const dim3 grid((B + 7) / 8, nch);
-    unsigned short *qt16 = reinterpret_cast<unsigned short *>(qt);
+    const dim3 grid((B + 31) / 32, nch);
     dispatch_dsub(dsub, [&](auto D) {
         constexpr int DS = decltype(D)::value;
-        if (metric == LGPU_DOT) {
-            qtable_minmax_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
-            qtable_quant_kernel<DS, true><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt16, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
-        } else {
-            qtable_minmax_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
-            qtable_quant_kernel<DS, false><<<grid, 256, 0, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt16, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
-        }
+        constexpr size_t s1 = QtSmem<DS>::TOTAL_MINMAX, s2 = QtSmem<DS>::TOTAL_QUANT;
+        auto run = [&](auto k1, auto k2) {
+            LGPU_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+            LGPU_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+            k1<<<grid, 256, s1, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
+            k2<<<grid, 256, s2, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
+        };
+        if (metric == LGPU_DOT) run(qtable_minmax_kernel<DS, true>, qtable_quant_kernel<DS, true>);
+        else run(qtable_minmax_kernel<DS, false>, qtable_quant_kernel<DS, false>);
     });
     LGPU_CUDA(cudaGetLastError());
 }
@@ -546,7 +706,7 @@ void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
         set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity >= k");
         throw Failure{LGPU_RUNTIME};
     }
-    const size_t smem = (size_t)a.cand_cap * 20;
+    const size_t smem = (size_t)a.cand_cap * 28 + (size_t)a.dim * 4;
     dispatch_dsub(a.dsub, [&](auto D) {
         auto kern = cand_finalize_kernel<decltype(D)::value>;
         LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -8,7 +8,7 @@ tail -3 gpurun_out/${TAG}_bench.err
 python - <<PY
 import json
 j=json.load(open('gpurun_out/${TAG}_bench.json'))
-print({k:j[k] for k in ('value','ms_per_step','gpu_launches')}); print(j['stage_ms']); print('frac',j['roofline']['frac'], 'e2e', j['e2e']['value'], j['e2e']['pipelined']['value'])
+print({k:j[k] for k in ('value','ms_per_step','gpu_launches')}); print(j['stage_ms'], j.get('filter_stats')); print('frac',j['roofline']['frac'], 'e2e', j['e2e']['value'], j['e2e']['pipelined']['value'])
 PY
 KREGEX='regex:scan3_kernel|scan2_kernel|tile_desc|select|dist_matrix|group_|normalize|pair_distance|gemm_dist|bf16|band|threshold|overflow|filter_dense|qtable|probe_terms|pq_rescore|pack_records|count_below|finalize|slack|coarse'
 timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -s 300 -c 60 --csv \
