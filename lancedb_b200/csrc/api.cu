@@ -508,19 +508,23 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         // from ~1M (query, centroid) pairs the tensor-core shortlist wins (C2: 0.16 vs 0.19 ms)
         const bool big = (uint64_t)B * nlist >= ((uint64_t)1 << 20) || getenv("LGPU_FORCE_TC_COARSE");
         if (ix->has_tc && tc_enabled() && ix->metric != LGPU_DOT && B >= 8 && nlist >= 256 && kp > nprobes && big) {
-            // tcgen05 GEMM shortlist + exact re-score (bit-identical probe sets, see gemm.cu)
+            // tcgen05 GEMM scores + one finishing kernel per query (threshold, exact re-score in lance order, top
+            // nprobes): bit-identical probe sets; queries whose candidate band overflowed are redone exactly
             mark();
-            if (nlist >= 1024 && nprobes <= 64 && !getenv("LGPU_COARSE_DENSE"))
-                // sampled threshold + filtering epilogue (as in the flat path): no 64-wide block select
-                tc_topk_l2_filtered(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
-                                    ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes,
-                                    ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(),
-                                    ws->probe_cnt.as<uint32_t>(), ws->D.as<float>(), ldc, 1024, 512);
-            else
-                tc_topk_l2(ws, st, ix->num_sms, qsearch, B, ix->centroids.as<float>(), ix->cent_b.p,
-                           ix->cent_n2.as<float>(), ix->cent_max, nlist, dim, nullptr, nprobes, std::min(kp, nlist),
-                           ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(), ws->probe_cnt.as<uint32_t>(),
-                           ws->D.as<float>(), ldc);
+            ws->qb.ensure((size_t)B * dim * 2); ws->qn2.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
+            launch_to_bf16(qsearch, B, dim, ws->qb.p, ws->qn2.as<float>(), st);
+            launch_gemm_dist(ws->qb.p, ix->cent_b.p, ix->cent_n2.as<float>(), B, nlist, dim, ws->D.as<float>(), ldc,
+                             ix->num_sms, st);
+            launch_coarse_finish(ws->D.as<float>(), ldc, B, nlist, qsearch, ix->centroids.as<float>(), ws->qn2.as<float>(),
+                                 ix->cent_max, dim, nprobes, ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(),
+                                 ws->probe_cnt.as<uint32_t>(), ws->flags.as<uint32_t>(), st);
+            launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, 0, nullptr, nullptr, ws->D.as<float>(), ldc,
+                               st, ws->flags.as<uint32_t>());
+            SelectArgs sc{};
+            sc.mode = 1; sc.dense = ws->D.as<float>(); sc.ncols = nlist; sc.row_stride = ldc;
+            sc.B = B; sc.k = nprobes; sc.out_ids = ws->probes.as<uint64_t>(); sc.out_dist = ws->probe_dist.as<float>();
+            sc.out_count = ws->probe_cnt.as<uint32_t>(); sc.only = ws->flags.as<uint32_t>();
+            launch_select(sc, st);
         } else {
             launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, ix->metric == LGPU_DOT ? 1 : 0,
                                nullptr, nullptr, ws->D.as<float>(), ldc, st);

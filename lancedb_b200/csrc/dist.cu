@@ -194,7 +194,127 @@ __global__ void pair_distance_kernel(const float *__restrict__ Q, const float *_
     if (hl == 0) out[pair] = v;
 }
 
+// ---- the coarse step after the tensor-core GEMM, in one kernel (one CTA per query):
+// S[q][x] = |x|^2 - 2 bf16(q).bf16(x) differs from |q - x|^2 - |q|^2 by at most E_q (gemm.cu's band).  (1) an upper
+// bound tau of the k-th smallest S of the row by counting bisection; (2) every column with S <= tau + 2 E_q -- a
+// superset of the exact k nearest -- is (3) re-scored exactly in lance's lane order, half a warp per column, and
+// (4) the k best by (distance, column) are written.  More than `cap` candidates (ties, degenerate data): flags[q] = 1
+// and the caller's exact kernels redo the query.
+constexpr int CF_THREADS = 256;
+__global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *__restrict__ S, uint64_t ld, uint32_t N,
+                                                                   const float *__restrict__ Q, const float *__restrict__ C,
+                                                                   const float *__restrict__ qn2, float xmax, uint32_t d,
+                                                                   uint32_t k, uint32_t cap, int staged,
+                                                                   uint64_t *__restrict__ out_ids, float *__restrict__ out_dist,
+                                                                   uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char csm[];
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(csm);           // [cap] candidate columns
+    uint32_t *s_key = s_col + cap;                                  // [cap] exact distance keys
+    float *s_row = reinterpret_cast<float *>(s_key + cap);          // [N] when staged
+    __shared__ uint32_t s_lo, s_hi, s_valid, s_n, s_cnt[24];
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float *grow = S + (size_t)q * ld;
+    const float *row = staged ? s_row : grow;
+    if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_valid = 0u; s_n = 0u; }
+    if (tid < 24) s_cnt[tid] = 0u;
+    __syncthreads();
+    uint32_t kmin = 0xffffffffu, kmax = 0u, nv = 0;
+    for (uint32_t i = tid; i < N; i += CF_THREADS) {
+        const float v = grow[i];
+        if (staged) s_row[i] = v;
+        if (v == v) { const uint32_t kk = f32_key(v); kmin = min(kmin, kk); kmax = max(kmax, kk); nv++; }
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    if (lane == 0) { atomicMin(&s_lo, kmin); atomicMax(&s_hi, kmax); atomicAdd(&s_valid, nv); }
+    __syncthreads();
+    const uint32_t kk = min(k, s_valid);
+    float thr = -CUDART_INF_F;
+    if (kk > 0) {
+        float lo = key_f32(s_lo), hi = key_f32(s_hi);               // invariant: count(S <= hi) >= kk
+        if (hi < CUDART_INF_F && lo > -CUDART_INF_F) {
+            for (int it = 0; it < 20; it++) {
+                const float mid = 0.5f * lo + 0.5f * hi;
+                uint32_t c = 0;
+                for (uint32_t i = tid; i < N; i += CF_THREADS) c += row[i] <= mid ? 1u : 0u;
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0 && c) atomicAdd(&s_cnt[it], c);
+                __syncthreads();
+                if (s_cnt[it] >= kk) hi = mid; else lo = mid;
+            }
+        }
+        const float qn = sqrtf(qn2[q]);
+        const float sm = qn + xmax;
+        const float E = 0.0078125f * 1.00390625f * qn * xmax + 4.0f * (float)d * 5.9604645e-8f * sm * sm;
+        thr = hi + 2.0f * E;
+    }
+    for (uint32_t i = tid; i < N; i += CF_THREADS) {
+        if (row[i] <= thr) {
+            const uint32_t at = atomicAdd(&s_n, 1u);
+            if (at < cap) s_col[at] = i;
+        }
+    }
+    __syncthreads();
+    const uint32_t total = s_n, n = min(total, cap);
+    if (tid == 0) flags[q] = total > cap ? 1u : 0u;
+    // exact re-score, half a warp per candidate column (lance's l2: 16 lane accumulators, sequential lane sum)
+    const int hl = lane & 15, hbase = lane & 16;
+    const unsigned hmask = 0xffffu << hbase;
+    const float *x = Q + (size_t)q * d;
+    for (uint32_t c0 = 0; c0 < n; c0 += CF_THREADS / 16) {
+        const uint32_t c = c0 + (tid >> 4);
+        if (c < n) {                                                 // a whole half-warp takes the branch together
+            const float v = halfwarp_l2(x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
+            if (hl == 0) s_key[c] = (v != v) ? 0xffffffffu : f32_key(v == 0.f ? 0.f : v);
+        }
+    }
+    __syncthreads();
+    uint32_t n2 = 2;
+    while (n2 < n) n2 <<= 1;
+    for (uint32_t i = n + tid; i < n2 && i < cap; i += CF_THREADS) { s_key[i] = 0xffffffffu; s_col[i] = 0xffffffffu; }
+    __syncthreads();
+    for (uint32_t size = 2; size <= n2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = tid; i < (n2 >> 1); i += CF_THREADS) {
+                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const uint32_t ka = s_key[lo], kb = s_key[hi], ia = s_col[lo], ib = s_col[hi];
+                if ((kb < ka || (kb == ka && ib < ia)) == ((lo & size) == 0)) {
+                    s_key[lo] = kb; s_key[hi] = ka; s_col[lo] = ib; s_col[hi] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    uint32_t have = 0;                                               // NaN distances sort last and are dropped
+    for (uint32_t i = tid; i < k; i += CF_THREADS) {
+        const bool ok = i < n && s_key[i] != 0xffffffffu;
+        out_ids[(size_t)q * k + i] = ok ? (uint64_t)s_col[i] : UINT64_MAX;
+        out_dist[(size_t)q * k + i] = ok ? key_f32(s_key[i]) : CUDART_INF_F;
+        have += ok ? 1u : 0u;
+    }
+    have = __reduce_add_sync(0xffffffffu, have);
+    if (tid == 0) out_cnt[q] = 0;
+    __syncthreads();
+    if (lane == 0 && have) atomicAdd(out_cnt + q, have);
+}
+
 }  // namespace
+
+void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, const float *Q, const float *C,
+                          const float *qn2, float xmax, uint32_t d, uint32_t k, uint64_t *out_ids, float *out_dist,
+                          uint32_t *out_cnt, uint32_t *flags, cudaStream_t st)
+{
+    if (B == 0 || N == 0) return;
+    uint32_t cap = 256;
+    while (cap < 4 * k) cap <<= 1;                                   // power of two >= 4 k
+    const int staged = (size_t)N * 4 <= 96 * 1024 ? 1 : 0;
+    const size_t smem = (size_t)cap * 8 + (staged ? (size_t)N * 4 : 0);
+    LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    coarse_finish_kernel<<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, staged, out_ids, out_dist, out_cnt, flags); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaGetLastError());
+}
 
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
                         const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st,

@@ -110,6 +110,12 @@ void launch_group(const GroupArgs &a, cudaStream_t st);
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
                         const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st,
                         const uint32_t *only = nullptr);
+// coarse step after the tensor-core GEMM, one kernel: from S[B][ld] = |x|^2 - 2 bf16(q).bf16(x) (N columns) to the k
+// columns with the smallest EXACT l2 distance (lance lane order), ascending by (distance, column); flags[q] = 1 when
+// the candidate band overflowed and the caller must redo the query with the exact kernels
+void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, const float *Q, const float *C,
+                          const float *qn2, float xmax, uint32_t d, uint32_t k, uint64_t *out_ids, float *out_dist,
+                          uint32_t *out_cnt, uint32_t *flags, cudaStream_t st);
 // row norms |x| = sqrt(dot(x,x)) in lance order; out[n]
 void launch_row_norms(const float *X, uint64_t n, uint32_t d, float *out, cudaStream_t st);
 // out[q] = x[q] / |x[q]|
