@@ -89,6 +89,8 @@ struct DevBuf {
 
 struct Workspace {
     cudaStream_t stream = nullptr;     // private stream (host-buffer entry points)
+    cudaStream_t aux = nullptr;        // side stream: the per-query tables are built while the coarse step runs
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
     cudaEvent_t ev[8] = {};
     DevBuf q, qn, xnorm, D, probes, probe_dist, probe_cnt;
@@ -107,10 +109,14 @@ struct Workspace {
     DevBuf qt, qt_mm, qt_step, qt_base, qt_bad;   // filter scan (scan3.cu): quantised per-query tables
     DevBuf s_ids, s_lb, s_pos, s_cnt, s_exact;    // filter scan (dense mode): shortlist by lower bound, exact re-score
     DevBuf c_stats;                               // candidate-mode counters (profiling only)
+    DevBuf c_work, c_wcnt, c_surv, c_exd, c_exi, c_exp;   // candidate mode: survivor work list and exact results
     DevBuf c_thr, c_slack, c_cnt, c_rec;          // filter scan (candidate mode): thresholds, bands, candidate lists
     Workspace()
     {
         LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        LGPU_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        LGPU_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        LGPU_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         LGPU_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
         for (auto &e : ev) LGPU_CUDA(cudaEventCreate(&e));
     }
@@ -118,6 +124,9 @@ struct Workspace {
     {
         if (graph) cudaGraphExecDestroy(graph);
         if (stream) cudaStreamDestroy(stream);
+        if (aux) cudaStreamDestroy(aux);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (done) cudaEventDestroy(done);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
     }
@@ -303,6 +312,7 @@ struct WsLease {
     }
     ~WsLease()
     {
+        cudaStreamWaitEvent(st, ws->ev_join, 0);        // side-stream work of a call that failed half-way (no-op otherwise)
         cudaEventRecord(ws->done, st);
         pool.give(ws);
     }
@@ -492,6 +502,25 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         launch_normalize(d_q, B, dim, ws->qn.as<float>(), st);
         qsearch = ws->qn.as<float>();
     }
+    // ---- which scan: filter + verify (scan3.cu) unless the request needs every exact distance.  The filter's
+    // per-query tables depend on the queries alone, so they are built on a side stream while the coarse step and the
+    // regrouping (small kernels that leave most SMs idle) run on this one ----
+    // the PQ top-`kk` of every query (kk = k, or k * refine_factor candidates for the exact re-rank)
+    const uint32_t kk = sp.refine_factor ? sp.k * sp.refine_factor : sp.k;
+    const uint32_t kp = kk <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * kk + 32);
+    const bool filter_scan = ix->has_tables && !exact_scan_forced() && !sp.has_lower && !sp.has_upper && !forced_probes &&
+                             d_ids && kp > kk && ix->m <= 512 && !only;
+    if (filter_scan) {
+        ws->qt.ensure((size_t)B * ix->nch * 256 * 16); ws->qt_mm.ensure((size_t)B * ix->nch * 8 * 8);
+        ws->qt_step.ensure((size_t)B * 4); ws->qt_base.ensure((size_t)B * 4); ws->qt_bad.ensure((size_t)B * 4);
+        ws->sbound.ensure((size_t)B * 4);
+        LGPU_CUDA(cudaEventRecord(ws->ev_fork, st));
+        LGPU_CUDA(cudaStreamWaitEvent(ws->aux, ws->ev_fork, 0));
+        launch_query_tables_q16(qsearch, ix->cb_tiled.as<float>(), ix->cb_n2.as<float>(), B, dim, ix->m, ix->nch, ix->dsub,
+                                ix->metric, ws->qt_mm.as<float>(), ws->qt.as<uint4>(), ws->qt_step.as<float>(),
+                                ws->qt_base.as<float>(), ws->sbound.as<float>(), ws->qt_bad.as<uint32_t>(), ws->aux);
+        LGPU_CUDA(cudaEventRecord(ws->ev_join, ws->aux));
+    }
     // ---- K1: exact centroid distances + nprobes nearest ----
     ws->probes.ensure((size_t)slots * 8);
     ws->probe_dist.ensure((size_t)slots * 4);
@@ -565,12 +594,6 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         ws->tile_desc.ensure((size_t)max_tiles * sizeof(TileDesc));
         ga.tile_desc = ws->tile_desc.as<TileDesc>(); ga.max_tiles = (uint32_t)max_tiles;
     }
-    // the PQ top-`kk` of every query (kk = k, or k * refine_factor candidates for the exact re-rank)
-    const uint32_t kk = sp.refine_factor ? sp.k * sp.refine_factor : sp.k;
-    // ---- which scan: filter + verify (scan3.cu) unless the request needs every exact distance ----
-    const uint32_t kp = kk <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * kk + 32);
-    const bool filter_scan = ix->has_tables && !exact_scan_forced() && !sp.has_lower && !sp.has_upper && !forced_probes &&
-                             d_ids && kp > kk && ix->m <= 512 && !only;
     ga.only = only;
     ga.rows_tile = filter_scan ? SCAN3_ROWS_TILE : SCAN_ROWS_TILE_MID;
     launch_group(ga, st);
@@ -611,14 +634,10 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     if (filter_scan) {
         // per-query 16-bit tables, per-probe scalars
         const bool dot = ix->metric == LGPU_DOT;
-        ws->qt.ensure((size_t)B * ix->nch * 256 * 16); ws->qt_mm.ensure((size_t)B * ix->nch * 8 * 8);
-        ws->qt_step.ensure((size_t)B * 4); ws->qt_base.ensure((size_t)B * 4); ws->qt_bad.ensure((size_t)B * 4);
-        ws->sbound.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
+        ws->flags.ensure((size_t)B * 4);
         ws->s_ids.ensure((size_t)B * kp * 8); ws->s_lb.ensure((size_t)B * kp * 4); ws->s_pos.ensure((size_t)B * kp * 8);
         ws->s_cnt.ensure((size_t)B * 4); ws->s_exact.ensure((size_t)B * kp * 4);
-        launch_query_tables_q16(qsearch, ix->cb_tiled.as<float>(), ix->cb_n2.as<float>(), B, dim, ix->m, ix->nch, ix->dsub, ix->metric,
-                                ws->qt_mm.as<float>(), ws->qt.as<uint4>(), ws->qt_step.as<float>(), ws->qt_base.as<float>(),
-                                ws->sbound.as<float>(), ws->qt_bad.as<uint32_t>(), st);
+        LGPU_CUDA(cudaStreamWaitEvent(st, ws->ev_join, 0));        // the tables, built on the side stream
         ws->qn2.ensure((size_t)B * 4);
         if (!dot) {
             ws->probe_A.ensure((size_t)slots * 4); ws->amax.ensure((size_t)B * 4);
@@ -635,7 +654,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
             // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
             static const uint32_t cap_env = getenv("LGPU_CAND_CAP") ? (uint32_t)atoi(getenv("LGPU_CAND_CAP")) : 0u;
             uint32_t cap = 512;
-            if (cap_env >= 32 && cap_env <= 4096 && !(cap_env & (cap_env - 1))) cap = cap_env;
+            if (cap_env >= 32 && cap_env <= 512 && !(cap_env & (cap_env - 1))) cap = cap_env;
             ws->c_thr.ensure((size_t)B * 4); ws->c_slack.ensure((size_t)B * 4); ws->c_cnt.ensure((size_t)B * 4);
             ws->c_rec.ensure((size_t)B * cap * sizeof(CandRec));
             launch_cand_prepare(ws->qt_step.as<float>(), ws->sbound.as<float>(), dot ? nullptr : ws->amax.as<float>(),
@@ -655,6 +674,11 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
             fa.B = B; fa.dim = dim; fa.m = ix->m; fa.dsub = ix->dsub; fa.k = kk; fa.metric = ix->metric;
             fa.out_ids = pq_ids; fa.out_dist = pq_dist; fa.out_count = pq_cnt; fa.out_pos = pq_pos;
             fa.flags = ws->flags.as<uint32_t>();
+            ws->c_work.ensure((size_t)B * cap * 8); ws->c_wcnt.ensure(16); ws->c_surv.ensure((size_t)B * 4);
+            ws->c_exd.ensure((size_t)B * cap * 4); ws->c_exi.ensure((size_t)B * cap * 8); ws->c_exp.ensure((size_t)B * cap * 8);
+            fa.work = ws->c_work.as<uint2>(); fa.work_cnt = ws->c_wcnt.as<uint32_t>(); fa.surv_cnt = ws->c_surv.as<uint32_t>();
+            fa.ex_dist = ws->c_exd.as<float>(); fa.ex_id = ws->c_exi.as<uint64_t>(); fa.ex_pos = ws->c_exp.as<uint64_t>();
+            fa.num_sms = ix->num_sms;
             if (prof) {
                 ws->c_stats.ensure(32);
                 LGPU_CUDA(cudaMemsetAsync(ws->c_stats.p, 0, 32, st));

@@ -154,6 +154,7 @@ struct SelectArgs {
     const uint64_t *col_ids;      // mode 1: optional id per column (NULL => column index)
     const uint64_t *cand_ids;     // mode 2: id per entry (same addressing as dense)
     const uint64_t *cand_pos;     // mode 2: optional pos per entry
+    const uint32_t *ncols_q;      // mode 2: optional [B] candidates of each query (<= ncols)
     const TopkRecord *cand_rec;   // mode 2: optional packed (id, dist) entries instead of dense + cand_ids
     // common
     uint32_t B, k;
@@ -247,6 +248,12 @@ struct FinalizeArgs {
     uint32_t B, dim, m, dsub, k; int metric;
     uint64_t *out_ids; float *out_dist; uint32_t *out_count; uint64_t *out_pos; uint32_t *flags;
     unsigned long long *stats;    // optional [4]: candidates appended, survivors re-scored, queries flagged, queries
+    // scratch of the three finalize kernels
+    uint2 *work;                  // [B * cand_cap] survivors to re-score: (query, candidate index << 16 | survivor slot)
+    uint32_t *work_cnt;           // [1]
+    uint32_t *surv_cnt;           // [B] survivors per query
+    float *ex_dist; uint64_t *ex_id; uint64_t *ex_pos;   // [B][cand_cap] exact distance / row id / storage position
+    int num_sms;
 };
 void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st);
 // flags[q] = 1 when the shortlist of q (lower bounds `lb` ascending, [B][kp], cnt valid) cannot be proven to hold

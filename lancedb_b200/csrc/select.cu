@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
             if (s_cnt >= trigger) compact();
         }
     } else {
-        for (uint64_t c0 = 0; c0 < a.ncols; c0 += SEL_ITER) {
+        const uint64_t ncols = a.ncols_q ? min((uint64_t)a.ncols_q[q], a.ncols) : a.ncols;
+        for (uint64_t c0 = 0; c0 < ncols; c0 += SEL_ITER) {
             uint64_t c = c0 + (uint64_t)tid * 4;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
             bool ok[4];
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 ok[u] = false; idv[u] = UINT64_MAX;
-                if (c + u < a.ncols) {
+                if (c + u < ncols) {
                     uint64_t cc = c + u;
                     uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
                     if (a.cand_rec) { const TopkRecord r = a.cand_rec[addr]; idv[u] = r.id; v[u] = r.dist; }
@@ -371,12 +372,13 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
             scan256(src, c0, a.ncols, vec, 0, a.col_ids);
         }
     } else {
-        for (uint64_t c0 = (uint64_t)w * 32; c0 < a.ncols; c0 += 32 * SELW_WARPS) {
+        const uint64_t ncols = a.ncols_q ? min((uint64_t)a.ncols_q[q], a.ncols) : a.ncols;
+        for (uint64_t c0 = (uint64_t)w * 32; c0 < ncols; c0 += 32 * SELW_WARPS) {
             const uint64_t cc = c0 + lane;
             bool pass = false;
             uint32_t key = 0;
             uint64_t id = UINT64_MAX, pos = cc;
-            if (cc < a.ncols) {
+            if (cc < ncols) {
                 const uint64_t addr = (cc / a.inner) * a.outer_stride + (uint64_t)q * a.row_stride + cc % a.inner;
                 float f;
                 if (a.cand_rec) { const TopkRecord r = a.cand_rec[addr]; id = r.id; f = r.dist; }

@@ -453,101 +453,91 @@ __global__ void cand_prepare_kernel(const float *__restrict__ step, const float 
     cand_cnt[q] = 0u;
 }
 
-constexpr int FIN_THREADS = 256;
-// bitonic sort of n2 (power of two) shared-memory entries by (key, tie), ascending; `payload` follows
-template <class Swap>
-__device__ __forceinline__ void bitonic_smem(uint32_t n2, int tid, Swap &&cmp_swap)
+// ---- candidate mode, after the scan.  Three fully parallel kernels instead of one latency chain per query:
+//   cand_filter_kernel   one warp per query: the k-th smallest lower bound of the query's candidates (the tightest
+//                        threshold this family of bounds allows: every row with L <= tau is in the list and the list
+//                        holds k of them) -> the survivors L <= L_(k) + slack go to a batch-wide work list;
+//   cand_rescore_kernel  persistent warps over the work list: exact distance (oracle arithmetic), row id, position;
+//   launch_select        mode 2 over each query's survivors: the k best by (_distance, _rowid).
+constexpr int FLT_THREADS = 128;
+__global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a)
 {
-    for (uint32_t size = 2; size <= n2; size <<= 1) {
-        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
-            for (uint32_t i = tid; i < (n2 >> 1); i += FIN_THREADS) {
-                const uint32_t lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                cmp_swap(lo, hi, (lo & size) == 0);
-            }
-            __syncthreads();
+    const uint32_t q = (blockIdx.x * FLT_THREADS + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= a.B) return;
+    const uint32_t total = a.cand_cnt[q];
+    const uint32_t n = min(total, a.cand_cap);
+    const bool flagged = total > a.cand_cap || a.bad[q];
+    const CandRec *cand = a.cand + (size_t)q * a.cand_cap;
+    constexpr int PER = 16;                                  // cand_cap <= 512
+    uint32_t key[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const uint32_t i = (uint32_t)j * 32 + lane;
+        key[j] = i < n ? f32_key(cand[i].lb) : 0xffffffffu;
+    }
+    const uint32_t tkey = a.thr[q];
+    float tau = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey);
+    if (n >= a.k && !flagged) {
+        uint32_t kth = 0;                                   // largest v with count(key < v) < k  ==  k-th smallest key
+#pragma unroll 1
+        for (int bit = 31; bit >= 0; bit--) {
+            const uint32_t probe = kth | (1u << bit);
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < PER; j++) c += key[j] < probe ? 1u : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c < a.k) kth = probe;
+        }
+        tau = fminf(tau, key_f32(kth));
+    }
+    const float lim = tau + a.slack[q];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++) mine += ((uint32_t)j * 32 + lane < n && key_f32(key[j]) <= lim) ? 1u : 0u;
+    uint32_t pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+    const uint32_t cnt = __shfl_sync(0xffffffffu, pre, 31);
+    uint32_t base = 0;
+    if (lane == 31 && cnt) base = atomicAdd(a.work_cnt, cnt);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    uint32_t at = pre - mine;
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const uint32_t i = (uint32_t)j * 32 + lane;
+        if (i < n && key_f32(key[j]) <= lim) { a.work[base + at] = make_uint2(q, (i << 16) | at); at++; }
+    }
+    if (lane == 0) {
+        a.surv_cnt[q] = cnt;
+        a.flags[q] = flagged ? 1u : 0u;
+        if (a.stats) {
+            atomicAdd(a.stats + 0, (unsigned long long)total); atomicAdd(a.stats + 1, (unsigned long long)cnt);
+            atomicAdd(a.stats + 2, (unsigned long long)(flagged ? 1 : 0)); atomicAdd(a.stats + 3, 1ull);
         }
     }
 }
 
-// One CTA per query.  (1) sort the query's candidates by lower bound; their k-th smallest L is the tightest
-// threshold this family of bounds allows (every row with L <= tau is in the list, and the list holds k of them), so
-// only candidates with L <= L_(k) + slack are (2) re-scored exactly, one warp per candidate, the query staged in
-// shared memory; (3) the survivors are sorted by (distance, row id) and the best k written out.
+constexpr int RSC_THREADS = 256;
 template <int DSUB>
-__global__ void __launch_bounds__(FIN_THREADS) cand_finalize_kernel(FinalizeArgs a)
+__global__ void __launch_bounds__(RSC_THREADS) cand_rescore_kernel(FinalizeArgs a)
 {
-    extern __shared__ __align__(16) unsigned char fsm[];
-    uint64_t *s_id = reinterpret_cast<uint64_t *>(fsm);
-    uint64_t *s_pos = s_id + a.cand_cap;
-    uint32_t *s_key = reinterpret_cast<uint32_t *>(s_pos + a.cand_cap);
-    uint32_t *s_lkey = s_key + a.cand_cap;                  // lower-bound keys, then candidate order
-    uint32_t *s_lidx = s_lkey + a.cand_cap;
-    float *s_q = reinterpret_cast<float *>(s_lidx + a.cand_cap);
-    __shared__ uint32_t s_n;
-    const uint32_t q = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const uint32_t total = a.cand_cnt[q];
-    const uint32_t n = min(total, a.cand_cap);
-    if (tid == 0) {
-        s_n = 0;
-        a.flags[q] = (total > a.cand_cap || a.bad[q]) ? 1u : 0u;
-    }
-    const CandRec *cand = a.cand + (size_t)q * a.cand_cap;
-    for (uint32_t t = tid; t < a.dim; t += FIN_THREADS) s_q[t] = a.Q[(size_t)q * a.dim + t];
-    uint32_t n2 = 2;
-    while (n2 < n) n2 <<= 1;
-    for (uint32_t i = tid; i < n2; i += FIN_THREADS) {
-        s_lkey[i] = i < n ? f32_key(cand[i].lb) : 0xffffffffu;
-        s_lidx[i] = i;
-    }
-    __syncthreads();
-    bitonic_smem(n2, tid, [&](uint32_t lo, uint32_t hi, bool asc) {
-        const uint32_t ka = s_lkey[lo], kb = s_lkey[hi], ia = s_lidx[lo], ib = s_lidx[hi];
-        if ((kb < ka || (kb == ka && ib < ia)) == asc) { s_lkey[lo] = kb; s_lkey[hi] = ka; s_lidx[lo] = ib; s_lidx[hi] = ia; }
-    });
-    // threshold: the scanners' tau_q, tightened to the k-th smallest lower bound when the list has k rows
-    const uint32_t tkey = a.thr[q];
-    float tau = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey);
-    if (n >= a.k && total <= a.cand_cap) tau = fminf(tau, key_f32(s_lkey[a.k - 1]));
-    const float lim = tau + a.slack[q];
-    for (uint32_t c = w; c < n; c += FIN_THREADS / 32) {
-        if (!(key_f32(s_lkey[c]) <= lim)) break;            // sorted: nothing further can pass
-        const CandRec rec = cand[s_lidx[c]];
-        float d = exact_pq_distance_warp<DSUB>(s_q, a.centroids + (size_t)rec.p * a.dim, a.codes, a.code_base[rec.p],
-                                               a.part_npad[rec.p], rec.row, a.cb_tiled, a.m, a.metric, lane);
-        if (d != d) continue;                               // FilterExec: _distance IS NOT NULL
-        if (d == 0.f) d = 0.f;                              // -0 and +0 tie
+    const int lane = threadIdx.x & 31;
+    const uint32_t total = *a.work_cnt;
+    const uint32_t nwarps = gridDim.x * (RSC_THREADS / 32);
+    for (uint32_t it = blockIdx.x * (RSC_THREADS / 32) + (threadIdx.x >> 5); it < total; it += nwarps) {
+        const uint2 wk = a.work[it];
+        const uint32_t q = wk.x, ci = wk.y >> 16, slot = wk.y & 0xffffu;
+        const CandRec rec = a.cand[(size_t)q * a.cand_cap + ci];
+        float d = exact_pq_distance_warp<DSUB>(a.Q + (size_t)q * a.dim, a.centroids + (size_t)rec.p * a.dim, a.codes,
+                                               a.code_base[rec.p], a.part_npad[rec.p], rec.row, a.cb_tiled, a.m, a.metric,
+                                               lane);
         if (lane == 0) {
-            const uint32_t at = atomicAdd(&s_n, 1u);
             const uint64_t ps = a.part_off[rec.p] + rec.row;
-            s_key[at] = f32_key(d); s_id[at] = a.row_ids[ps]; s_pos[at] = ps;
+            const size_t o = (size_t)q * a.cand_cap + slot;
+            a.ex_dist[o] = d; a.ex_id[o] = a.row_ids[ps]; a.ex_pos[o] = ps;
         }
     }
-    __syncthreads();
-    const uint32_t cnt = s_n;
-    if (a.stats && tid == 0) {
-        atomicAdd(a.stats + 0, (unsigned long long)total); atomicAdd(a.stats + 1, (unsigned long long)cnt);
-        atomicAdd(a.stats + 2, (unsigned long long)((total > a.cand_cap || a.bad[q]) ? 1 : 0)); atomicAdd(a.stats + 3, 1ull);
-    }
-    uint32_t m2 = 2;
-    while (m2 < cnt) m2 <<= 1;
-    for (uint32_t i = cnt + tid; i < m2; i += FIN_THREADS) { s_key[i] = 0xffffffffu; s_id[i] = UINT64_MAX; s_pos[i] = UINT64_MAX; }
-    __syncthreads();
-    bitonic_smem(m2, tid, [&](uint32_t lo, uint32_t hi, bool asc) {
-        const uint32_t ka = s_key[lo], kb = s_key[hi];
-        const uint64_t ia = s_id[lo], ib = s_id[hi];
-        if ((kb < ka || (kb == ka && ib < ia)) == asc) {
-            s_key[lo] = kb; s_key[hi] = ka; s_id[lo] = ib; s_id[hi] = ia;
-            const uint64_t pa = s_pos[lo]; s_pos[lo] = s_pos[hi]; s_pos[hi] = pa;
-        }
-    });
-    for (uint32_t i = tid; i < a.k; i += FIN_THREADS) {
-        const bool have = i < cnt;
-        a.out_ids[(size_t)q * a.k + i] = have ? s_id[i] : UINT64_MAX;
-        a.out_dist[(size_t)q * a.k + i] = have ? key_f32(s_key[i]) : CUDART_INF_F;
-        if (a.out_pos) a.out_pos[(size_t)q * a.k + i] = have ? s_pos[i] : UINT64_MAX;
-    }
-    if (tid == 0) a.out_count[q] = min(cnt, a.k);
 }
 
 // probe_A[slot] = coarse_dist - |q|^2 ; amax[q] = max_j coarse + |q|^2
@@ -702,16 +692,21 @@ void launch_cand_prepare(const float *step, const float *sbound, const float *am
 void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
 {
     if (a.B == 0) return;
-    if (a.m > 512 || a.cand_cap < 2 || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
-        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity >= k");
+    if (a.m > 512 || a.cand_cap < 32 || a.cand_cap > 512 || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
+        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity in [32, 512] >= k");
         throw Failure{LGPU_RUNTIME};
     }
-    const size_t smem = (size_t)a.cand_cap * 28 + (size_t)a.dim * 4;
+    LGPU_CUDA(cudaMemsetAsync(a.work_cnt, 0, 4, st));
+    cand_filter_kernel<<<(a.B * 32 + FLT_THREADS - 1) / FLT_THREADS, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     dispatch_dsub(a.dsub, [&](auto D) {
-        auto kern = cand_finalize_kernel<decltype(D)::value>;
-        LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<a.B, FIN_THREADS, smem, st>>>(a); LGPU_COUNT_LAUNCH();
+        cand_rescore_kernel<decltype(D)::value><<<a.num_sms * 4, RSC_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     });
+    SelectArgs sb{};
+    sb.mode = 2; sb.dense = a.ex_dist; sb.cand_ids = a.ex_id; sb.cand_pos = a.ex_pos; sb.ncols_q = a.surv_cnt;
+    sb.ncols = a.cand_cap; sb.inner = a.cand_cap; sb.row_stride = a.cand_cap; sb.outer_stride = 0;
+    sb.B = a.B; sb.k = a.k; sb.out_ids = a.out_ids; sb.out_dist = a.out_dist; sb.out_count = a.out_count;
+    sb.out_pos = a.out_pos;
+    launch_select(sb, st);
     LGPU_CUDA(cudaGetLastError());
 }
 
