@@ -541,18 +541,20 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
             // nprobes): bit-identical probe sets; queries whose candidate band overflowed are redone exactly
             mark();
             ws->qb.ensure((size_t)B * dim * 2); ws->qn2.ensure((size_t)B * 4); ws->flags.ensure((size_t)B * 4);
+            ws->c_wcnt.ensure(16);
+            uint32_t *cgate = ws->c_wcnt.as<uint32_t>() + 2;    // 0 = no query overflowed: the exact fix-up returns at once
             launch_to_bf16(qsearch, B, dim, ws->qb.p, ws->qn2.as<float>(), st);
             launch_gemm_dist(ws->qb.p, ix->cent_b.p, ix->cent_n2.as<float>(), B, nlist, dim, ws->D.as<float>(), ldc,
                              ix->num_sms, st);
             launch_coarse_finish(ws->D.as<float>(), ldc, B, nlist, qsearch, ix->centroids.as<float>(), ws->qn2.as<float>(),
                                  ix->cent_max, dim, nprobes, ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(),
-                                 ws->probe_cnt.as<uint32_t>(), ws->flags.as<uint32_t>(), st);
+                                 ws->probe_cnt.as<uint32_t>(), ws->flags.as<uint32_t>(), cgate, st);
             launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, 0, nullptr, nullptr, ws->D.as<float>(), ldc,
-                               st, ws->flags.as<uint32_t>());
+                               st, ws->flags.as<uint32_t>(), cgate);
             SelectArgs sc{};
             sc.mode = 1; sc.dense = ws->D.as<float>(); sc.ncols = nlist; sc.row_stride = ldc;
             sc.B = B; sc.k = nprobes; sc.out_ids = ws->probes.as<uint64_t>(); sc.out_dist = ws->probe_dist.as<float>();
-            sc.out_count = ws->probe_cnt.as<uint32_t>(); sc.only = ws->flags.as<uint32_t>();
+            sc.out_count = ws->probe_cnt.as<uint32_t>(); sc.only = ws->flags.as<uint32_t>(); sc.gate = cgate;
             launch_select(sc, st);
         } else {
             launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, ix->metric == LGPU_DOT ? 1 : 0,
@@ -634,7 +636,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     if (filter_scan) {
         // per-query 16-bit tables, per-probe scalars
         const bool dot = ix->metric == LGPU_DOT;
-        ws->flags.ensure((size_t)B * 4);
+        ws->flags.ensure((size_t)B * 4); ws->c_wcnt.ensure(16);
         ws->s_ids.ensure((size_t)B * kp * 8); ws->s_lb.ensure((size_t)B * kp * 4); ws->s_pos.ensure((size_t)B * kp * 8);
         ws->s_cnt.ensure((size_t)B * 4); ws->s_exact.ensure((size_t)B * kp * 4);
         LGPU_CUDA(cudaStreamWaitEvent(st, ws->ev_join, 0));        // the tables, built on the side stream
@@ -653,8 +655,8 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         if (cand_mode) {
             // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
             static const uint32_t cap_env = getenv("LGPU_CAND_CAP") ? (uint32_t)atoi(getenv("LGPU_CAND_CAP")) : 0u;
-            uint32_t cap = 512;
-            if (cap_env >= 32 && cap_env <= 512 && !(cap_env & (cap_env - 1))) cap = cap_env;
+            uint32_t cap = kk <= 32 ? 512 : 1024;
+            if (cap_env >= 32 && cap_env <= 1024 && !(cap_env & (cap_env - 1)) && cap_env >= kk) cap = cap_env;
             ws->c_thr.ensure((size_t)B * 4); ws->c_slack.ensure((size_t)B * 4); ws->c_cnt.ensure((size_t)B * 4);
             ws->c_rec.ensure((size_t)B * cap * sizeof(CandRec));
             launch_cand_prepare(ws->qt_step.as<float>(), ws->sbound.as<float>(), dot ? nullptr : ws->amax.as<float>(),
@@ -697,7 +699,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         launch_band_check3(ws->s_lb.as<float>(), ws->s_cnt.as<uint32_t>(), ws->qt_step.as<float>(), ws->sbound.as<float>(),
                            dot ? nullptr : ws->amax.as<float>(), dot ? nullptr : ix->rmax_bits.as<int>(),
                            ws->qt_bad.as<uint32_t>(), ws->qn2.as<float>(), ix->cb2, mscale, ix->m, B, kk, kp,
-                           ws->flags.as<uint32_t>(), st);
+                           ws->flags.as<uint32_t>(), ws->c_wcnt.as<uint32_t>() + 1, st);
         // exact PQ distances of the shortlist (oracle arithmetic), then the kk best of those
         launch_pq_rescore(qsearch, ws->s_pos.as<uint64_t>(), B, kp, ix->codes.as<unsigned char>(),
                           ix->code_base.as<uint64_t>(), ix->part_npad.as<uint32_t>(), ix->part_off.as<uint64_t>(), nlist,
@@ -712,14 +714,15 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         }
         // fix-up of the queries whose shortlist could not be proven (no tiles, hence no work, unless one is
         // flagged): regroup them alone, exact scan, exact top-kk over their segments
-        ga.only = ws->flags.as<uint32_t>();
+        const uint32_t *gate = ws->c_wcnt.as<uint32_t>() + 1;   // 0 = nothing flagged: every kernel below returns at once
+        ga.only = ws->flags.as<uint32_t>(); ga.gate = gate;
         ga.rows_tile = SCAN_ROWS_TILE_MID;
         launch_group(ga, st);
-        sc.rows_tile = SCAN_ROWS_TILE_MID;
+        sc.rows_tile = SCAN_ROWS_TILE_MID; sc.gate = gate;
         launch_scan2(sc, ix->dsub, ix->num_sms, st);
         SelectArgs sf = sa;
         sf.k = kk; sf.out_ids = pq_ids; sf.out_dist = pq_dist; sf.out_count = pq_cnt; sf.out_pos = pq_pos;
-        sf.only = ws->flags.as<uint32_t>();
+        sf.only = ws->flags.as<uint32_t>(); sf.gate = gate;
         launch_select(sf, st);
         mark();
     } else {

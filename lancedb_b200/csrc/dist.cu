@@ -23,8 +23,9 @@ constexpr int DM_Q = 16, DM_C = 32, DM_KT = 32, DM_STR = 36, DM_THREADS = 256;
 __global__ void __launch_bounds__(DM_THREADS) dist_matrix_kernel(
     const float *__restrict__ Q, const float *__restrict__ C, uint32_t B, uint64_t N, uint32_t d, int mode,
     const float *__restrict__ xnorm, const float *__restrict__ ysqrt, float *__restrict__ D, uint64_t ldD,
-    const uint32_t *__restrict__ only)
+    const uint32_t *__restrict__ only, const uint32_t *__restrict__ gate)
 {
+    if (gate && *gate == 0) return;              // fix-up pass with nothing flagged
     if (only) {                                  // fix-up pass: skip query tiles with no flagged query
         bool any = false;
         for (uint32_t i = 0; i < DM_Q; i++) {
@@ -206,7 +207,8 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
                                                                    const float *__restrict__ qn2, float xmax, uint32_t d,
                                                                    uint32_t k, uint32_t cap, int staged,
                                                                    uint64_t *__restrict__ out_ids, float *__restrict__ out_dist,
-                                                                   uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ flags)
+                                                                   uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ flags,
+                                                                   uint32_t *__restrict__ gate)
 {
     extern __shared__ __align__(16) unsigned char csm[];
     uint32_t *s_col = reinterpret_cast<uint32_t *>(csm);           // [cap] candidate columns
@@ -234,20 +236,29 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     float thr = -CUDART_INF_F;
     if (kk > 0) {
         float lo = key_f32(s_lo), hi = key_f32(s_hi);               // invariant: count(S <= hi) >= kk
+        const float qn = sqrtf(qn2[q]);
+        const float sm = qn + xmax;
+        const float E = 0.0078125f * 1.00390625f * qn * xmax + 4.0f * (float)d * 5.9604645e-8f * sm * sm;
         if (hi < CUDART_INF_F && lo > -CUDART_INF_F) {
-            for (int it = 0; it < 20; it++) {
+            const bool vec = (N & 3) == 0 && (ld & 3) == 0;          // rows are 16-byte aligned then (staged or global)
+            for (int it = 0; it < 20 && hi - lo > 0.25f * E; it++) {    // the band is 2E wide anyway
                 const float mid = 0.5f * lo + 0.5f * hi;
                 uint32_t c = 0;
-                for (uint32_t i = tid; i < N; i += CF_THREADS) c += row[i] <= mid ? 1u : 0u;
+                if (vec) {
+                    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+                    for (uint32_t i = tid; i < N / 4; i += CF_THREADS) {
+                        const float4 v = r4[i];
+                        c += (v.x <= mid ? 1u : 0u) + (v.y <= mid ? 1u : 0u) + (v.z <= mid ? 1u : 0u) + (v.w <= mid ? 1u : 0u);
+                    }
+                } else {
+                    for (uint32_t i = tid; i < N; i += CF_THREADS) c += row[i] <= mid ? 1u : 0u;
+                }
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0 && c) atomicAdd(&s_cnt[it], c);
                 __syncthreads();
                 if (s_cnt[it] >= kk) hi = mid; else lo = mid;
             }
         }
-        const float qn = sqrtf(qn2[q]);
-        const float sm = qn + xmax;
-        const float E = 0.0078125f * 1.00390625f * qn * xmax + 4.0f * (float)d * 5.9604645e-8f * sm * sm;
         thr = hi + 2.0f * E;
     }
     for (uint32_t i = tid; i < N; i += CF_THREADS) {
@@ -258,7 +269,10 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     }
     __syncthreads();
     const uint32_t total = s_n, n = min(total, cap);
-    if (tid == 0) flags[q] = total > cap ? 1u : 0u;
+    if (tid == 0) {
+        flags[q] = total > cap ? 1u : 0u;
+        if (total > cap && gate) *gate = 1u;                        // opens the gate of the caller's exact fix-up
+    }
     // exact re-score, half a warp per candidate column (lance's l2: 16 lane accumulators, sequential lane sum)
     const int hl = lane & 15, hbase = lane & 16;
     const unsigned hmask = 0xffffu << hbase;
@@ -304,27 +318,28 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
 
 void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, const float *Q, const float *C,
                           const float *qn2, float xmax, uint32_t d, uint32_t k, uint64_t *out_ids, float *out_dist,
-                          uint32_t *out_cnt, uint32_t *flags, cudaStream_t st)
+                          uint32_t *out_cnt, uint32_t *flags, uint32_t *gate, cudaStream_t st)
 {
     if (B == 0 || N == 0) return;
+    if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
     uint32_t cap = 256;
     while (cap < 4 * k) cap <<= 1;                                   // power of two >= 4 k
     const int staged = (size_t)N * 4 <= 96 * 1024 ? 1 : 0;
     const size_t smem = (size_t)cap * 8 + (staged ? (size_t)N * 4 : 0);
     LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    coarse_finish_kernel<<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, staged, out_ids, out_dist, out_cnt, flags); LGPU_COUNT_LAUNCH();
+    coarse_finish_kernel<<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, staged, out_ids, out_dist, out_cnt, flags, gate); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
                         const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st,
-                        const uint32_t *only)
+                        const uint32_t *only, const uint32_t *gate)
 {
     if (B == 0 || N == 0) return;
     // the fix-up pass (`only`) is almost always a no-op: keep its CTA count small
     const uint64_t ct = (N + DM_C - 1) / DM_C;
     dim3 grid((unsigned)std::min<uint64_t>(ct, only ? 256 : ((uint64_t)1 << 30)), (B + DM_Q - 1) / DM_Q);
-    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only); LGPU_COUNT_LAUNCH();
+    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only, gate); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -16,6 +16,7 @@ __device__ __forceinline__ uint64_t pad4(uint64_t n) { return (n + 3) & ~3ull; }
 // out back to back (each padded to 4 floats)
 __global__ void group_count_kernel(GroupArgs a)
 {
+    if (a.gate && *a.gate == 0) return;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.B) return;
     const bool take = !a.only || a.only[q];             // fix-up pass: only flagged queries get tiles
@@ -44,6 +45,10 @@ __global__ void group_scan_kernel(GroupArgs a)
     __shared__ uint64_t s_part[1024];
     __shared__ uint64_t s_carry;
     const int tid = threadIdx.x;
+    if (a.gate && *a.gate == 0) {                       // nothing flagged: no tiles for the exact kernel
+        if (tid == 0) { *a.total_tiles = 0; *a.tile_counter = 0; }
+        return;
+    }
     // --- queries: qtot -> exclusive prefix (in place) ---
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -103,6 +108,7 @@ __global__ void group_scan_kernel(GroupArgs a)
 
 __global__ void group_fill_kernel(GroupArgs a)
 {
+    if (a.gate && *a.gate == 0) return;
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.B * a.nprobes) return;
     uint32_t q = slot / a.nprobes;
@@ -115,6 +121,7 @@ __global__ void group_fill_kernel(GroupArgs a)
 // Tiles are numbered partition-major.
 __global__ void tile_desc_kernel(GroupArgs a)
 {
+    if (a.gate && *a.gate == 0) return;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t t = gid / SCAN_G, g = gid % SCAN_G;
     const uint32_t total = *a.total_tiles;

@@ -39,7 +39,9 @@ struct alignas(16) CandRec {
     uint32_t pad;
 };
 constexpr uint32_t CAND_NO_THR = 0xffffffffu;
-constexpr uint32_t CAND_TOPK_MAX = 32;
+constexpr uint32_t CAND_TOPK_MAX = 32;       // candidate mode serves k (or k * refine_factor) up to this: for larger k
+                                             // the per-tile thresholds are too loose before tau_q has settled (measured on
+                                             // BASELINE config 3, k = 100: every list overflowed); those requests use dense mode
 
 struct ScanArgs {
     // index (device)
@@ -58,6 +60,7 @@ struct ScanArgs {
     uint32_t *tile_counter;       // [1], zeroed before launch
     float *dist_out;
     const TileDesc *tile_desc;    // [total_tiles]
+    const uint32_t *gate;         // optional [1] (exact kernel as fix-up pass): 0 = nothing to do
     // filter pass (scan3.cu, tables.cu); unused by the exact kernel
     const uint4 *qt;              // [B][nch][256] x (8 x u16): quantised per-query tables, rotated (tables.cu)
     const float *qt_step;         // [B] quantisation step
@@ -67,7 +70,7 @@ struct ScanArgs {
     const uint64_t *part_off;     // [nlist+1]
     // filter pass, candidate mode (cand != nullptr): instead of one f32 per (row, query) in dist_out, the scanners
     // keep a running per-query threshold and append only the rows that can still be among the exact top-k
-    uint32_t nprobes, topk;       // probe slots per query; k (the number of neighbours the threshold is for, <= 32)
+    uint32_t nprobes, topk;       // probe slots per query; k (the number of neighbours the threshold is for)
     uint32_t *thr;                // [B] ordered-uint key (f32_key) of tau_q, CAND_NO_THR = none yet; atomicMin
     const float *slack;           // [B] scale (W + 2E): a row survives iff L <= tau_q + slack_q
     uint32_t *cand_cnt;           // [B] appended candidates (may exceed cand_cap: the overflow is dropped and flagged)
@@ -98,6 +101,7 @@ struct GroupArgs {
     uint32_t *tile_counter;       // [1]
     unsigned long long *scanned_rows;  // [1] sum over probe slots of n_p (roofline bytes / m)
     const uint32_t *only;         // optional [B]: regroup only the flagged queries (fix-up pass)
+    const uint32_t *gate;         // optional [1]: 0 = no query is flagged, the whole fix-up pass returns at once
     TileDesc *tile_desc;          // optional [max_tiles] tile descriptors for the streaming scan kernel
     uint32_t max_tiles;           // capacity of tile_desc (host bound on the tile count)
 };
@@ -109,13 +113,13 @@ void launch_group(const GroupArgs &a, cudaStream_t st);
 // `only` (optional, [B]): rows whose flag is 0 are skipped (used by the tensor-core paths' fix-up pass)
 void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, uint32_t d, int mode,
                         const float *xnorm, const float *ysqrt, float *D, uint64_t ldD, cudaStream_t st,
-                        const uint32_t *only = nullptr);
+                        const uint32_t *only = nullptr, const uint32_t *gate = nullptr);
 // coarse step after the tensor-core GEMM, one kernel: from S[B][ld] = |x|^2 - 2 bf16(q).bf16(x) (N columns) to the k
 // columns with the smallest EXACT l2 distance (lance lane order), ascending by (distance, column); flags[q] = 1 when
 // the candidate band overflowed and the caller must redo the query with the exact kernels
 void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, const float *Q, const float *C,
                           const float *qn2, float xmax, uint32_t d, uint32_t k, uint64_t *out_ids, float *out_dist,
-                          uint32_t *out_cnt, uint32_t *flags, cudaStream_t st);
+                          uint32_t *out_cnt, uint32_t *flags, uint32_t *gate, cudaStream_t st);
 // row norms |x| = sqrt(dot(x,x)) in lance order; out[n]
 void launch_row_norms(const float *X, uint64_t n, uint32_t d, float *out, cudaStream_t st);
 // out[q] = x[q] / |x[q]|
@@ -166,6 +170,7 @@ struct SelectArgs {
     TopkRecord *out_rec;          // optional [B][k]: packed output instead of out_ids / out_dist
     uint64_t *out_pos;            // optional [B][k] storage position (mode 0) / column (mode 1)
     const uint32_t *only;         // optional [B]: queries whose flag is 0 are left untouched
+    const uint32_t *gate;         // optional [1]: 0 = no query is flagged (the kernel returns at once)
     // prefilter (query.rs:489-507): optional row-id allow-list bitmap; a candidate whose id has bit 0 (or is
     // >= allow_bits) is dropped before it can enter the top-k
     const uint32_t *allow;
@@ -250,7 +255,7 @@ struct FinalizeArgs {
     unsigned long long *stats;    // optional [4]: candidates appended, survivors re-scored, queries flagged, queries
     // scratch of the three finalize kernels
     uint2 *work;                  // [B * cand_cap] survivors to re-score: (query, candidate index << 16 | survivor slot)
-    uint32_t *work_cnt;           // [1]
+    uint32_t *work_cnt;           // [2]: survivors; gate word of the fix-up pass (set when a query is flagged)
     uint32_t *surv_cnt;           // [B] survivors per query
     float *ex_dist; uint64_t *ex_id; uint64_t *ex_pos;   // [B][cand_cap] exact distance / row id / storage position
     int num_sms;
@@ -262,7 +267,7 @@ void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st);
 // (dot).  cb2 = sum_i max_c |codebook_i[c]|^2.
 void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
                         const int *rmax_bits, const uint32_t *bad, const float *qn2, float cb2, float scale, uint32_t m,
-                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st);
+                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, uint32_t *gate, cudaStream_t st);
 
 // ---------------- index build (build.cu) ----------------------------------------------
 // codes[row][i] = argmin_c entry(row's residual sub-vector i, codebook_i[c]) (ties: lowest c); X normalised for cosine

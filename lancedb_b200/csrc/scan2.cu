@@ -500,6 +500,7 @@ __global__ void __launch_bounds__(S2_NT, 1) scan2_kernel(ScanArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x;
+    if (a.gate && *a.gate == 0) return;
     const uint32_t total = *a.total_tiles;
     unsigned char *const tiles = smem + Smem<DSUB>::TILES;
 

@@ -283,47 +283,47 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
         bar_sync(BAR_SCAN, S3_CT);
         uint32_t tkey = sh[0];
         const uint32_t rank = slot - q * a.nprobes;
-        if (tkey == CAND_NO_THR || rank < 3u) {              // uniform over the CTA's scanners
-            kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
-            nvalid = __reduce_add_sync(0xffffffffu, nvalid);
-            if (lane == 0) {
-                atomicMin(const_cast<uint32_t *>(sh + 1), kmin); atomicMax(const_cast<uint32_t *>(sh + 2), kmax);
-                atomicAdd(const_cast<uint32_t *>(sh + 3), nvalid);
-            }
-            bar_sync(BAR_SCAN, S3_CT);
+        // Tighten tau_q from this tile when it pays: always for a query without a threshold and for its three nearest
+        // partitions (that is where the small distances are); otherwise only when this tile alone holds 2k or more
+        // rows under the current threshold (one counting pass decides) -- without that a loose early threshold, set
+        // by whichever far partition happened to finish first, would let whole near partitions through.
+        bool bisect = tkey == CAND_NO_THR || rank < 3u;
+        float cur = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey);
+        kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+        nvalid = __reduce_add_sync(0xffffffffu, nvalid);
+        uint32_t cunder = 0;
+        if (tkey != CAND_NO_THR) {
+#pragma unroll
+            for (int r = 0; r < R; r++) cunder += L[r] <= cur ? 1u : 0u;
+            cunder = __reduce_add_sync(0xffffffffu, cunder);
+        }
+        if (lane == 0) {
+            atomicMin(const_cast<uint32_t *>(sh + 1), kmin); atomicMax(const_cast<uint32_t *>(sh + 2), kmax);
+            atomicAdd(const_cast<uint32_t *>(sh + 3), nvalid);
+            if (cunder) atomicAdd(const_cast<uint32_t *>(sh + 4), cunder);
+        }
+        bar_sync(BAR_SCAN, S3_CT);
+        {
             float lo = key_f32(sh[1]), hi = key_f32(sh[2]);
-            if (sh[3] >= k && hi < CUDART_INF_F && lo == lo && hi == hi) {
-                // only values below the current threshold can improve it: start from hi = min(hi, tau) if that
-                // still has k rows under it (first counter), else this tile cannot tighten tau
-                bool ok = true;
-                if (tkey != CAND_NO_THR && key_f32(tkey) < hi) {
-                    const float cur = key_f32(tkey);
+            const uint32_t under = sh[4];                    // rows of this tile with L <= current threshold
+            if (tkey != CAND_NO_THR) { bisect = bisect ? under >= k : under >= 2u * k; if (cur < hi) hi = cur; }
+            if (bisect && sh[3] >= k && hi < CUDART_INF_F && lo == lo && hi == hi) {
+                // invariant: count(L <= hi) >= k
+#pragma unroll 1
+                for (int it = 0; it < 8; it++) {
+                    const float mid = 0.5f * lo + 0.5f * hi;
                     uint32_t c = 0;
 #pragma unroll
-                    for (int r = 0; r < R; r++) c += L[r] <= cur ? 1u : 0u;
+                    for (int r = 0; r < R; r++) c += L[r] <= mid ? 1u : 0u;
                     c = __reduce_add_sync(0xffffffffu, c);
-                    if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 4), c);
+                    if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 5 + it), c);
                     bar_sync(BAR_SCAN, S3_CT);
-                    ok = sh[4] >= k;
-                    hi = cur;
+                    if (sh[5 + it] >= k) hi = mid; else lo = mid;
                 }
-                if (ok) {                                   // invariant: count(L <= hi) >= k
-#pragma unroll 1
-                    for (int it = 0; it < 8; it++) {
-                        const float mid = 0.5f * lo + 0.5f * hi;
-                        uint32_t c = 0;
-#pragma unroll
-                        for (int r = 0; r < R; r++) c += L[r] <= mid ? 1u : 0u;
-                        c = __reduce_add_sync(0xffffffffu, c);
-                        if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 5 + it), c);
-                        bar_sync(BAR_SCAN, S3_CT);
-                        if (sh[5 + it] >= k) hi = mid; else lo = mid;
-                    }
-                    const uint32_t nk = f32_key(hi);
-                    if (nk < tkey) {
-                        if (ct == 0) atomicMin(a.thr + q, nk);
-                        tkey = nk;
-                    }
+                const uint32_t nk = f32_key(hi);
+                if (nk < tkey) {
+                    if (ct == 0) atomicMin(a.thr + q, nk);
+                    tkey = nk;
                 }
             }
         }

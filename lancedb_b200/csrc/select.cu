@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint3
     __shared__ uint32_t s_cnt, s_tau;
 
     const uint32_t q = blockIdx.x;
+    if (a.gate && *a.gate == 0) return;
     if (a.only && !a.only[q]) return;                       // fix-up pass: untouched query
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid == 0) { s_cnt = 0; s_tau = 0xffffffffu; }
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs
     __shared__ uint64_t m_pos[SELW_WARPS - 1][POS ? 32 * NQ : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const uint32_t q = blockIdx.x;
+    if (a.gate && *a.gate == 0) return;
     if (a.only && !a.only[q]) return;                       // fix-up pass: untouched query
     const uint32_t k = a.k;
     uint32_t qk[NQ];

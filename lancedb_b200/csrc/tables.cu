@@ -460,6 +460,7 @@ __global__ void cand_prepare_kernel(const float *__restrict__ step, const float 
 //   cand_rescore_kernel  persistent warps over the work list: exact distance (oracle arithmetic), row id, position;
 //   launch_select        mode 2 over each query's survivors: the k best by (_distance, _rowid).
 constexpr int FLT_THREADS = 128;
+template <int PER>                                           // candidates per lane: cand_cap <= 32 * PER
 __global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a)
 {
     const uint32_t q = (blockIdx.x * FLT_THREADS + threadIdx.x) >> 5;
@@ -469,7 +470,6 @@ __global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a
     const uint32_t n = min(total, a.cand_cap);
     const bool flagged = total > a.cand_cap || a.bad[q];
     const CandRec *cand = a.cand + (size_t)q * a.cand_cap;
-    constexpr int PER = 16;                                  // cand_cap <= 512
     uint32_t key[PER];
 #pragma unroll
     for (int j = 0; j < PER; j++) {
@@ -511,6 +511,7 @@ __global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a
     if (lane == 0) {
         a.surv_cnt[q] = cnt;
         a.flags[q] = flagged ? 1u : 0u;
+        if (flagged) a.work_cnt[1] = 1u;                    // opens the gate of the exact fix-up pass
         if (a.stats) {
             atomicAdd(a.stats + 0, (unsigned long long)total); atomicAdd(a.stats + 1, (unsigned long long)cnt);
             atomicAdd(a.stats + 2, (unsigned long long)(flagged ? 1 : 0)); atomicAdd(a.stats + 3, 1ull);
@@ -581,7 +582,8 @@ __global__ void band_check3_kernel(const float *__restrict__ lb, const uint32_t 
                                    const float *__restrict__ step, const float *__restrict__ sbound,
                                    const float *__restrict__ amax, const int *__restrict__ rmax_bits,
                                    const uint32_t *__restrict__ bad, const float *__restrict__ qn2, float cb2, float scale,
-                                   uint32_t m, uint32_t B, uint32_t k, uint32_t kp, uint32_t *__restrict__ flags)
+                                   uint32_t m, uint32_t B, uint32_t k, uint32_t kp, uint32_t *__restrict__ flags,
+                                   uint32_t *__restrict__ gate)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
@@ -596,6 +598,7 @@ __global__ void band_check3_kernel(const float *__restrict__ lb, const uint32_t 
         f = (k >= kp || !(last > kth + scale * (W + 2.0f * E))) ? 1u : 0u;
     }
     flags[q] = f;
+    if (f && gate) *gate = 1u;                              // opens the gate of the exact fix-up pass
 }
 
 template <class F> void dispatch_dsub(uint32_t dsub, F &&f)
@@ -692,12 +695,13 @@ void launch_cand_prepare(const float *step, const float *sbound, const float *am
 void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
 {
     if (a.B == 0) return;
-    if (a.m > 512 || a.cand_cap < 32 || a.cand_cap > 512 || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
-        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity in [32, 512] >= k");
+    if (a.m > 512 || a.cand_cap < 32 || a.cand_cap > 1024 || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
+        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity in [32, 1024] >= k");
         throw Failure{LGPU_RUNTIME};
     }
-    LGPU_CUDA(cudaMemsetAsync(a.work_cnt, 0, 4, st));
-    cand_filter_kernel<<<(a.B * 32 + FLT_THREADS - 1) / FLT_THREADS, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaMemsetAsync(a.work_cnt, 0, 8, st));       // survivor counter + fix-up gate
+    if (a.cand_cap <= 512) { cand_filter_kernel<16><<<(a.B * 32 + FLT_THREADS - 1) / FLT_THREADS, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
+    else { cand_filter_kernel<32><<<(a.B * 32 + FLT_THREADS - 1) / FLT_THREADS, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
     dispatch_dsub(a.dsub, [&](auto D) {
         cand_rescore_kernel<decltype(D)::value><<<a.num_sms * 4, RSC_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     });
@@ -712,10 +716,11 @@ void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
 
 void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
                         const int *rmax_bits, const uint32_t *bad, const float *qn2, float cb2, float scale, uint32_t m,
-                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, cudaStream_t st)
+                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, uint32_t *gate, cudaStream_t st)
 {
     if (B == 0) return;
-    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, qn2, cb2, scale, m, B, k, kp, flags); LGPU_COUNT_LAUNCH();
+    if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
+    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, qn2, cb2, scale, m, B, k, kp, flags, gate); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -60,11 +60,11 @@ torch.cuda.synchronize()
 ms = float(np.mean([s.elapsed_time(e) for s, e in ev]))
 _native.set_profiling(True)
 gpu.search_device(dq[(a.steps - 1) % 2].data_ptr(), a.batch, p, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), st)
-stage = _native.last_stage_ms(); code_bytes = _native.last_scanned_code_bytes()
+stage = _native.last_stage_ms(); code_bytes = _native.last_scanned_code_bytes(); fstats = _native.last_filter_stats()
 _native.set_profiling(False)
 out = {"config": vars(a), "rows": n, "index_open_s": open_s, "ms_per_batch": ms, "qps": a.batch / (ms / 1e3),
        "stage_ms": stage, "scan_algorithmic_GBps": code_bytes / (stage["scan"] / 1e3) / 1e9,
-       "index_device_bytes": gpu.device_bytes()}
+       "index_device_bytes": gpu.device_bytes(), "filter_stats": fstats}
 if a.check:
     import oracle
     gi = oi.cpu().numpy().view(np.uint64); gd = od.cpu().numpy(); gc = oc.cpu().numpy()

@@ -353,5 +353,6 @@ def test_filter_scan_modes_and_candidate_overflow(mode, monkeypatch):
     ix = random_index(rng, dim=64, nlist=40, m=8, n=60000)
     _check_search(ix, queries(rng, 90, 64), k=10, nprobes=12)
     _check_search(ix, queries(rng, 90, 64), k=32, nprobes=12)
+    _check_search(ix, queries(rng, 40, 64), k=100, nprobes=12)       # 1024-entry candidate lists, block selector
     ixv = random_index(rng, dim=48, nlist=6, m=6, metric="cosine", n=4000, with_vectors=True)
     _check_search(ixv, queries(rng, 17, 48), k=5, nprobes=3, refine_factor=4)
