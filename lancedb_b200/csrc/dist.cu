@@ -202,10 +202,13 @@ __global__ void pair_distance_kernel(const float *__restrict__ Q, const float *_
 // (4) the k best by (distance, column) are written.  More than `cap` candidates (ties, degenerate data): flags[q] = 1
 // and the caller's exact kernels redo the query.
 constexpr int CF_THREADS = 256;
+// VPT = row values per thread, held in registers for the counting passes (N <= 256 VPT); VPT == 0: the row is
+// re-read from global memory (L2) in every pass (flat-sized rows)
+template <int VPT>
 __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *__restrict__ S, uint64_t ld, uint32_t N,
                                                                    const float *__restrict__ Q, const float *__restrict__ C,
                                                                    const float *__restrict__ qn2, float xmax, uint32_t d,
-                                                                   uint32_t k, uint32_t cap, int staged,
+                                                                   uint32_t k, uint32_t cap,
                                                                    uint64_t *__restrict__ out_ids, float *__restrict__ out_dist,
                                                                    uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ flags,
                                                                    uint32_t *__restrict__ gate)
@@ -213,20 +216,28 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     extern __shared__ __align__(16) unsigned char csm[];
     uint32_t *s_col = reinterpret_cast<uint32_t *>(csm);           // [cap] candidate columns
     uint32_t *s_key = s_col + cap;                                  // [cap] exact distance keys
-    float *s_row = reinterpret_cast<float *>(s_key + cap);          // [N] when staged
     __shared__ uint32_t s_lo, s_hi, s_valid, s_n, s_cnt[24];
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
-    const float *grow = S + (size_t)q * ld;
-    const float *row = staged ? s_row : grow;
+    const float *row = S + (size_t)q * ld;
     if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_valid = 0u; s_n = 0u; }
     if (tid < 24) s_cnt[tid] = 0u;
     __syncthreads();
+    constexpr int NV = VPT > 0 ? VPT : 1;
+    float v[NV];
     uint32_t kmin = 0xffffffffu, kmax = 0u, nv = 0;
-    for (uint32_t i = tid; i < N; i += CF_THREADS) {
-        const float v = grow[i];
-        if (staged) s_row[i] = v;
-        if (v == v) { const uint32_t kk = f32_key(v); kmin = min(kmin, kk); kmax = max(kmax, kk); nv++; }
+    if constexpr (VPT > 0) {
+#pragma unroll
+        for (int j = 0; j < VPT; j++) {
+            const uint32_t i = (uint32_t)j * CF_THREADS + tid;
+            v[j] = i < N ? row[i] : CUDART_NAN_F;                   // NaN never counts
+            if (v[j] == v[j]) { const uint32_t kk = f32_key(v[j]); kmin = min(kmin, kk); kmax = max(kmax, kk); nv++; }
+        }
+    } else {
+        for (uint32_t i = tid; i < N; i += CF_THREADS) {
+            const float x = row[i];
+            if (x == x) { const uint32_t kk = f32_key(x); kmin = min(kmin, kk); kmax = max(kmax, kk); nv++; }
+        }
     }
     kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
     nv = __reduce_add_sync(0xffffffffu, nv);
@@ -240,16 +251,12 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
         const float sm = qn + xmax;
         const float E = 0.0078125f * 1.00390625f * qn * xmax + 4.0f * (float)d * 5.9604645e-8f * sm * sm;
         if (hi < CUDART_INF_F && lo > -CUDART_INF_F) {
-            const bool vec = (N & 3) == 0 && (ld & 3) == 0;          // rows are 16-byte aligned then (staged or global)
             for (int it = 0; it < 20 && hi - lo > 0.25f * E; it++) {    // the band is 2E wide anyway
                 const float mid = 0.5f * lo + 0.5f * hi;
                 uint32_t c = 0;
-                if (vec) {
-                    const float4 *r4 = reinterpret_cast<const float4 *>(row);
-                    for (uint32_t i = tid; i < N / 4; i += CF_THREADS) {
-                        const float4 v = r4[i];
-                        c += (v.x <= mid ? 1u : 0u) + (v.y <= mid ? 1u : 0u) + (v.z <= mid ? 1u : 0u) + (v.w <= mid ? 1u : 0u);
-                    }
+                if constexpr (VPT > 0) {
+#pragma unroll
+                    for (int j = 0; j < VPT; j++) c += v[j] <= mid ? 1u : 0u;
                 } else {
                     for (uint32_t i = tid; i < N; i += CF_THREADS) c += row[i] <= mid ? 1u : 0u;
                 }
@@ -261,10 +268,20 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
         }
         thr = hi + 2.0f * E;
     }
-    for (uint32_t i = tid; i < N; i += CF_THREADS) {
-        if (row[i] <= thr) {
-            const uint32_t at = atomicAdd(&s_n, 1u);
-            if (at < cap) s_col[at] = i;
+    if constexpr (VPT > 0) {
+#pragma unroll
+        for (int j = 0; j < VPT; j++) {
+            if (v[j] <= thr) {
+                const uint32_t at = atomicAdd(&s_n, 1u);
+                if (at < cap) s_col[at] = (uint32_t)j * CF_THREADS + tid;
+            }
+        }
+    } else {
+        for (uint32_t i = tid; i < N; i += CF_THREADS) {
+            if (row[i] <= thr) {
+                const uint32_t at = atomicAdd(&s_n, 1u);
+                if (at < cap) s_col[at] = i;
+            }
         }
     }
     __syncthreads();
@@ -280,8 +297,8 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     for (uint32_t c0 = 0; c0 < n; c0 += CF_THREADS / 16) {
         const uint32_t c = c0 + (tid >> 4);
         if (c < n) {                                                 // a whole half-warp takes the branch together
-            const float v = halfwarp_l2(x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
-            if (hl == 0) s_key[c] = (v != v) ? 0xffffffffu : f32_key(v == 0.f ? 0.f : v);
+            const float dv = halfwarp_l2(x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
+            if (hl == 0) s_key[c] = (dv != dv) ? 0xffffffffu : f32_key(dv == 0.f ? 0.f : dv);
         }
     }
     __syncthreads();
@@ -324,10 +341,14 @@ void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, c
     if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
     uint32_t cap = 256;
     while (cap < 4 * k) cap <<= 1;                                   // power of two >= 4 k
-    const int staged = (size_t)N * 4 <= 96 * 1024 ? 1 : 0;
-    const size_t smem = (size_t)cap * 8 + (staged ? (size_t)N * 4 : 0);
-    LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    coarse_finish_kernel<<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, staged, out_ids, out_dist, out_cnt, flags, gate); LGPU_COUNT_LAUNCH();
+    const size_t smem = (size_t)cap * 8;
+#define LGPU_CF(V) coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate)
+    if (N <= 4 * CF_THREADS) LGPU_CF(4);
+    else if (N <= 16 * CF_THREADS) LGPU_CF(16);
+    else if (N <= 64 * CF_THREADS) LGPU_CF(64);
+    else LGPU_CF(0);
+#undef LGPU_CF
+    LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

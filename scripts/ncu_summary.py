@@ -38,30 +38,35 @@ def stall_mix(d):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    lines = ["ncu --set full --clock-control none on 1 x B200 (under gpurun); per-launch values.",
-             "scan: bench.py C2 workload (1M x 768, nlist 1024, m 96, nprobes 20, k 10, B 1024);",
-             "gemm: scripts/bench_flat.py (1M x 1536, B 1024), launch captured = the full-set pass with the filtering epilogue.",
-             "Sources: gpurun_out/scan_full.ncu-rep, gpurun_out/gemm_full.ncu-rep (scratch, not tracked).", ""]
-    for name in ("scan_full", "gemm_full"):
-        rep = os.path.join(ROOT, "gpurun_out", name + ".ncu-rep")
+    """python scripts/ncu_summary.py <tag> [label=report.ncu-rep ...]; the first report is the scan kernel (its DRAM
+    traffic goes to profiles/<tag>_scan_traffic.json, which bench.py reads for roofline.traffic)."""
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    reps = [a.split("=", 1) for a in sys.argv[2:]] or [["scan", "gpurun_out/r02_scan3.ncu-rep"], ["finalize", "gpurun_out/r02_fin.ncu-rep"]]
+    lines = ["ncu --set full --clock-control none --import-source on, 1 x B200 (under gpurun); per-launch values of the",
+             "steady-state launch (bench.py C2 workload: 1M x 768, nlist 1024, m 96, nprobes 20, k 10, B 1024) unless the",
+             "label says otherwise.  Sources: " + ", ".join(r for _, r in reps) + " (scratch, not tracked).", ""]
+    first = True
+    for label, rep in reps:
+        rep = rep if os.path.isabs(rep) else os.path.join(ROOT, rep)
         if not os.path.exists(rep):
             continue
         d = raw_page(rep)
         kern = d.get("Kernel Name", ("?", ""))[0]
-        lines.append(f"kernel: {kern}")
-        for m in METRICS:
+        lines.append(f"[{label}] kernel: {kern}")
+        for m in METRICS + ["l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+                            "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]:
             if m in d:
                 lines.append(f"  {m:75s} {d[m][0]} {d[m][1]}")
         lines.append(f"  stall reasons: {stall_mix(d)}")
         lines.append("")
-        if name == "scan_full":
+        if first:
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tr = sum(float(d[k][0]) * scale.get(d[k][1], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
             with open(os.path.join(ROOT, "profiles", f"{tag}_scan_traffic.json"), "w") as f:
                 json.dump({"kernel": kern, "dram_bytes_per_launch": tr,
                            "source": f"profiles/{tag}_ncu_summary.txt (ncu --set full, 1 launch)"}, f)
                 f.write("\n")
+            first = False
     with open(os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.txt"), "w") as f:
         f.write("\n".join(lines))
     print("\n".join(lines))
