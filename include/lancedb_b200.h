@@ -205,6 +205,17 @@ int lgpu_pq_encode(const float *centroids, const float *codebook, uint32_t nlist
                    int metric, const float *vectors, const uint32_t *parts, uint64_t n, int device,
                    unsigned char *out_codes);
 
+/* k-means TRAINING on the GPU (the Lloyd loops of the IVF_PQ build; parameters max_iterations / sample_rate at
+ * rust/lancedb/src/index/vector.rs:286-297).  x: HOST [n][dim] training rows (already sampled, normalised for cosine).
+ * centroids: in = initial centres (e.g. k sampled rows), out = trained centres.  Assignment is the search's own coarse
+ * step (exact nearest centre), empty clusters keep their previous centre.  *inertia_out (optional) = sum of squared
+ * distances of the rows to their nearest trained centre. */
+int lgpu_kmeans_train(const float *x, uint64_t n, uint32_t dim, float *centroids, uint32_t k, uint32_t iters, int device,
+                      double *inertia_out);
+/* the 256-entry PQ codebooks of all m sub-spaces: x = HOST [n][dim] rows to quantise (residuals for l2 / cosine, raw rows
+ * for dot); codebook [m][256][dim/m] in = initial codewords, out = trained */
+int lgpu_pq_train(const float *x, uint64_t n, uint32_t dim, uint32_t m, float *codebook, uint32_t iters, int device);
+
 /* ---- flat / brute force (LanceRead -> KNNVectorDistance -> TopK) --------- */
 int  lgpu_flat_open(const float *vectors, uint64_t nrows, uint32_t dim,
                     const uint64_t *row_ids /* NULL => 0..nrows-1 */, int device,

@@ -29,7 +29,7 @@ EXPORTS = [
     "lgpu_comm_unique_id", "lgpu_comm_init", "lgpu_comm_destroy", "lgpu_search_sharded", "lgpu_search_sharded_device",
     "lgpu_comm_last_stage_ms",
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
-    "lgpu_ivf_assign", "lgpu_pq_encode",
+    "lgpu_ivf_assign", "lgpu_pq_encode", "lgpu_kmeans_train", "lgpu_pq_train",
     "lgpu_debug_coarse", "lgpu_debug_partition_distances", "lgpu_debug_gemm", "lgpu_last_stage_ms", "lgpu_set_profiling",
     "lgpu_kernel_launch_count", "lgpu_last_filter_stats",
 ]
@@ -101,6 +101,8 @@ def load():
     lib.lgpu_flat_close.restype = None
     lib.lgpu_ivf_assign.argtypes = [vp, u32, u32, i32, vp, C.c_uint64, i32, vp]
     lib.lgpu_pq_encode.argtypes = [vp, vp, u32, u32, u32, i32, vp, vp, C.c_uint64, i32, vp]
+    lib.lgpu_kmeans_train.argtypes = [vp, C.c_uint64, u32, vp, u32, u32, i32, C.POINTER(C.c_double)]
+    lib.lgpu_pq_train.argtypes = [vp, C.c_uint64, u32, u32, vp, u32, i32]
     lib.lgpu_flat_search.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp]
     lib.lgpu_flat_search_filtered.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_flat_search_device.argtypes = [vp, i32, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
@@ -297,6 +299,24 @@ def pq_encode(centroids, codebook, vectors, parts, metric: str = "l2", device: i
     check(load().lgpu_pq_encode(_ptr(c), _ptr(cb), c.shape[0], c.shape[1], m, METRICS[metric], _ptr(v), _ptr(p),
                                 v.shape[0], device, _ptr(out)))
     return out
+
+
+def kmeans_train(vectors, init_centroids, iters: int, device: int = 0, want_inertia: bool = False):
+    """Lloyd k-means on the GPU (lgpu_kmeans_train): returns the trained centres (and the inertia)."""
+    v = np.ascontiguousarray(vectors, np.float32)
+    c = np.array(init_centroids, np.float32, order="C", copy=True)
+    inertia = C.c_double(0.0)
+    check(load().lgpu_kmeans_train(_ptr(v), v.shape[0], v.shape[1], _ptr(c), c.shape[0], int(iters), device,
+                                   C.byref(inertia) if want_inertia else None))
+    return (c, inertia.value) if want_inertia else c
+
+
+def pq_train(vectors, init_codebook, iters: int, device: int = 0) -> np.ndarray:
+    """The m x 256 PQ codewords (lgpu_pq_train); vectors = what gets quantised (residuals for l2 / cosine)."""
+    v = np.ascontiguousarray(vectors, np.float32)
+    cb = np.array(init_codebook, np.float32, order="C", copy=True)
+    check(load().lgpu_pq_train(_ptr(v), v.shape[0], v.shape[1], cb.shape[0], _ptr(cb), int(iters), device))
+    return cb
 
 
 def allow_bitmap(row_ids, nbits: int) -> np.ndarray:

@@ -1680,6 +1680,107 @@ int lgpu_ivf_assign(const float *centroids, uint32_t nlist, uint32_t dim, int me
     });
 }
 
+// nearest centre of every row (device buffers): the search's coarse step with nprobes = 1 -- tcgen05 GEMM scores +
+// coarse_finish_kernel (exact re-score, lance arithmetic) where the shape allows it, the exact kernels otherwise
+static void assign_nearest(const float *d_x, uint64_t n, uint32_t dim, const float *d_cent, uint32_t k, int num_sms,
+                           uint64_t *d_ids, float *d_dist, cudaStream_t st)
+{
+    const uint64_t ld = (k + 3ull) & ~3ull;
+    const uint64_t CH = std::max<uint64_t>(256, std::min<uint64_t>(65536, ((uint64_t)1 << 28) / (ld * 4)));
+    DevBuf D, cnt, flags, gate, xb, xn2, cb, cn2;
+    D.ensure((size_t)CH * ld * 4); cnt.ensure((size_t)CH * 4);
+    const bool tc = gemm_shape_supported(dim) && k >= 256 && tc_enabled();
+    float cmax = 0.f;
+    if (tc) {
+        flags.ensure((size_t)CH * 4); gate.ensure(16);
+        xb.ensure((size_t)CH * dim * 2); xn2.ensure((size_t)CH * 4);
+        prepare_tc_operand(d_cent, k, dim, cb, cn2, cmax, st);
+    }
+    for (uint64_t r0 = 0; r0 < n; r0 += CH) {
+        const uint32_t b = (uint32_t)std::min<uint64_t>(CH, n - r0);
+        const float *q = d_x + r0 * dim;
+        SelectArgs sa{};
+        sa.mode = 1; sa.dense = D.as<float>(); sa.ncols = k; sa.row_stride = ld; sa.B = b; sa.k = 1;
+        sa.out_ids = d_ids + r0; sa.out_dist = d_dist + r0; sa.out_count = cnt.as<uint32_t>();
+        if (tc) {
+            launch_to_bf16(q, b, dim, xb.p, xn2.as<float>(), st);
+            launch_gemm_dist(xb.p, cb.p, cn2.as<float>(), b, k, dim, D.as<float>(), ld, num_sms, st);
+            launch_coarse_finish(D.as<float>(), ld, b, k, q, d_cent, xn2.as<float>(), cmax, dim, 1, d_ids + r0, d_dist + r0,
+                                 cnt.as<uint32_t>(), flags.as<uint32_t>(), gate.as<uint32_t>(), st);
+            launch_dist_matrix(q, d_cent, b, k, dim, 0, nullptr, nullptr, D.as<float>(), ld, st, flags.as<uint32_t>(),
+                               gate.as<uint32_t>());
+            sa.only = flags.as<uint32_t>(); sa.gate = gate.as<uint32_t>();
+            launch_select(sa, st);
+        } else {
+            launch_dist_matrix(q, d_cent, b, k, dim, 0, nullptr, nullptr, D.as<float>(), ld, st);
+            launch_select(sa, st);
+        }
+    }
+    LGPU_CUDA(cudaStreamSynchronize(st));                            // the scratch buffers die with this scope
+}
+
+int lgpu_kmeans_train(const float *x, uint64_t n, uint32_t dim, float *centroids, uint32_t k, uint32_t iters, int device,
+                      double *inertia_out)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(x && centroids && n > 0 && dim > 0 && k > 0, "null argument / empty shape");
+        LGPU_REQUIRE(n < (1ull << 32), "too many training rows (sample them: sample_rate * num_partitions)");
+        require_device(device);
+        cudaDeviceProp prop;
+        LGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+        cudaStream_t st = nullptr;
+        DevBuf dx, dc, ids, dist, counts, offsets, cursor, rows, inert;
+        dx.ensure((size_t)n * dim * 4); dc.ensure((size_t)k * dim * 4);
+        ids.ensure((size_t)n * 8); dist.ensure((size_t)n * 4);
+        counts.ensure((size_t)k * 4); offsets.ensure((size_t)(k + 1) * 4); cursor.ensure((size_t)k * 4);
+        rows.ensure((size_t)n * 4); inert.ensure(16);
+        LGPU_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st));
+        LGPU_CUDA(cudaMemcpyAsync(dc.p, centroids, (size_t)k * dim * 4, cudaMemcpyHostToDevice, st));
+        for (uint32_t it = 0; it < std::max<uint32_t>(iters, 1); it++) {
+            assign_nearest(dx.as<float>(), n, dim, dc.as<float>(), k, prop.multiProcessorCount, ids.as<uint64_t>(),
+                           dist.as<float>(), st);
+            launch_kmeans_update(ids.as<uint64_t>(), dx.as<float>(), n, dim, k, counts.as<uint32_t>(), offsets.as<uint32_t>(),
+                                 cursor.as<uint32_t>(), rows.as<uint32_t>(), dc.as<float>(), st);
+        }
+        if (inertia_out) {                                           // of the trained centres
+            assign_nearest(dx.as<float>(), n, dim, dc.as<float>(), k, prop.multiProcessorCount, ids.as<uint64_t>(),
+                           dist.as<float>(), st);
+            launch_kmeans_inertia(dist.as<float>(), n, inert.as<double>(), st);
+            LGPU_CUDA(cudaMemcpyAsync(inertia_out, inert.p, 8, cudaMemcpyDeviceToHost, st));
+        }
+        LGPU_CUDA(cudaMemcpyAsync(centroids, dc.p, (size_t)k * dim * 4, cudaMemcpyDeviceToHost, st));
+        LGPU_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int lgpu_pq_train(const float *x, uint64_t n, uint32_t dim, uint32_t m, float *codebook, uint32_t iters, int device)
+{
+    return guarded([&] {
+        LGPU_REQUIRE(x && codebook && n > 0 && dim > 0 && m > 0, "null argument / empty shape");
+        LGPU_REQUIRE(dim % m == 0 && scan_dsub_supported(dim / m),
+                     "unsupported PQ sub-vector length (dim/num_sub_vectors must be 1,2,4,8,16 or 32)");
+        require_device(device);
+        cudaStream_t st = nullptr;
+        const uint32_t dsub = dim / m;
+        DevBuf dx, cb, zero, parts, codes, sums, counts;
+        dx.ensure((size_t)n * dim * 4); cb.ensure((size_t)m * 256 * dsub * 4); zero.ensure((size_t)dim * 4);
+        parts.ensure((size_t)n * 4); codes.ensure((size_t)n * m); sums.ensure((size_t)m * 256 * dsub * 8);
+        counts.ensure((size_t)m * 256 * 4);
+        LGPU_CUDA(cudaMemcpyAsync(dx.p, x, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st));
+        LGPU_CUDA(cudaMemcpyAsync(cb.p, codebook, (size_t)m * 256 * dsub * 4, cudaMemcpyHostToDevice, st));
+        LGPU_CUDA(cudaMemsetAsync(zero.p, 0, (size_t)dim * 4, st));          // one all-zero "centroid": residual = row
+        LGPU_CUDA(cudaMemsetAsync(parts.p, 0, (size_t)n * 4, st));
+        for (uint32_t it = 0; it < std::max<uint32_t>(iters, 1); it++) {
+            launch_pq_encode(dx.as<float>(), parts.as<uint32_t>(), zero.as<float>(), cb.as<float>(), n, dim, m, LGPU_L2,
+                             codes.as<unsigned char>(), st);
+            launch_pq_update(dx.as<float>(), codes.as<unsigned char>(), n, dim, m, sums.as<double>(), counts.as<uint32_t>(),
+                             cb.as<float>(), st);
+        }
+        LGPU_CUDA(cudaMemcpyAsync(codebook, cb.p, (size_t)m * 256 * dsub * 4, cudaMemcpyDeviceToHost, st));
+        LGPU_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
 int lgpu_pq_encode(const float *centroids, const float *codebook, uint32_t nlist, uint32_t dim, uint32_t m,
                    int metric, const float *vectors, const uint32_t *parts, uint64_t n, int device,
                    unsigned char *out_codes)

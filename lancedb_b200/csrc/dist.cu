@@ -140,7 +140,15 @@ __device__ __forceinline__ float halfwarp_l2(const float *__restrict__ x, const 
 {
     const uint32_t d16 = d & ~15u;
     float a = 0.f;
-    for (uint32_t k = hl; k < d16; k += 16) { float df = __fsub_rn(x[k], y[k]); a = __fadd_rn(a, __fmul_rn(df, df)); }
+    uint32_t k = hl;
+    for (; k + 7 * 16 < d16; k += 8 * 16) {             // eight independent loads of each operand in flight
+        float xv[8], yv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) { xv[u] = x[k + 16 * u]; yv[u] = y[k + 16 * u]; }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { const float df = __fsub_rn(xv[u], yv[u]); a = __fadd_rn(a, __fmul_rn(df, df)); }
+    }
+    for (; k < d16; k += 16) { float df = __fsub_rn(x[k], y[k]); a = __fadd_rn(a, __fmul_rn(df, df)); }
     float t = 0.f;
 #pragma unroll
     for (int l = 0; l < 16; l++) t = __fadd_rn(t, __shfl_sync(hmask, a, hbase + l));
@@ -227,10 +235,13 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     float v[NV];
     uint32_t kmin = 0xffffffffu, kmax = 0u, nv = 0;
     if constexpr (VPT > 0) {
+        // all loads first (clamped index, no predicate, nothing consuming them in between): with the checks folded in,
+        // ptxas issued load -> use -> load and the kernel spent 3/4 of its time on 64 serial DRAM round trips
+#pragma unroll
+        for (int j = 0; j < VPT; j++) v[j] = __ldg(row + min((uint32_t)j * CF_THREADS + tid, N - 1));
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
-            const uint32_t i = (uint32_t)j * CF_THREADS + tid;
-            v[j] = i < N ? row[i] : CUDART_NAN_F;                   // NaN never counts
+            if ((uint32_t)j * CF_THREADS + tid >= N) v[j] = CUDART_NAN_F;       // NaN never counts
             if (v[j] == v[j]) { const uint32_t kk = f32_key(v[j]); kmin = min(kmin, kk); kmax = max(kmax, kk); nv++; }
         }
     } else {

@@ -274,6 +274,17 @@ void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step,
 void launch_pq_encode(const float *X, const uint32_t *parts, const float *centroids, const float *codebook,
                       uint64_t n, uint32_t dim, uint32_t m, int metric, unsigned char *codes, cudaStream_t st);
 
+// ---------------- index training (kmeans.cu) ----------------------------------------------
+// one Lloyd update: rows bucketed by `assign` (u64 centre id per row, >= k = unassigned), every non-empty centre replaced
+// by the mean of its rows (f64 sums in ascending row order).  counts [k], offsets [k+1], cursor [k], rows [n]: scratch
+void launch_kmeans_update(const uint64_t *assign, const float *x, uint64_t n, uint32_t dim, uint32_t k, uint32_t *counts,
+                          uint32_t *offsets, uint32_t *cursor, uint32_t *rows, float *centroids, cudaStream_t st);
+// *out = sum of the finite dist[i]
+void launch_kmeans_inertia(const float *dist, uint64_t n, double *out, cudaStream_t st);
+// one Lloyd update of all m PQ codebooks: codebook[i][c] = mean of the sub-vectors i of the rows with codes[row][i] == c
+void launch_pq_update(const float *x, const unsigned char *codes, uint64_t n, uint32_t dim, uint32_t m, double *sums,
+                      uint32_t *counts, float *codebook, cudaStream_t st);
+
 // ---------------- index re-layout (open time) --------------------------------------
 void launch_retile_codes(const unsigned char *codes, int layout, const uint64_t *part_off, uint32_t nlist,
                          uint64_t nrows, uint32_t m, uint32_t nch, const uint64_t *code_base,

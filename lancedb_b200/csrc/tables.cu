@@ -382,21 +382,39 @@ __device__ __forceinline__ float exact_pq_distance_warp(const float *qv, const f
 {
     float tv[16];
 #pragma unroll
-    for (int it = 0; it < 16; it++) {
-        tv[it] = 0.f;
-        const uint32_t i = (uint32_t)it * 32 + lane;
-        if ((uint32_t)it * 32 < m && i < m) {
-            const uint32_t c = stream_code(codes, cbase, npad, row, i);
-            const float *cb = cb_tiled + (((size_t)(i >> 3) * 256 + c) * 8 + (i & 7)) * DSUB;
-            // 16-byte loads: with 4-byte loads a warp re-touches the same 32 sectors DSUB times per array and the
-            // L1 sector throughput, not latency, bounds the kernel
-            float r[DSUB], cv[DSUB], qq[DSUB], cc[DSUB];
-            load_cb<DSUB>(cv, cb);
-            load_any<DSUB>(qq, qv + i * DSUB);
-            if (metric != LGPU_DOT) load_cb<DSUB>(cc, cen + i * DSUB);
+    for (int it = 0; it < 16; it++) tv[it] = 0.f;
+    // U sub-spaces per lane at a time, in three phases (code bytes -> operands -> arithmetic) so that the loads of a
+    // phase are all in flight together: interleaved, ptxas serialised them into one L2 round trip after the other.
+    // U = 3 covers m = 96 in one block at DSUB <= 8; longer sub-vectors keep the register count down with U = 1.
+    constexpr int U = DSUB <= 8 ? 3 : 1;
 #pragma unroll
-            for (int t = 0; t < DSUB; t++) r[t] = (metric == LGPU_DOT) ? qq[t] : __fsub_rn(qq[t], cc[t]);
-            tv[it] = (metric == LGPU_DOT) ? subvec_dot_dist<DSUB>(r, cv) : subvec_l2<DSUB>(r, cv);
+    for (int blk = 0; blk * U < 16; blk++) {
+        if ((uint32_t)blk * U * 32 < m) {
+            uint32_t c[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = (uint32_t)(blk * U + u) * 32 + lane;
+                c[u] = i < m ? stream_code(codes, cbase, npad, row, i) : 0u;
+            }
+            float cv[U][DSUB], qq[U][DSUB], cc[U][DSUB];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const uint32_t i = min((uint32_t)(blk * U + u) * 32 + lane, m - 1);
+                load_cb<DSUB>(cv[u], cb_tiled + (((size_t)(i >> 3) * 256 + c[u]) * 8 + (i & 7)) * DSUB);
+                load_any<DSUB>(qq[u], qv + i * DSUB);
+                if (metric != LGPU_DOT) load_cb<DSUB>(cc[u], cen + i * DSUB);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (blk * U + u < 16) {
+                    const uint32_t i = (uint32_t)(blk * U + u) * 32 + lane;
+                    float r[DSUB];
+#pragma unroll
+                    for (int t = 0; t < DSUB; t++) r[t] = (metric == LGPU_DOT) ? qq[u][t] : __fsub_rn(qq[u][t], cc[u][t]);
+                    const float e = (metric == LGPU_DOT) ? subvec_dot_dist<DSUB>(r, cv[u]) : subvec_l2<DSUB>(r, cv[u]);
+                    tv[blk * U + u] = i < m ? e : 0.f;
+                }
+            }
         }
     }
     float acc = 0.f;
@@ -414,7 +432,7 @@ __device__ __forceinline__ float exact_pq_distance_warp(const float *qv, const f
 
 // one warp per (query, candidate position) pair
 template <int DSUB>
-__global__ void __launch_bounds__(256) pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *__restrict__ pos,
+__global__ void __launch_bounds__(256, 2) pq_rescore_kernel(const float *__restrict__ Q, const uint64_t *__restrict__ pos,
                                                          uint32_t B, uint32_t nc, const unsigned char *__restrict__ codes,
                                                          const uint64_t *__restrict__ code_base,
                                                          const uint32_t *__restrict__ part_npad,
@@ -521,7 +539,7 @@ __global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a
 
 constexpr int RSC_THREADS = 256;
 template <int DSUB>
-__global__ void __launch_bounds__(RSC_THREADS) cand_rescore_kernel(FinalizeArgs a)
+__global__ void __launch_bounds__(RSC_THREADS, 2) cand_rescore_kernel(FinalizeArgs a)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t total = *a.work_cnt;

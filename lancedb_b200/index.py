@@ -11,7 +11,8 @@ transposed PQ codes and row ids.  The same arrays are handed to the C-ABI
 283-303): num_partitions, num_sub_vectors (default dim/16, else dim/8, else 1),
 num_bits = 8, sample_rate = 256, max_iterations = 50, distance_type.  Training itself
 lives in the un-vendored lance crate; this is a plain k-means / PQ trainer written with
-torch ops (CPU or CUDA) -- index *quality* is not on the hot path, and both the CUDA
+torch ops (CPU or CUDA), or, with `native_passes` (the `accelerator="cuda"` build), the library's own
+training kernels (csrc/kmeans.cu) -- index *quality* is not on the hot path, and both the CUDA
 path and the oracle consume the identical arrays it produces.
 """
 from __future__ import annotations
@@ -136,6 +137,17 @@ def _kmeans(x, k, iters, gen, chunk=1 << 16):
     return c
 
 
+def _init_rows(x, k, gen):
+    """k initial centres: distinct random rows (jittered copies when there are fewer rows than centres)."""
+    import torch
+    n = x.shape[0]
+    c = x[torch.randperm(n, generator=gen, device="cpu")[:k].to(x.device)].clone()
+    if c.shape[0] < k:
+        extra = x[torch.randint(0, n, (k - c.shape[0],), generator=gen, device="cpu").to(x.device)]
+        c = torch.cat([c, extra + 1e-3 * torch.randn(extra.shape, generator=gen).to(x.device)])
+    return c
+
+
 def _assign(x, c, chunk=1 << 16, metric="l2"):
     """Partition of every row, ranked like the search's coarse step: L2 for l2/cosine, 1 - x.c for dot."""
     import torch
@@ -178,7 +190,8 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
     native_passes: run the two passes over every row (IVF assignment, PQ encoding) through the C ABI
     (`lgpu_ivf_assign` / `lgpu_pq_encode`, csrc/build.cu) -- the search kernels' own arithmetic, so a row
     always lands in the partition its own vector probes first -- instead of torch's GEMM-form argmin.
-    The k-means training loops stay in torch either way.
+    With native_passes the k-means training loops run in the library too (`lgpu_kmeans_train` / `lgpu_pq_train`,
+    csrc/kmeans.cu); otherwise they are torch ops.
     """
     import torch
     metric = distance_type.lower()
@@ -211,10 +224,17 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
 
     ns = min(n, sample_rate * nlist)
     samp = x[torch.randperm(n, generator=gen, device="cpu")[:ns].to(x.device)] if ns < n else x
-    centroids = _kmeans(samp, nlist, max_iterations, gen)
     dev_index = x.device.index or 0 if x.device.type == "cuda" else 0
     if native_passes:
+        # accelerator path: the Lloyd loops run in the library's own kernels (csrc/kmeans.cu through
+        # lgpu_kmeans_train): no torch op inside the loop, only the random initial sample is drawn here
         from . import _native
+        samp_np = samp.detach().cpu().numpy()
+        init = _init_rows(samp, nlist, gen).cpu().numpy()
+        centroids = torch.as_tensor(_native.kmeans_train(samp_np, init, max_iterations, dev_index), device=x.device)
+    else:
+        centroids = _kmeans(samp, nlist, max_iterations, gen)
+    if native_passes:
         raw_np = raw.detach().cpu().numpy()
         assign = torch.as_tensor(_native.ivf_assign(centroids.cpu().numpy(), raw_np, metric, dev_index).astype(np.int64),
                                  device=x.device)
@@ -225,8 +245,15 @@ def train_ivf_pq(vectors, *, num_partitions: Optional[int] = None, num_sub_vecto
     nps = min(n, max(256, sample_rate) * 256)
     pidx = torch.randperm(n, generator=gen, device="cpu")[:nps].to(x.device)
     ps = x[pidx] - centroids[assign[pidx]] if metric != "dot" else x[pidx]
-    ps = ps.reshape(nps, m, dsub).transpose(0, 1).contiguous()           # [m, nps, dsub]
-    codebook = _batched_kmeans(ps, 256, max_iterations, gen)             # [m, 256, dsub]
+    if native_passes:
+        init_cb = torch.stack([ps[torch.randperm(nps, generator=gen, device="cpu")[:256].to(x.device) if nps >= 256
+                                  else torch.randint(0, nps, (256,), generator=gen, device="cpu").to(x.device)]
+                               .reshape(256, m, dsub)[:, i, :] for i in range(m)])              # [m, 256, dsub]
+        codebook = torch.as_tensor(_native.pq_train(ps.detach().cpu().numpy(), init_cb.cpu().numpy(), max_iterations,
+                                                    dev_index), device=x.device)
+    else:
+        ps3 = ps.reshape(nps, m, dsub).transpose(0, 1).contiguous()      # [m, nps, dsub]
+        codebook = _batched_kmeans(ps3, 256, max_iterations, gen)        # [m, 256, dsub]
 
     cbn = (codebook * codebook).sum(2)                                     # [m, 256]
     codes = torch.empty((n, m), dtype=torch.uint8, device=x.device)

@@ -60,3 +60,77 @@ def test_index_built_with_native_passes(metric):
     oi, od, oc = orc.search(q, k=5, nprobes=4, nthreads=4)
     gpu.close()
     assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32)) and np.array_equal(gc, oc)
+
+
+def test_kmeans_training_kernels_match_a_torch_lloyd_run():
+    """lgpu_kmeans_train (csrc/kmeans.cu): from the same initial centres and the same number of iterations the
+    GPU Lloyd run must end within 1 % of the inertia of a plain torch Lloyd run; one iteration
+    from the same centres must give the same centres up to f32 rounding of the means."""
+    import torch
+    from lancedb_b200 import _native
+    rng = np.random.default_rng(61)
+    cen = rng.standard_normal((24, 64)).astype(np.float32) * 3
+    x = (cen[rng.integers(0, 24, 30000)] + rng.standard_normal((30000, 64))).astype(np.float32)
+    for k in (16, 300):                                   # 300: the tensor-core assignment (k >= 256)
+        init = x[rng.choice(len(x), k, replace=False)].copy()
+
+        def lloyd(c, iters):
+            xt, ct = torch.from_numpy(x), torch.from_numpy(c.copy())
+            for _ in range(iters):
+                a = torch.cdist(xt.double(), ct.double()).argmin(1)      # exact nearest centre, as the kernels assign
+                for j in range(k):
+                    sel = a == j
+                    if sel.any():
+                        ct[j] = xt[sel].double().mean(0).float()
+            d = torch.cdist(xt.double(), ct.double()).min(1).values
+            return ct.numpy(), float((d.double() ** 2).sum())
+        one_ref, _ = lloyd(init, 1)
+        one_gpu = _native.kmeans_train(x, init, 1)
+        assert np.allclose(one_gpu, one_ref, rtol=1e-4, atol=1e-4)
+        ref_c, ref_inertia = lloyd(init, 12)
+        gpu_c, gpu_inertia = _native.kmeans_train(x, init, 12, want_inertia=True)
+        assert abs(gpu_inertia - ref_inertia) <= 0.01 * ref_inertia, (k, gpu_inertia, ref_inertia)
+
+
+def test_pq_training_kernel_reduces_quantisation_error():
+    from lancedb_b200 import _native
+    rng = np.random.default_rng(62)
+    x = rng.standard_normal((20000, 32)).astype(np.float32)
+    m, dsub = 4, 8
+    init = np.stack([x[rng.choice(len(x), 256, replace=False)].reshape(256, m, dsub)[:, i, :] for i in range(m)])
+
+    def qerr(cb):
+        xs = x.reshape(-1, m, dsub)
+        return sum(float(((xs[:, i, None, :] - cb[i][None, :, :]) ** 2).sum(2).min(1).sum()) for i in range(m))
+    e0 = qerr(init)
+    cb1 = _native.pq_train(x, init, 1)
+    cb10 = _native.pq_train(x, init, 10)
+    assert qerr(cb1) < e0 and qerr(cb10) < qerr(cb1) * 0.999
+    # one Lloyd step from `init`, restated with numpy
+    xs = x.reshape(-1, m, dsub)
+    for i in range(m):
+        a = ((xs[:, i, None, :] - init[i][None, :, :]) ** 2).sum(2).argmin(1)
+        for c in range(0, 256, 37):
+            if (a == c).any():
+                assert np.allclose(cb1[i, c], xs[a == c, i].astype(np.float64).mean(0), rtol=1e-4, atol=1e-5)
+
+
+def test_create_index_with_accelerator_trains_on_the_gpu_and_matches_the_oracle():
+    import lancedb_b200 as lancedb
+    rng = np.random.default_rng(63)
+    x = rng.standard_normal((8000, 64)).astype(np.float32)
+    t = lancedb.connect("memory://").create_table("v", {"vector": x, "id": np.arange(8000)})
+    n0 = _native_launches()
+    t.create_index(metric="l2", num_partitions=16, num_sub_vectors=8, max_iterations=5, accelerator="cuda")
+    assert _native_launches() > n0
+    q = rng.standard_normal((4, 64)).astype(np.float32)
+    orc = oracle.OracleIndex.from_data(t._index_data["vector"])
+    oi, od, oc = orc.search(q, k=10, nprobes=6)
+    for i in range(4):
+        out = t.search(q[i]).nprobes(6).limit(10).with_row_id(True).to_arrow()
+        assert out["_rowid"].to_pylist() == [int(v) for v in oi[i, :10]]
+
+
+def _native_launches():
+    from lancedb_b200 import _native
+    return _native.kernel_launch_count()
