@@ -136,6 +136,14 @@ int lgpu_search_async(lgpu_index *ix, const float *queries, uint32_t B,
 int lgpu_ticket_poll(lgpu_ticket *ticket, int *done);   /* *done = 1 when the results are in place */
 int lgpu_ticket_wait(lgpu_ticket *ticket);              /* blocks, frees the ticket, returns the call's status */
 
+/* Single-vector search that may share a batch with concurrent callers (SURVEY.md 8b "Threading": the reference serves
+ * many one-vector queries from tokio workers, each through its own plan -- rust/lancedb/src/table/query.rs:201-215).
+ * Calls with identical parameters arriving within a short window (LGPU_COALESCE_US, default 50 us) are gathered by the
+ * first arrival into ONE lgpu_search; every caller gets exactly the rows a solitary lgpu_search(B = 1) would return.
+ * query: [dim]; out_ids / out_dist: [k]; out_count: [1]. */
+int lgpu_search_coalesced(lgpu_index *ix, const float *query, const lgpu_search_params *params,
+                          uint64_t *out_ids, float *out_dist, uint32_t *out_count);
+
 /* Prefiltered search: the reference's default filter mode ("filtering will be performed
  * before the vector search", rust/lancedb/src/query.rs:489-507; the row-id allow-list the
  * scalar filter produced is what lance hands to the ANN nodes as a pre-filter [lance,

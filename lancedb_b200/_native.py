@@ -25,7 +25,7 @@ EXPORTS = [
     "lgpu_last_error", "lgpu_abi_version", "lgpu_device_count",
     "lgpu_index_open", "lgpu_index_close", "lgpu_index_device_bytes", "lgpu_last_scanned_code_bytes",
     "lgpu_search", "lgpu_search_filtered", "lgpu_search_device", "lgpu_merge_topk_device",
-    "lgpu_search_async", "lgpu_ticket_poll", "lgpu_ticket_wait",
+    "lgpu_search_async", "lgpu_ticket_poll", "lgpu_ticket_wait", "lgpu_search_coalesced",
     "lgpu_comm_unique_id", "lgpu_comm_init", "lgpu_comm_destroy", "lgpu_search_sharded", "lgpu_search_sharded_device",
     "lgpu_comm_last_stage_ms",
     "lgpu_flat_open", "lgpu_flat_close", "lgpu_flat_search", "lgpu_flat_search_filtered", "lgpu_flat_search_device",
@@ -86,6 +86,7 @@ def load():
     lib.lgpu_search_async.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, C.POINTER(vp)]
     lib.lgpu_ticket_poll.argtypes = [vp, C.POINTER(C.c_int)]
     lib.lgpu_ticket_wait.argtypes = [vp]
+    lib.lgpu_search_coalesced.argtypes = [vp, vp, C.POINTER(SearchParams), vp, vp, vp]
     lib.lgpu_search_filtered.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, C.c_uint64, vp, vp, vp]
     lib.lgpu_search_device.argtypes = [vp, vp, u32, C.POINTER(SearchParams), vp, vp, vp, vp]
     lib.lgpu_merge_topk_device.argtypes = [i32, u32, u32, u32, vp, vp, vp, vp, vp, vp]
@@ -207,6 +208,15 @@ class GpuIvfPq:
         """Host-buffer search into caller-owned (e.g. pinned) arrays; no allocation."""
         check(load().lgpu_search(self._h, q.ctypes.data, q.shape[0], C.byref(p), ids.ctypes.data,
                                  dist.ctypes.data, cnt.ctypes.data))
+
+    def search_one(self, query, k=10, nprobes=20, refine_factor=0):
+        """One query vector through the micro-batcher (lgpu_search_coalesced): concurrent callers share a batch.
+        ctypes releases the GIL for the duration of the call, so Python threads do coalesce."""
+        q = np.ascontiguousarray(query, np.float32).reshape(self.dim)
+        ids = np.empty(k, np.uint64); dist = np.empty(k, np.float32); cnt = np.zeros(1, np.uint32)
+        p = make_params(k, nprobes, refine_factor)
+        check(load().lgpu_search_coalesced(self._h, _ptr(q), C.byref(p), _ptr(ids), _ptr(dist), _ptr(cnt)))
+        return ids, dist, int(cnt[0])
 
     def search_async(self, q: np.ndarray, p: SearchParams, ids: np.ndarray, dist: np.ndarray, cnt: np.ndarray):
         """lgpu_search_async into caller-owned (pinned) arrays; returns a ticket for ticket_wait()."""

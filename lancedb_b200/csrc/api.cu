@@ -206,8 +206,27 @@ template <class H> static bool retire_handle(H *p)
 }
 }  // namespace lgpu
 
+// micro-batcher of concurrent single-vector calls (SURVEY.md 8b "Threading": many tokio workers each with one query
+// vector).  Callers with identical parameters that arrive within a short window ride one batched search: the first
+// arrival leads -- waits for the window (or a full batch), takes the queue, runs lgpu_search on the gathered
+// queries, scatters the rows -- the others sleep on the condition variable until their row is filled in.
+namespace lgpu {
+struct PendingQuery {
+    const float *q; uint64_t *ids; float *dist; uint32_t *cnt;
+    int status = LGPU_OK; bool done = false; std::string err;
+};
+struct Coalescer {
+    std::mutex mu;
+    std::condition_variable cv;
+    struct Lane { lgpu_search_params params; std::vector<PendingQuery *> queue; bool leader = false; };
+    std::vector<Lane *> lanes;                           // one per distinct parameter set seen (a handful)
+    ~Coalescer() { for (auto *l : lanes) delete l; }
+};
+}  // namespace lgpu
+
 struct lgpu_index {
     std::atomic<int> refs{0};
+    Coalescer coalescer;
     int device = 0, num_sms = 0;
     uint32_t dim = 0, nlist = 0, m = 0, dsub = 0, nch = 0;
     uint32_t max_nrb = 1;          // row blocks (of 1536 rows) of the largest partition: bounds the tile count
@@ -1228,6 +1247,62 @@ int lgpu_search_filtered(lgpu_index *ixh, const float *queries, uint32_t B, cons
                       ivf_search_device(ix.h, ws, st, dq, B, *params, di, dd, dc, rf, &dl);
                   }, false);
     });
+}
+
+int lgpu_search_coalesced(lgpu_index *ixh, const float *query, const lgpu_search_params *params, uint64_t *out_ids,
+                          float *out_dist, uint32_t *out_count)
+{
+    static const uint32_t window_us = getenv("LGPU_COALESCE_US") ? (uint32_t)atoi(getenv("LGPU_COALESCE_US")) : 50u;
+    constexpr size_t MAX_BATCH = 256;
+    PendingQuery me{query, out_ids, out_dist, out_count};
+    std::vector<PendingQuery *> batch;
+    lgpu_search_params p{};
+    int rc = guarded([&] {
+        HandleRef<lgpu_index> ix(ixh, "index");
+        check_ivf_call(ix.h, query, 1, params, out_ids, out_dist, out_count);
+        p = *params;
+        Coalescer &co = ix->coalescer;
+        std::unique_lock<std::mutex> lk(co.mu);
+        Coalescer::Lane *lane = nullptr;
+        for (auto *l : co.lanes) if (memcmp(&l->params, &p, sizeof(p)) == 0) { lane = l; break; }
+        if (!lane) { lane = new Coalescer::Lane(); lane->params = p; co.lanes.push_back(lane); }
+        lane->queue.push_back(&me);
+        if (lane->leader) {                               // follower: the lane's leader will fill our row in
+            if (lane->queue.size() >= MAX_BATCH) co.cv.notify_all();
+            co.cv.wait(lk, [&] { return me.done; });
+            return;
+        }
+        lane->leader = true;                              // leader: collect for one window, then search the batch
+        co.cv.wait_for(lk, std::chrono::microseconds(window_us), [&] { return lane->queue.size() >= MAX_BATCH; });
+        batch.swap(lane->queue);
+        lane->leader = false;
+        lk.unlock();
+        const uint32_t B = (uint32_t)batch.size();
+        const uint32_t dim = ix->dim, k = p.k;
+        std::vector<float> q((size_t)B * dim);
+        std::vector<uint64_t> ids((size_t)B * k);
+        std::vector<float> dist((size_t)B * k);
+        std::vector<uint32_t> cnt(B);
+        for (uint32_t i = 0; i < B; i++) memcpy(q.data() + (size_t)i * dim, batch[i]->q, (size_t)dim * 4);
+        const int brc = lgpu_search(ix.h, q.data(), B, &p, ids.data(), dist.data(), cnt.data());
+        const std::string berr = brc == LGPU_OK ? std::string() : std::string(lgpu_last_error());
+        lk.lock();
+        for (uint32_t i = 0; i < B; i++) {
+            PendingQuery *pq = batch[i];
+            pq->status = brc; pq->err = berr;
+            if (brc == LGPU_OK) {
+                memcpy(pq->ids, ids.data() + (size_t)i * k, (size_t)k * 8);
+                memcpy(pq->dist, dist.data() + (size_t)i * k, (size_t)k * 4);
+                *pq->cnt = cnt[i];
+            }
+            pq->done = true;
+        }
+        lk.unlock();
+        co.cv.notify_all();
+    });
+    if (rc != LGPU_OK) return rc;
+    if (me.status != LGPU_OK) { set_error(me.err); return me.status; }
+    return LGPU_OK;
 }
 
 int lgpu_search_device(lgpu_index *ixh, const float *d_queries, uint32_t B, const lgpu_search_params *params,

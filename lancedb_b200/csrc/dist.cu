@@ -370,7 +370,7 @@ void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, 
     if (B == 0 || N == 0) return;
     // the fix-up pass (`only`) is almost always a no-op: keep its CTA count small
     const uint64_t ct = (N + DM_C - 1) / DM_C;
-    dim3 grid((unsigned)std::min<uint64_t>(ct, only ? 256 : ((uint64_t)1 << 30)), (B + DM_Q - 1) / DM_Q);
+    dim3 grid((unsigned)std::min<uint64_t>(ct, only ? 16 : ((uint64_t)1 << 30)), (B + DM_Q - 1) / DM_Q);
     dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only, gate); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }

@@ -38,71 +38,52 @@ __global__ void group_count_kernel(GroupArgs a)
     if (!a.only) atomicAdd(a.scanned_rows, (unsigned long long)rows);
 }
 
-// single CTA: exclusive scans over queries (segment bases) and partitions (query-list
-// and tile offsets)
+// single CTA: exclusive scans over queries (segment bases) and partitions (query-list and tile offsets).  Every thread
+// sums a contiguous run of elements, one 1024-wide block scan combines the runs, the thread then writes its run back:
+// one block scan per array whatever B / nlist are (the chunked form took 72 us at nlist = 16384).
+template <class Get, class Put>
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint32_t n, uint64_t *s_part, int tid, Get &&get, Put &&put)
+{
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = min(n, (uint32_t)tid * per), e = min(n, b + per);
+    uint64_t sum = 0;
+    for (uint32_t i = b; i < e; i++) sum += get(i);
+    s_part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const uint64_t t = tid >= o ? s_part[tid - o] : 0;
+        __syncthreads();
+        s_part[tid] += t;
+        __syncthreads();
+    }
+    uint64_t run = s_part[tid] - sum;
+    for (uint32_t i = b; i < e; i++) { const uint64_t v = get(i); put(i, run); run += v; }
+    const uint64_t total = s_part[1023];
+    __syncthreads();
+    return total;
+}
+
 __global__ void group_scan_kernel(GroupArgs a)
 {
     __shared__ uint64_t s_part[1024];
-    __shared__ uint64_t s_carry;
     const int tid = threadIdx.x;
     if (a.gate && *a.gate == 0) {                       // nothing flagged: no tiles for the exact kernel
         if (tid == 0) { *a.total_tiles = 0; *a.tile_counter = 0; }
         return;
     }
-    // --- queries: qtot -> exclusive prefix (in place) ---
-    if (tid == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < a.B; base += 1024) {
-        uint32_t i = base + tid;
-        uint64_t v = i < a.B ? a.qtot[i] : 0;
-        s_part[tid] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            uint64_t t = tid >= o ? s_part[tid - o] : 0;
-            __syncthreads();
-            s_part[tid] += t;
-            __syncthreads();
-        }
-        uint64_t incl = s_part[tid], carry = s_carry;
-        if (i < a.B) a.qtot[i] = carry + incl - v;
-        __syncthreads();
-        if (tid == 1023) s_carry = carry + incl;
-        __syncthreads();
-    }
-    // --- partitions: query-list offsets and tile offsets ---
-    for (int pass = 0; pass < 2; pass++) {
-        if (tid == 0) s_carry = 0;
-        __syncthreads();
-        for (uint32_t base = 0; base < a.nlist; base += 1024) {
-            uint32_t p = base + tid;
-            uint64_t v = 0;
-            if (p < a.nlist) {
-                uint32_t cnt = a.part_cnt[p];
-                v = pass == 0 ? cnt : (uint64_t)((cnt + SCAN_G - 1) / SCAN_G) * scan_nrb(a.part_n[p], a.rows_tile);
-            }
-            s_part[tid] = v;
-            __syncthreads();
-            for (int o = 1; o < 1024; o <<= 1) {
-                uint64_t t = tid >= o ? s_part[tid - o] : 0;
-                __syncthreads();
-                s_part[tid] += t;
-                __syncthreads();
-            }
-            uint64_t incl = s_part[tid], carry = s_carry;
-            if (p < a.nlist) {
-                if (pass == 0) a.qlist_off[p] = (uint32_t)(carry + incl - v);
-                else a.tile_off[p] = (uint32_t)(carry + incl - v);
-            }
-            __syncthreads();
-            if (tid == 1023) s_carry = carry + incl;
-            __syncthreads();
-        }
-        if (pass == 1 && tid == 0) {
-            a.tile_off[a.nlist] = (uint32_t)s_carry;
-            *a.total_tiles = (uint32_t)s_carry;
-            *a.tile_counter = 0;
-        }
-        __syncthreads();
+    // queries: qtot -> exclusive prefix (in place)
+    block_exclusive_scan(a.B, s_part, tid, [&](uint32_t i) { return a.qtot[i]; }, [&](uint32_t i, uint64_t v) { a.qtot[i] = v; });
+    // partitions: query-list offsets, then tile offsets
+    block_exclusive_scan(a.nlist, s_part, tid, [&](uint32_t p) { return (uint64_t)a.part_cnt[p]; },
+                         [&](uint32_t p, uint64_t v) { a.qlist_off[p] = (uint32_t)v; });
+    const uint64_t tiles = block_exclusive_scan(
+        a.nlist, s_part, tid,
+        [&](uint32_t p) { return (uint64_t)((a.part_cnt[p] + SCAN_G - 1) / SCAN_G) * scan_nrb(a.part_n[p], a.rows_tile); },
+        [&](uint32_t p, uint64_t v) { a.tile_off[p] = (uint32_t)v; });
+    if (tid == 0) {
+        a.tile_off[a.nlist] = (uint32_t)tiles;
+        *a.total_tiles = (uint32_t)tiles;
+        *a.tile_counter = 0;
     }
 }
 

@@ -296,3 +296,38 @@ def test_flat_search_device_matches_host_call():
     assert np.array_equal(oi.cpu().numpy().view(np.uint64), want[0])
     assert np.array_equal(od.cpu().numpy().view(np.uint32), want[1].view(np.uint32))
     fl.close()
+
+
+def test_coalesced_single_vector_calls_share_batches(monkeypatch):
+    """lgpu_search_coalesced: 48 threads each with one query vector get exactly the rows of a solitary search, and
+    the batcher turns them into far fewer kernel launches than 48 separate searches would take."""
+    import threading
+    monkeypatch.setenv("LGPU_COALESCE_US", "3000")      # (read once, at the first coalesced call of the process)
+    from lancedb_b200 import _native
+    from tests.util import queries, random_index
+    rng = np.random.default_rng(37)
+    ix = random_index(rng, dim=64, nlist=32, m=8, n=30000)
+    gpu = _native.GpuIvfPq(ix)
+    q = queries(rng, 48, 64)
+    want = gpu.search(q, k=10, nprobes=6)
+    n0 = _native.kernel_launch_count()
+    gpu.search(q[:1], k=10, nprobes=6)
+    per_call = _native.kernel_launch_count() - n0
+    got = [None] * 48
+    barrier = threading.Barrier(48)
+
+    def worker(i):
+        barrier.wait()
+        got[i] = gpu.search_one(q[i], k=10, nprobes=6)
+    n1 = _native.kernel_launch_count()
+    ths = [threading.Thread(target=worker, args=(i,)) for i in range(48)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    used = _native.kernel_launch_count() - n1
+    for i in range(48):
+        assert np.array_equal(got[i][0], want[0][i]) and got[i][2] == want[2][i]
+        assert np.array_equal(got[i][1].view(np.uint32), want[1][i].view(np.uint32))
+    assert used < 48 * per_call / 2, (used, per_call)          # at least half of the calls rode someone else's batch
+    gpu.close()
