@@ -1,6 +1,8 @@
 """The reference-facing Python surface end to end on the GPU: `connect().create_table().search()...`
 with the reference's own doctest inputs (python/python/lancedb/table.py:3587-3603,
 query.py:1555-1571) and an IVF_PQ table checked against the oracle through the same builder calls."""
+import json
+
 import numpy as np
 import pytest
 
@@ -331,3 +333,25 @@ def test_coalesced_single_vector_calls_share_batches(monkeypatch):
         assert np.array_equal(got[i][1].view(np.uint32), want[1][i].view(np.uint32))
     assert used < 48 * per_call / 2, (used, per_call)          # at least half of the calls rode someone else's batch
     gpu.close()
+
+
+def test_remote_wire_format_query_node():
+    """a `/v1/table/{name}/query/` JSON body (as the reference's remote client builds it,
+    rust/lancedb/src/remote/table.rs:724-929) served by the GPU path, Arrow IPC file back."""
+    from lancedb_b200 import remote
+    rng = np.random.default_rng(38)
+    x = rng.standard_normal((5000, 32)).astype(np.float32)
+    t = lancedb.connect("memory://").create_table("v", {"vector": x, "id": np.arange(5000), "grp": np.arange(5000) % 5})
+    t.create_index(metric="l2", num_partitions=8, num_sub_vectors=4, max_iterations=4, accelerator="cuda")
+    q = rng.standard_normal(32).astype(np.float32)
+    body = remote.build_query_body(q, k=7, minimum_nprobes=4, maximum_nprobes=4, filter="grp = 2", columns=["id", "grp"],
+                                   with_row_id=True)
+    out = remote.read_ipc_file(remote.handle_query(t, json.dumps(body)))
+    want = t.search(q).nprobes(4).limit(7).where("grp = 2").select(["id", "grp"]).with_row_id(True).to_arrow()
+    assert out.equals(want) and out.schema.names == ["id", "grp", "_distance", "_rowid"]
+    assert all(g == 2 for g in out["grp"].to_pylist())
+    multi = remote.build_query_body(np.stack([q, -q]), k=3, minimum_nprobes=4, maximum_nprobes=4, bypass_vector_index=True)
+    out = remote.read_ipc_file(remote.handle_query(t, multi))
+    assert out.num_rows == 6 and out["query_index"].to_pylist() == [0, 0, 0, 1, 1, 1]
+    with pytest.raises(NotImplementedError):
+        remote.handle_query(t, remote.build_query_body([], k=3))

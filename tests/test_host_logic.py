@@ -1,6 +1,7 @@
 """Host-side logic that needs no GPU: builder defaults / validation mirroring the reference,
 index parameter defaults, partition sharding, and the world_size-2 all-gather + merge pattern
 over gloo (the oracle stands in for the per-rank GPU search)."""
+import json
 import os
 import socket
 import sys
@@ -267,3 +268,38 @@ def test_full_size_property_checker_on_the_oracle():
         return cache[id(data)][1].search(qq, k=10, nprobes=20, nthreads=4)
 
     check_properties(search, ix, q, 10, 20)
+
+
+# ---------------------------------------------------------------- remote wire format
+def test_remote_query_bodies_match_the_reference_mock_server_pins():
+    """The request bodies pinned by the reference's own tests: test_query_vector_default_values
+    (rust/lancedb/src/remote/table.rs:4650-4671) and test_query_vector_all_params (:4809-4840)."""
+    from lancedb_b200 import remote
+    v = np.asarray([0.1, 0.2, 0.3], np.float32)
+    assert remote.build_query_body(v) == {
+        "prefilter": True, "nprobes": 20, "minimum_nprobes": 20, "maximum_nprobes": 20, "lower_bound": None,
+        "upper_bound": None, "k": 10, "ef": None, "refine_factor": None, "version": None,
+        "vector": [float(x) for x in v]}
+    got = remote.build_query_body(v, k=42, offset=10, prefilter=False, columns=["a", "b"], distance_type="Cosine",
+                                  minimum_nprobes=12, maximum_nprobes=12, refine_factor=2, vector_column="my_vector",
+                                  bypass_vector_index=True)
+    want = {"vector_column": "my_vector", "prefilter": False, "k": 42, "offset": 10, "distance_type": "cosine",
+            "bypass_vector_index": True, "columns": ["a", "b"], "nprobes": 12, "minimum_nprobes": 12,
+            "maximum_nprobes": 12, "lower_bound": None, "upper_bound": None, "ef": None, "refine_factor": 2,
+            "version": None, "vector": [float(x) for x in v]}
+    assert got == want                                                   # (order_by is not a vector-query parameter here)
+    assert remote.build_query_body(v, maximum_nprobes=None)["maximum_nprobes"] == 0      # None -> 0 = unbounded
+    assert remote.build_query_body(np.zeros((2, 3), np.float32))["vector"] == [[0.0] * 3] * 2
+    assert remote.build_query_body([])["vector"] == []
+    assert remote.QUERY_PATH.format(name="my_table") == "/v1/table/my_table/query/"
+    # the f32 -> f64 widening serde does: 0.1f32 is not 0.1f64
+    assert json.loads(json.dumps(remote.build_query_body(v)))["vector"][0] == float(np.float32(0.1)) != 0.1
+
+
+def test_remote_ipc_file_round_trip():
+    import pyarrow as pa
+    from lancedb_b200 import remote
+    t = pa.table({"a": pa.array([1, 2, 3], pa.int32()), "_distance": pa.array([0.0, 0.5, 2.0], pa.float32())})
+    data = remote._ipc_file(t)
+    assert data[:6] == b"ARROW1"                                          # the IPC *file* framing the client expects
+    assert remote.read_ipc_file(data).equals(t)
