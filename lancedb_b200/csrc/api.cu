@@ -94,7 +94,7 @@ struct Workspace {
     cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
     cudaEvent_t ev[8] = {};
     DevBuf q, qn, xnorm, D, probes, probe_dist, probe_cnt;
-    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, qlist, scalars, tile_desc, allow;
+    DevBuf part_cnt, slot_pos, seg_local, qtot, seg_off, qlist_off, tile_off, tile_off_b, qlist, scalars, tile_desc, allow;
     DevBuf dist_out, out_ids, out_dist, out_count;
     DevBuf t_ids, t_dist, t_pos, t_cnt, t_exact;
     DevBuf widen;                       // maximum_nprobes widening: queries that found fewer than k rows
@@ -595,7 +595,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     ws->qtot.ensure((size_t)B * 8);
     ws->seg_off.ensure((size_t)slots * 8);
     ws->qlist_off.ensure((size_t)nlist * 4);
-    ws->tile_off.ensure((size_t)(nlist + 1) * 4);
+    ws->tile_off.ensure((size_t)(nlist + 1) * 4); ws->tile_off_b.ensure((size_t)(nlist + 1) * 4);
     ws->qlist.ensure((size_t)slots * 4);
     ws->scalars.ensure(64);
     GroupArgs ga{};
@@ -603,7 +603,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     ga.part_n = ix->part_n.as<uint32_t>(); ga.part_cnt = ws->part_cnt.as<uint32_t>();
     ga.slot_pos = ws->slot_pos.as<uint32_t>(); ga.seg_local = ws->seg_local.as<uint64_t>();
     ga.qtot = ws->qtot.as<uint64_t>(); ga.seg_off = ws->seg_off.as<uint64_t>();
-    ga.qlist_off = ws->qlist_off.as<uint32_t>(); ga.tile_off = ws->tile_off.as<uint32_t>();
+    ga.qlist_off = ws->qlist_off.as<uint32_t>(); ga.tile_off = ws->tile_off.as<uint32_t>(); ga.tile_off_b = ws->tile_off_b.as<uint32_t>();
     ga.qlist = ws->qlist.as<uint32_t>();
     ga.total_tiles = ws->scalars.as<uint32_t>(); ga.tile_counter = ws->scalars.as<uint32_t>() + 1;
     ga.scanned_rows = reinterpret_cast<unsigned long long *>(ws->scalars.as<char>() + 16);
@@ -670,7 +670,9 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         const float mscale = ix->metric == LGPU_COSINE ? 0.5f : 1.0f;
         // candidate mode (no prefilter, k <= 32): the scanners threshold the rows themselves, nothing dense is written
         static const bool dense_forced = getenv("LGPU_DENSE_FILTER") != nullptr;
-        const bool cand_mode = !rf.bits && kk <= CAND_TOPK_MAX && !dense_forced;
+        static const uint32_t cand_kmax = getenv("LGPU_CAND_KMAX")
+            ? std::min<uint32_t>(CAND_TOPK_MAX, (uint32_t)atoi(getenv("LGPU_CAND_KMAX"))) : 32u;
+        const bool cand_mode = !rf.bits && kk <= cand_kmax && !dense_forced;
         if (cand_mode) {
             // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
             static const uint32_t cap_env = getenv("LGPU_CAND_CAP") ? (uint32_t)atoi(getenv("LGPU_CAND_CAP")) : 0u;

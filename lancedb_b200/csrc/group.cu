@@ -13,13 +13,22 @@ namespace {
 __device__ __forceinline__ uint64_t pad4(uint64_t n) { return (n + 3) & ~3ull; }
 
 // one thread per query: count probes per partition, lay the query's distance segments
-// out back to back (each padded to 4 floats)
-__global__ void group_count_kernel(GroupArgs a)
+// out back to back (each padded to 4 floats).  Two launches: `first` handles every query's NEAREST probe only, the
+// second the others, so that inside a partition the queries for which it is the nearest come first in the query
+// list -- they end up in the partition's first tile group, and those groups are scanned first (tile_desc_kernel):
+// the filter scan's per-query thresholds settle on each query's best partition before the bulk of its tiles run.
+__global__ void group_count_kernel(GroupArgs a, int first)
 {
     if (a.gate && *a.gate == 0) return;
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.B) return;
     const bool take = !a.only || a.only[q];             // fix-up pass: only flagged queries get tiles
+    if (first) {
+        const uint32_t slot = q * a.nprobes;
+        const uint64_t pp = a.probes[slot];
+        a.slot_pos[slot] = (take && pp < a.nlist) ? atomicAdd(&a.part_cnt[(uint32_t)pp], 1u) : 0xffffffffu;
+        return;
+    }
     uint64_t off = 0, rows = 0;
     for (uint32_t j = 0; j < a.nprobes; j++) {
         uint32_t slot = q * a.nprobes + j;
@@ -29,7 +38,7 @@ __global__ void group_count_kernel(GroupArgs a)
         const bool valid = pp < a.nlist;
         uint32_t p = valid ? (uint32_t)pp : 0u;
         uint32_t n = valid ? a.part_n[p] : 0u;
-        a.slot_pos[slot] = (take && valid) ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
+        if (j > 0) a.slot_pos[slot] = (take && valid) ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
         a.seg_local[slot] = off;
         off += pad4(n);
         rows += n;
@@ -76,13 +85,23 @@ __global__ void group_scan_kernel(GroupArgs a)
     // partitions: query-list offsets, then tile offsets
     block_exclusive_scan(a.nlist, s_part, tid, [&](uint32_t p) { return (uint64_t)a.part_cnt[p]; },
                          [&](uint32_t p, uint64_t v) { a.qlist_off[p] = (uint32_t)v; });
-    const uint64_t tiles = block_exclusive_scan(
+    // tiles are numbered in two classes: A = the first query group of every probed partition (all its row blocks),
+    // B = the remaining groups; both partition-major
+    const uint64_t tiles_a = block_exclusive_scan(
         a.nlist, s_part, tid,
-        [&](uint32_t p) { return (uint64_t)((a.part_cnt[p] + SCAN_G - 1) / SCAN_G) * scan_nrb(a.part_n[p], a.rows_tile); },
+        [&](uint32_t p) { return a.part_cnt[p] ? (uint64_t)scan_nrb(a.part_n[p], a.rows_tile) : 0ull; },
         [&](uint32_t p, uint64_t v) { a.tile_off[p] = (uint32_t)v; });
+    const uint64_t tiles_b = block_exclusive_scan(
+        a.nlist, s_part, tid,
+        [&](uint32_t p) {
+            const uint32_t groups = (a.part_cnt[p] + SCAN_G - 1) / SCAN_G;
+            return groups > 1 ? (uint64_t)(groups - 1) * scan_nrb(a.part_n[p], a.rows_tile) : 0ull;
+        },
+        [&](uint32_t p, uint64_t v) { a.tile_off_b[p] = (uint32_t)(tiles_a + v); });
     if (tid == 0) {
-        a.tile_off[a.nlist] = (uint32_t)tiles;
-        *a.total_tiles = (uint32_t)tiles;
+        a.tile_off[a.nlist] = (uint32_t)tiles_a;
+        a.tile_off_b[a.nlist] = (uint32_t)(tiles_a + tiles_b);
+        *a.total_tiles = (uint32_t)(tiles_a + tiles_b);
         *a.tile_counter = 0;
     }
 }
@@ -107,16 +126,18 @@ __global__ void tile_desc_kernel(GroupArgs a)
     const uint32_t t = gid / SCAN_G, g = gid % SCAN_G;
     const uint32_t total = *a.total_tiles;
     if (t >= total || t >= a.max_tiles) return;
-    uint32_t lo = 0, hi = a.nlist - 1;          // smallest p with tile_off[p+1] > t
+    const bool class_a = t < a.tile_off[a.nlist];
+    const uint32_t *off = class_a ? a.tile_off : a.tile_off_b;
+    uint32_t lo = 0, hi = a.nlist - 1;          // smallest p with off[p+1] > t
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;
-        if (a.tile_off[mid + 1] > t) hi = mid; else lo = mid + 1;
+        if (off[mid + 1] > t) hi = mid; else lo = mid + 1;
     }
     const uint32_t p = lo;
     const uint32_t n_p = a.part_n[p];
     const uint32_t nrb = scan_nrb(n_p, a.rows_tile), rbr = scan_rb_rows(n_p, nrb);
-    const uint32_t local = t - a.tile_off[p];
-    const uint32_t grp = local / nrb, rb = local - grp * nrb;
+    const uint32_t local = t - off[p];
+    const uint32_t grp = class_a ? 0u : 1u + local / nrb, rb = class_a ? local : local % nrb;
     const uint32_t ng = min((uint32_t)SCAN_G, a.part_cnt[p] - grp * SCAN_G);
     const uint32_t row0 = rb * rbr;
     TileDesc *d = a.tile_desc + t;
@@ -142,7 +163,8 @@ void launch_group(const GroupArgs &a, cudaStream_t st)
     if (a.B == 0) return;
     LGPU_CUDA(cudaMemsetAsync(a.part_cnt, 0, sizeof(uint32_t) * a.nlist, st));
     if (!a.only) LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
-    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a, 1); LGPU_COUNT_LAUNCH();
+    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a, 0); LGPU_COUNT_LAUNCH();
     group_scan_kernel<<<1, 1024, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     uint32_t slots = a.B * a.nprobes;
     group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a); LGPU_COUNT_LAUNCH();

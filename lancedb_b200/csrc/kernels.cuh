@@ -39,9 +39,8 @@ struct alignas(16) CandRec {
     uint32_t pad;
 };
 constexpr uint32_t CAND_NO_THR = 0xffffffffu;
-constexpr uint32_t CAND_TOPK_MAX = 32;       // candidate mode serves k (or k * refine_factor) up to this: for larger k
-                                             // the per-tile thresholds are too loose before tau_q has settled (measured on
-                                             // BASELINE config 3, k = 100: every list overflowed); those requests use dense mode
+constexpr uint32_t CAND_TOPK_MAX = 128;      // largest k (or k * refine_factor) the candidate mode can serve; api.cu uses it
+                                             // up to LGPU_CAND_KMAX (default 32): for larger k the lists tend to overflow
 
 struct ScanArgs {
     // index (device)
@@ -95,7 +94,8 @@ struct GroupArgs {
     uint64_t *qtot;               // [B]
     uint64_t *seg_off;            // [B*nprobes]
     uint32_t *qlist_off;          // [nlist]
-    uint32_t *tile_off;           // [nlist+1]
+    uint32_t *tile_off;           // [nlist+1] first tile of each partition's first query group (class A)
+    uint32_t *tile_off_b;         // [nlist+1] first tile of each partition's remaining groups (class B, after all of A)
     uint32_t *qlist;              // [B*nprobes]
     uint32_t *total_tiles;        // [1]
     uint32_t *tile_counter;       // [1]
