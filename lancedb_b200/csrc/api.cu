@@ -527,8 +527,14 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     // the PQ top-`kk` of every query (kk = k, or k * refine_factor candidates for the exact re-rank)
     const uint32_t kk = sp.refine_factor ? sp.k * sp.refine_factor : sp.k;
     const uint32_t kp = kk <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * kk + 32);
+    // tiny batches (a single query, a micro-batch): one CTA per (query, probe) pair with the exact table in shared
+    // memory (small.cu) -- 4 launches instead of ~25; LGPU_SMALL_SLOTS = 0 disables
+    static const uint32_t small_slots = getenv("LGPU_SMALL_SLOTS") ? (uint32_t)atoi(getenv("LGPU_SMALL_SLOTS")) : 1024u;
+    const bool small_path = d_ids && !forced_probes && !only && slots <= small_slots &&
+                            small_scan_smem(ix->m, dim) <= 200 * 1024 &&
+                            (size_t)slots * ix->pad_prefix[1] * 4 <= workspace_budget();
     const bool filter_scan = ix->has_tables && !exact_scan_forced() && !sp.has_lower && !sp.has_upper && !forced_probes &&
-                             d_ids && kp > kk && ix->m <= 512 && !only;
+                             d_ids && kp > kk && ix->m <= 512 && !only && !small_path;
     if (filter_scan) {
         ws->qt.ensure((size_t)B * ix->nch * 256 * 16); ws->qt_mm.ensure((size_t)B * ix->nch * 8 * 8);
         ws->qt_step.ensure((size_t)B * 4); ws->qt_base.ensure((size_t)B * 4); ws->qt_bad.ensure((size_t)B * 4);
@@ -588,6 +594,47 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         }
     }
     mark();
+    if (small_path) {
+        mark();                                          // (no regrouping)
+        const uint64_t stride = std::max<uint64_t>(ix->pad_prefix[1], 4);
+        ws->seg_off.ensure((size_t)slots * 8);
+        ws->dist_out.ensure((size_t)slots * stride * 4);
+        SmallScanArgs ss{};
+        ss.centroids = ix->centroids.as<float>(); ss.cb_tiled = ix->cb_tiled.as<float>();
+        ss.codes = ix->codes.as<unsigned char>(); ss.code_base = ix->code_base.as<uint64_t>();
+        ss.part_n = ix->part_n.as<uint32_t>(); ss.part_npad = ix->part_npad.as<uint32_t>();
+        ss.dim = dim; ss.m = ix->m; ss.nch = ix->nch; ss.metric = (uint32_t)ix->metric; ss.nlist = nlist; ss.nprobes = nprobes;
+        ss.queries = qsearch; ss.probes = ws->probes.as<uint64_t>(); ss.seg_stride = stride;
+        ss.seg_off = ws->seg_off.as<uint64_t>(); ss.dist_out = ws->dist_out.as<float>();
+        launch_small_scan(ss, ix->dsub, slots, st);
+        mark();
+        SelectArgs sa{};
+        sa.mode = 0; sa.dist = ws->dist_out.as<float>(); sa.seg_off = ws->seg_off.as<uint64_t>();
+        sa.probes = ws->probes.as<uint64_t>(); sa.nprobes = nprobes; sa.nlist = nlist;
+        sa.part_n = ix->part_n.as<uint32_t>(); sa.part_off = ix->part_off.as<uint64_t>();
+        sa.row_ids = ix->row_ids.as<uint64_t>(); sa.B = B;
+        sa.allow = rf.bits; sa.allow_bits = rf.nbits;
+        sa.has_lower = sp.has_lower; sa.has_upper = sp.has_upper; sa.lower = sp.lower; sa.upper = sp.upper;
+        sa.k = kk; sa.out_ids = d_ids; sa.out_dist = d_dist; sa.out_count = d_cnt;
+        if (sp.refine_factor) {
+            ws->t_ids.ensure((size_t)B * kk * 8); ws->t_dist.ensure((size_t)B * kk * 4);
+            ws->t_pos.ensure((size_t)B * kk * 8); ws->t_cnt.ensure((size_t)B * 4); ws->t_exact.ensure((size_t)B * kk * 4);
+            sa.out_ids = ws->t_ids.as<uint64_t>(); sa.out_dist = ws->t_dist.as<float>();
+            sa.out_count = ws->t_cnt.as<uint32_t>(); sa.out_pos = ws->t_pos.as<uint64_t>();
+        }
+        launch_select(sa, st);
+        mark();
+        if (sp.refine_factor == 0) { mark(); return; }
+        launch_pair_distance(d_q, ix->vectors.as<float>(), ws->t_pos.as<uint64_t>(), B, kk, dim, ix->metric,
+                             ws->t_exact.as<float>(), st);
+        SelectArgs sr{};
+        sr.mode = 2; sr.dense = ws->t_exact.as<float>(); sr.cand_ids = ws->t_ids.as<uint64_t>();
+        sr.ncols = kk; sr.inner = kk; sr.row_stride = kk; sr.outer_stride = 0;
+        sr.B = B; sr.k = sp.k; sr.out_ids = d_ids; sr.out_dist = d_dist; sr.out_count = d_cnt;
+        launch_select(sr, st);
+        mark();
+        return;
+    }
     // ---- regroup probe slots by partition ----
     ws->part_cnt.ensure((size_t)nlist * 4);
     ws->slot_pos.ensure((size_t)slots * 4);

@@ -83,6 +83,20 @@ void launch_scan2(const ScanArgs &a, uint32_t dsub, int grid, cudaStream_t st);
 // filter kernel (scan3.cu): lower bounds from 16-bit per-query tables; rows_tile == SCAN3_ROWS_TILE
 void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st);
 
+// ---------------- tiny batches: one CTA per (query, probed partition) pair (small.cu) ----------------
+struct SmallScanArgs {
+    const float *centroids; const float *cb_tiled; const unsigned char *codes; const uint64_t *code_base;
+    const uint32_t *part_n; const uint32_t *part_npad;
+    uint32_t dim, m, nch, metric, nlist, nprobes;
+    const float *queries;         // [B][dim] (normalised for cosine)
+    const uint64_t *probes;       // [B*nprobes]
+    uint64_t seg_stride;          // floats per probe slot in dist_out (>= the largest partition, multiple of 4)
+    uint64_t *seg_off;            // [B*nprobes], written here: slot * seg_stride
+    float *dist_out;
+};
+size_t small_scan_smem(uint32_t m, uint32_t dim);
+void launch_small_scan(const SmallScanArgs &a, uint32_t dsub, uint32_t slots, cudaStream_t st);
+
 // ---------------- batch preparation (grouping probes by partition) ----------------
 struct GroupArgs {
     const uint64_t *probes;       // [B*nprobes] partition ids (u64 from the selector)
