@@ -110,7 +110,7 @@ struct Workspace {
     DevBuf s_ids, s_lb, s_pos, s_cnt, s_exact;    // filter scan (dense mode): shortlist by lower bound, exact re-score
     DevBuf c_stats;                               // candidate-mode counters (profiling only)
     DevBuf c_work, c_wcnt, c_surv, c_exd, c_exi, c_exp;   // candidate mode: survivor work list and exact results
-    DevBuf c_thr, c_slack, c_cnt, c_rec;          // filter scan (candidate mode): thresholds, bands, candidate lists
+    DevBuf c_thr, c_slack, c_cnt, c_rec, c_key, c_last;          // filter scan (candidate mode): thresholds, bands, candidate lists
     Workspace()
     {
         LGPU_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -379,6 +379,29 @@ static bool exact_scan_forced()
     return e && e[0] == '1';
 }
 
+// Mode switches of the IVF path, re-read on every call (tests flip them between calls; getenv is ~100 ns) and folded
+// into the CUDA-graph key so a captured launch sequence is never replayed under a different mode.
+struct ScanModes {
+    bool exact, dense_forced;
+    uint32_t cand_kmax, cap_env, small_slots;
+    uint64_t signature() const
+    {
+        return ((uint64_t)exact | (uint64_t)dense_forced << 1 | (uint64_t)cand_kmax << 8 | (uint64_t)cap_env << 20 |
+                (uint64_t)small_slots << 36) * 0x9e3779b97f4a7c15ull;
+    }
+};
+static ScanModes scan_modes()
+{
+    auto num = [](const char *name, uint32_t dflt) { const char *e = getenv(name); return e ? (uint32_t)atoi(e) : dflt; };
+    ScanModes m;
+    m.exact = exact_scan_forced();
+    m.dense_forced = getenv("LGPU_DENSE_FILTER") != nullptr;
+    m.cand_kmax = std::min<uint32_t>(CAND_TOPK_MAX, num("LGPU_CAND_KMAX", CAND_TOPK_MAX));
+    m.cap_env = num("LGPU_CAND_CAP", 0u);
+    m.small_slots = num("LGPU_SMALL_SLOTS", 1024u);
+    return m;
+}
+
 static bool tc_enabled()
 {
     static int v = -1;
@@ -529,11 +552,11 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     const uint32_t kp = kk <= 16 ? 32u : std::min<uint32_t>(SELECT_KMAX, 2 * kk + 32);
     // tiny batches (a single query, a micro-batch): one CTA per (query, probe) pair with the exact table in shared
     // memory (small.cu) -- 4 launches instead of ~25; LGPU_SMALL_SLOTS = 0 disables
-    static const uint32_t small_slots = getenv("LGPU_SMALL_SLOTS") ? (uint32_t)atoi(getenv("LGPU_SMALL_SLOTS")) : 1024u;
-    const bool small_path = d_ids && !forced_probes && !only && slots <= small_slots &&
+    const ScanModes modes = scan_modes();
+    const bool small_path = d_ids && !forced_probes && !only && slots <= modes.small_slots &&
                             small_scan_smem(ix->m, dim) <= 200 * 1024 &&
                             (size_t)slots * ix->pad_prefix[1] * 4 <= workspace_budget();
-    const bool filter_scan = ix->has_tables && !exact_scan_forced() && !sp.has_lower && !sp.has_upper && !forced_probes &&
+    const bool filter_scan = ix->has_tables && !modes.exact && !sp.has_lower && !sp.has_upper && !forced_probes &&
                              d_ids && kp > kk && ix->m <= 512 && !only && !small_path;
     if (filter_scan) {
         ws->qt.ensure((size_t)B * ix->nch * 256 * 16); ws->qt_mm.ensure((size_t)B * ix->nch * 8 * 8);
@@ -702,7 +725,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     if (filter_scan) {
         // per-query 16-bit tables, per-probe scalars
         const bool dot = ix->metric == LGPU_DOT;
-        ws->flags.ensure((size_t)B * 4); ws->c_wcnt.ensure(16);
+        ws->flags.ensure((size_t)B * 4); ws->c_wcnt.ensure(16); ws->c_surv.ensure((size_t)B * 4);
         ws->s_ids.ensure((size_t)B * kp * 8); ws->s_lb.ensure((size_t)B * kp * 4); ws->s_pos.ensure((size_t)B * kp * 8);
         ws->s_cnt.ensure((size_t)B * 4); ws->s_exact.ensure((size_t)B * kp * 4);
         LGPU_CUDA(cudaStreamWaitEvent(st, ws->ev_join, 0));        // the tables, built on the side stream
@@ -716,26 +739,26 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         sc.qt = ws->qt.as<uint4>(); sc.qt_step = ws->qt_step.as<float>(); sc.qt_base = ws->qt_base.as<float>();
         const float mscale = ix->metric == LGPU_COSINE ? 0.5f : 1.0f;
         // candidate mode (no prefilter, k <= 32): the scanners threshold the rows themselves, nothing dense is written
-        static const bool dense_forced = getenv("LGPU_DENSE_FILTER") != nullptr;
-        static const uint32_t cand_kmax = getenv("LGPU_CAND_KMAX")
-            ? std::min<uint32_t>(CAND_TOPK_MAX, (uint32_t)atoi(getenv("LGPU_CAND_KMAX"))) : 32u;
-        const bool cand_mode = !rf.bits && kk <= cand_kmax && !dense_forced;
+        const bool cand_mode = !rf.bits && kk <= modes.cand_kmax && !modes.dense_forced;
         if (cand_mode) {
             // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
-            static const uint32_t cap_env = getenv("LGPU_CAND_CAP") ? (uint32_t)atoi(getenv("LGPU_CAND_CAP")) : 0u;
-            uint32_t cap = kk <= 32 ? 512 : 1024;
-            if (cap_env >= 32 && cap_env <= 1024 && !(cap_env & (cap_env - 1)) && cap_env >= kk) cap = cap_env;
+            const uint32_t cap_env = modes.cap_env;
+            uint32_t cap = kk <= 32 ? 512 : (kk <= 64 ? 1024 : CAND_CAP_MAX);
+            if (cap_env >= 32 && cap_env <= CAND_CAP_MAX && !(cap_env & (cap_env - 1)) && cap_env >= kk) cap = cap_env;
             ws->c_thr.ensure((size_t)B * 4); ws->c_slack.ensure((size_t)B * 4); ws->c_cnt.ensure((size_t)B * 4);
             ws->c_rec.ensure((size_t)B * cap * sizeof(CandRec));
+            ws->c_key.ensure((size_t)B * cap * 4); ws->c_last.ensure((size_t)B * 4);
             launch_cand_prepare(ws->qt_step.as<float>(), ws->sbound.as<float>(), dot ? nullptr : ws->amax.as<float>(),
                                 dot ? nullptr : ix->rmax_bits.as<int>(), ws->qn2.as<float>(), ix->cb2, mscale, ix->m, B,
-                                ws->c_slack.as<float>(), ws->c_thr.as<uint32_t>(), ws->c_cnt.as<uint32_t>(), st);
+                                ws->c_slack.as<float>(), ws->c_thr.as<uint32_t>(), ws->c_cnt.as<uint32_t>(),
+                                ws->c_last.as<uint32_t>(), ws->c_key.as<uint32_t>(), cap, st);
+            sc.cand_key = ws->c_key.as<uint32_t>(); sc.cand_last = ws->c_last.as<uint32_t>();
             sc.nprobes = nprobes; sc.topk = kk; sc.thr = ws->c_thr.as<uint32_t>(); sc.slack = ws->c_slack.as<float>();
             sc.cand_cnt = ws->c_cnt.as<uint32_t>(); sc.cand = ws->c_rec.as<CandRec>(); sc.cand_cap = cap;
             launch_scan3(sc, ix->num_sms, st);
             mark();
             FinalizeArgs fa{};
-            fa.Q = qsearch; fa.cand = sc.cand; fa.cand_cnt = sc.cand_cnt; fa.cand_cap = cap; fa.thr = sc.thr;
+            fa.Q = qsearch; fa.cand = sc.cand; fa.cand_cnt = sc.cand_cnt; fa.cand_cap = cap; fa.cand_key = sc.cand_key; fa.thr = sc.thr;
             fa.slack = sc.slack; fa.bad = ws->qt_bad.as<uint32_t>();
             fa.codes = ix->codes.as<unsigned char>(); fa.code_base = ix->code_base.as<uint64_t>();
             fa.part_npad = ix->part_npad.as<uint32_t>(); fa.part_off = ix->part_off.as<uint64_t>();
@@ -767,15 +790,15 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         launch_band_check3(ws->s_lb.as<float>(), ws->s_cnt.as<uint32_t>(), ws->qt_step.as<float>(), ws->sbound.as<float>(),
                            dot ? nullptr : ws->amax.as<float>(), dot ? nullptr : ix->rmax_bits.as<int>(),
                            ws->qt_bad.as<uint32_t>(), ws->qn2.as<float>(), ix->cb2, mscale, ix->m, B, kk, kp,
-                           ws->flags.as<uint32_t>(), ws->c_wcnt.as<uint32_t>() + 1, st);
+                           ws->flags.as<uint32_t>(), ws->c_wcnt.as<uint32_t>() + 1, ws->c_surv.as<uint32_t>(), st);
         // exact PQ distances of the shortlist (oracle arithmetic), then the kk best of those
         launch_pq_rescore(qsearch, ws->s_pos.as<uint64_t>(), B, kp, ix->codes.as<unsigned char>(),
                           ix->code_base.as<uint64_t>(), ix->part_npad.as<uint32_t>(), ix->part_off.as<uint64_t>(), nlist,
                           ix->centroids.as<float>(), ix->cb_tiled.as<float>(), dim, ix->m, ix->dsub, ix->metric,
-                          ws->s_exact.as<float>(), st);
+                          ws->c_surv.as<uint32_t>(), ws->s_exact.as<float>(), st);
         SelectArgs sb{};
         sb.mode = 2; sb.dense = ws->s_exact.as<float>(); sb.cand_ids = ws->s_ids.as<uint64_t>();
-        sb.cand_pos = ws->s_pos.as<uint64_t>();
+        sb.cand_pos = ws->s_pos.as<uint64_t>(); sb.ncols_q = ws->c_surv.as<uint32_t>();
         sb.ncols = kp; sb.inner = kp; sb.row_stride = kp; sb.outer_stride = 0;
         sb.B = B; sb.k = kk; sb.out_ids = pq_ids; sb.out_dist = pq_dist; sb.out_count = pq_cnt; sb.out_pos = pq_pos;
         launch_select(sb, st);
@@ -1053,7 +1076,7 @@ static inline void make_key(uint64_t (&key)[4], uint64_t tag, uint32_t B, const 
     key[1] = (uint64_t)p.k | ((uint64_t)p.nprobes << 32);
     key[2] = (uint64_t)p.refine_factor | ((uint64_t)(p.has_lower ? 1 : 0) << 32) | ((uint64_t)(p.has_upper ? 1 : 0) << 33) |
              ((uint64_t)(p.max_nprobes & 0x3fffffu) << 34);
-    key[3] = (uint64_t)lo | ((uint64_t)hi << 32);
+    key[3] = ((uint64_t)lo | ((uint64_t)hi << 32)) ^ scan_modes().signature();
 }
 
 }  // namespace

@@ -157,6 +157,31 @@ __device__ __forceinline__ float halfwarp_l2(const float *__restrict__ x, const 
     return __fadd_rn(s, t);
 }
 
+// the same sum with x in shared memory and U loads of y in flight per lane: one or two L2 round trips per candidate row
+// instead of d / 128 (coarse_finish_kernel re-scores ~100 centroids per query at nlist 16384, a latency chain each)
+template <int U>
+__device__ __forceinline__ float halfwarp_l2_sx(const float *sx, const float *__restrict__ y, uint32_t d, int hl,
+                                                unsigned hmask, int hbase)
+{
+    const uint32_t d16 = d & ~15u;
+    float a = 0.f;
+    for (uint32_t k0 = 0; k0 < d16; k0 += 16 * U) {
+        float yv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) yv[u] = __ldg(y + min(k0 + 16 * u + hl, d - 1));
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (k0 + 16 * u < d16) { const float df = __fsub_rn(sx[k0 + 16 * u + hl], yv[u]); a = __fadd_rn(a, __fmul_rn(df, df)); }
+        }
+    }
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 16; l++) t = __fadd_rn(t, __shfl_sync(hmask, a, hbase + l));
+    float s = 0.f;
+    for (uint32_t i = d16; i < d; i++) { float df = __fsub_rn(sx[i], y[i]); s = __fadd_rn(s, __fmul_rn(df, df)); }
+    return __fadd_rn(s, t);
+}
+
 __global__ void row_norms_kernel(const float *__restrict__ X, uint64_t n, uint32_t d, float *__restrict__ out)
 {
     const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -224,12 +249,14 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     extern __shared__ __align__(16) unsigned char csm[];
     uint32_t *s_col = reinterpret_cast<uint32_t *>(csm);           // [cap] candidate columns
     uint32_t *s_key = s_col + cap;                                  // [cap] exact distance keys
+    float *s_x = reinterpret_cast<float *>(s_key + cap);            // [d] the query
     __shared__ uint32_t s_lo, s_hi, s_valid, s_n, s_cnt[24];
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const float *row = S + (size_t)q * ld;
     if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_valid = 0u; s_n = 0u; }
     if (tid < 24) s_cnt[tid] = 0u;
+    for (uint32_t t = tid; t < d; t += CF_THREADS) s_x[t] = Q[(size_t)q * d + t];
     __syncthreads();
     constexpr int NV = VPT > 0 ? VPT : 1;
     float v[NV];
@@ -304,11 +331,10 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     // exact re-score, half a warp per candidate column (lance's l2: 16 lane accumulators, sequential lane sum)
     const int hl = lane & 15, hbase = lane & 16;
     const unsigned hmask = 0xffffu << hbase;
-    const float *x = Q + (size_t)q * d;
     for (uint32_t c0 = 0; c0 < n; c0 += CF_THREADS / 16) {
         const uint32_t c = c0 + (tid >> 4);
         if (c < n) {                                                 // a whole half-warp takes the branch together
-            const float dv = halfwarp_l2(x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
+            const float dv = halfwarp_l2_sx<24>(s_x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
             if (hl == 0) s_key[c] = (dv != dv) ? 0xffffffffu : f32_key(dv == 0.f ? 0.f : dv);
         }
     }
@@ -350,10 +376,14 @@ void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, c
 {
     if (B == 0 || N == 0) return;
     if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
-    uint32_t cap = 256;
+    uint32_t cap = 512;                                              // (only the entries in use are sorted)
     while (cap < 4 * k) cap <<= 1;                                   // power of two >= 4 k
-    const size_t smem = (size_t)cap * 8;
-#define LGPU_CF(V) coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate)
+    const size_t smem = (size_t)cap * 8 + (size_t)d * 4;
+    if (smem > 200 * 1024) { set_error("internal: coarse_finish candidate list does not fit in shared memory"); throw Failure{LGPU_RUNTIME}; }
+#define LGPU_CF(V) do { \
+        if (smem > 48 * 1024) LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate); \
+    } while (0)
     if (N <= 4 * CF_THREADS) LGPU_CF(4);
     else if (N <= 16 * CF_THREADS) LGPU_CF(16);
     else if (N <= 64 * CF_THREADS) LGPU_CF(64);

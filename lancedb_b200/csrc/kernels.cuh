@@ -39,8 +39,8 @@ struct alignas(16) CandRec {
     uint32_t pad;
 };
 constexpr uint32_t CAND_NO_THR = 0xffffffffu;
-constexpr uint32_t CAND_TOPK_MAX = 128;      // largest k (or k * refine_factor) the candidate mode can serve; api.cu uses it
-                                             // up to LGPU_CAND_KMAX (default 32): for larger k the lists tend to overflow
+constexpr uint32_t CAND_TOPK_MAX = 128;      // largest k (or k * refine_factor) the candidate mode serves (LGPU_CAND_KMAX lowers it)
+constexpr uint32_t CAND_CAP_MAX = 2048;      // largest per-query candidate list
 
 struct ScanArgs {
     // index (device)
@@ -75,6 +75,9 @@ struct ScanArgs {
     uint32_t *cand_cnt;           // [B] appended candidates (may exceed cand_cap: the overflow is dropped and flagged)
     CandRec *cand;                // [B][cand_cap]
     uint32_t cand_cap;
+    uint32_t *cand_key;           // [B][cand_cap] f32_key(lb) of every appended record, 0xffffffff where none is yet: what
+                                  // the scanners re-read to tighten tau_q from the list itself (scan3.cu)
+    uint32_t *cand_last;          // [B] list length at the query's last list-based tightening
 };
 bool scan_dsub_supported(uint32_t dsub);
 // exact kernel (scan2.cu): residual -> f32 table chunk -> sequential code scan, bit-identical to the oracle;
@@ -244,16 +247,16 @@ void launch_row_const(const unsigned char *codes, const uint64_t *code_base, con
 void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t nc, const unsigned char *codes,
                        const uint64_t *code_base, const uint32_t *part_npad, const uint64_t *part_off, uint32_t nlist,
                        const float *centroids, const float *cb_tiled, uint32_t dim, uint32_t m, uint32_t dsub, int metric,
-                       float *out, cudaStream_t st);
+                       const uint32_t *ncols_q, float *out, cudaStream_t st);   // ncols_q: optional [B] pairs of each query (<= nc)
 // probe_A[slot] = coarse_dist[slot] - |q|^2, amax[q] = max_j coarse + |q|^2, qn2[q] = |q|^2
 // (probe_A / amax may be null: dot has no residual)
 void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uint32_t nprobes, uint32_t dim,
                         float *probe_A, float *amax, float *qn2, cudaStream_t st);
 // the band of every query, for the candidate mode: slack[q] = scale (W + 2E) (same W, E as launch_band_check3);
-// also resets thr[q] = CAND_NO_THR and cand_cnt[q] = 0
+// also resets thr[q] = CAND_NO_THR, cand_cnt[q] = cand_last[q] = 0 and every key of cand_key to 0xffffffff
 void launch_cand_prepare(const float *step, const float *sbound, const float *amax, const int *rmax_bits, const float *qn2,
                          float cb2, float scale, uint32_t m, uint32_t B, float *slack, uint32_t *thr, uint32_t *cand_cnt,
-                         cudaStream_t st);
+                         uint32_t *cand_last, uint32_t *cand_key, uint32_t cand_cap, cudaStream_t st);
 // candidate mode, after the scan: per query, drop the candidates above the final threshold, re-score the survivors
 // exactly (oracle arithmetic, as launch_pq_rescore), and write the k best by (_distance, _rowid) -- ids, distances,
 // count and (optional) storage positions.  flags[q] = 1 when the query must be redone by the exact kernels (list
@@ -261,6 +264,7 @@ void launch_cand_prepare(const float *step, const float *sbound, const float *am
 struct FinalizeArgs {
     const float *Q;               // [B][dim] (normalised for cosine)
     const CandRec *cand; const uint32_t *cand_cnt; uint32_t cand_cap;
+    const uint32_t *cand_key;     // [B][cand_cap] keys of the records (coalesced copy of CandRec::lb)
     const uint32_t *thr; const float *slack; const uint32_t *bad;
     const unsigned char *codes; const uint64_t *code_base; const uint32_t *part_npad; const uint64_t *part_off;
     const uint64_t *row_ids; const float *centroids; const float *cb_tiled;
@@ -278,10 +282,11 @@ void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st);
 // flags[q] = 1 when the shortlist of q (lower bounds `lb` ascending, [B][kp], cnt valid) cannot be proven to hold
 // the exact top-k: proven iff cnt < kp or lb[kp-1] > lb[k-1] + scale (W + 2E),  W = m step (1 + 2^-10),
 // E = 2^-15 ceil(m/96) (sbound + amax + rmax + m + 2 (qn2 + cb2)); also 1 when bad[q].  amax / rmax_bits may be null
-// (dot).  cb2 = sum_i max_c |codebook_i[c]|^2.
+// (dot).  cb2 = sum_i max_c |codebook_i[c]|^2.  surv (optional, [B]): the length of the ascending prefix
+// lb <= lb[k-1] + scale (W + 2E) -- the only rows that can be among the exact top-k, hence the only ones to re-score.
 void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
                         const int *rmax_bits, const uint32_t *bad, const float *qn2, float cb2, float scale, uint32_t m,
-                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, uint32_t *gate, cudaStream_t st);
+                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, uint32_t *gate, uint32_t *surv, cudaStream_t st);
 
 // ---------------- index build (build.cu) ----------------------------------------------
 // codes[row][i] = argmin_c entry(row's residual sub-vector i, codebook_i[c]) (ties: lowest c); X normalised for cosine

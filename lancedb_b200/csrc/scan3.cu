@@ -52,7 +52,10 @@ static_assert(S3_PT * S3_PREG + S3_CT * S3_CREG <= 32768, "register budget of ha
 constexpr int S3_BUF = 32768;                       // one chunk buffer
 constexpr int S3_SLOTS = 4, S3_SLOT_BYTES = 128;    // tile-descriptor ring
 constexpr size_t S3_TILES = 3 * (size_t)S3_BUF;
-constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES + 128;   // + 2 x 16 words of threshold scratch
+constexpr int S3_SCR = 32;                          // words per bank of threshold scratch
+constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES + 2 * S3_SCR * 4;   // + two banks of threshold scratch
+constexpr int S3_LIST_PER = CAND_CAP_MAX / S3_CT;  // list keys per scanner thread in a list-based tightening
+constexpr int S3_LIST_STEPS = 10;
 constexpr int BAR_SCAN = 8;                         // named barrier of the 256 scanner threads (candidate mode)
 static_assert(SCAN3_ROWS_TILE == S3_CT * S3_RMAX, "rows_tile");
 static_assert(S3_PT == 256, "one stager thread per code");
@@ -257,12 +260,67 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
     const int lane = ct & 31;
     const uint32_t k = a.topk;
     // scratch, two banks alternating by query so that the reset for query g+1 cannot overtake a slow warp still
-    // reading query g's counters: [0] threshold key, [1] min key, [2] max key, [3] valid rows, [4..12] counters
+    // reading query g's counters: [0] threshold key, [1] min key, [2] max key, [3] valid rows, [4..12] counters of the
+    // tile bisection; [13] list length, [14] list length at the last list tightening, [15] smallest list key,
+    // [16..16+S3_LIST_STEPS] counters of the list bisection
 #pragma unroll 1
     for (int g = 0; g < ng; g++) {
         volatile uint32_t *const sh =
-            reinterpret_cast<volatile uint32_t *>(smem + S3_TILES + S3_SLOTS * S3_SLOT_BYTES) + (g & 1) * 16;
+            reinterpret_cast<volatile uint32_t *>(smem + S3_TILES + S3_SLOTS * S3_SLOT_BYTES) + (g & 1) * S3_SCR;
         const uint32_t q = T->q[g], slot = T->slot[g];
+        if (ct < S3_SCR) {
+            uint32_t v = 0u;
+            if (ct == 0) v = __ldcg(a.thr + q);
+            else if (ct == 1 || ct == 15) v = 0xffffffffu;
+            else if (ct == 13) v = min(__ldcg(a.cand_cnt + q), a.cand_cap);
+            else if (ct == 14) v = __ldcg(a.cand_last + q);
+            sh[ct] = v;
+        }
+        bar_sync(BAR_SCAN, S3_CT);
+        uint32_t tkey = sh[0];
+        // ---- tau_q from the list itself.  Tile-local bisection cannot get below the k-th smallest of ONE tile (the
+        // 100 k / rows_tile quantile); the list holds every row seen so far that was under the threshold of its time,
+        // so its k-th smallest key is the k-th smallest of everything scanned for the query.  Any k keys of the list
+        // give a valid tau (records still in flight read as 0xffffffff and only make the bound looser).  Triggered
+        // each time the list grew by k since the last time, i.e. about once per doubling of the rows seen.
+        {
+            const uint32_t ln = sh[13], last = sh[14];
+            if (tkey != CAND_NO_THR && ln >= 2u * k && ln >= last + k) {
+                const uint32_t *keys = a.cand_key + (size_t)q * a.cand_cap;
+                uint32_t lk[S3_LIST_PER];
+                uint32_t mn = 0xffffffffu, c0 = 0;
+#pragma unroll
+                for (int j = 0; j < S3_LIST_PER; j++) {
+                    const uint32_t i = (uint32_t)j * S3_CT + ct;
+                    lk[j] = i < ln ? __ldcg(keys + i) : 0xffffffffu;
+                }
+#pragma unroll
+                for (int j = 0; j < S3_LIST_PER; j++) { mn = min(mn, lk[j]); c0 += lk[j] <= tkey ? 1u : 0u; }
+                mn = __reduce_min_sync(0xffffffffu, mn); c0 = __reduce_add_sync(0xffffffffu, c0);
+                if (lane == 0) { atomicMin(const_cast<uint32_t *>(sh + 15), mn); if (c0) atomicAdd(const_cast<uint32_t *>(sh + 16), c0); }
+                bar_sync(BAR_SCAN, S3_CT);
+                if (sh[16] >= k) {                          // invariant: count(list key <= hi) >= k
+                    float lo = key_f32(sh[15]), hi = key_f32(tkey);
+#pragma unroll 1
+                    for (int it = 0; it < S3_LIST_STEPS; it++) {
+                        const uint32_t mid = f32_key(0.5f * lo + 0.5f * hi);
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int j = 0; j < S3_LIST_PER; j++) c += lk[j] <= mid ? 1u : 0u;
+                        c = __reduce_add_sync(0xffffffffu, c);
+                        if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 17 + it), c);
+                        bar_sync(BAR_SCAN, S3_CT);
+                        if (sh[17 + it] >= k) hi = key_f32(mid); else lo = key_f32(mid);
+                    }
+                    const uint32_t nk = f32_key(hi);
+                    if (nk < tkey) {
+                        if (ct == 0) atomicMin(a.thr + q, nk);
+                        tkey = nk;
+                    }
+                }
+                if (ct == 0) a.cand_last[q] = ln;
+            }
+        }
         const float step = __ldg(a.qt_step + q);
         const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + slot) : 0.f);
         const float slack = __ldg(a.slack + q);
@@ -275,13 +333,7 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
             L[r] = valid[r] ? (fmaf(step, (float)s, cst) + rr[r]) * scale : CUDART_INF_F;
             if (valid[r]) { const uint32_t kk = f32_key(L[r]); kmin = min(kmin, kk); kmax = max(kmax, kk); nvalid++; }
         }
-        if (ct == 0) {
-            sh[0] = __ldcg(a.thr + q); sh[1] = 0xffffffffu; sh[2] = 0u; sh[3] = 0u;
-#pragma unroll
-            for (int i = 0; i < 9; i++) sh[4 + i] = 0u;
-        }
-        bar_sync(BAR_SCAN, S3_CT);
-        uint32_t tkey = sh[0];
+
         const uint32_t rank = slot - q * a.nprobes;
         // Tighten tau_q from this tile when it pays: always for a query without a threshold and for its three nearest
         // partitions (that is where the small distances are); otherwise only when this tile alone holds 2k or more
@@ -344,10 +396,15 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
             base = __shfl_sync(0xffffffffu, base, 31);
             uint32_t at = base + pre - npass;
             CandRec *dst = a.cand + (size_t)q * a.cand_cap;
+            uint32_t *dkey = a.cand_key + (size_t)q * a.cand_cap;
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (valid[r] && L[r] <= lim) {
-                    if (at < a.cand_cap) { CandRec rec; rec.lb = L[r]; rec.p = p; rec.row = row0 + ct + r * S3_CT; rec.pad = 0u; dst[at] = rec; }
+                    if (at < a.cand_cap) {
+                        CandRec rec; rec.lb = L[r]; rec.p = p; rec.row = row0 + ct + r * S3_CT; rec.pad = 0u;
+                        dst[at] = rec;
+                        dkey[at] = f32_key(L[r]);
+                    }
                     at++;
                 }
             }
@@ -413,7 +470,7 @@ __global__ void __launch_bounds__(S3_NT, 2) scan3_kernel(ScanArgs a)
 void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st)
 {
     if (!a.qt || !a.qt_step || !a.qt_base || !a.tile_desc || a.rows_tile != SCAN3_ROWS_TILE || !a.part_off ||
-        (a.cand && (!a.thr || !a.slack || !a.cand_cnt || a.topk < 1 || a.topk > CAND_TOPK_MAX || a.nprobes < 1))) {
+        (a.cand && (!a.thr || !a.slack || !a.cand_cnt || !a.cand_key || !a.cand_last || a.cand_cap > CAND_CAP_MAX || a.topk < 1 || a.topk > CAND_TOPK_MAX || a.nprobes < 1))) {
         set_error("internal: the filter scan needs query tables and tile descriptors built with rows_tile 1536");
         throw Failure{LGPU_RUNTIME};
     }

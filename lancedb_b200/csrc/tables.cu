@@ -439,14 +439,16 @@ __global__ void __launch_bounds__(256, 2) pq_rescore_kernel(const float *__restr
                                                          const uint64_t *__restrict__ part_off, uint32_t nlist,
                                                          const float *__restrict__ centroids,
                                                          const float *__restrict__ cb_tiled, uint32_t dim, uint32_t m,
-                                                         int metric, float *__restrict__ out)
+                                                         int metric, const uint32_t *__restrict__ ncols_q,
+                                                         float *__restrict__ out)
 {
     const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (pair >= (uint64_t)B * nc) return;
+    const uint32_t q = (uint32_t)(pair / nc);
+    if (ncols_q && (uint32_t)(pair - (uint64_t)q * nc) >= ncols_q[q]) return;      // beyond the query's proven prefix
     const uint64_t ps = pos[pair];
     if (ps == UINT64_MAX) { if (lane == 0) out[pair] = CUDART_INF_F; return; }
-    const uint32_t q = (uint32_t)(pair / nc);
     const uint32_t p = find_partition(part_off, nlist, ps);
     const uint32_t row = (uint32_t)(ps - part_off[p]);
     const float d = exact_pq_distance_warp<DSUB>(Q + (size_t)q * dim, centroids + (size_t)p * dim, codes, code_base[p],
@@ -458,7 +460,8 @@ __global__ void __launch_bounds__(256, 2) pq_rescore_kernel(const float *__restr
 __global__ void cand_prepare_kernel(const float *__restrict__ step, const float *__restrict__ sbound,
                                     const float *__restrict__ amax, const int *__restrict__ rmax_bits,
                                     const float *__restrict__ qn2, float cb2, float scale, uint32_t m, uint32_t B,
-                                    float *__restrict__ slack, uint32_t *__restrict__ thr, uint32_t *__restrict__ cand_cnt)
+                                    float *__restrict__ slack, uint32_t *__restrict__ thr, uint32_t *__restrict__ cand_cnt,
+                                    uint32_t *__restrict__ cand_last)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
@@ -469,6 +472,7 @@ __global__ void cand_prepare_kernel(const float *__restrict__ step, const float 
     slack[q] = scale * (W + 2.0f * E);
     thr[q] = CAND_NO_THR;
     cand_cnt[q] = 0u;
+    cand_last[q] = 0u;
 }
 
 // ---- candidate mode, after the scan.  Three fully parallel kernels instead of one latency chain per query:
@@ -487,12 +491,12 @@ __global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a
     const uint32_t total = a.cand_cnt[q];
     const uint32_t n = min(total, a.cand_cap);
     const bool flagged = total > a.cand_cap || a.bad[q];
-    const CandRec *cand = a.cand + (size_t)q * a.cand_cap;
+    const uint32_t *ckey = a.cand_key + (size_t)q * a.cand_cap;
     uint32_t key[PER];
 #pragma unroll
     for (int j = 0; j < PER; j++) {
         const uint32_t i = (uint32_t)j * 32 + lane;
-        key[j] = i < n ? f32_key(cand[i].lb) : 0xffffffffu;
+        key[j] = i < n ? __ldcg(ckey + i) : 0xffffffffu;
     }
     const uint32_t tkey = a.thr[q];
     float tau = tkey == CAND_NO_THR ? CUDART_INF_F : key_f32(tkey);
@@ -601,11 +605,25 @@ __global__ void band_check3_kernel(const float *__restrict__ lb, const uint32_t 
                                    const float *__restrict__ amax, const int *__restrict__ rmax_bits,
                                    const uint32_t *__restrict__ bad, const float *__restrict__ qn2, float cb2, float scale,
                                    uint32_t m, uint32_t B, uint32_t k, uint32_t kp, uint32_t *__restrict__ flags,
-                                   uint32_t *__restrict__ gate)
+                                   uint32_t *__restrict__ gate, uint32_t *__restrict__ surv)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
     uint32_t f = bad[q] ? 1u : 0u;
+    if (surv) {
+        // the rows that can still be among the exact top-k: the ascending prefix with L <= L_(k) + scale (W + 2E)
+        const uint32_t n = min(cnt[q], kp);
+        uint32_t pre = n;
+        if (n > k && !f) {
+            const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m +
+                              2.0f * (qn2[q] + cb2);
+            const float lim = lb[(size_t)q * kp + k - 1] +
+                              scale * ((float)m * step[q] * 1.0009765625f + 2.0f * 3.0517578125e-5f * (float)((m + 95u) / 96u) * mag);
+            pre = k;
+            while (pre < n && !(lb[(size_t)q * kp + pre] > lim)) pre++;
+        }
+        surv[q] = pre;
+    }
     if (!f && cnt[q] >= kp && kp > 0) {
         const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m +
                           2.0f * (qn2[q] + cb2);
@@ -681,14 +699,14 @@ void launch_row_const(const unsigned char *codes, const uint64_t *code_base, con
 void launch_pq_rescore(const float *Q, const uint64_t *pos, uint32_t B, uint32_t nc, const unsigned char *codes,
                        const uint64_t *code_base, const uint32_t *part_npad, const uint64_t *part_off, uint32_t nlist,
                        const float *centroids, const float *cb_tiled, uint32_t dim, uint32_t m, uint32_t dsub, int metric,
-                       float *out, cudaStream_t st)
+                       const uint32_t *ncols_q, float *out, cudaStream_t st)
 {
     if (B == 0 || nc == 0) return;
     if (m > 512) { set_error("internal: pq_rescore supports m <= 512"); throw Failure{LGPU_RUNTIME}; }
     const uint64_t total = (uint64_t)B * nc * 32;              // one warp per pair
     dispatch_dsub(dsub, [&](auto D) {
         pq_rescore_kernel<decltype(D)::value><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            Q, pos, B, nc, codes, code_base, part_npad, part_off, nlist, centroids, cb_tiled, dim, m, metric, out); LGPU_COUNT_LAUNCH();
+            Q, pos, B, nc, codes, code_base, part_npad, part_off, nlist, centroids, cb_tiled, dim, m, metric, ncols_q, out); LGPU_COUNT_LAUNCH();
     });
     LGPU_CUDA(cudaGetLastError());
 }
@@ -703,23 +721,26 @@ void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uin
 
 void launch_cand_prepare(const float *step, const float *sbound, const float *amax, const int *rmax_bits, const float *qn2,
                          float cb2, float scale, uint32_t m, uint32_t B, float *slack, uint32_t *thr, uint32_t *cand_cnt,
-                         cudaStream_t st)
+                         uint32_t *cand_last, uint32_t *cand_key, uint32_t cand_cap, cudaStream_t st)
 {
     if (B == 0) return;
-    cand_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(step, sbound, amax, rmax_bits, qn2, cb2, scale, m, B, slack, thr, cand_cnt); LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaMemsetAsync(cand_key, 0xff, (size_t)B * cand_cap * 4, st));
+    cand_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(step, sbound, amax, rmax_bits, qn2, cb2, scale, m, B, slack, thr, cand_cnt, cand_last); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
 void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
 {
     if (a.B == 0) return;
-    if (a.m > 512 || a.cand_cap < 32 || a.cand_cap > 1024 || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
-        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity in [32, 1024] >= k");
+    if (a.m > 512 || a.cand_cap < 32 || a.cand_cap > CAND_CAP_MAX || (a.cand_cap & (a.cand_cap - 1)) || a.k > a.cand_cap) {
+        set_error("internal: cand_finalize needs m <= 512 and a power-of-two candidate capacity in [32, 2048] >= k");
         throw Failure{LGPU_RUNTIME};
     }
     LGPU_CUDA(cudaMemsetAsync(a.work_cnt, 0, 8, st));       // survivor counter + fix-up gate
-    if (a.cand_cap <= 512) { cand_filter_kernel<16><<<(a.B * 32 + FLT_THREADS - 1) / FLT_THREADS, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
-    else { cand_filter_kernel<32><<<(a.B * 32 + FLT_THREADS - 1) / FLT_THREADS, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
+    const unsigned fgrid = (a.B * 32 + FLT_THREADS - 1) / FLT_THREADS;
+    if (a.cand_cap <= 512) { cand_filter_kernel<16><<<fgrid, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
+    else if (a.cand_cap <= 1024) { cand_filter_kernel<32><<<fgrid, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
+    else { cand_filter_kernel<64><<<fgrid, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
     dispatch_dsub(a.dsub, [&](auto D) {
         cand_rescore_kernel<decltype(D)::value><<<a.num_sms * 4, RSC_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     });
@@ -734,11 +755,11 @@ void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
 
 void launch_band_check3(const float *lb, const uint32_t *cnt, const float *step, const float *sbound, const float *amax,
                         const int *rmax_bits, const uint32_t *bad, const float *qn2, float cb2, float scale, uint32_t m,
-                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, uint32_t *gate, cudaStream_t st)
+                        uint32_t B, uint32_t k, uint32_t kp, uint32_t *flags, uint32_t *gate, uint32_t *surv, cudaStream_t st)
 {
     if (B == 0) return;
     if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
-    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, qn2, cb2, scale, m, B, k, kp, flags, gate); LGPU_COUNT_LAUNCH();
+    band_check3_kernel<<<(B + 127) / 128, 128, 0, st>>>(lb, cnt, step, sbound, amax, rmax_bits, bad, qn2, cb2, scale, m, B, k, kp, flags, gate, surv); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -340,19 +340,43 @@ def test_maximum_nprobes_widening_under_a_selective_prefilter(metric):
     assert np.array_equal(a[0], b[0])
 
 
-@pytest.mark.parametrize("mode", ["cand_overflow", "dense"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_candidate_lists_hold_for_large_k(metric):
+    """k = 100 over ~60 tiles per query of i.i.d. data: tile-local thresholds stop at the k-th smallest of ONE tile,
+    so every tile would append ~k rows; the scanners tighten tau from the query's own list (scan3.cu) and the 2048-entry
+    lists must not overflow -- no query may fall back to the exact kernels -- while the result stays bit-identical."""
+    rng = np.random.default_rng(61)
+    ix = random_index(rng, dim=64, nlist=40, m=8, metric=metric, n=300000)
+    q = queries(rng, 48, 64)
+    _native.set_profiling(True)
+    try:
+        _check_search(ix, q, k=100, nprobes=12)
+        st = _native.last_filter_stats()
+        assert st["queries"] == 48 and st["flagged_queries"] == 0, st
+        assert st["candidates"] <= 48 * 1400, st               # well inside the capacity
+        _check_search(ix, q, k=128, nprobes=12)
+        assert _native.last_filter_stats()["flagged_queries"] == 0
+        _check_search(ix, q[:9], k=40, nprobes=40)               # 1024-entry lists, every partition probed
+        assert _native.last_filter_stats()["flagged_queries"] == 0
+    finally:
+        _native.set_profiling(False)
+
+
+@pytest.mark.parametrize("mode", ["cand_overflow", "dense", "dense_above_32"])
 def test_filter_scan_modes_and_candidate_overflow(mode, monkeypatch):
     """The filter scan's candidate mode (thresholds inside the scanners, per-query candidate lists) against its
     dense mode (LGPU_DENSE_FILTER=1: one lower bound per row + shortlist select) and against a candidate capacity
     of 32 (LGPU_CAND_CAP), which overflows for most queries and sends them through the exact fix-up pass."""
     if mode == "dense":
         monkeypatch.setenv("LGPU_DENSE_FILTER", "1")
+    elif mode == "dense_above_32":
+        monkeypatch.setenv("LGPU_CAND_KMAX", "32")               # k = 100 below: dense lower bounds + proven prefix
     else:
         monkeypatch.setenv("LGPU_CAND_CAP", "32")
     rng = np.random.default_rng(51)
     ix = random_index(rng, dim=64, nlist=40, m=8, n=60000)
     _check_search(ix, queries(rng, 90, 64), k=10, nprobes=12)
     _check_search(ix, queries(rng, 90, 64), k=32, nprobes=12)
-    _check_search(ix, queries(rng, 40, 64), k=100, nprobes=12)       # 1024-entry candidate lists, block selector
+    _check_search(ix, queries(rng, 40, 64), k=100, nprobes=12)       # 2048-entry candidate lists, block selector
     ixv = random_index(rng, dim=48, nlist=6, m=6, metric="cosine", n=4000, with_vectors=True)
     _check_search(ixv, queries(rng, 17, 48), k=5, nprobes=3, refine_factor=4)
