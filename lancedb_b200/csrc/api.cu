@@ -91,6 +91,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;     // private stream (host-buffer entry points)
     cudaStream_t aux = nullptr;        // side stream: the per-query tables are built while the coarse step runs
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool aux_open = false;              // an EAGER fork onto `aux` has not been joined yet (a call failed half-way)
     cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
     cudaEvent_t ev[8] = {};
     DevBuf q, qn, xnorm, D, probes, probe_dist, probe_cnt;
@@ -327,12 +328,18 @@ struct WsLease {
     {
         st = use_user ? user : ws->stream;
         // the workspace may still be in use by an earlier call on another stream
-        cudaStreamWaitEvent(st, ws->done, 0);
+        if (cudaStreamWaitEvent(st, ws->done, 0) != cudaSuccess) cudaGetLastError();
     }
     ~WsLease()
     {
-        cudaStreamWaitEvent(st, ws->ev_join, 0);        // side-stream work of a call that failed half-way (no-op otherwise)
-        cudaEventRecord(ws->done, st);
+        // side-stream work of a call that failed half-way.  Only after an eager fork: an event whose last record sits
+        // inside a captured graph cannot be waited on outside the capture (cudaErrorInvalidValue, which would then be
+        // reported by the next cudaGetLastError() of an unrelated launch).
+        if (ws->aux_open) {
+            if (cudaStreamWaitEvent(st, ws->ev_join, 0) != cudaSuccess) cudaGetLastError();
+            ws->aux_open = false;
+        }
+        if (cudaEventRecord(ws->done, st) != cudaSuccess) cudaGetLastError();
         pool.give(ws);
     }
 };
@@ -568,6 +575,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
                                 ix->metric, ws->qt_mm.as<float>(), ws->qt.as<uint4>(), ws->qt_step.as<float>(),
                                 ws->qt_base.as<float>(), ws->sbound.as<float>(), ws->qt_bad.as<uint32_t>(), ws->aux);
         LGPU_CUDA(cudaEventRecord(ws->ev_join, ws->aux));
+        ws->aux_open = !g_capturing;
     }
     // ---- K1: exact centroid distances + nprobes nearest ----
     ws->probes.ensure((size_t)slots * 8);
@@ -729,6 +737,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         ws->s_ids.ensure((size_t)B * kp * 8); ws->s_lb.ensure((size_t)B * kp * 4); ws->s_pos.ensure((size_t)B * kp * 8);
         ws->s_cnt.ensure((size_t)B * 4); ws->s_exact.ensure((size_t)B * kp * 4);
         LGPU_CUDA(cudaStreamWaitEvent(st, ws->ev_join, 0));        // the tables, built on the side stream
+        ws->aux_open = false;
         ws->qn2.ensure((size_t)B * 4);
         if (!dot) {
             ws->probe_A.ensure((size_t)slots * 4); ws->amax.ensure((size_t)B * 4);
