@@ -454,6 +454,7 @@ def ivf_extra_workload(torch, _native, name, icfg, runner, peak_gbs, steps=4, ch
     _native.set_profiling(True)
     fn(steps - 1)
     stage = _native.last_stage_ms(); code_bytes = _native.last_scanned_code_bytes()
+    fstats = _native.last_filter_stats()
     _native.set_profiling(False)
     torch.cuda.synchronize()
     got = (oi.cpu().numpy().view(np.uint64)[:check], od.cpu().numpy()[:check], oc.cpu().numpy().view(np.uint32)[:check])
@@ -465,7 +466,7 @@ def ivf_extra_workload(torch, _native, name, icfg, runner, peak_gbs, steps=4, ch
                                        f"{icfg['nprobes']}, k={k}, batch={B}, {icfg['metric']}; synthetic uniform "
                                        "partitions, random codes (untrained)",
            "ms_per_batch": float(np.mean(ms)), "qps": B / (float(np.mean(ms)) / 1e3), "steps": steps,
-           "stage_ms": stage, "oracle_check": same(got, want), "oracle_check_queries": check,
+           "stage_ms": stage, "filter_stats": fstats, "oracle_check": same(got, want), "oracle_check_queries": check,
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                         "frac": achieved / peak_gbs, "kernel_ms": stage["scan"],
                         "algorithmic_bytes_per_launch": code_bytes,

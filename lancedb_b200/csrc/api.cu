@@ -91,6 +91,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;     // private stream (host-buffer entry points)
     cudaStream_t aux = nullptr;        // side stream: the per-query tables are built while the coarse step runs
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int stats_mode = 0;                 // profiling: 1 = the last sub-batch ran the candidate mode, 2 = the dense filter
     bool aux_open = false;              // an EAGER fork onto `aux` has not been joined yet (a call failed half-way)
     cudaEvent_t done = nullptr;        // last use, for cross-stream reuse
     cudaEvent_t ev[8] = {};
@@ -544,6 +545,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     int evi = 0;
     auto mark = [&]() { if (prof) cudaEventRecord(ws->ev[evi++], st); };
     mark();
+    ws->stats_mode = 0;
     // ---- queries (normalised copy for cosine) ----
     const float *qsearch = d_q;
     if (ix->metric == LGPU_COSINE) {
@@ -748,12 +750,27 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         sc.qt = ws->qt.as<uint4>(); sc.qt_step = ws->qt_step.as<float>(); sc.qt_base = ws->qt_base.as<float>();
         const float mscale = ix->metric == LGPU_COSINE ? 0.5f : 1.0f;
         // candidate mode (no prefilter, k <= 32): the scanners threshold the rows themselves, nothing dense is written
-        const bool cand_mode = !rf.bits && kk <= modes.cand_kmax && !modes.dense_forced;
+        // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
+        const uint32_t cap_env = modes.cap_env;
+        uint32_t cap = kk <= 32 ? 512 : (kk <= 64 ? 1024 : CAND_CAP_MAX);
+        bool cap_forced = false;
+        if (cap_env >= 32 && cap_env <= CAND_CAP_MAX && !(cap_env & (cap_env - 1)) && cap_env >= kk) { cap = cap_env; cap_forced = true; }
+        // A tile whose query has no threshold yet appends about k rows.  With few queries fanned out over many tiles
+        // (small B, many probes, long partitions) most of a query's tiles run at the same moment on the 2 x SMs CTAs,
+        // before any of them has published a threshold, and the list overflows whatever the scanners tighten later:
+        // estimate that concurrency from the averages and take the dense mode (cheap at such B) when it is too high.
+        bool cand_fits = true;
+        if (!cap_forced) {
+            const uint64_t rows_part = std::max<uint64_t>(1, ix->pad_prefix[np_eff] / np_eff);
+            const uint64_t tiles_part = (rows_part + SCAN3_ROWS_TILE - 1) / SCAN3_ROWS_TILE;
+            const uint64_t parts = std::min<uint64_t>(nlist, slots);
+            const uint64_t groups_part = std::max<uint64_t>(1, (slots / parts + SCAN_G - 1) / SCAN_G);
+            const double total = (double)parts * groups_part * tiles_part;
+            const double conc = (double)np_eff * tiles_part * std::min(1.0, 2.0 * ix->num_sms / total);
+            cand_fits = conc * kk <= 2.0 * cap;
+        }
+        const bool cand_mode = !rf.bits && kk <= modes.cand_kmax && !modes.dense_forced && cand_fits;
         if (cand_mode) {
-            // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
-            const uint32_t cap_env = modes.cap_env;
-            uint32_t cap = kk <= 32 ? 512 : (kk <= 64 ? 1024 : CAND_CAP_MAX);
-            if (cap_env >= 32 && cap_env <= CAND_CAP_MAX && !(cap_env & (cap_env - 1)) && cap_env >= kk) cap = cap_env;
             ws->c_thr.ensure((size_t)B * 4); ws->c_slack.ensure((size_t)B * 4); ws->c_cnt.ensure((size_t)B * 4);
             ws->c_rec.ensure((size_t)B * cap * sizeof(CandRec));
             ws->c_key.ensure((size_t)B * cap * 4); ws->c_last.ensure((size_t)B * 4);
@@ -785,6 +802,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
                 ws->c_stats.ensure(32);
                 LGPU_CUDA(cudaMemsetAsync(ws->c_stats.p, 0, 32, st));
                 fa.stats = ws->c_stats.as<unsigned long long>();
+                ws->stats_mode = 1;
             }
             launch_cand_finalize(fa, st);
             sc.cand = nullptr;                      // (the fix-up pass below is the exact kernel)
@@ -796,6 +814,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         ss.k = kp; ss.out_ids = ws->s_ids.as<uint64_t>(); ss.out_dist = ws->s_lb.as<float>();
         ss.out_count = ws->s_cnt.as<uint32_t>(); ss.out_pos = ws->s_pos.as<uint64_t>();
         launch_select(ss, st);
+        ws->stats_mode = 2;
         launch_band_check3(ws->s_lb.as<float>(), ws->s_cnt.as<uint32_t>(), ws->qt_step.as<float>(), ws->sbound.as<float>(),
                            dot ? nullptr : ws->amax.as<float>(), dot ? nullptr : ix->rmax_bits.as<int>(),
                            ws->qt_bad.as<uint32_t>(), ws->qn2.as<float>(), ix->cb2, mscale, ix->m, B, kk, kp,
@@ -890,7 +909,13 @@ void ivf_search_device(lgpu_index *ix, Workspace *ws, cudaStream_t st, const flo
         LGPU_CUDA(cudaMemcpy(&rows, ws->scalars.as<char>() + 16, 8, cudaMemcpyDeviceToHost));
         g_scanned_bytes = (uint64_t)rows * ix->m;
         memset(g_filter_stats, 0, sizeof(g_filter_stats));
-        if (ws->c_stats.p) LGPU_CUDA(cudaMemcpy(g_filter_stats, ws->c_stats.p, 32, cudaMemcpyDeviceToHost));
+        if (ws->stats_mode == 1) LGPU_CUDA(cudaMemcpy(g_filter_stats, ws->c_stats.p, 32, cudaMemcpyDeviceToHost));
+        else if (ws->stats_mode == 2) {                       // dense filter: queries the band check could not prove
+            std::vector<uint32_t> fl(B);
+            LGPU_CUDA(cudaMemcpy(fl.data(), ws->flags.p, (size_t)B * 4, cudaMemcpyDeviceToHost));
+            for (uint32_t f : fl) g_filter_stats[2] += f ? 1 : 0;
+            g_filter_stats[3] = B;
+        }
     }
 }
 

@@ -170,7 +170,52 @@ __device__ __forceinline__ void stager_loop(const ScanArgs &a, uint32_t total, i
 }
 
 // ---------------------------------------------------------------- scanner side
-template <int R>
+// ---- tau_q from the list itself.  Tile-local bisection cannot get below the k-th smallest of ONE tile (the
+// 100 k / rows_tile quantile); the list holds every row seen so far that was under the threshold of its time, so its
+// k-th smallest key is the k-th smallest of everything scanned for the query.  Any k keys of the list give a valid tau
+// (records still in flight read as 0xffffffff and only make the bound looser).  Triggered each time the list grew by
+// k since the last time, i.e. about once per doubling of the rows seen.  Out of line: its S3_LIST_PER key registers
+// must not take part in the register allocation of the gather loop.
+__device__ __noinline__ uint32_t tighten_from_list(const uint32_t *keys, uint32_t *thr_q, uint32_t *last_q,
+                                                   volatile uint32_t *sh, uint32_t ln, uint32_t tkey, uint32_t k, int ct)
+{
+    const int lane = ct & 31;
+    uint32_t lk[S3_LIST_PER];
+    uint32_t mn = 0xffffffffu, c0 = 0;
+#pragma unroll
+    for (int j = 0; j < S3_LIST_PER; j++) {
+        const uint32_t i = (uint32_t)j * S3_CT + ct;
+        lk[j] = i < ln ? __ldcg(keys + i) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < S3_LIST_PER; j++) { mn = min(mn, lk[j]); c0 += lk[j] <= tkey ? 1u : 0u; }
+    mn = __reduce_min_sync(0xffffffffu, mn); c0 = __reduce_add_sync(0xffffffffu, c0);
+    if (lane == 0) { atomicMin(const_cast<uint32_t *>(sh + 15), mn); if (c0) atomicAdd(const_cast<uint32_t *>(sh + 16), c0); }
+    bar_sync(BAR_SCAN, S3_CT);
+    if (sh[16] >= k) {                          // invariant: count(list key <= hi) >= k
+        float lo = key_f32(sh[15]), hi = key_f32(tkey);
+#pragma unroll 1
+        for (int it = 0; it < S3_LIST_STEPS; it++) {
+            const uint32_t mid = f32_key(0.5f * lo + 0.5f * hi);
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < S3_LIST_PER; j++) c += lk[j] <= mid ? 1u : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 17 + it), c);
+            bar_sync(BAR_SCAN, S3_CT);
+            if (sh[17 + it] >= k) hi = key_f32(mid); else lo = key_f32(mid);
+        }
+        const uint32_t nk = f32_key(hi);
+        if (nk < tkey) {
+            if (ct == 0) atomicMin(thr_q, nk);
+            tkey = nk;
+        }
+    }
+    if (ct == 0) *last_q = ln;
+    return tkey;
+}
+
+template <int R, bool LIST>
 __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, bool next_exists, int b, int ct)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -283,43 +328,10 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
         // so its k-th smallest key is the k-th smallest of everything scanned for the query.  Any k keys of the list
         // give a valid tau (records still in flight read as 0xffffffff and only make the bound looser).  Triggered
         // each time the list grew by k since the last time, i.e. about once per doubling of the rows seen.
-        {
+        if (LIST) {
             const uint32_t ln = sh[13], last = sh[14];
-            if (tkey != CAND_NO_THR && ln >= 2u * k && ln >= last + k) {
-                const uint32_t *keys = a.cand_key + (size_t)q * a.cand_cap;
-                uint32_t lk[S3_LIST_PER];
-                uint32_t mn = 0xffffffffu, c0 = 0;
-#pragma unroll
-                for (int j = 0; j < S3_LIST_PER; j++) {
-                    const uint32_t i = (uint32_t)j * S3_CT + ct;
-                    lk[j] = i < ln ? __ldcg(keys + i) : 0xffffffffu;
-                }
-#pragma unroll
-                for (int j = 0; j < S3_LIST_PER; j++) { mn = min(mn, lk[j]); c0 += lk[j] <= tkey ? 1u : 0u; }
-                mn = __reduce_min_sync(0xffffffffu, mn); c0 = __reduce_add_sync(0xffffffffu, c0);
-                if (lane == 0) { atomicMin(const_cast<uint32_t *>(sh + 15), mn); if (c0) atomicAdd(const_cast<uint32_t *>(sh + 16), c0); }
-                bar_sync(BAR_SCAN, S3_CT);
-                if (sh[16] >= k) {                          // invariant: count(list key <= hi) >= k
-                    float lo = key_f32(sh[15]), hi = key_f32(tkey);
-#pragma unroll 1
-                    for (int it = 0; it < S3_LIST_STEPS; it++) {
-                        const uint32_t mid = f32_key(0.5f * lo + 0.5f * hi);
-                        uint32_t c = 0;
-#pragma unroll
-                        for (int j = 0; j < S3_LIST_PER; j++) c += lk[j] <= mid ? 1u : 0u;
-                        c = __reduce_add_sync(0xffffffffu, c);
-                        if (lane == 0 && c) atomicAdd(const_cast<uint32_t *>(sh + 17 + it), c);
-                        bar_sync(BAR_SCAN, S3_CT);
-                        if (sh[17 + it] >= k) hi = key_f32(mid); else lo = key_f32(mid);
-                    }
-                    const uint32_t nk = f32_key(hi);
-                    if (nk < tkey) {
-                        if (ct == 0) atomicMin(a.thr + q, nk);
-                        tkey = nk;
-                    }
-                }
-                if (ct == 0) a.cand_last[q] = ln;
-            }
+            if (tkey != CAND_NO_THR && ln >= 2u * k && ln >= last + k)
+                tkey = tighten_from_list(a.cand_key + (size_t)q * a.cand_cap, a.thr + q, a.cand_last + q, sh, ln, tkey, k, ct);
         }
         const float step = __ldg(a.qt_step + q);
         const float cst = __ldg(a.qt_base + q) + (a.probe_A ? __ldg(a.probe_A + slot) : 0.f);
@@ -413,6 +425,7 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
     return b;
 }
 
+template <bool LIST>
 __device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -424,7 +437,7 @@ __device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
         if (T->ng == 0) break;
         const bool next_exists = slot3(tiles, n + 1)->ng != 0;
         const int R = (int)((T->nrows + S3_CT - 1) / S3_CT);
-#define LGPU_SCAN3(RR) b = scan_tile<RR>(a, T, next_exists, b, ct)
+#define LGPU_SCAN3(RR) b = scan_tile<RR, LIST>(a, T, next_exists, b, ct)
         if (R <= 2) LGPU_SCAN3(2);
         else if (R <= 4) LGPU_SCAN3(4);
         else LGPU_SCAN3(6);
@@ -432,6 +445,10 @@ __device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
     }
 }
 
+// LIST: the scanners also tighten tau_q from the query's own candidate list (k > 32: tile-local thresholds alone would
+// overflow the lists).  A separate instantiation, so that the list keys held in registers there do not cost the
+// k <= 32 kernel (BASELINE config 2) spills inside its gather loop.
+template <bool LIST>
 __global__ void __launch_bounds__(S3_NT, 2) scan3_kernel(ScanArgs a)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -461,7 +478,7 @@ __global__ void __launch_bounds__(S3_NT, 2) scan3_kernel(ScanArgs a)
         stager_loop(a, total, tid);
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(S3_CREG));
-        scanner_loop(a, tid);
+        scanner_loop<LIST>(a, tid);
     }
 }
 
@@ -474,8 +491,10 @@ void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st)
         set_error("internal: the filter scan needs query tables and tile descriptors built with rows_tile 1536");
         throw Failure{LGPU_RUNTIME};
     }
-    LGPU_CUDA(cudaFuncSetAttribute(scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
-    scan3_kernel<<<2 * grid, S3_NT, S3_SMEM, st>>>(a); LGPU_COUNT_LAUNCH();   // two CTAs per SM
+    const bool list = a.cand && a.topk > 32;
+    auto kern = list ? scan3_kernel<true> : scan3_kernel<false>;
+    LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
+    kern<<<2 * grid, S3_NT, S3_SMEM, st>>>(a); LGPU_COUNT_LAUNCH();   // two CTAs per SM
     LGPU_CUDA(cudaGetLastError());
 }
 
