@@ -246,26 +246,45 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
                                                                    uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ flags,
                                                                    uint32_t *__restrict__ gate)
 {
+    // long rows only are staged through shared memory: at VPT 4 / 16 the few register loads are cheaper than the
+    // extra barrier (measured: C2 and C3 coarse steps 4 % slower with staging, C5's 35 % faster)
+    constexpr bool STAGED = VPT >= 64;
+    constexpr int NV0 = STAGED ? VPT : 0;
     extern __shared__ __align__(16) unsigned char csm[];
-    uint32_t *s_col = reinterpret_cast<uint32_t *>(csm);           // [cap] candidate columns
+    float *s_row = reinterpret_cast<float *>(csm);                  // [VPT * CF_THREADS] the score row (VPT > 0)
+    uint32_t *s_col = reinterpret_cast<uint32_t *>(s_row + (size_t)NV0 * CF_THREADS);   // [cap] candidate columns
     uint32_t *s_key = s_col + cap;                                  // [cap] exact distance keys
     float *s_x = reinterpret_cast<float *>(s_key + cap);            // [d] the query
     __shared__ uint32_t s_lo, s_hi, s_valid, s_n, s_cnt[24];
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const float *row = S + (size_t)q * ld;
+    if constexpr (STAGED) {
+        // The row goes global -> shared with cp.async (16 B per request, all VPT / 4 requests of a thread in flight at
+        // once), then shared -> registers.  Register loads, however they were written, came out of ptxas as
+        // load -> use -> load: 64 serial DRAM round trips per thread, 60 % of the kernel's stall samples at nlist 16384
+        // (profiles/r02_ncu_summary.txt).  ld is a multiple of 4 floats and the buffer holds ld floats per row.
+        const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_row);
+        for (uint32_t i = (uint32_t)tid * 4; i < ld && i < (uint32_t)VPT * CF_THREADS; i += CF_THREADS * 4)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + i * 4), "l"(row + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     if (tid == 0) { s_lo = 0xffffffffu; s_hi = 0u; s_valid = 0u; s_n = 0u; }
     if (tid < 24) s_cnt[tid] = 0u;
     for (uint32_t t = tid; t < d; t += CF_THREADS) s_x[t] = Q[(size_t)q * d + t];
+    if constexpr (STAGED) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     constexpr int NV = VPT > 0 ? VPT : 1;
     float v[NV];
     uint32_t kmin = 0xffffffffu, kmax = 0u, nv = 0;
     if constexpr (VPT > 0) {
-        // all loads first (clamped index, no predicate, nothing consuming them in between): with the checks folded in,
-        // ptxas issued load -> use -> load and the kernel spent 3/4 of its time on 64 serial DRAM round trips
+        if constexpr (STAGED) {
 #pragma unroll
-        for (int j = 0; j < VPT; j++) v[j] = __ldg(row + min((uint32_t)j * CF_THREADS + tid, N - 1));
+            for (int j = 0; j < VPT; j++) v[j] = s_row[min((uint32_t)j * CF_THREADS + tid, N - 1)];
+        } else {
+#pragma unroll
+            for (int j = 0; j < VPT; j++) v[j] = __ldg(row + min((uint32_t)j * CF_THREADS + tid, N - 1));
+        }
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
             if ((uint32_t)j * CF_THREADS + tid >= N) v[j] = CUDART_NAN_F;       // NaN never counts
@@ -378,15 +397,17 @@ void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, c
     if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
     uint32_t cap = 512;                                              // (only the entries in use are sorted)
     while (cap < 4 * k) cap <<= 1;                                   // power of two >= 4 k
-    const size_t smem = (size_t)cap * 8 + (size_t)d * 4;
-    if (smem > 200 * 1024) { set_error("internal: coarse_finish candidate list does not fit in shared memory"); throw Failure{LGPU_RUNTIME}; }
+    const size_t smem0 = (size_t)cap * 8 + (size_t)d * 4;
+    if (smem0 > 128 * 1024) { set_error("internal: coarse_finish candidate list does not fit in shared memory"); throw Failure{LGPU_RUNTIME}; }
 #define LGPU_CF(V) do { \
+        const size_t smem = smem0 + ((V) >= 64 ? (size_t)(V) * CF_THREADS * 4 : 0); \
         if (smem > 48 * 1024) LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate); \
     } while (0)
-    if (N <= 4 * CF_THREADS) LGPU_CF(4);
-    else if (N <= 16 * CF_THREADS) LGPU_CF(16);
-    else if (N <= 64 * CF_THREADS) LGPU_CF(64);
+    const bool staged = (ld & 3u) == 0 && ld >= N;                  // cp.async needs 16-byte rows
+    if (staged && N <= 4 * CF_THREADS) LGPU_CF(4);
+    else if (staged && N <= 16 * CF_THREADS) LGPU_CF(16);
+    else if (staged && N <= 64 * CF_THREADS) LGPU_CF(64);
     else LGPU_CF(0);
 #undef LGPU_CF
     LGPU_COUNT_LAUNCH();
