@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     for (uint32_t c0 = 0; c0 < n; c0 += CF_THREADS / 16) {
         const uint32_t c = c0 + (tid >> 4);
         if (c < n) {                                                 // a whole half-warp takes the branch together
-            const float dv = halfwarp_l2_sx<24>(s_x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
+            const float dv = halfwarp_l2_sx<48>(s_x, C + (size_t)s_col[c] * d, d, hl, hmask, hbase);
             if (hl == 0) s_key[c] = (dv != dv) ? 0xffffffffu : f32_key(dv == 0.f ? 0.f : dv);
         }
     }

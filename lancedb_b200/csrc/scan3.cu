@@ -53,10 +53,19 @@ constexpr int S3_BUF = 32768;                       // one chunk buffer
 constexpr int S3_SLOTS = 4, S3_SLOT_BYTES = 128;    // tile-descriptor ring
 constexpr size_t S3_TILES = 3 * (size_t)S3_BUF;
 constexpr int S3_SCR = 32;                          // words per bank of threshold scratch
-constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES + 2 * S3_SCR * 4;   // + two banks of threshold scratch
+constexpr size_t S3_SMEM = S3_TILES + S3_SLOTS * S3_SLOT_BYTES + 2 * S3_SCR * 4 + 32;   // + two banks of threshold scratch + mbarriers
 constexpr int S3_LIST_PER = CAND_CAP_MAX / S3_CT;  // list keys per scanner thread in a list-based tightening
 constexpr int S3_LIST_STEPS = 10;
 constexpr int BAR_SCAN = 8;                         // named barrier of the 256 scanner threads (candidate mode)
+// FULL hand-over (stagers -> scanners) as mbarriers, one per ring buffer: a named barrier made the 8 scanner warps
+// wait for EACH OTHER at every stage (bar.sync counts all of them), so a stage took as long as its slowest warp; with
+// an mbarrier only the stagers arrive (one elected lane per warp) and every scanner warp goes on as soon as the
+// buffer is full.  The scanners can then drift apart by at most two stages (the EMPTY barrier, which the stagers
+// wait on, needs all of them).  LGPU_S3_NAMED_FULL=1 at build time restores the named barrier (A/B).
+#ifndef LGPU_S3_NAMED_FULL
+#define LGPU_S3_NAMED_FULL 0
+#endif
+constexpr size_t S3_MBAR_OFF = S3_TILES + S3_SLOTS * S3_SLOT_BYTES + 2 * S3_SCR * 4;   // 3 x 8 bytes, 8-byte aligned
 static_assert(SCAN3_ROWS_TILE == S3_CT * S3_RMAX, "rows_tile");
 static_assert(S3_PT == 256, "one stager thread per code");
 
@@ -74,6 +83,26 @@ __device__ __forceinline__ uint4 lds128u(uint32_t addr)
 __device__ __forceinline__ void sts128u(uint32_t addr, uint4 v)
 {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ uint32_t word_of(const uint4 &v, int w)
 {
@@ -161,7 +190,12 @@ __device__ __forceinline__ void stager_loop(const ScanArgs &a, uint32_t total, i
             }
             if (pw == 0 && ch == 1 && lane < (int)(sizeof(TileDesc) / 4))   // publish tile n+2 before FULL(stage 1)
                 reinterpret_cast<uint32_t *>(const_cast<TileDesc *>(slot3(tiles, n + 2)))[lane] = t_word;
+#if LGPU_S3_NAMED_FULL
             bar_arrive(BAR_FULL + b, S3_NT);
+#else
+            __syncwarp();
+            if (lane == 0) mbar_arrive(lut + (uint32_t)S3_MBAR_OFF + 8u * (uint32_t)b);
+#endif
             bar_sync(BAR_PROD, S3_PT);
             b = ring_next3(b);
             gs++;
@@ -216,7 +250,7 @@ __device__ __noinline__ uint32_t tighten_from_list(const uint32_t *keys, uint32_
 }
 
 template <int R, bool LIST>
-__device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, bool next_exists, int b, int ct)
+__device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, bool next_exists, int b, int ct, uint32_t &ph)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t lut = (uint32_t)__cvta_generic_to_shared(smem);
@@ -250,7 +284,12 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
                 wn[r] = valid[r] ? __ldg(cs + (size_t)(it + 1) * npad + row) : make_uint2(0u, 0u);
             }
         }
+#if LGPU_S3_NAMED_FULL
         bar_sync(BAR_FULL + b, S3_NT);
+#else
+        mbar_wait(lut + (uint32_t)S3_MBAR_OFF + 8u * (uint32_t)b, (ph >> b) & 1u);
+        ph ^= 1u << b;
+#endif
         const int bp = b == 0 ? 2 : b - 1;                 // buffer of the previous stage
         const uint32_t base_cur = lut + (uint32_t)b * S3_BUF;
         const uint32_t base_prev = lut + (uint32_t)bp * S3_BUF;
@@ -432,12 +471,13 @@ __device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
     const unsigned char *const tiles = smem + S3_TILES;
     const int ct = tid - S3_PT;
     int b = 0;
+    uint32_t ph = 0u;                                   // bit b: parity of ring buffer b's next FULL phase
     for (uint32_t n = 0;; n++) {
         const TileDesc *T = slot3(tiles, n);
         if (T->ng == 0) break;
         const bool next_exists = slot3(tiles, n + 1)->ng != 0;
         const int R = (int)((T->nrows + S3_CT - 1) / S3_CT);
-#define LGPU_SCAN3(RR) b = scan_tile<RR, LIST>(a, T, next_exists, b, ct)
+#define LGPU_SCAN3(RR) b = scan_tile<RR, LIST>(a, T, next_exists, b, ct, ph)
         if (R <= 2) LGPU_SCAN3(2);
         else if (R <= 4) LGPU_SCAN3(4);
         else LGPU_SCAN3(6);
@@ -458,6 +498,13 @@ __global__ void __launch_bounds__(S3_NT, 2) scan3_kernel(ScanArgs a)
 
     // "stage -1" of the first tile: zero code-0 row in ring buffer 2
     if (tid < 32) reinterpret_cast<uint32_t *>(smem + 2 * S3_BUF)[tid] = 0u;
+#if !LGPU_S3_NAMED_FULL
+    if (tid == 0) {
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)S3_MBAR_OFF;
+        for (int i = 0; i < 3; i++) mbar_init(mb + 8u * i, S3_PW);      // one arrival per stager warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
     // tiles 0 and 1 of this CTA
     if (tid < 32) {
         uint32_t t0 = 0, t1 = 0;

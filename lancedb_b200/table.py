@@ -122,6 +122,26 @@ class Table:
         self._index_data[column] = data
         self._index[column] = _native.GpuIvfPq(data, device=self._device)
 
+    # ---- on-disk Lance index (layout [lance, recalled], see lance_index.py) ----
+    def load_lance_index(self, index_dir: str, vector_column_name: Optional[str] = None) -> None:
+        """Pin the IVF_PQ index stored under ``<table>.lance/_indices/<uuid>/`` in HBM.  Row ids must be row offsets
+        of this table (what a freshly written Lance table has); the raw vectors for ``refine_factor`` are gathered
+        from the table's own column in the index's partition order."""
+        from .lance_index import read_ivf_pq_index
+        data = read_ivf_pq_index(index_dir)
+        column = vector_column_name or self._infer_vector_column(None)
+        if self._dim(column) != data.dim:
+            raise ValueError(f"index dimension {data.dim} does not match column {column} ({self._dim(column)})")
+        if data.nrows and int(data.row_ids.max()) >= self._data.num_rows:
+            raise ValueError("the index addresses rows this table does not have")
+        data.vectors = np.ascontiguousarray(self._vectors(column)[data.row_ids.astype(np.int64)])
+        self._attach_index(column, data)
+
+    def save_lance_index(self, index_dir: str, vector_column_name: Optional[str] = None, transposed: bool = True) -> None:
+        from .lance_index import write_ivf_pq_index
+        column = vector_column_name or self._infer_vector_column(None)
+        write_ivf_pq_index(index_dir, self._index_data[column], transposed=transposed)
+
     def prewarm_index(self, name: str):           # rust/lancedb/src/table.rs:3283-3286
         return None                                # indexes are pinned in HBM at create/open time
 

@@ -355,3 +355,29 @@ def test_remote_wire_format_query_node():
     assert out.num_rows == 6 and out["query_index"].to_pylist() == [0, 0, 0, 1, 1, 1]
     with pytest.raises(NotImplementedError):
         remote.handle_query(t, remote.build_query_body([], k=3))
+
+
+def test_index_loaded_from_lance_files_searches_like_the_in_memory_one(tmp_path):
+    """an IVF_PQ index read back from `_indices/<uuid>/{index.idx,auxiliary.idx}` (layout recalled,
+    lancedb_b200/lance_index.py) gives the same ids and distance bits as the index it was written from, plain and with
+    refine_factor (raw vectors re-gathered from the table by row id)."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((5000, 32)).astype(np.float32)
+    db = lancedb.connect("memory://")
+    t = db.create_table("v", {"vector": x, "id": np.arange(5000)})
+    t.create_index(metric="l2", num_partitions=12, num_sub_vectors=4, max_iterations=4, accelerator="cuda")
+    d = str(tmp_path / "v.lance" / "_indices" / "11111111-2222")
+    t.save_lance_index(d)
+    t2 = db.create_table("w", {"vector": x, "id": np.arange(5000)})
+    t2.load_lance_index(d)
+    assert t2.list_indices()[0]["index_type"] == "IVF_PQ"
+    q = rng.standard_normal((40, 32)).astype(np.float32)
+    for kw in ({}, {"refine": 3}):
+        a = t.search(q).nprobes(5).limit(7)
+        b = t2.search(q).nprobes(5).limit(7)
+        if kw:
+            a, b = a.refine_factor(3), b.refine_factor(3)
+        a, b = a.with_row_id(True).to_arrow(), b.with_row_id(True).to_arrow()
+        assert a["_rowid"].to_pylist() == b["_rowid"].to_pylist()
+        assert np.array_equal(np.asarray(a["_distance"].to_pylist(), np.float32).view(np.uint32),
+                              np.asarray(b["_distance"].to_pylist(), np.float32).view(np.uint32))

@@ -303,3 +303,52 @@ def test_remote_ipc_file_round_trip():
     data = remote._ipc_file(t)
     assert data[:6] == b"ARROW1"                                          # the IPC *file* framing the client expects
     assert remote.read_ipc_file(data).equals(t)
+
+
+# ---------------------------------------------------------------------------------------------- Lance index files
+def test_lance_index_file_round_trip_and_rejections(tmp_path):
+    """`_indices/<uuid>/{index.idx,auxiliary.idx}` -> the arrays of lgpu_index_desc.  The layout is
+    recalled (no Lance file or writer exists in the reference tree), so what is pinned here is self-consistency:
+    writer -> reader reproduces every array for both code layouts and paged columns, the footer / offset tables are
+    range-checked, and pieces outside the handled subset fail loudly."""
+    import struct
+    from lancedb_b200 import lance_index as L
+    from tests.util import random_index
+    rng = np.random.default_rng(12)
+    ix = random_index(rng, dim=32, nlist=9, m=4, metric="cosine", n=700)
+    for transposed in (True, False):
+        for page_rows in (0, 100):
+            d = str(tmp_path / f"i{int(transposed)}{page_rows}")
+            L.write_ivf_pq_index(d, ix, transposed=transposed, page_rows=page_rows)
+            got = L.read_ivf_pq_index(d)
+            got.validate()
+            assert got.metric == "cosine" and (got.dim, got.nlist, got.m) == (32, 9, 4)
+            for name in ("centroids", "codebook", "part_offsets", "codes_t", "row_ids"):
+                assert np.array_equal(getattr(got, name), getattr(ix, name)), name
+    # protobuf helpers: packed and unpacked repeated ints, nested messages
+    msg = L.pb_int(1, 300) + L.pb_packed(2, [1, 128, 1 << 40]) + L.pb_int(2, 7) + L.pb_bytes(3, L.pb_int(1, 5))
+    f = L.pb_fields(msg)
+    assert f[1] == [300] and L.pb_repeated_ints(f[2]) == [1, 128, 1 << 40, 7] and L.pb_fields(f[3][0])[1] == [5]
+    # rejections
+    base = str(tmp_path / "i10")
+    raw = open(base + "/auxiliary.idx", "rb").read()
+    bad = tmp_path / "bad"; bad.mkdir()
+    (bad / "index.idx").write_bytes(open(base + "/index.idx", "rb").read())
+    (bad / "auxiliary.idx").write_bytes(raw[:-4] + b"XXXX")
+    with pytest.raises(L.LanceFormatError, match="magic"):
+        L.read_ivf_pq_index(str(bad))
+    foot = bytearray(raw)
+    struct.pack_into("<H", foot, len(foot) - 6, 1)                       # minor version 1: format 2.1 page layouts
+    (bad / "auxiliary.idx").write_bytes(bytes(foot))
+    with pytest.raises(L.LanceFormatError, match="2.1"):
+        L.read_ivf_pq_index(str(bad))
+    foot = bytearray(raw)
+    struct.pack_into("<Q", foot, len(foot) - 40 + 8, len(raw))           # column-metadata offset table past the end
+    (bad / "auxiliary.idx").write_bytes(bytes(foot))
+    with pytest.raises(L.LanceFormatError, match="out of range"):
+        L.read_ivf_pq_index(str(bad))
+    assert L.find_index_dirs(str(tmp_path)) == []
+    tbl = tmp_path / "t.lance" / "_indices" / "0000-uuid"
+    tbl.mkdir(parents=True)
+    L.write_ivf_pq_index(str(tbl), ix)
+    assert L.find_index_dirs(str(tmp_path / "t.lance")) == [str(tbl)]
