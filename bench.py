@@ -849,6 +849,7 @@ def clustered_workload(torch, _native, oracle, args, device, runner, peak_gbs):
     _native.set_profiling(True)
     fn(0)
     stage = _native.last_stage_ms(); code_bytes = _native.last_scanned_code_bytes()
+    fstats = _native.last_filter_stats()
     _native.set_profiling(False)
     sizes = np.diff(ix.part_offsets.astype(np.int64))
     ix.vectors = None
@@ -864,7 +865,11 @@ def clustered_workload(torch, _native, oracle, args, device, runner, peak_gbs):
             "partition_size_std_over_mean": float(sizes.std() / sizes.mean()), "index_build_s": build_s,
             "cpu_qps": cpu["value"], "cpu_threads": cpu["cores"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                         "kernel_ms": stage["scan"], "algorithmic_bytes_per_launch": code_bytes}}
+                         "kernel_ms": stage["scan"], "algorithmic_bytes_per_launch": code_bytes,
+                         "note": ("algorithmic bytes count a partition's codes once per query that probes it; the kernel "
+                                  "reads them from HBM once per tile of <= 8 queries, so a value above 1.0 is on-chip "
+                                  "reuse (large partitions: many queries per tile), not more than the HBM peak")},
+            "filter_stats": fstats}
 
 
 def sharded_block(torch, dist, _native, oracle, cfg, full_ix, gpu_full, rank, local, world, flush, peak_gbs, steps=20):

@@ -240,6 +240,8 @@ struct lgpu_index {
     float cb2 = 0.f;                    // sum_i max_c |codebook_i[c]|^2 (error budget of the filter's table entries)
     bool has_tables = false;
     DevBuf cent_b, cent_n2;             // bf16 centroids + |c|^2 for the tensor-core coarse step
+    DevBuf cent_sb, cent_sn2;           // every COARSE_SAMPLE_STRIDE-th centroid (bf16 + |c|^2): the threshold sample
+    uint32_t cent_ns = 0;               // rows of the sample (0: none)
     float cent_max = 0.f;
     bool has_tc = false;
     bool has_vectors = false;
@@ -391,11 +393,11 @@ static bool exact_scan_forced()
 // into the CUDA-graph key so a captured launch sequence is never replayed under a different mode.
 struct ScanModes {
     bool exact, dense_forced;
-    uint32_t cand_kmax, cap_env, small_slots;
+    uint32_t cand_kmax, cap_env, small_slots, coarse_list_min;
     uint64_t signature() const
     {
         return ((uint64_t)exact | (uint64_t)dense_forced << 1 | (uint64_t)cand_kmax << 8 | (uint64_t)cap_env << 20 |
-                (uint64_t)small_slots << 36) * 0x9e3779b97f4a7c15ull;
+                (uint64_t)small_slots << 36 | (uint64_t)(coarse_list_min & 0xffffu) << 48) * 0x9e3779b97f4a7c15ull;
     }
 };
 static ScanModes scan_modes()
@@ -407,6 +409,7 @@ static ScanModes scan_modes()
     m.cand_kmax = std::min<uint32_t>(CAND_TOPK_MAX, num("LGPU_CAND_KMAX", CAND_TOPK_MAX));
     m.cap_env = num("LGPU_CAND_CAP", 0u);
     m.small_slots = num("LGPU_SMALL_SLOTS", 1024u);
+    m.coarse_list_min = num("LGPU_COARSE_LIST_MIN", 8192u);     // nlist from which the coarse GEMM filters (0: never)
     return m;
 }
 
@@ -602,11 +605,44 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
             ws->c_wcnt.ensure(16);
             uint32_t *cgate = ws->c_wcnt.as<uint32_t>() + 2;    // 0 = no query overflowed: the exact fix-up returns at once
             launch_to_bf16(qsearch, B, dim, ws->qb.p, ws->qn2.as<float>(), st);
-            launch_gemm_dist(ws->qb.p, ix->cent_b.p, ix->cent_n2.as<float>(), B, nlist, dim, ws->D.as<float>(), ldc,
-                             ix->num_sms, st);
-            launch_coarse_finish(ws->D.as<float>(), ldc, B, nlist, qsearch, ix->centroids.as<float>(), ws->qn2.as<float>(),
-                                 ix->cent_max, dim, nprobes, ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(),
-                                 ws->probe_cnt.as<uint32_t>(), ws->flags.as<uint32_t>(), cgate, st);
+            if (modes.coarse_list_min && nlist >= modes.coarse_list_min && ix->cent_ns >= 4 * nprobes && nprobes <= 64) {
+                // Many lists (C5: 16384): a dense [B][nlist] score matrix is 537 MB written and read back, which bounds
+                // the GEMM (tensor pipe 34 %).  Instead: (1) dense scores of a strided SAMPLE of the centroids; their
+                // nprobes-th smallest + 2 E_q bounds, per query, the scores of every true probe; (2) the full GEMM runs
+                // with the filtering epilogue and appends (column, score) of the few columns under that bound to the
+                // query's list; (3) the finishing kernel works on the list (second-level threshold from the list's own
+                // nprobes-th smallest, exact re-score, sort).  Overflowing lists are redone by the exact kernels.
+                const uint32_t ns = ix->cent_ns, lds = (ns + 3u) & ~3u, lcap = 1024;
+                ws->t_dist.ensure((size_t)B * nprobes * 4); ws->t_ids.ensure((size_t)B * nprobes * 8);
+                ws->t_cnt.ensure((size_t)B * 4); ws->probe_A.ensure((size_t)B * 4); ws->amax.ensure((size_t)B * 4);
+                ws->t_pos.ensure((size_t)B * lcap * 8); ws->t_exact.ensure((size_t)B * lcap * 4);
+                launch_gemm_dist(ws->qb.p, ix->cent_sb.p, ix->cent_sn2.as<float>(), B, ns, dim, ws->D.as<float>(), lds,
+                                 ix->num_sms, st);
+                if (!launch_sample_kth_threshold(ws->D.as<float>(), lds, ns, ws->qn2.as<float>(), ix->cent_max, dim, B, nprobes,
+                                                 ws->probe_A.as<float>(), st)) {
+                    SelectArgs ss{};
+                    ss.mode = 1; ss.dense = ws->D.as<float>(); ss.ncols = ns; ss.row_stride = lds; ss.B = B; ss.k = nprobes;
+                    ss.out_ids = ws->t_ids.as<uint64_t>(); ss.out_dist = ws->t_dist.as<float>(); ss.out_count = ws->t_cnt.as<uint32_t>();
+                    launch_select(ss, st);
+                    launch_sample_threshold(ws->t_dist.as<float>(), ws->t_cnt.as<uint32_t>(), ws->qn2.as<float>(), ix->cent_max, dim,
+                                            B, nprobes, ws->probe_A.as<float>(), st);
+                }
+                LGPU_CUDA(cudaMemsetAsync(ws->amax.p, 0, (size_t)B * 4, st));
+                GemmFilter flt{};
+                flt.thr = ws->probe_A.as<float>(); flt.count = ws->amax.as<uint32_t>(); flt.cand_pos = ws->t_pos.as<uint64_t>();
+                flt.cand_ids = nullptr; flt.col_ids = nullptr; flt.cap = lcap; flt.cand_s = ws->t_exact.as<float>();
+                launch_gemm_dist(ws->qb.p, ix->cent_b.p, ix->cent_n2.as<float>(), B, nlist, dim, nullptr, 0, ix->num_sms, st, &flt);
+                launch_coarse_finish(ws->t_exact.as<float>(), lcap, B, lcap, qsearch, ix->centroids.as<float>(),
+                                     ws->qn2.as<float>(), ix->cent_max, dim, nprobes, ws->probes.as<uint64_t>(),
+                                     ws->probe_dist.as<float>(), ws->probe_cnt.as<uint32_t>(), ws->flags.as<uint32_t>(), cgate,
+                                     st, ws->t_pos.as<uint64_t>(), ws->amax.as<uint32_t>());
+            } else {
+                launch_gemm_dist(ws->qb.p, ix->cent_b.p, ix->cent_n2.as<float>(), B, nlist, dim, ws->D.as<float>(), ldc,
+                                 ix->num_sms, st);
+                launch_coarse_finish(ws->D.as<float>(), ldc, B, nlist, qsearch, ix->centroids.as<float>(), ws->qn2.as<float>(),
+                                     ix->cent_max, dim, nprobes, ws->probes.as<uint64_t>(), ws->probe_dist.as<float>(),
+                                     ws->probe_cnt.as<uint32_t>(), ws->flags.as<uint32_t>(), cgate, st);
+            }
             launch_dist_matrix(qsearch, ix->centroids.as<float>(), B, nlist, dim, 0, nullptr, nullptr, ws->D.as<float>(), ldc,
                                st, ws->flags.as<uint32_t>(), cgate);
             SelectArgs sc{};
@@ -1195,6 +1231,20 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             LGPU_CUDA(cudaStreamSynchronize(st));
             prepare_tc_operand(ix->centroids.as<float>(), nlist, d->dim, ix->cent_b, ix->cent_n2, ix->cent_max, st);
             ix->device_bytes += ix->cent_b.bytes + ix->cent_n2.bytes;
+            if (nlist >= 1024) {
+                // every 8th centroid, for the sampled threshold of the coarse step (strided: whatever order the
+                // trainer left the lists in -- hierarchical k-means groups neighbours -- the sample spans all of them)
+                constexpr uint32_t COARSE_SAMPLE_STRIDE = 8;
+                const uint32_t ns = nlist / COARSE_SAMPLE_STRIDE;
+                ix->cent_sb.ensure((size_t)ns * d->dim * 2); ix->cent_sn2.ensure((size_t)ns * 4);
+                LGPU_CUDA(cudaMemcpy2DAsync(ix->cent_sb.p, (size_t)d->dim * 2, ix->cent_b.p, (size_t)COARSE_SAMPLE_STRIDE * d->dim * 2,
+                                            (size_t)d->dim * 2, ns, cudaMemcpyDeviceToDevice, st));
+                LGPU_CUDA(cudaMemcpy2DAsync(ix->cent_sn2.p, 4, ix->cent_n2.p, (size_t)COARSE_SAMPLE_STRIDE * 4, 4, ns,
+                                            cudaMemcpyDeviceToDevice, st));
+                LGPU_CUDA(cudaStreamSynchronize(st));
+                ix->cent_ns = ns;
+                ix->device_bytes += ix->cent_sb.bytes + ix->cent_sn2.bytes;
+            }
             ix->has_tc = true;
         }
         // codebook -> [nch][256][8][dsub]

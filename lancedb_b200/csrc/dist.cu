@@ -238,13 +238,15 @@ constexpr int CF_THREADS = 256;
 // VPT = row values per thread, held in registers for the counting passes (N <= 256 VPT); VPT == 0: the row is
 // re-read from global memory (L2) in every pass (flat-sized rows)
 template <int VPT>
-__global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *__restrict__ S, uint64_t ld, uint32_t N,
+__global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *__restrict__ S, uint64_t ld, uint32_t N_,
                                                                    const float *__restrict__ Q, const float *__restrict__ C,
                                                                    const float *__restrict__ qn2, float xmax, uint32_t d,
                                                                    uint32_t k, uint32_t cap,
                                                                    uint64_t *__restrict__ out_ids, float *__restrict__ out_dist,
                                                                    uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ flags,
-                                                                   uint32_t *__restrict__ gate)
+                                                                   uint32_t *__restrict__ gate,
+                                                                   const uint64_t *__restrict__ list_pos,
+                                                                   const uint32_t *__restrict__ list_cnt)
 {
     // long rows only are staged through shared memory: at VPT 4 / 16 the few register loads are cheaper than the
     // extra barrier (measured: C2 and C3 coarse steps 4 % slower with staging, C5's 35 % faster)
@@ -259,6 +261,11 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const float *row = S + (size_t)q * ld;
+    // list mode (large nlist): the row is the query's list of admitted scores from the GEMM's filtering epilogue,
+    // list_pos maps a list entry to its column; every column with S <= (k-th smallest S of a column sample) + 2 E_q is in
+    // the list, so the k-th smallest of the list is the k-th smallest of the whole row and the band below is complete
+    const uint32_t listed = list_cnt ? list_cnt[q] : 0u;
+    const uint32_t N = list_cnt ? min(listed, (uint32_t)ld) : N_;
     if constexpr (STAGED) {
         // The row goes global -> shared with cp.async (16 B per request, all VPT / 4 requests of a thread in flight at
         // once), then shared -> registers.  Register loads, however they were written, came out of ptxas as
@@ -283,7 +290,7 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
             for (int j = 0; j < VPT; j++) v[j] = s_row[min((uint32_t)j * CF_THREADS + tid, N - 1)];
         } else {
 #pragma unroll
-            for (int j = 0; j < VPT; j++) v[j] = __ldg(row + min((uint32_t)j * CF_THREADS + tid, N - 1));
+            for (int j = 0; j < VPT; j++) v[j] = __ldg(row + min((uint32_t)j * CF_THREADS + tid, N ? N - 1 : 0u));
         }
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
@@ -330,22 +337,26 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
         for (int j = 0; j < VPT; j++) {
             if (v[j] <= thr) {
                 const uint32_t at = atomicAdd(&s_n, 1u);
-                if (at < cap) s_col[at] = (uint32_t)j * CF_THREADS + tid;
+                if (at < cap) {
+                    const uint32_t idx = (uint32_t)j * CF_THREADS + tid;
+                    s_col[at] = list_pos ? (uint32_t)list_pos[(size_t)q * ld + idx] : idx;
+                }
             }
         }
     } else {
         for (uint32_t i = tid; i < N; i += CF_THREADS) {
             if (row[i] <= thr) {
                 const uint32_t at = atomicAdd(&s_n, 1u);
-                if (at < cap) s_col[at] = i;
+                if (at < cap) s_col[at] = list_pos ? (uint32_t)list_pos[(size_t)q * ld + i] : i;
             }
         }
     }
     __syncthreads();
     const uint32_t total = s_n, n = min(total, cap);
     if (tid == 0) {
-        flags[q] = total > cap ? 1u : 0u;
-        if (total > cap && gate) *gate = 1u;                        // opens the gate of the caller's exact fix-up
+        const bool redo = total > cap || listed > ld;               // (a list that overflowed is not a superset)
+        flags[q] = redo ? 1u : 0u;
+        if (redo && gate) *gate = 1u;                               // opens the gate of the caller's exact fix-up
     }
     // exact re-score, half a warp per candidate column (lance's l2: 16 lane accumulators, sequential lane sum)
     const int hl = lane & 15, hbase = lane & 16;
@@ -391,7 +402,8 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
 
 void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, const float *Q, const float *C,
                           const float *qn2, float xmax, uint32_t d, uint32_t k, uint64_t *out_ids, float *out_dist,
-                          uint32_t *out_cnt, uint32_t *flags, uint32_t *gate, cudaStream_t st)
+                          uint32_t *out_cnt, uint32_t *flags, uint32_t *gate, cudaStream_t st,
+                          const uint64_t *list_pos, const uint32_t *list_cnt)
 {
     if (B == 0 || N == 0) return;
     if (gate) LGPU_CUDA(cudaMemsetAsync(gate, 0, 4, st));
@@ -402,8 +414,11 @@ void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, c
 #define LGPU_CF(V) do { \
         const size_t smem = smem0 + ((V) >= 64 ? (size_t)(V) * CF_THREADS * 4 : 0); \
         if (smem > 48 * 1024) LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate); \
+        coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate, list_pos, list_cnt); \
     } while (0)
+    if ((list_pos == nullptr) != (list_cnt == nullptr) || (list_pos && N != ld)) {
+        set_error("internal: coarse_finish list mode needs positions, counts and N == list capacity"); throw Failure{LGPU_RUNTIME};
+    }
     const bool staged = (ld & 3u) == 0 && ld >= N;                  // cp.async needs 16-byte rows
     if (staged && N <= 4 * CF_THREADS) LGPU_CF(4);
     else if (staged && N <= 16 * CF_THREADS) LGPU_CF(16);

@@ -112,12 +112,17 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
 // N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t G_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GN >> 3) << 17) | ((uint32_t)(GM >> 4) << 24);
 
+// LIST: the filtering epilogue for DENSE hit rates (coarse step at many lists), see the epilogue; a separate
+// instantiation so that the dense / sparse-filter kernel of the flat path and of the small coarse problems is
+// unchanged (staging |x|^2 through shared memory and the per-tile barrier cost the flat C4 launch 15 %).
+template <bool LIST>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_x,
                  const float *__restrict__ xnorm2, float *__restrict__ out, uint64_t ld_out, uint32_t B, uint64_t N,
                  uint32_t num_kb, GemmFilter flt)
 {
     extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(16) float s_xn[LIST ? 2 : 1][LIST ? GN : 4];  // LIST: |x|^2 of the current tile's columns, per accumulator
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // SWIZZLE_128B needs 1024 B alignment
     const uint32_t smem_a = base, smem_b = base + GSTAGES * A_STAGE_BYTES;
     const uint32_t bars = base + G_SMEM_TILES;
@@ -193,11 +198,93 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint32_t acc = it & 1, acc_phase = (it >> 1) & 1;
             const uint32_t m_tile = (uint32_t)(t % num_m);
             const uint64_t n_tile = t / num_m;
+            const uint64_t x0 = n_tile * GN;
+            if constexpr (LIST) {
+                // |x|^2 of the tile's 256 columns -> shared memory while the MMAs of the tile still run (read from global
+                // memory chunk by chunk, each chunk exposed an L2 round trip behind its TMEM load).  Columns past N read
+                // as 0 and are masked where it matters.  The barrier also keeps a warp from overwriting the buffer of tile
+                // i + 2 while another still reads tile i's.
+                const int et = (int)threadIdx.x - 64;                    // 0..127 among the epilogue threads
+                s_xn[acc][et] = x0 + et < N ? __ldg(xnorm2 + x0 + et) : 0.f;
+                s_xn[acc][et + 128] = x0 + et + 128 < N ? __ldg(xnorm2 + x0 + et + 128) : 0.f;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t q = m_tile * GM + quad * 32 + lane;
-            const uint64_t x0 = n_tile * GN;
             float *orow = out + (size_t)q * ld_out;
+#define LGPU_TMEM_LD32(r, taddr)                                                                                        \
+    asm volatile(                                                                                                       \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                       \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                       \
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),               \
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),         \
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),       \
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])        \
+        : "r"(taddr));                                                                                                  \
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory")
+            [[maybe_unused]] const float *xn_s = s_xn[LIST ? acc : 0];
+            if constexpr (LIST) {
+                // Filtering epilogue for DENSE hit rates (the coarse step's lists: ~1.5 % of the columns pass, so nearly
+                // every 32-column chunk holds one).  One returning atomic per hit, as in the sparse form below, made this
+                // launch 3.5x slower than writing the dense matrix.  Two passes over the accumulator, which stays in
+                // TMEM until it is released: (1) hit masks of the tile's 8 chunks + their count, ONE atomicAdd per
+                // (query, tile) reserves the slots; (2) the chunks that hold hits are loaded again and their (column,
+                // score) pairs stored.  tcgen05.ld is warp-collective, so pass 2 re-loads a chunk when ANY lane has a hit.
+                const bool live = q < B;
+                const float thr = live ? flt.thr[q] : 0.f;
+                uint32_t tot = 0, slot = 0;
+                // ROLLED loops, one chunk body run 2 x 8 times: fully unrolled (masks kept in registers between the
+                // passes) the kernel grew to 17 k instructions and stalled on instruction fetch (ncu: no_inst) -- 3x
+                // slower than writing the dense matrix.  Pass 1 recomputes nothing it can keep: only the count.
+#pragma unroll 1
+                for (int pass = 0; pass < 2; pass++) {
+                    if (pass == 1) {
+                        if (!__any_sync(0xffffffffu, tot != 0u)) break;
+                        if (tot) slot = atomicAdd(flt.count + q, tot);
+                    }
+#pragma unroll 1
+                    for (int c = 0; c < GN / 32; c++) {
+                        uint32_t r[32];
+                        const uint32_t taddr = tmem_base + acc * GN + c * 32 + ((uint32_t)(quad * 32) << 16);
+                        LGPU_TMEM_LD32(r, taddr);
+                        const uint64_t xb = x0 + (uint64_t)c * 32;
+                        unsigned hit = 0;
+                        if (live && xb + 32 <= N) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 xn = *reinterpret_cast<const float4 *>(xn_s + c * 32 + j);
+                                hit |= (xn.x - 2.0f * __uint_as_float(r[j]) <= thr ? 1u : 0u) << j;
+                                hit |= (xn.y - 2.0f * __uint_as_float(r[j + 1]) <= thr ? 1u : 0u) << (j + 1);
+                                hit |= (xn.z - 2.0f * __uint_as_float(r[j + 2]) <= thr ? 1u : 0u) << (j + 2);
+                                hit |= (xn.w - 2.0f * __uint_as_float(r[j + 3]) <= thr ? 1u : 0u) << (j + 3);
+                            }
+                        } else if (live) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++)
+                                if (xb + j < N && xn_s[c * 32 + j] - 2.0f * __uint_as_float(r[j]) <= thr) hit |= 1u << j;
+                        }
+                        if (pass == 0) {
+                            tot += __popc(hit);
+                        } else if (hit) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) {
+                                if ((hit >> j) & 1u) {
+                                    if (slot < flt.cap) {
+                                        flt.cand_pos[(size_t)q * flt.cap + slot] = xb + j;
+                                        flt.cand_s[(size_t)q * flt.cap + slot] = xn_s[c * 32 + j] - 2.0f * __uint_as_float(r[j]);
+                                    }
+                                    slot++;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(tempty_bar + 8 * acc);
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < GN; c0 += 32) {
                 uint32_t r[32];
@@ -221,7 +308,7 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         const uint32_t slot = atomicAdd(flt.count + q, 1u);
                         if (slot < flt.cap) {
                             flt.cand_pos[(size_t)q * flt.cap + slot] = x;
-                            flt.cand_ids[(size_t)q * flt.cap + slot] = flt.col_ids ? flt.col_ids[x] : x;
+                            if (flt.cand_ids) flt.cand_ids[(size_t)q * flt.cap + slot] = flt.col_ids ? flt.col_ids[x] : x;
                         }
                     };
                     if (xb + 32 <= N) {
@@ -367,6 +454,64 @@ __global__ void sample_threshold_kernel(const float *__restrict__ approx, const 
     }
     thr[q] = t;
 }
+// The same threshold straight from the dense sample scores D[B][ld] (ns columns), one warp per query: the k-th smallest
+// by counting bisection over the lane's register copy of the row (no ids, no sorted output -- a top-k select over
+// 8192 x 2048 scores took 0.21 ms), stopped when the bracket is a quarter of the band it feeds; any hi with
+// count(S <= hi) >= k is a valid bound.  NaN scores never count.  ns <= 32 * VPL.
+template <int VPL>
+__global__ void __launch_bounds__(128) sample_kth_threshold_kernel(const float *__restrict__ D, uint64_t ld, uint32_t ns,
+                                                                  const float *__restrict__ qnorm2, float xmax, uint32_t d,
+                                                                  uint32_t B, uint32_t k, float *__restrict__ thr)
+{
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= B) return;
+    const float *row = D + (size_t)q * ld;
+    // global -> shared with cp.async (all of a lane's requests in flight), then shared -> registers: plain register
+    // loads come out of ptxas as load -> use -> load, one DRAM round trip after the other (see coarse_finish_kernel)
+    __shared__ __align__(16) float s_rows[4][VPL * 32];
+    float *srow = s_rows[threadIdx.x >> 5];
+    {
+        const uint32_t sb = (uint32_t)__cvta_generic_to_shared(srow);
+        for (uint32_t i = (uint32_t)lane * 4; i < ld && i < (uint32_t)VPL * 32; i += 128)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + i * 4), "l"(row + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+    }
+    float v[VPL];
+#pragma unroll
+    for (int j = 0; j < VPL; j++) v[j] = srow[min((uint32_t)j * 32 + lane, ns - 1)];
+    float lo = __int_as_float(0x7f800000), hi = -lo;
+    uint32_t nv = 0;
+#pragma unroll
+    for (int j = 0; j < VPL; j++) {
+        if ((uint32_t)j * 32 + lane >= ns) v[j] = __int_as_float(0x7fc00000);
+        if (v[j] == v[j]) { lo = fminf(lo, v[j]); hi = fmaxf(hi, v[j]); nv++; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    nv = __reduce_add_sync(0xffffffffu, nv);
+    float t = __int_as_float(0x7f800000);
+    if (nv >= k && hi < __int_as_float(0x7f800000) && lo > -__int_as_float(0x7f800000)) {
+        const float qn = sqrtf(qnorm2[q]);
+        const float s = qn + xmax;
+        const float E = 0.0078125f * 1.00390625f * qn * xmax + 4.0f * (float)d * 5.9604645e-8f * s * s;
+        for (int it = 0; it < 24 && hi - lo > 0.25f * E; it++) {        // invariant: count(S <= hi) >= k
+            const float mid = 0.5f * lo + 0.5f * hi;
+            uint32_t c = 0;
+#pragma unroll
+            for (int j = 0; j < VPL; j++) c += v[j] <= mid ? 1u : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (c >= k) hi = mid; else lo = mid;
+        }
+        t = hi + 2.0f * E;
+    }
+    if (lane == 0) thr[q] = t;
+}
+
 __global__ void overflow_flags_kernel(const uint32_t *__restrict__ count, uint32_t cap, uint32_t B, uint32_t *__restrict__ flags)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -381,6 +526,19 @@ void launch_sample_threshold(const float *approx, const uint32_t *cnt, const flo
     if (B == 0) return;
     sample_threshold_kernel<<<(B + 127) / 128, 128, 0, st>>>(approx, cnt, qnorm2, xmax, d, B, k, thr); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
+}
+
+bool launch_sample_kth_threshold(const float *D, uint64_t ld, uint32_t ns, const float *qnorm2, float xmax, uint32_t d,
+                                 uint32_t B, uint32_t k, float *thr, cudaStream_t st)
+{
+    if (B == 0) return true;
+    if (ns == 0 || ns > 2048 || (ld & 3) || ld < ns) return false;       // caller falls back to select + threshold
+    const unsigned grid = (B + 3) / 4;
+    if (ns <= 1024) sample_kth_threshold_kernel<32><<<grid, 128, 0, st>>>(D, ld, ns, qnorm2, xmax, d, B, k, thr);
+    else sample_kth_threshold_kernel<64><<<grid, 128, 0, st>>>(D, ld, ns, qnorm2, xmax, d, B, k, thr);
+    LGPU_COUNT_LAUNCH();
+    LGPU_CUDA(cudaGetLastError());
+    return true;
 }
 
 void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint32_t *flags, cudaStream_t st)
@@ -442,12 +600,14 @@ void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint3
     LGPU_REQUIRE(gemm_shape_supported(d), "tensor-core path needs a dimension that is a multiple of 8");
     CUtensorMap mq = make_map(Qb, B, d, GM);
     CUtensorMap mx = make_map(Xb, N, d, GN);
-    LGPU_CUDA(cudaFuncSetAttribute(gemm_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
     const uint64_t tiles = (uint64_t)((B + GM - 1) / GM) * ((N + GN - 1) / GN);
     const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)num_sms);
     GemmFilter flt{};
     if (filter) flt = *filter;
-    gemm_dist_kernel<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK, flt); LGPU_COUNT_LAUNCH();
+    const bool list = flt.thr && flt.cand_s;                  // dense hit rates: two-pass list epilogue
+    auto kern = list ? gemm_dist_kernel<true> : gemm_dist_kernel<false>;
+    LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
+    kern<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK, flt); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -20,31 +20,52 @@ __device__ __forceinline__ uint64_t pad4(uint64_t n) { return (n + 3) & ~3ull; }
 __global__ void group_count_kernel(GroupArgs a, int first)
 {
     if (a.gate && *a.gate == 0) return;
-    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.B) return;
-    const bool take = !a.only || a.only[q];             // fix-up pass: only flagged queries get tiles
     if (first) {
+        const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+        if (q >= a.B) return;
+        const bool take = !a.only || a.only[q];         // fix-up pass: only flagged queries get tiles
         const uint32_t slot = q * a.nprobes;
         const uint64_t pp = a.probes[slot];
         a.slot_pos[slot] = (take && pp < a.nlist) ? atomicAdd(&a.part_cnt[(uint32_t)pp], 1u) : 0xffffffffu;
         return;
     }
+    // a warp per query, a lane per probe (32 at a time): the loads and atomics of a query's probes are in flight
+    // together (one thread per query walked them one after the other: 20 dependent round trips, 14 us at C2), and the
+    // segment offsets come from a warp scan
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= a.B) return;
+    const bool take = !a.only || a.only[q];
     uint64_t off = 0, rows = 0;
-    for (uint32_t j = 0; j < a.nprobes; j++) {
-        uint32_t slot = q * a.nprobes + j;
+    for (uint32_t j0 = 0; j0 < a.nprobes; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool in = j < a.nprobes;
+        const uint32_t slot = q * a.nprobes + (in ? j : 0u);
         // a query with fewer than nprobes finite centroid distances (NaN / Inf input, zero cosine query)
         // leaves UINT64_MAX in its unused probe slots: those behave as empty partitions
-        const uint64_t pp = a.probes[slot];
+        const uint64_t pp = in ? a.probes[slot] : UINT64_MAX;
         const bool valid = pp < a.nlist;
-        uint32_t p = valid ? (uint32_t)pp : 0u;
-        uint32_t n = valid ? a.part_n[p] : 0u;
-        if (j > 0) a.slot_pos[slot] = (take && valid) ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
-        a.seg_local[slot] = off;
-        off += pad4(n);
-        rows += n;
+        const uint32_t p = valid ? (uint32_t)pp : 0u;
+        const uint32_t n = valid ? a.part_n[p] : 0u;
+        if (in && j > 0) a.slot_pos[slot] = (take && valid) ? atomicAdd(&a.part_cnt[p], 1u) : 0xffffffffu;
+        const uint64_t mine = pad4(n);
+        uint64_t pre = mine;                                // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += t;
+        }
+        if (in) a.seg_local[slot] = off + pre - mine;
+        off += __shfl_sync(0xffffffffu, pre, 31);
+        uint64_t r = n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+        rows += r;
     }
-    a.qtot[q] = off;
-    if (!a.only) atomicAdd(a.scanned_rows, (unsigned long long)rows);
+    if (lane == 0) {
+        a.qtot[q] = off;
+        if (!a.only) atomicAdd(a.scanned_rows, (unsigned long long)rows);
+    }
 }
 
 // single CTA: exclusive scans over queries (segment bases) and partitions (query-list and tile offsets).  Every thread
@@ -57,17 +78,31 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint32_t n, uint64_t *s
     const uint32_t b = min(n, (uint32_t)tid * per), e = min(n, b + per);
     uint64_t sum = 0;
     for (uint32_t i = b; i < e; i++) sum += get(i);
-    s_part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        const uint64_t t = tid >= o ? s_part[tid - o] : 0;
-        __syncthreads();
-        s_part[tid] += t;
-        __syncthreads();
+    // warp scan by shuffles, then the 32 warp totals by warp 0: three barriers per array (the shared-memory
+    // Hillis-Steele form took twenty)
+    const int lane = tid & 31, w = tid >> 5;
+    uint64_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    uint64_t run = s_part[tid] - sum;
+    if (lane == 31) s_part[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint64_t v = s_part[lane], wi = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        s_part[32 + lane] = wi - v;                        // exclusive prefix of the warp totals
+        if (lane == 31) s_part[64] = wi;                    // grand total
+    }
+    __syncthreads();
+    uint64_t run = s_part[32 + w] + inc - sum;
     for (uint32_t i = b; i < e; i++) { const uint64_t v = get(i); put(i, run); run += v; }
-    const uint64_t total = s_part[1023];
+    const uint64_t total = s_part[64];
     __syncthreads();
     return total;
 }
@@ -164,7 +199,7 @@ void launch_group(const GroupArgs &a, cudaStream_t st)
     LGPU_CUDA(cudaMemsetAsync(a.part_cnt, 0, sizeof(uint32_t) * a.nlist, st));
     if (!a.only) LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
     group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a, 1); LGPU_COUNT_LAUNCH();
-    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a, 0); LGPU_COUNT_LAUNCH();
+    group_count_kernel<<<(a.B + 3) / 4, 128, 0, st>>>(a, 0); LGPU_COUNT_LAUNCH();       // a warp per query
     group_scan_kernel<<<1, 1024, 0, st>>>(a); LGPU_COUNT_LAUNCH();
     uint32_t slots = a.B * a.nprobes;
     group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a); LGPU_COUNT_LAUNCH();

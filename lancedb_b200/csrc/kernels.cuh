@@ -136,7 +136,10 @@ void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, 
 // the candidate band overflowed and the caller must redo the query with the exact kernels
 void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, const float *Q, const float *C,
                           const float *qn2, float xmax, uint32_t d, uint32_t k, uint64_t *out_ids, float *out_dist,
-                          uint32_t *out_cnt, uint32_t *flags, uint32_t *gate, cudaStream_t st);
+                          uint32_t *out_cnt, uint32_t *flags, uint32_t *gate, cudaStream_t st,
+                          const uint64_t *list_pos = nullptr, const uint32_t *list_cnt = nullptr);
+// list mode (list_pos / list_cnt given, N == ld == the list capacity): S[q] holds the list_cnt[q] scores the GEMM's
+// filtering epilogue admitted for query q and list_pos[q] their columns; a list longer than its capacity flags the query
 // row norms |x| = sqrt(dot(x,x)) in lance order; out[n]
 void launch_row_norms(const float *X, uint64_t n, uint32_t d, float *out, cudaStream_t st);
 // out[q] = x[q] / |x[q]|
@@ -213,6 +216,7 @@ struct GemmFilter {
     uint64_t *cand_ids;           // [B][cap] its id (col_ids[x] or x)
     const uint64_t *col_ids;      // optional
     uint32_t cap;
+    float *cand_s;                // optional [B][cap]: the admitted score itself (coarse step: second-level threshold)
 };
 void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint32_t B, uint64_t N, uint32_t d,
                       float *out, uint64_t ld_out, int num_sms, cudaStream_t st, const GemmFilter *filter = nullptr);
@@ -220,6 +224,9 @@ void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint3
 void launch_filter_dense(const float *D, uint64_t ld, uint32_t B, uint64_t N, const GemmFilter &flt, cudaStream_t st);
 void launch_sample_threshold(const float *approx, const uint32_t *cnt, const float *qnorm2, float xmax, uint32_t d,
                              uint32_t B, uint32_t k, float *thr, cudaStream_t st);
+// the same threshold straight from dense sample scores D[B][ld] (ns <= 4096 columns; false = shape not handled)
+bool launch_sample_kth_threshold(const float *D, uint64_t ld, uint32_t ns, const float *qnorm2, float xmax, uint32_t d,
+                                 uint32_t B, uint32_t k, float *thr, cudaStream_t st);
 void launch_overflow_flags(const uint32_t *count, uint32_t cap, uint32_t B, uint32_t *flags, cudaStream_t st);
 // flags[q] = 1 when the approximate shortlist of query q cannot be proven to contain the exact top-k:
 // approx[q][0..kp) ascending, cnt[q] entries valid; proven iff cnt < kp or approx[kp-1] > approx[k-1] + 2E_q,

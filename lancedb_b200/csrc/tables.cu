@@ -422,7 +422,14 @@ __device__ __forceinline__ float exact_pq_distance_warp(const float *qv, const f
     for (int it = 0; it < 16; it++) {
         if ((uint32_t)it * 32 < m) {
             const uint32_t lim = min(32u, m - (uint32_t)it * 32);
-            for (uint32_t l = 0; l < lim; l++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, tv[it], (int)l));
+            if (lim == 32u) {
+                // full group: unrolled, so the 32 shuffles issue back to back ahead of the dependent adds (rolled, every
+                // add waited for its own shuffle: ~30 cycles x m per row, a third of the re-score kernel at k = 100)
+#pragma unroll
+                for (int l = 0; l < 32; l++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, tv[it], l));
+            } else {
+                for (uint32_t l = 0; l < lim; l++) acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, tv[it], (int)l));
+            }
         }
     }
     if (metric == LGPU_COSINE) acc = __fmul_rn(acc, 0.5f);

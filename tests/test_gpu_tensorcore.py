@@ -77,6 +77,33 @@ def test_coarse_filtered_path_large_nlist(monkeypatch):
         assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
     gpu.close()
 
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_coarse_sampled_list_path(metric, monkeypatch):
+    """Many lists (default from nlist 8192, here forced at 4200): dense scores of every 8th centroid give a per-query
+    bound, the full GEMM's filtering epilogue appends (column, score) of the columns under it to a list, and the
+    finishing kernel works on the list.  Probe sets -- hence results -- must equal the oracle's, including for queries
+    that sit ON a centroid (distance 0, ties in the band) and with clustered centroids (a loose sample bound)."""
+    monkeypatch.setenv("LGPU_FORCE_TC_COARSE", "1")
+    monkeypatch.setenv("LGPU_COARSE_LIST_MIN", "1024")
+    rng = np.random.default_rng(19)
+    sizes = np.full(4200, 3, np.int64); sizes[::5] = 0
+    ix = random_index(rng, dim=64, nlist=4200, m=8, metric=metric, sizes=sizes)
+    # the first 600 centroids in one tight cluster (consecutive ids, like a hierarchical trainer leaves them)
+    ix.centroids[:600] = ix.centroids[0] + 0.01 * rng.standard_normal((600, 64)).astype(np.float32)
+    if metric == "cosine":
+        ix.centroids /= np.linalg.norm(ix.centroids, axis=1, keepdims=True)
+    q = queries(rng, 48, 64)
+    q[:6] = ix.centroids[[5, 100, 599, 700, 2000, 4199]]
+    q[6:9] = ix.centroids[3] * np.float32(1.0001)
+    gpu = _native.GpuIvfPq(ix)
+    orc = oracle.OracleIndex.from_data(ix)
+    for nprobes in (1, 20, 50):
+        gi, gd, gc = gpu.search(q, k=10, nprobes=nprobes)
+        oi, od, oc = orc.search(q, k=10, nprobes=nprobes, nthreads=8)
+        assert np.array_equal(gc, oc) and np.array_equal(gi, oi), nprobes
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    gpu.close()
+
 
 def test_coarse_default_path_c2_shape():
     """B x nlist >= 1M with nlist >= 1024 (BASELINE config 2's coarse shape) takes the tensor-core
