@@ -37,6 +37,13 @@ void set_error(const std::string &msg) { g_err = msg; }
 static std::atomic<uint64_t> g_kernel_launches{0};
 static thread_local bool g_capturing = false;        // launches made while capturing are counted per replay instead
 static thread_local uint64_t g_captured_launches = 0;
+bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("LGPU_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
+
 void count_launches(uint64_t n)
 {
     if (g_capturing) g_captured_launches += n;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 
 #include "../../include/lancedb_b200.h"
 
@@ -32,6 +33,34 @@ struct Failure { int status; };
 // kernels launched by this process through the library (bench.py reports the count of its timed region)
 void count_launches(uint64_t n);
 #define LGPU_COUNT_LAUNCH() ::lgpu::count_launches(1)
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------
+// A search step is ~25 launches, most of them a few microseconds long, and every kernel boundary costs a drain + launch
+// gap of 2-4 us (about 50 us of BASELINE config 2's 0.66 ms step).  launch_k() launches with the programmatic-stream-
+// serialization attribute and the kernels it is used for begin with pdl_entry(): they tell the scheduler that the NEXT
+// grid may be brought onto the SMs already, then wait until the PREVIOUS grid has completed and flushed before touching
+// memory.  Correctness needs nothing else: every kernel waits for its predecessor, which waited for its own.
+// LGPU_NO_PDL=1 launches without the attribute (the device-side wait is then a no-op).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_entry()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    if (e != cudaSuccess) { set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); throw Failure{LGPU_RUNTIME}; }
+}
+#endif
 
 static inline uint32_t ceil_div(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static inline uint64_t round_up64(uint64_t a, uint64_t b) { return (a + b - 1) / b * b; }

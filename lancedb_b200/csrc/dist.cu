@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(DM_THREADS) dist_matrix_kernel(
     const float *__restrict__ xnorm, const float *__restrict__ ysqrt, float *__restrict__ D, uint64_t ldD,
     const uint32_t *__restrict__ only, const uint32_t *__restrict__ gate)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     if (gate && *gate == 0) return;              // fix-up pass with nothing flagged
     if (only) {                                  // fix-up pass: skip query tiles with no flagged query
         bool any = false;
@@ -195,6 +196,7 @@ __global__ void row_norms_kernel(const float *__restrict__ X, uint64_t n, uint32
 
 __global__ void normalize_kernel(const float *__restrict__ X, uint32_t B, uint32_t d, float *__restrict__ out)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
     const unsigned hmask = 0xffffu << hbase;
@@ -208,6 +210,7 @@ __global__ void pair_distance_kernel(const float *__restrict__ Q, const float *_
                                      const uint64_t *__restrict__ pos, uint32_t B, uint32_t nc, uint32_t d,
                                      int metric, float *__restrict__ out)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const int lane = threadIdx.x & 31, hl = lane & 15, hbase = lane & 16;
     const unsigned hmask = 0xffffu << hbase;
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(CF_THREADS) coarse_finish_kernel(const float *
                                                                    const uint64_t *__restrict__ list_pos,
                                                                    const uint32_t *__restrict__ list_cnt)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     // long rows only are staged through shared memory: at VPT 4 / 16 the few register loads are cheaper than the
     // extra barrier (measured: C2 and C3 coarse steps 4 % slower with staging, C5's 35 % faster)
     constexpr bool STAGED = VPT >= 64;
@@ -414,7 +418,7 @@ void launch_coarse_finish(const float *S, uint64_t ld, uint32_t B, uint32_t N, c
 #define LGPU_CF(V) do { \
         const size_t smem = smem0 + ((V) >= 64 ? (size_t)(V) * CF_THREADS * 4 : 0); \
         if (smem > 48 * 1024) LGPU_CUDA(cudaFuncSetAttribute(coarse_finish_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        coarse_finish_kernel<V><<<B, CF_THREADS, smem, st>>>(S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate, list_pos, list_cnt); \
+        launch_k(coarse_finish_kernel<V>, dim3(B), dim3(CF_THREADS), smem, st, S, ld, N, Q, C, qn2, xmax, d, k, cap, out_ids, out_dist, out_cnt, flags, gate, list_pos, list_cnt); \
     } while (0)
     if ((list_pos == nullptr) != (list_cnt == nullptr) || (list_pos && N != ld)) {
         set_error("internal: coarse_finish list mode needs positions, counts and N == list capacity"); throw Failure{LGPU_RUNTIME};
@@ -437,7 +441,7 @@ void launch_dist_matrix(const float *Q, const float *C, uint32_t B, uint64_t N, 
     // the fix-up pass (`only`) is almost always a no-op: keep its CTA count small
     const uint64_t ct = (N + DM_C - 1) / DM_C;
     dim3 grid((unsigned)std::min<uint64_t>(ct, only ? 16 : ((uint64_t)1 << 30)), (B + DM_Q - 1) / DM_Q);
-    dist_matrix_kernel<<<grid, DM_THREADS, 0, st>>>(Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only, gate); LGPU_COUNT_LAUNCH();
+    launch_k(dist_matrix_kernel, grid, dim3(DM_THREADS), 0, st, Q, C, B, N, d, mode, xnorm, ysqrt, D, ldD, only, gate); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -453,7 +457,7 @@ void launch_normalize(const float *X, uint32_t B, uint32_t d, float *out, cudaSt
 {
     if (B == 0) return;
     uint64_t threads = (uint64_t)B * 16;
-    normalize_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, B, d, out); LGPU_COUNT_LAUNCH();
+    launch_k(normalize_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, X, B, d, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -462,7 +466,7 @@ void launch_pair_distance(const float *Q, const float *V, const uint64_t *pos, u
 {
     if (B == 0 || nc == 0) return;
     uint64_t threads = (uint64_t)B * nc * 16;
-    pair_distance_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Q, V, pos, B, nc, d, metric, out); LGPU_COUNT_LAUNCH();
+    launch_k(pair_distance_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, Q, V, pos, B, nc, d, metric, out); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

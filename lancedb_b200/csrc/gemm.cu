@@ -121,6 +121,7 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  const float *__restrict__ xnorm2, float *__restrict__ out, uint64_t ld_out, uint32_t B, uint64_t N,
                  uint32_t num_kb, GemmFilter flt)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(16) float s_xn[LIST ? 2 : 1][LIST ? GN : 4];  // LIST: |x|^2 of the current tile's columns, per accumulator
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;         // SWIZZLE_128B needs 1024 B alignment
@@ -365,6 +366,7 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 __global__ void to_bf16_norm_kernel(const float *__restrict__ X, uint64_t n, uint32_t d, __nv_bfloat16 *__restrict__ Xb,
                                     float *__restrict__ norm2)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint64_t row = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
@@ -463,6 +465,7 @@ __global__ void __launch_bounds__(128) sample_kth_threshold_kernel(const float *
                                                                   const float *__restrict__ qnorm2, float xmax, uint32_t d,
                                                                   uint32_t B, uint32_t k, float *__restrict__ thr)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= B) return;
@@ -534,8 +537,8 @@ bool launch_sample_kth_threshold(const float *D, uint64_t ld, uint32_t ns, const
     if (B == 0) return true;
     if (ns == 0 || ns > 2048 || (ld & 3) || ld < ns) return false;       // caller falls back to select + threshold
     const unsigned grid = (B + 3) / 4;
-    if (ns <= 1024) sample_kth_threshold_kernel<32><<<grid, 128, 0, st>>>(D, ld, ns, qnorm2, xmax, d, B, k, thr);
-    else sample_kth_threshold_kernel<64><<<grid, 128, 0, st>>>(D, ld, ns, qnorm2, xmax, d, B, k, thr);
+    if (ns <= 1024) launch_k(sample_kth_threshold_kernel<32>, dim3(grid), dim3(128), 0, st, D, ld, ns, qnorm2, xmax, d, B, k, thr);
+    else launch_k(sample_kth_threshold_kernel<64>, dim3(grid), dim3(128), 0, st, D, ld, ns, qnorm2, xmax, d, B, k, thr);
     LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
     return true;
@@ -562,7 +565,7 @@ void launch_to_bf16(const float *X, uint64_t n, uint32_t d, void *Xb, float *nor
 {
     if (n == 0) return;
     uint64_t threads = n * 32;
-    to_bf16_norm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, n, d, reinterpret_cast<__nv_bfloat16 *>(Xb), norm2); LGPU_COUNT_LAUNCH();
+    launch_k(to_bf16_norm_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, X, n, d, reinterpret_cast<__nv_bfloat16 *>(Xb), norm2); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -607,7 +610,7 @@ void launch_gemm_dist(const void *Qb, const void *Xb, const float *xnorm2, uint3
     const bool list = flt.thr && flt.cand_s;                  // dense hit rates: two-pass list epilogue
     auto kern = list ? gemm_dist_kernel<true> : gemm_dist_kernel<false>;
     LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM_BYTES));
-    kern<<<grid, G_THREADS, G_SMEM_BYTES, st>>>(mq, mx, xnorm2, out, ld_out, B, N, (d + GK - 1) / GK, flt); LGPU_COUNT_LAUNCH();
+    launch_k(kern, dim3(grid), dim3(G_THREADS), G_SMEM_BYTES, st, mq, mx, xnorm2, out, ld_out, B, N, (uint32_t)((d + GK - 1) / GK), flt); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

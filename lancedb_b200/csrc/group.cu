@@ -19,6 +19,7 @@ __device__ __forceinline__ uint64_t pad4(uint64_t n) { return (n + 3) & ~3ull; }
 // the filter scan's per-query thresholds settle on each query's best partition before the bulk of its tiles run.
 __global__ void group_count_kernel(GroupArgs a, int first)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     if (a.gate && *a.gate == 0) return;
     if (first) {
         const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +110,7 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint32_t n, uint64_t *s
 
 __global__ void group_scan_kernel(GroupArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     __shared__ uint64_t s_part[1024];
     const int tid = threadIdx.x;
     if (a.gate && *a.gate == 0) {                       // nothing flagged: no tiles for the exact kernel
@@ -143,6 +145,7 @@ __global__ void group_scan_kernel(GroupArgs a)
 
 __global__ void group_fill_kernel(GroupArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     if (a.gate && *a.gate == 0) return;
     uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= a.B * a.nprobes) return;
@@ -156,6 +159,7 @@ __global__ void group_fill_kernel(GroupArgs a)
 // Tiles are numbered partition-major.
 __global__ void tile_desc_kernel(GroupArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     if (a.gate && *a.gate == 0) return;
     const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t t = gid / SCAN_G, g = gid % SCAN_G;
@@ -198,14 +202,14 @@ void launch_group(const GroupArgs &a, cudaStream_t st)
     if (a.B == 0) return;
     LGPU_CUDA(cudaMemsetAsync(a.part_cnt, 0, sizeof(uint32_t) * a.nlist, st));
     if (!a.only) LGPU_CUDA(cudaMemsetAsync(a.scanned_rows, 0, sizeof(unsigned long long), st));
-    group_count_kernel<<<(a.B + 127) / 128, 128, 0, st>>>(a, 1); LGPU_COUNT_LAUNCH();
-    group_count_kernel<<<(a.B + 3) / 4, 128, 0, st>>>(a, 0); LGPU_COUNT_LAUNCH();       // a warp per query
-    group_scan_kernel<<<1, 1024, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+    launch_k(group_count_kernel, dim3((a.B + 127) / 128), dim3(128), 0, st, a, 1); LGPU_COUNT_LAUNCH();
+    launch_k(group_count_kernel, dim3((a.B + 3) / 4), dim3(128), 0, st, a, 0); LGPU_COUNT_LAUNCH();       // a warp per query
+    launch_k(group_scan_kernel, dim3(1), dim3(1024), 0, st, a); LGPU_COUNT_LAUNCH();
     uint32_t slots = a.B * a.nprobes;
-    group_fill_kernel<<<(slots + 255) / 256, 256, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+    launch_k(group_fill_kernel, dim3((slots + 255) / 256), dim3(256), 0, st, a); LGPU_COUNT_LAUNCH();
     if (a.tile_desc && a.max_tiles) {
         uint64_t threads = (uint64_t)a.max_tiles * SCAN_G;
-        tile_desc_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+        launch_k(tile_desc_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, st, a); LGPU_COUNT_LAUNCH();
     }
     LGPU_CUDA(cudaGetLastError());
 }

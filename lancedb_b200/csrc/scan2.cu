@@ -498,6 +498,7 @@ __device__ __forceinline__ void consumer_loop(const ScanArgs &a, int tid)
 template <int DSUB, bool DOT>
 __global__ void __launch_bounds__(S2_NT, 1) scan2_kernel(ScanArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x;
     if (a.gate && *a.gate == 0) return;
@@ -540,7 +541,7 @@ void launch2(const ScanArgs &a, int grid, cudaStream_t st)
     constexpr size_t smem = Smem<DSUB>::TOTAL;
     auto kern = scan2_kernel<DSUB, DOT>;
     LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, S2_NT, smem, st>>>(a); LGPU_COUNT_LAUNCH();
+    launch_k(kern, dim3(grid), dim3(S2_NT), smem, st, a); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 

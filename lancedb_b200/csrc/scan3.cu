@@ -491,6 +491,7 @@ __device__ __forceinline__ void scanner_loop(const ScanArgs &a, int tid)
 template <bool LIST>
 __global__ void __launch_bounds__(S3_NT, 2) scan3_kernel(ScanArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x;
     const uint32_t total = *a.total_tiles;
@@ -541,7 +542,7 @@ void launch_scan3(const ScanArgs &a, int grid, cudaStream_t st)
     const bool list = a.cand && a.topk > 32;
     auto kern = list ? scan3_kernel<true> : scan3_kernel<false>;
     LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S3_SMEM));
-    kern<<<2 * grid, S3_NT, S3_SMEM, st>>>(a); LGPU_COUNT_LAUNCH();   // two CTAs per SM
+    launch_k(kern, dim3(2 * grid), dim3(S3_NT), S3_SMEM, st, a); LGPU_COUNT_LAUNCH();   // two CTAs per SM
     LGPU_CUDA(cudaGetLastError());
 }
 

@@ -75,6 +75,7 @@ __device__ __forceinline__ void write_entry(const SelectArgs &a, size_t at, bool
 template <bool POS>
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(SelectArgs a, uint32_t cap, uint32_t trigger)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ __align__(16) unsigned char smem[];
     Stage st;
     st.ids = reinterpret_cast<uint64_t *>(smem);
@@ -257,6 +258,7 @@ constexpr int SELW_WARPS = SELW_WARPS_V;       // power of two
 template <bool POS, int NQ>
 __global__ void __launch_bounds__(SELW_WARPS * 32) select_warp_kernel(SelectArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     // NQ queue entries per lane: slot (i, lane) = i * 32 + lane, sorted ascending over slots; k <= 32 * NQ
     __shared__ uint32_t m_key[SELW_WARPS - 1][32 * NQ];
     __shared__ uint64_t m_id[SELW_WARPS - 1][32 * NQ];
@@ -467,7 +469,7 @@ void launch_select(const SelectArgs &a, cudaStream_t st)
     if (a.k <= 32) {
         const unsigned grid = a.B;
         const int nq = a.k <= 32 ? 1 : (a.k <= 64 ? 2 : 4);
-#define LGPU_SELW(P, N) select_warp_kernel<P, N><<<grid, SELW_WARPS * 32, 0, st>>>(a), LGPU_COUNT_LAUNCH()
+#define LGPU_SELW(P, N) launch_k(select_warp_kernel<P, N>, dim3(grid), dim3(SELW_WARPS * 32), 0, st, a), LGPU_COUNT_LAUNCH()
         if (a.out_pos) { if (nq == 1) LGPU_SELW(true, 1); else if (nq == 2) LGPU_SELW(true, 2); else LGPU_SELW(true, 4); }
         else { if (nq == 1) LGPU_SELW(false, 1); else if (nq == 2) LGPU_SELW(false, 2); else LGPU_SELW(false, 4); }
 #undef LGPU_SELW
@@ -481,10 +483,10 @@ void launch_select(const SelectArgs &a, cudaStream_t st)
     size_t smem = (size_t)cap * (pos ? 20 : 12);
     if (pos) {
         LGPU_CUDA(cudaFuncSetAttribute(select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        select_kernel<true><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger); LGPU_COUNT_LAUNCH();
+        launch_k(select_kernel<true>, dim3(a.B), dim3(SEL_THREADS), smem, st, a, cap, trigger); LGPU_COUNT_LAUNCH();
     } else {
         LGPU_CUDA(cudaFuncSetAttribute(select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        select_kernel<false><<<a.B, SEL_THREADS, smem, st>>>(a, cap, trigger); LGPU_COUNT_LAUNCH();
+        launch_k(select_kernel<false>, dim3(a.B), dim3(SEL_THREADS), smem, st, a, cap, trigger); LGPU_COUNT_LAUNCH();
     }
     LGPU_CUDA(cudaGetLastError());
 }

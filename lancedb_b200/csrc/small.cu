@@ -20,6 +20,7 @@ constexpr int SM_THREADS = 256;
 template <int DSUB, bool DOT>
 __global__ void __launch_bounds__(SM_THREADS) small_scan_kernel(SmallScanArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ __align__(16) unsigned char ssm[];
     float *lut = reinterpret_cast<float *>(ssm);                 // [m][256]
     float *res = lut + (size_t)a.m * 256;                        // [dim]
@@ -82,7 +83,7 @@ void launch_small_scan(const SmallScanArgs &a, uint32_t dsub, uint32_t slots, cu
         auto k0 = small_scan_kernel<D, false>; auto k1 = small_scan_kernel<D, true>;                            \
         auto kern = a.metric == LGPU_DOT ? k1 : k0;                                                             \
         LGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-        kern<<<slots, SM_THREADS, smem, st>>>(a); LGPU_COUNT_LAUNCH();                                          \
+        launch_k(kern, dim3(slots), dim3(SM_THREADS), smem, st, a); LGPU_COUNT_LAUNCH();                                          \
     } while (0)
     switch (dsub) {
     case 1: LGPU_SMALL(1); break;

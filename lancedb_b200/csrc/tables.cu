@@ -145,6 +145,7 @@ __global__ void __launch_bounds__(256) qtable_minmax_kernel(const float *__restr
                                                             const float *__restrict__ cb_n2, uint32_t B, uint32_t dim,
                                                             uint32_t m, uint32_t nch, float *__restrict__ mm)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ __align__(16) unsigned char qsm[];
     const uint32_t q0 = blockIdx.x * 32 + (threadIdx.x >> 5) * QT_NQ, ch = blockIdx.y;
     const int lane = threadIdx.x & 31, s = lane & 7, cq = lane >> 3;
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(256) qtable_quant_kernel(const float *__restri
                                                            float *__restrict__ base_out, float *__restrict__ sbound_out,
                                                            uint32_t *__restrict__ bad_out)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     extern __shared__ __align__(16) unsigned char qsm[];
     const int wid = threadIdx.x >> 5;
     const uint32_t q0 = blockIdx.x * 32 + wid * QT_NQ, ch = blockIdx.y;
@@ -470,6 +472,7 @@ __global__ void cand_prepare_kernel(const float *__restrict__ step, const float 
                                     float *__restrict__ slack, uint32_t *__restrict__ thr, uint32_t *__restrict__ cand_cnt,
                                     uint32_t *__restrict__ cand_last)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= B) return;
     const float mag = sbound[q] + (amax ? amax[q] : 0.f) + (rmax_bits ? __int_as_float(*rmax_bits) : 0.f) + (float)m +
@@ -492,6 +495,7 @@ constexpr int FLT_THREADS = 128;
 template <int PER>                                           // candidates per lane: cand_cap <= 32 * PER
 __global__ void __launch_bounds__(FLT_THREADS) cand_filter_kernel(FinalizeArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint32_t q = (blockIdx.x * FLT_THREADS + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= a.B) return;
@@ -552,6 +556,7 @@ constexpr int RSC_THREADS = 256;
 template <int DSUB>
 __global__ void __launch_bounds__(RSC_THREADS, 2) cand_rescore_kernel(FinalizeArgs a)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const int lane = threadIdx.x & 31;
     const uint32_t total = *a.work_cnt;
     const uint32_t nwarps = gridDim.x * (RSC_THREADS / 32);
@@ -575,6 +580,7 @@ __global__ void probe_terms_kernel(const float *__restrict__ probe_dist, const f
                                    uint32_t nprobes, uint32_t dim, float *__restrict__ probe_A,
                                    float *__restrict__ amax, float *__restrict__ qn2)
 {
+    pdl_entry();                                       // PDL: let the next grid in, wait for the previous one
     const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    // one warp per query
     const int lane = threadIdx.x & 31;
     if (q >= B) return;
@@ -671,8 +677,8 @@ void launch_query_tables_q16(const float *Q, const float *cb_tiled, const float 
         auto run = [&](auto k1, auto k2) {
             LGPU_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
             LGPU_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-            k1<<<grid, 256, s1, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
-            k2<<<grid, 256, s2, st>>>(Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
+            launch_k(k1, grid, dim3(256), s1, st, Q, cb_tiled, cb_n2, B, dim, m, nch, mm); LGPU_COUNT_LAUNCH();
+            launch_k(k2, grid, dim3(256), s2, st, Q, cb_tiled, cb_n2, B, dim, m, nch, mm, qt, step, base, sbound, bad); LGPU_COUNT_LAUNCH();
         };
         if (metric == LGPU_DOT) run(qtable_minmax_kernel<DS, true>, qtable_quant_kernel<DS, true>);
         else run(qtable_minmax_kernel<DS, false>, qtable_quant_kernel<DS, false>);
@@ -722,7 +728,7 @@ void launch_probe_terms(const float *probe_dist, const float *Q, uint32_t B, uin
                         float *probe_A, float *amax, float *qn2, cudaStream_t st)
 {
     if (B == 0) return;
-    probe_terms_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(probe_dist, Q, B, nprobes, dim, probe_A, amax, qn2); LGPU_COUNT_LAUNCH();
+    launch_k(probe_terms_kernel, dim3((B * 32 + 255) / 256), dim3(256), 0, st, probe_dist, Q, B, nprobes, dim, probe_A, amax, qn2); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -732,7 +738,7 @@ void launch_cand_prepare(const float *step, const float *sbound, const float *am
 {
     if (B == 0) return;
     LGPU_CUDA(cudaMemsetAsync(cand_key, 0xff, (size_t)B * cand_cap * 4, st));
-    cand_prepare_kernel<<<(B + 127) / 128, 128, 0, st>>>(step, sbound, amax, rmax_bits, qn2, cb2, scale, m, B, slack, thr, cand_cnt, cand_last); LGPU_COUNT_LAUNCH();
+    launch_k(cand_prepare_kernel, dim3((B + 127) / 128), dim3(128), 0, st, step, sbound, amax, rmax_bits, qn2, cb2, scale, m, B, slack, thr, cand_cnt, cand_last); LGPU_COUNT_LAUNCH();
     LGPU_CUDA(cudaGetLastError());
 }
 
@@ -745,11 +751,11 @@ void launch_cand_finalize(const FinalizeArgs &a, cudaStream_t st)
     }
     LGPU_CUDA(cudaMemsetAsync(a.work_cnt, 0, 8, st));       // survivor counter + fix-up gate
     const unsigned fgrid = (a.B * 32 + FLT_THREADS - 1) / FLT_THREADS;
-    if (a.cand_cap <= 512) { cand_filter_kernel<16><<<fgrid, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
-    else if (a.cand_cap <= 1024) { cand_filter_kernel<32><<<fgrid, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
-    else { cand_filter_kernel<64><<<fgrid, FLT_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH(); }
+    if (a.cand_cap <= 512) { launch_k(cand_filter_kernel<16>, dim3(fgrid), dim3(FLT_THREADS), 0, st, a); LGPU_COUNT_LAUNCH(); }
+    else if (a.cand_cap <= 1024) { launch_k(cand_filter_kernel<32>, dim3(fgrid), dim3(FLT_THREADS), 0, st, a); LGPU_COUNT_LAUNCH(); }
+    else { launch_k(cand_filter_kernel<64>, dim3(fgrid), dim3(FLT_THREADS), 0, st, a); LGPU_COUNT_LAUNCH(); }
     dispatch_dsub(a.dsub, [&](auto D) {
-        cand_rescore_kernel<decltype(D)::value><<<a.num_sms * 4, RSC_THREADS, 0, st>>>(a); LGPU_COUNT_LAUNCH();
+        launch_k(cand_rescore_kernel<decltype(D)::value>, dim3(a.num_sms * 4), dim3(RSC_THREADS), 0, st, a); LGPU_COUNT_LAUNCH();
     });
     SelectArgs sb{};
     sb.mode = 2; sb.dense = a.ex_dist; sb.cand_ids = a.ex_id; sb.cand_pos = a.ex_pos; sb.ncols_q = a.surv_cnt;
