@@ -104,6 +104,21 @@ def test_coarse_sampled_list_path(metric, monkeypatch):
         assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
     gpu.close()
 
+def test_coarse_sampled_list_path_default_switch():
+    """nlist 8192 with B x nlist >= 1M takes the sampled-bound + list-epilogue coarse step by default (no environment
+    switch): probe sets, hence ids and distance bits, equal the oracle's; empty partitions interleaved."""
+    rng = np.random.default_rng(29)
+    sizes = np.full(8192, 2, np.int64); sizes[::3] = 0
+    ix = random_index(rng, dim=64, nlist=8192, m=8, sizes=sizes)
+    q = queries(rng, 160, 64)
+    q[:4] = ix.centroids[[0, 8, 4097, 8191]]                     # on a sampled / unsampled centroid
+    gpu = _native.GpuIvfPq(ix)
+    gi, gd, gc = gpu.search(q, k=10, nprobes=20)
+    oi, od, oc = oracle.OracleIndex.from_data(ix).search(q, k=10, nprobes=20, nthreads=8)
+    gpu.close()
+    assert np.array_equal(gc, oc) and np.array_equal(gi, oi)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
 
 def test_coarse_default_path_c2_shape():
     """B x nlist >= 1M with nlist >= 1024 (BASELINE config 2's coarse shape) takes the tensor-core
