@@ -724,6 +724,7 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
     GroupArgs ga{};
     ga.probes = ws->probes.as<uint64_t>(); ga.B = B; ga.nprobes = nprobes; ga.nlist = nlist;
     ga.part_n = ix->part_n.as<uint32_t>(); ga.part_cnt = ws->part_cnt.as<uint32_t>();
+    ga.part_npad = ix->part_npad.as<uint32_t>(); ga.code_base = ix->code_base.as<uint64_t>(); ga.part_off = ix->part_off.as<uint64_t>();
     ga.slot_pos = ws->slot_pos.as<uint32_t>(); ga.seg_local = ws->seg_local.as<uint64_t>();
     ga.qtot = ws->qtot.as<uint64_t>(); ga.seg_off = ws->seg_off.as<uint64_t>();
     ga.qlist_off = ws->qlist_off.as<uint32_t>(); ga.tile_off = ws->tile_off.as<uint32_t>(); ga.tile_off_b = ws->tile_off_b.as<uint32_t>();
@@ -1189,6 +1190,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
                      "unsupported PQ sub-vector length (dim/num_sub_vectors must be 1,2,4,8,16 or 32)");
         LGPU_REQUIRE(d->centroids && d->codebook && d->part_offsets, "null index array");
         LGPU_REQUIRE(d->nrows == 0 || (d->codes && d->row_ids), "null codes / row_ids");
+        LGPU_REQUIRE(d->nrows < (1ull << 32), "more than 2^32 rows in one GPU shard are not supported (shard the index)");
         LGPU_REQUIRE(d->part_offsets[0] == 0 && d->part_offsets[d->nlist] == d->nrows,
                      "part_offsets must start at 0 and end at nrows");
         for (uint32_t p = 0; p < d->nlist; p++) {
@@ -1213,6 +1215,7 @@ int lgpu_index_open(const lgpu_index_desc *d, lgpu_index **out)
             part_n[p] = n; part_npad[p] = (n + 31u) & ~31u;
             code_base[p] = cb;
             cb += (uint64_t)(ix->nch + 1) * part_npad[p] * 8;
+            LGPU_REQUIRE((cb >> 3) < (1ull << 32), "index too large for one GPU shard (re-laid-out codes above 32 GiB)");
             pads[p] = (n + 3ull) & ~3ull;
         }
         ix->h_part_n = part_n;

@@ -199,6 +199,8 @@ __global__ void tile_desc_kernel(GroupArgs a)
     TileDesc *d = a.tile_desc + t;
     if (g == 0) {
         d->p = p; d->row0 = row0; d->nrows = row0 < n_p ? min(rbr, n_p - row0) : 0; d->ng = ng;
+        d->n_p = n_p; d->npad = a.part_npad[p];
+        d->code_base8 = (uint32_t)(a.code_base[p] >> 3); d->part_off32 = (uint32_t)a.part_off[p];
     }
     if (g < ng) {
         const uint32_t e = a.qlist[a.qlist_off[p] + grp * SCAN_G + g];

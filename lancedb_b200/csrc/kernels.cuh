@@ -22,15 +22,20 @@ __host__ __device__ __forceinline__ uint32_t scan_rb_rows(uint32_t n, uint32_t n
 }
 
 // One scan tile, precomputed by the regroup step (group.cu) so the persistent scan CTAs fetch a tile with a
-// single 112-byte read: partition p, rows [row0, row0+nrows), ng (1..8) queries q[] (probe slots slot[]) whose
+// single 128-byte read: partition p, rows [row0, row0+nrows), ng (1..8) queries q[] (probe slots slot[]) whose
 // distances go to dist_out + out[g].  ng == 0 marks "no tile" inside the kernel's shared-memory copy.
 struct alignas(16) TileDesc {
     uint32_t p, row0, nrows, ng;
     uint32_t q[SCAN_G];
     uint32_t slot[SCAN_G];        // probe slot (q * nprobes + j) of each query
     uint32_t out[SCAN_G];         // offset (floats) of the slot's distance segment; sub-batches keep it < 2^32
+    // the partition's constants, copied in by the regroup step: read from the shared-memory copy of the descriptor, a
+    // tile's first code-word load and its row-constant load go out at once instead of behind a dependent global read
+    uint32_t n_p, npad;           // rows / padded rows of partition p
+    uint32_t code_base8;          // code_base[p] / 8
+    uint32_t part_off32;          // part_off[p] (row position of the partition's first row)
 };
-static_assert(sizeof(TileDesc) == 112, "TileDesc layout");
+static_assert(sizeof(TileDesc) == 128, "TileDesc layout");
 
 // one surviving row of the filter scan's candidate mode
 struct alignas(16) CandRec {
@@ -105,6 +110,9 @@ struct GroupArgs {
     const uint64_t *probes;       // [B*nprobes] partition ids (u64 from the selector)
     uint32_t B, nprobes, nlist, rows_tile;
     const uint32_t *part_n;
+    const uint32_t *part_npad;    // (tile descriptors) padded rows per partition
+    const uint64_t *code_base;    // (tile descriptors) byte offset of each partition's code blocks, multiple of 8
+    const uint64_t *part_off;     // (tile descriptors) row position of each partition's first row, < 2^32
     uint32_t *part_cnt;           // [nlist] zeroed before
     uint32_t *slot_pos;           // [B*nprobes]
     uint64_t *seg_local;          // [B*nprobes] offset inside the query's block

@@ -258,8 +258,8 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
     const uint32_t p = T->p, row0 = T->row0, nrows = T->nrows;
     const int ng = (int)T->ng;
     const int sig = ct & 7;                               // this lane's skew (== row % 8)
-    const uint32_t n_p = a.part_n[p], npad = a.part_npad[p];
-    const uint2 *cs = reinterpret_cast<const uint2 *>(a.codes + a.code_base[p]);   // [nch+1][npad]
+    const uint32_t n_p = T->n_p, npad = T->npad;                                    // (copied into the descriptor)
+    const uint2 *cs = reinterpret_cast<const uint2 *>(a.codes + ((uint64_t)T->code_base8 << 3));   // [nch+1][npad]
 
     uint32_t acc[R][4];
     bool valid[R];
@@ -310,7 +310,7 @@ __device__ __forceinline__ int scan_tile(const ScanArgs &a, const TileDesc *T, b
 
     // ---- epilogue: lower bound L = step_q * sum + (base_q + A(q,p)) + R(row) per (row, query) ----
     const float scale = a.metric == LGPU_COSINE ? 0.5f : 1.0f;
-    const uint64_t pos0 = a.part_off[p];
+    const uint64_t pos0 = T->part_off32;
     float rr[R];
 #pragma unroll
     for (int r = 0; r < R; r++)
