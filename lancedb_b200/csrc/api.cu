@@ -797,6 +797,13 @@ void ivf_sub_batch(lgpu_index *ix, Workspace *ws, cudaStream_t st, const float *
         // candidate capacity per query (power of two >= k); LGPU_CAND_CAP shrinks it to exercise the overflow path
         const uint32_t cap_env = modes.cap_env;
         uint32_t cap = kk <= 32 ? 512 : (kk <= 64 ? 1024 : CAND_CAP_MAX);
+        {
+            // long partitions put more rows inside the band around the k-th distance (clustered data: a query near a
+            // big blob sees thousands of nearly equidistant rows): give them longer lists rather than the exact fix-up
+            const uint64_t rows_probe = std::max<uint64_t>(1, ix->pad_prefix[np_eff] / np_eff);   // mean of the np largest
+            if (rows_probe > 16384) cap = std::max<uint32_t>(cap, CAND_CAP_MAX);
+            else if (rows_probe > 4096) cap = std::max<uint32_t>(cap, 1024);
+        }
         bool cap_forced = false;
         if (cap_env >= 32 && cap_env <= CAND_CAP_MAX && !(cap_env & (cap_env - 1)) && cap_env >= kk) { cap = cap_env; cap_forced = true; }
         // A tile whose query has no threshold yet appends about k rows.  With few queries fanned out over many tiles
