@@ -11,7 +11,12 @@ toolchain), so this fixture is oracle output, not reference output: it freezes t
 (a change to oracle.c that alters any value fails `-m "not gpu"`), and the GPU tests check the CUDA path
 against the same committed bytes.  "IVF_PQ parity unpinned" (oracle/oracle.h) still applies.
 
-Run from the repo root:  python tests/golden/make_golden.py
+lance_ivfpq_small/ -- the cosine index of ivfpq_small.npz written as Lance index files (index.idx + auxiliary.idx)
+by lancedb_b200/lance_index.py's fixture writer.  The layout is RECALLED, not verified against a real Lance file
+(none exists in the reference tree): the fixture freezes the reader's and writer's bytes between rounds
+(tests/test_host_logic.py), nothing more.
+
+Run from the repo root:  python tests/golden/make_golden.py   (does not rewrite ivfpq_small.npz unless --all)
 """
 import json
 import os
@@ -39,7 +44,20 @@ PINS = {
 }
 
 
+def lance_fixture():
+    from lancedb_b200 import lance_index
+    from lancedb_b200.index import IvfPqIndexData
+    z = np.load(os.path.join(HERE, "ivfpq_small.npz"))
+    ix = IvfPqIndexData(32, 8, 4, "cosine", z["cosine_centroids"], z["cosine_codebook"], z["cosine_part_offsets"],
+                        z["cosine_codes_t"], z["cosine_row_ids"], None)
+    lance_index.write_ivf_pq_index(os.path.join(HERE, "lance_ivfpq_small"), ix, transposed=True, page_rows=256)
+
+
 def main():
+    if "--all" not in sys.argv:
+        lance_fixture()
+        print("wrote lance_ivfpq_small/ (pass --all to regenerate the oracle fixtures too)")
+        return
     import oracle
     from tests.util import queries, random_index
     with open(os.path.join(HERE, "reference_pins.json"), "w") as f:
@@ -65,6 +83,7 @@ def main():
         fi, fd, fc = oracle.flat_search(ix.vectors, q, k=7, metric=metric, row_ids=ix.row_ids)
         out[f"{metric}_flat_ids"], out[f"{metric}_flat_dist"], out[f"{metric}_flat_cnt"] = fi, fd, fc
     np.savez_compressed(os.path.join(HERE, "ivfpq_small.npz"), **out)
+    lance_fixture()
     print("wrote", sorted(os.listdir(HERE)))
 
 

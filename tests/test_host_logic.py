@@ -352,3 +352,23 @@ def test_lance_index_file_round_trip_and_rejections(tmp_path):
     tbl.mkdir(parents=True)
     L.write_ivf_pq_index(str(tbl), ix)
     assert L.find_index_dirs(str(tmp_path / "t.lance")) == [str(tbl)]
+
+
+def test_lance_index_golden_fixture(tmp_path):
+    """The committed Lance index files (tests/golden/lance_ivfpq_small, written by the fixture writer from the cosine
+    index of ivfpq_small.npz; layout recalled -- see lance_index.py) read back to exactly those arrays, and the
+    writer still produces the same bytes: a change of either side of the recalled layout shows up here."""
+    from lancedb_b200 import lance_index as L
+    from lancedb_b200.index import IvfPqIndexData
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "ivfpq_small.npz"))
+    got = L.read_ivf_pq_index(os.path.join(gold, "lance_ivfpq_small"))
+    got.validate()
+    assert got.metric == "cosine" and (got.dim, got.nlist, got.m) == (32, 8, 4)
+    for name in ("centroids", "codebook", "part_offsets", "codes_t", "row_ids"):
+        assert np.array_equal(getattr(got, name), z[f"cosine_{name}"]), name
+    ix = IvfPqIndexData(32, 8, 4, "cosine", z["cosine_centroids"], z["cosine_codebook"], z["cosine_part_offsets"],
+                        z["cosine_codes_t"], z["cosine_row_ids"], None)
+    L.write_ivf_pq_index(str(tmp_path / "again"), ix, transposed=True, page_rows=256)
+    for f in ("index.idx", "auxiliary.idx"):
+        assert open(tmp_path / "again" / f, "rb").read() == open(os.path.join(gold, "lance_ivfpq_small", f), "rb").read(), f
