@@ -19,6 +19,13 @@ for m in USETMAXREG "BAR.SYNC" "BAR.ARV" "LDS.128" "STS.128" PRMT IADD3 "LDG.E.1
 sass scan3.o | grep USETMAXREG
 sass scan3.o | grep -m 2 "LDS.128"; sass scan3.o | grep -m 2 "IADD3 R"; sass scan3.o | grep -m 2 "STS.128"
 echo
+echo "## scan3.o :: mbarrier FULL hand-over (SYNCS) and programmatic dependent launch (griddepcontrol.launch_dependents -> PREEXIT, griddepcontrol.wait -> ACQBULK)"
+for m in "SYNCS" "ACQBULK" "PREEXIT"; do echo "count $m = $(sass scan3.o | grep -c "$m")"; done
+sass scan3.o | grep -m 2 "SYNCS"
+echo
+echo "## dist.o / gemm.o :: cp.async staging of long score rows (LDGSTS), list epilogue kept in TMEM for two passes (LDTM count above)"
+echo "count LDGSTS (dist.o) = $(sass dist.o | grep -c LDGSTS)"; echo "count LDGSTS (gemm.o) = $(sass gemm.o | grep -c LDGSTS)"
+echo
 echo "## tables.o :: qtable_* (per-query tables): packed f32x2 FMA"
 echo "count FFMA2 = $(sass tables.o | grep -c FFMA2)"; sass tables.o | grep -m 2 FFMA2
 echo
