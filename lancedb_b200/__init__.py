@@ -8,9 +8,10 @@ the reference's builder surface plus a ctypes binding.  There is no CPU fallback
 from .index import IvfPqIndexData, train_ivf_pq, suggested_num_sub_vectors, suggested_num_partitions
 from .query import LanceVectorQueryBuilder, DEFAULT_TOP_K, DEFAULT_NPROBES
 from .table import DBConnection, Table, connect
+from .aio import AsyncConnection, AsyncTable, connect_async
 
 __all__ = [
-    "connect", "DBConnection", "Table", "LanceVectorQueryBuilder", "IvfPqIndexData", "train_ivf_pq",
+    "connect", "connect_async", "DBConnection", "AsyncConnection", "Table", "AsyncTable", "LanceVectorQueryBuilder", "IvfPqIndexData", "train_ivf_pq",
     "suggested_num_sub_vectors", "suggested_num_partitions", "DEFAULT_TOP_K", "DEFAULT_NPROBES",
 ]
 __version__ = "0.1.0"

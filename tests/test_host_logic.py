@@ -372,3 +372,74 @@ def test_lance_index_golden_fixture(tmp_path):
     L.write_ivf_pq_index(str(tmp_path / "again"), ix, transposed=True, page_rows=256)
     for f in ("index.idx", "auxiliary.idx"):
         assert open(tmp_path / "again" / f, "rb").read() == open(os.path.join(gold, "lance_ivfpq_small", f), "rb").read(), f
+
+
+# ---------------------------------------------------------------------------------------------- async surface
+def _stub_vector_search(monkeypatch):
+    """Route Table._vector_search to the CPU oracle's flat search so the async plumbing is testable without a GPU
+    (the GPU tests cover the same surface against the library)."""
+    import oracle
+    from lancedb_b200.table import Table
+
+    def fake(self, queries, *, column, k, nprobes, refine_factor, distance_type, lower, upper, use_index,
+             allow_mask=None, max_nprobes=0, timeout_ms=0):
+        assert nprobes > 0 and k > 0
+        x = self._vectors(column)
+        kw = {}
+        if allow_mask is not None:
+            kw = dict(allow=oracle.allow_bitmap(np.nonzero(allow_mask)[0].astype(np.uint64), len(allow_mask)),
+                      allow_bits=len(allow_mask))
+        return oracle.flat_search(x, queries, k=k, metric=distance_type or "l2", lower=lower, upper=upper, **kw)
+    monkeypatch.setattr(Table, "_vector_search", fake)
+
+
+def test_async_query_surface_matches_the_sync_builder(monkeypatch):
+    """python/python/lancedb/query.py:3307-3405, 3551-3723, 2867-2960: AsyncTable.query().nearest_to(...) with the
+    reference's setter names and defaults, multi-vector queries tagged with query_index, concurrent coroutines."""
+    import asyncio
+    from lancedb_b200 import aio
+    _stub_vector_search(monkeypatch)
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((300, 8)).astype(np.float32)
+    q = rng.standard_normal((6, 8)).astype(np.float32)
+
+    async def main():
+        db = await aio.connect_async("memory://")
+        t = await db.create_table("v", {"vector": x, "id": np.arange(300), "b": np.arange(300) % 7})
+        assert await t.count_rows() == 300 and await t.count_rows("b = 3") == len([i for i in range(300) if i % 7 == 3])
+        sync = t._table
+        one = await t.query().nearest_to(q[0]).to_arrow()
+        ref = sync.search(q[0]).to_arrow()
+        assert one.num_rows == 10 and one.equals(ref)                                  # default limit 10
+        assert "query_index" not in one.column_names
+        # every setter, against the sync builder with the same request
+        got = await (t.query().where("b < 5").nearest_to(q[1]).column("vector").distance_type("cosine").nprobes(7)
+                     .refine_factor(2).distance_range(0.0, 1.5).limit(4).offset(1).select(["id"]).with_row_id()
+                     .to_arrow())
+        want = (sync.search(q[1], vector_column_name="vector").where("b < 5").distance_type("cosine").nprobes(7)
+                .refine_factor(2).distance_range(0.0, 1.5).limit(4).offset(1).select(["id"]).with_row_id(True).to_arrow())
+        assert got.equals(want) and got.column_names == ["id", "_distance", "_rowid"]
+        post = await t.query().where("b = 2").postfilter().nearest_to(q[2]).limit(20).to_list()
+        assert all(r["b"] == 2 for r in post) and len(post) < 20                      # filters the 20 results
+        # several vectors: list form and add_query_vector give the same union, tagged with query_index
+        multi = await t.query().nearest_to([q[0], q[1], q[2]]).limit(3).to_arrow()
+        added = await t.vector_search(q[0]).add_query_vector(q[1]).add_query_vector(q[2]).limit(3).to_arrow()
+        assert multi.equals(added) and multi["query_index"].to_pylist() == [0] * 3 + [1] * 3 + [2] * 3
+        # concurrent coroutines (tokio workers in the reference, worker threads here)
+        outs = await asyncio.gather(*[t.vector_search(v).limit(5).to_arrow() for v in q])
+        for v, o in zip(q, outs):
+            assert o.equals(sync.search(v).limit(5).to_arrow())
+        reader = await t.vector_search(q[3]).limit(9).to_batches(max_batch_length=4)
+        sizes = [b.num_rows async for b in reader]
+        assert sizes == [4, 4, 1] and (await reader.read_all()).num_rows == 0
+        # plain scan (host side), and the builder's validation errors surface unchanged
+        scan = await t.query().where("b = 6").select(["id"]).limit(3).offset(1).to_list()
+        assert [r["id"] for r in scan] == [13, 20, 27]
+        with pytest.raises(ValueError, match="query_vector can not be None"):
+            t.query().nearest_to(None)
+        with pytest.raises(ValueError, match="minimum_nprobes must be greater than 0"):
+            await t.vector_search(q[0]).nprobes(0).to_arrow()
+        with pytest.raises(ValueError, match="No vector column found to match"):
+            await t.vector_search(np.zeros(5, np.float32)).to_arrow()
+        assert list(await db.table_names()) == ["v"]
+    asyncio.run(main())
