@@ -138,8 +138,10 @@ class AsyncVectorQuery(_AsyncQueryBase):
         self._vectors: List[np.ndarray] = [np.asarray(v, np.float32) for v in (q if multi else [q])]
         self._column: Optional[str] = None
         self._distance_type: Optional[str] = None
-        self._minimum_nprobes: Optional[int] = None
-        self._maximum_nprobes: Optional[int] = None
+        # the request's defaults (rust/lancedb/src/query.rs:1097-1113); the setters below validate EAGERLY against the
+        # current state like the Rust builder they call into (query.rs:1232-1275), so the order of calls matters
+        self._minimum_nprobes: int = 20
+        self._maximum_nprobes: Optional[int] = 20       # None = no limit
         self._lower: Optional[float] = None
         self._upper: Optional[float] = None
         self._refine_factor: Optional[int] = None
@@ -154,15 +156,26 @@ class AsyncVectorQuery(_AsyncQueryBase):
         return self
 
     def nprobes(self, nprobes: int):
-        self._minimum_nprobes = self._maximum_nprobes = nprobes
+        if nprobes <= 0:
+            raise ValueError("minimum_nprobes must be greater than 0")
+        self._minimum_nprobes = self._maximum_nprobes = int(nprobes)
         return self
 
     def minimum_nprobes(self, minimum_nprobes: int):
-        self._minimum_nprobes = minimum_nprobes
+        if minimum_nprobes <= 0:
+            raise ValueError("minimum_nprobes must be greater than 0")
+        if self._maximum_nprobes is not None and minimum_nprobes > self._maximum_nprobes:
+            raise ValueError("minimum_nprobes must be less than or equal to maximum_nprobes")
+        self._minimum_nprobes = int(minimum_nprobes)
         return self
 
     def maximum_nprobes(self, maximum_nprobes: int):
-        self._maximum_nprobes = maximum_nprobes
+        if maximum_nprobes == 0:                         # "no limit" (python/src/query.rs:949-954)
+            self._maximum_nprobes = None
+            return self
+        if maximum_nprobes < self._minimum_nprobes:
+            raise ValueError("maximum_nprobes must be greater than or equal to minimum_nprobes")
+        self._maximum_nprobes = int(maximum_nprobes)
         return self
 
     def distance_range(self, lower_bound: Optional[float] = None, upper_bound: Optional[float] = None):
@@ -192,10 +205,7 @@ class AsyncVectorQuery(_AsyncQueryBase):
         b = self._table.search(q, vector_column_name=self._column)
         if self._distance_type is not None:
             b.distance_type(self._distance_type)
-        if self._minimum_nprobes is not None:
-            b.minimum_nprobes(self._minimum_nprobes)
-        if self._maximum_nprobes is not None:
-            b.maximum_nprobes(self._maximum_nprobes)
+        b.minimum_nprobes(self._minimum_nprobes).maximum_nprobes(self._maximum_nprobes or 0)   # validated above
         if self._lower is not None or self._upper is not None:
             b.distance_range(self._lower, self._upper)
         if self._refine_factor is not None:

@@ -128,13 +128,19 @@ class LanceVectorQueryBuilder:
     def _resolve(self):
         lim = self._limit if self._limit is not None else DEFAULT_TOP_K
         k = lim + self._offset                          # table/query.rs:231
-        min_np = self._minimum_nprobes if self._minimum_nprobes is not None else DEFAULT_NPROBES
-        max_np = self._maximum_nprobes if self._maximum_nprobes is not None else (
-            min_np if self._minimum_nprobes is not None else DEFAULT_NPROBES)
+        # The request starts at minimum_nprobes = 20, maximum_nprobes = Some(20) (query.rs:1097-1113) and the sync builder
+        # is lowered onto it as python/python/lancedb/table.py:5777-5787 does: both set -> nprobes(min) then
+        # maximum_nprobes(max); one set -> that setter alone, validated against the OTHER one's default of 20
+        # (query.rs:1232-1275).  maximum_nprobes 0 means "no limit" (python/src/query.rs:949-954).
+        mn, mx = self._minimum_nprobes, self._maximum_nprobes
+        min_np = mn if mn is not None else DEFAULT_NPROBES
+        max_np = mx if mx is not None else DEFAULT_NPROBES
         if min_np <= 0:
             raise ValueError("minimum_nprobes must be greater than 0")     # query.rs:1233-1236
+        if mx is None and min_np > DEFAULT_NPROBES:
+            raise ValueError("minimum_nprobes must be less than or equal to maximum_nprobes")   # query.rs:1238-1245
         if max_np != 0 and max_np < min_np:
-            raise ValueError("maximum_nprobes must be greater than or equal to minimum_nprobes")
+            raise ValueError("maximum_nprobes must be greater than or equal to minimum_nprobes")  # query.rs:1268-1273
         # with no filter every probed partition yields rows, so min == effective probes;
         # maximum_nprobes only matters for filtered queries (query.py:1676-1692, query.rs:1250-1275):
         # 0 = "search as many partitions as needed" -> every partition

@@ -63,6 +63,18 @@ def test_builder_validation_errors():
         LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").limit(0)
     with pytest.raises(ValueError, match="maximum_nprobes"):
         LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").minimum_nprobes(10).maximum_nprobes(5).to_arrow()
+    # one setter alone is validated against the OTHER one's default of 20 (table.py:5777-5787 lowering onto
+    # query.rs:1232-1275; python/python/tests/test_query.py:936-961); the final state counts, not the call order
+    with pytest.raises(ValueError, match="minimum_nprobes must be less than or equal to maximum_nprobes"):
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").minimum_nprobes(100).to_arrow()
+    with pytest.raises(ValueError, match="maximum_nprobes must be greater than or equal to minimum_nprobes"):
+        LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").maximum_nprobes(5).to_arrow()
+    B = lambda: LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector")
+    assert B().minimum_nprobes(5)._resolve()[2:] == (5, 20)                     # maximum stays at its default
+    assert B().maximum_nprobes(50)._resolve()[2:] == (20, 50)
+    assert B().minimum_nprobes(2).maximum_nprobes(4)._resolve()[2:] == (2, 4)
+    assert B().nprobes(30).maximum_nprobes(20).minimum_nprobes(20)._resolve()[2:] == (20, 20)
+    assert B().minimum_nprobes(300).maximum_nprobes(0)._resolve()[2:] == (300, 1 << 30)   # 0 = no limit
     b = LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").where("a > 1").where("a < 5", prefilter=False)
     assert b._where == "(a > 1) AND (a < 5)" and b._postfilter        # test_query.py:600-604
     with pytest.raises(NotImplementedError):
@@ -438,7 +450,16 @@ def test_async_query_surface_matches_the_sync_builder(monkeypatch):
         with pytest.raises(ValueError, match="query_vector can not be None"):
             t.query().nearest_to(None)
         with pytest.raises(ValueError, match="minimum_nprobes must be greater than 0"):
-            await t.vector_search(q[0]).nprobes(0).to_arrow()
+            await t.vector_search(q[0]).minimum_nprobes(0).to_list()
+        # python/python/tests/test_query.py:948-961: validated against the request's defaults (20 / 20), eagerly
+        with pytest.raises(ValueError, match="maximum_nprobes must be greater than or equal to minimum_nprobes"):
+            await t.vector_search(q[0]).maximum_nprobes(5).to_list()
+        with pytest.raises(ValueError, match="minimum_nprobes must be less than or equal to maximum_nprobes"):
+            await t.vector_search(q[0]).minimum_nprobes(100).to_list()
+        with pytest.raises(ValueError, match="minimum_nprobes must be less than or equal to maximum_nprobes"):
+            t.vector_search(q[0]).minimum_nprobes(30).maximum_nprobes(40)          # order matters, as in Rust
+        await t.vector_search(q[0]).maximum_nprobes(40).minimum_nprobes(30).to_list()
+        await t.vector_search(q[0]).maximum_nprobes(0).minimum_nprobes(300).to_list()  # 0 = no limit
         with pytest.raises(ValueError, match="No vector column found to match"):
             await t.vector_search(np.zeros(5, np.float32)).to_arrow()
         assert list(await db.table_names()) == ["v"]
