@@ -27,6 +27,8 @@ DEFAULT_NPROBES = 20        # rust/lancedb/src/query.rs:1097-1113
 class LanceVectorQueryBuilder:
     def __init__(self, table, query, vector_column: str):
         self._table = table
+        if isinstance(query, (list, tuple)) and (len(query) == 0 or (isinstance(query[0], (list, tuple)) and len(query[0]) == 0)):
+            raise ValueError("Vector query must be a non-empty list")      # ensure_vector_query, query.py:332-350
         q = np.asarray(query, dtype=np.float32)      # every query vector is cast to Float32 (query.rs:1013)
         if q.ndim == 1:
             q = q[None, :]
@@ -163,6 +165,15 @@ class LanceVectorQueryBuilder:
         if self._query.shape[1] != t._dim(self._vector_column):
             raise ValueError(
                 f"No vector column found to match with the query vector dimension: {self._query.shape[1]}")
+        if t.count_rows() == 0:
+            # searching an empty table returns no rows (python/python/tests/test_query.py:1990-2004), not an error
+            tbl = t._take(np.zeros(0, np.int64), self._columns)
+            tbl = tbl.append_column("_distance", pa.array(np.zeros(0, np.float32), pa.float32()))
+            if self._with_row_id:
+                tbl = tbl.append_column("_rowid", pa.array(np.zeros(0, np.uint64), pa.uint64()))
+            if self._multi:
+                tbl = tbl.append_column("query_index", pa.array(np.zeros(0, np.int32), pa.int32()))
+            return tbl
         mask = None
         if self._where is not None:
             mask = _filter.evaluate(t._data, self._where)          # row id == row position

@@ -204,11 +204,16 @@ class DBConnection:
         self._device = device
         self._tables: Dict[str, Table] = {}
 
-    def create_table(self, name: str, data=None, mode: str = "create", exist_ok: bool = False, **_ignored) -> Table:
+    def create_table(self, name: str, data=None, schema: Optional[pa.Schema] = None, mode: str = "create",
+                     exist_ok: bool = False, **_ignored) -> Table:
         if name in self._tables and mode != "overwrite" and not exist_ok:
             raise ValueError(f"Table {name} already exists")
         if name in self._tables and exist_ok and mode != "overwrite":
             return self._tables[name]
+        if data is None:
+            if schema is None:
+                raise ValueError("Either data or schema must be provided")
+            data = schema.empty_table()                      # an empty table is searchable (returns no rows)
         t = Table(name, _to_arrow_table(data), self._device)
         self._tables[name] = t
         return t

@@ -23,6 +23,9 @@ class _FakeTable:
     def _dim(self, column):
         return self.dim
 
+    def count_rows(self):
+        return 100
+
     def _vector_search(self, q, **kw):
         self.calls.append(kw)
         B, k = q.shape[0], kw["k"]
@@ -75,6 +78,9 @@ def test_builder_validation_errors():
     assert B().minimum_nprobes(2).maximum_nprobes(4)._resolve()[2:] == (2, 4)
     assert B().nprobes(30).maximum_nprobes(20).minimum_nprobes(20)._resolve()[2:] == (20, 20)
     assert B().minimum_nprobes(300).maximum_nprobes(0)._resolve()[2:] == (300, 1 << 30)   # 0 = no limit
+    for empty in ([], [[]]):                                            # test_query.py:2007-2016
+        with pytest.raises(ValueError, match="non-empty"):
+            LanceVectorQueryBuilder(t, empty, "vector")
     b = LanceVectorQueryBuilder(t, [1, 2, 3, 4], "vector").where("a > 1").where("a < 5", prefilter=False)
     assert b._where == "(a > 1) AND (a < 5)" and b._postfilter        # test_query.py:600-604
     with pytest.raises(NotImplementedError):
@@ -464,3 +470,17 @@ def test_async_query_surface_matches_the_sync_builder(monkeypatch):
             await t.vector_search(np.zeros(5, np.float32)).to_arrow()
         assert list(await db.table_names()) == ["v"]
     asyncio.run(main())
+
+
+def test_search_on_an_empty_table_returns_no_rows():
+    """python/python/tests/test_query.py:1990-2004 (issue 303): no crash, no GPU call, the result schema intact."""
+    import pyarrow as pa
+    import lancedb_b200 as lancedb
+    db = lancedb.connect("memory://")
+    schema = pa.schema([pa.field("vector", pa.list_(pa.float32(), 2)), pa.field("id", pa.int64())])
+    t = db.create_table("test_empty_search", schema=schema)
+    assert t.search([1.0, 2.0]).limit(5).to_list() == []
+    out = t.search([[1.0, 2.0], [0.0, 1.0]]).with_row_id(True).to_arrow()
+    assert out.num_rows == 0 and out.column_names == ["vector", "id", "_distance", "_rowid", "query_index"]
+    with pytest.raises(ValueError, match="Either data or schema"):
+        db.create_table("nothing")
