@@ -95,3 +95,48 @@ def test_band_is_narrow_relative_to_the_spread_of_distances():
     assert W + 2 * E < 0.25 * d.std()
     order = np.argsort(L, kind="stable")
     assert L[order[31]] > L[order[9]] + W + 2 * E      # the proof condition of band_check3 for k=10, kp=32
+
+
+def test_candidate_lists_hold_the_exact_topk_under_any_tile_order():
+    """The scanners' threshold protocol (scan3.cu, candidate mode) restated on the host: tau_q may be ANY value such that
+    at least k rows seen so far have L <= tau_q (a tile's own k-th smallest, found from above by bisection; the k-th
+    smallest of the list so far; a stale copy read before another tile lowered it); a tile appends its rows with
+    L <= tau + W + 2E, or every row while no threshold exists.  Whatever the tile order, the staleness and the mix of
+    tightening rules, the union of the appended rows must contain the exact top-k by (d*, row) -- the property that lets
+    the finalize step re-score only the list."""
+    rng = np.random.default_rng(8)
+    ix = random_index(rng, dim=64, nlist=5, m=8, sizes=[900, 1500, 40, 2300, 700])
+    orc = oracle.OracleIndex.from_data(ix)
+    k = 10
+    for q in queries(rng, 4, 64):
+        rows = []                                             # (L, d*, partition, row), band per partition
+        Wm, Em = F(0), F(0)
+        for p in range(5):
+            L, W, E, d = _bounds(ix, orc, q, p)
+            Wm, Em = max(Wm, W), max(Em, E)
+            rows += [(float(L[r]), float(d[r]), p, r) for r in range(len(L))]
+        slack = float(Wm + 2 * Em)
+        truth = set(map(lambda t: (t[2], t[3]), sorted(rows, key=lambda t: (t[1], t[2], t[3]))[:k]))
+        for trial in range(6):
+            order = rng.permutation(len(rows))
+            tiles = np.array_split(order, rng.integers(3, 40))
+            tau, stale, appended = None, None, []
+            for tile in tiles:
+                Ls = np.array([rows[i][0] for i in tile])
+                use = stale if (stale is not None and rng.random() < 0.4) else tau      # a threshold read earlier
+                rule = rng.integers(0, 3)
+                if use is None or rule == 0:                  # tile-local: an upper bound of the tile's k-th smallest
+                    if len(Ls) >= k:
+                        kth = np.sort(Ls)[k - 1]
+                        cand = kth + rng.random() * 0.1 * abs(kth)              # bisection stops above it
+                        use = cand if use is None else min(use, cand)
+                elif rule == 1 and len(appended) >= k:        # list-based: k-th smallest key of the list so far
+                    use = min(use, np.sort([rows[i][0] for i in appended])[k - 1])
+                lim = np.inf if use is None else use + slack
+                appended += [i for i in tile if rows[i][0] <= lim]
+                stale = tau
+                if use is not None:
+                    tau = use if tau is None else min(tau, use)
+            got = {(rows[i][2], rows[i][3]) for i in appended}
+            assert truth <= got, (trial, len(got))
+            assert len(got) < len(rows)                       # and the filter does filter
