@@ -167,3 +167,22 @@ def test_golden_ivfpq_fixture_matches_oracle(metric):
     for name, (kw, want) in cases.items():
         assert same_result(orc.search(q, **kw), want), name
     assert same_result(oracle.flat_search(ix.vectors, q, k=7, metric=metric, row_ids=ix.row_ids), flat)
+
+
+def test_ivfpq_distance_range_relational():
+    """python/python/tests/test_query.py:723-787 (the ANN half; appended un-indexed rows are out of scope): on an IVF_PQ
+    index with one partition and two sub-vectors, [lower, upper) filters the ANN distances it reports."""
+    rng = np.random.default_rng(7)
+    x = rng.random((256, 2)).astype(np.float32)
+    oix = oracle.OracleIndex.from_data(train_ivf_pq(x, num_partitions=1, num_sub_vectors=2, max_iterations=4))
+    q = np.zeros((1, 2), np.float32)
+    ids, dist, cnt = oix.search(q, k=10, nprobes=1)
+    assert cnt[0] == 10 and (np.diff(dist[0]) >= 0).all()
+    lo, hi = float(dist[0, 0]), float(dist[0, 9])
+    assert oix.search(q, k=10, nprobes=1, upper=lo)[2][0] == 0
+    d = oix.search(q, k=10, nprobes=1, lower=hi)
+    assert d[2][0] >= 1 and (d[1][0, :d[2][0]] >= hi).all()
+    d = oix.search(q, k=10, nprobes=1, upper=hi)
+    assert (d[1][0, :d[2][0]] < hi).all()
+    d = oix.search(q, k=10, nprobes=1, lower=lo)
+    assert d[2][0] == 10 and (d[1][0] >= lo).all()
