@@ -86,6 +86,15 @@ class Table:
     def list_indices(self):
         return [{"name": f"{c}_idx", "index_type": "IVF_PQ", "columns": [c]} for c in self._index]
 
+    def index_stats(self, index_name: str):
+        """python/python/tests/test_index.py:366-372: every row is indexed (there is no append path here)."""
+        col = index_name[:-4] if index_name.endswith("_idx") else index_name
+        if col not in self._index_data:
+            return None
+        d = self._index_data[col]
+        return {"index_type": "IVF_PQ", "distance_type": d.metric, "num_indexed_rows": d.nrows,
+                "num_unindexed_rows": self.count_rows() - d.nrows, "num_indices": 1}
+
     def _vectors(self, column: str) -> np.ndarray:
         col = self._data.column(column).combine_chunks()
         dim = col.type.list_size
@@ -105,7 +114,7 @@ class Table:
             raise ValueError("only num_bits=8 is supported")
         column = vector_column_name or self._infer_vector_column(None)
         if column in self._index and not replace:
-            raise ValueError(f"index on {column} already exists")
+            raise RuntimeError(f"index {column}_idx already exists (pass replace=True)")   # python/python/tests/test_index.py:357
         dev = None
         if accelerator in ("cuda", "gpu"):
             dev = f"cuda:{self._device}"
